@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — HyperEx primer-search-and-extract hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path (classify -> Myers scan of every forward primer and every
+reverse-complemented reverse primer -> pairing) over one batch of synthetic records.  Workload =
+BASELINE.json configs[1]: 1 M synthetic full-length 16S reads (~1.5 kb, every built-in primer site
+planted), all 10 built-in regions, -m 0, per GPU.  With N > 1 (torchrun, one rank per GPU) every rank
+scans its own shard of N x 1 M records; no collective is on the data path, timing is the
+max over ranks.
+
+  value        Gbases/s with the arena resident in HBM (CUDA events on the launching stream)
+  e2e          Gbases/s through hx_run_batch with HOST buffers: pinned arena -> H2D -> kernels -> D2H
+               result table, every step
+  roofline     the Myers kernel against the measured integer-ALU peak (hx_int_peak) and HBM peak
+  cpu_baseline the CPU oracle (C port of the reference path) on a bounded sample, one thread like the
+               single-threaded reference
+  --impl reference   the same port on all host threads, as the reference arm
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tools")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+CELLS_PER_BASE_DEFAULT = 393  # sum over the 10 built-in pairs of len(fwd)+len(rev)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--records", type=int, default=1_000_000, help="records per GPU")
+    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=-1, help="Myers step variant (-1: library default)")
+    ap.add_argument("--cpu-sample", type=int, default=60_000, help="records of the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=0, help="records per step of the reference arm (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def pairs_and_cells():
+    from oracle import oracle as O  # only for the primer table of the CPU legs; the product has its own
+    pairs = O.default_pairs()
+    return pairs, sum(len(f) + len(r) for f, r in pairs)
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_port_run(arena, offsets, n, pairs, k, nthreads, rebuild=True):
+    """times the oracle (C port of utils.rs:270-351 + rust-bio Myers) on the first n records"""
+    from oracle import oracle as O
+    sub_o = np.ascontiguousarray(offsets[:n + 1])
+    sub_a = arena[:int(sub_o[-1])]
+    t0 = time.perf_counter()
+    O.run_batch(sub_a, sub_o, pairs, k, nthreads=nthreads, rebuild_per_record=rebuild)
+    dt = time.perf_counter() - t0
+    return int(sub_o[-1] - sub_o[0]), dt
+
+
+def run_reference(args, rank, world):
+    """reference arm: the CPU port of the reference path on all host threads (rank 0 only)"""
+    if rank != 0:
+        return
+    import hx_synth
+    pairs, cells = pairs_and_cells()
+    cores = os.cpu_count() or 1
+    n = args.ref_sample or max(2000, 2500 * cores)
+    arena, offsets = hx_synth.gen_reads(n, seed=2)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_port_run(arena, offsets, min(n, 500 * cores), pairs, args.k, cores)
+    times, bases = [], 0
+    for _ in range(args.steps):
+        bases, dt = cpu_port_run(arena, offsets, n, pairs, args.k, cores)
+        times.append(dt)
+    dt = sum(times) / len(times)
+    gb = bases / dt / 1e9
+    line = {"impl": "reference", "metric": "Gbases/s", "value": gb, "unit": "Gbases/s", "gcups": gb * cells,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "c2: synthetic full-length 16S reads ~1.5 kb, 10 built-in regions, -m 0 "
+                                   f"(bounded sample of {n} records per step)", "records": n, "pairs": len(pairs),
+                       "k": args.k},
+            "cpu_baseline": {"value": gb, "unit": "Gbases/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} records ({bases} bases) per step, {cores} threads; C port of the "
+                                       "reference path (Rust toolchain absent: SURVEY.md §8c), Peq rebuilt per "
+                                       "record x pair like utils.rs:301-302"},
+            "e2e": {"value": gb, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import hx_synth
+    import hyperex_b200 as hx
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+
+    pairs, cells = pairs_and_cells()
+    n = args.records
+    # every rank owns a different shard of the N x records job (weak scaling); seed = config index + rank
+    arena, offsets = hx_synth.gen_reads(n, seed=2 + 1000 * rank)
+    bases = int(offsets[-1])
+    npairs = len(pairs)
+
+    ctx = hx.Context((local,))
+    if args.variant >= 0:
+        ctx.set_option("step_variant", args.variant)
+    ctx.set_primers(pairs, args.k)
+
+    # ---- device-resident leg ("value") -------------------------------------------------------
+    pad = (-bases) % 16 + 16
+    d_arena = torch.empty(bases + pad, dtype=torch.uint8, device="cuda")
+    d_arena[:bases].copy_(torch.from_numpy(arena))
+    d_arena[bases:].zero_()
+    d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
+    d_out = torch.empty(n * npairs * 12, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def dev_step():
+        ctx.run_batch_device(d_arena.data_ptr(), d_off.data_ptr(), n, bases, d_out.data_ptr(),
+                             stream=stream.cuda_stream, dev_slot=0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        dev_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.set_option("time_kernels", 1)
+    ctx.kernel_time(reset=True)
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        dev_step()
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    myers_ms, myers_launches = ctx.kernel_time(reset=True)
+    ctx.set_option("time_kernels", 0)
+
+    # ---- end-to-end leg ("e2e"): host arena in, host result table out, every step ----------------
+    h_arena = hx.pinned_empty(bases + 64)
+    h_arena[:bases] = arena
+    h_out_raw = hx.pinned_empty(n * npairs * 12)
+    h_out = h_out_raw.view(hx.RESULT_DTYPE).reshape(n, npairs)
+    for _ in range(min(args.warmup, 2)):
+        ctx.run_batch(h_arena[:bases], offsets, out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.run_batch(h_arena[:bases], offsets, out=h_out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # results sanity: device-resident and host legs agree, every planted region found (k = 0)
+    dev_res = d_out.cpu().numpy().view(hx.RESULT_DTYPE).reshape(n, npairs)
+    assert dev_res.tobytes() == h_out.tobytes(), "device-resident and host legs disagree"
+    found = int((h_out["flags"] & 4).astype(bool).sum())
+
+    # ---- max over ranks ---------------------------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_s * 1e3, myers_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(bases), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max, myers_ms_max = (float(x) for x in t.cpu())
+    total_bases, total_launches = (float(x) for x in tot.cpu())
+
+    if rank == 0:
+        value = total_bases * args.steps / (dev_ms_max * 1e-3) / 1e9
+        e2e = total_bases * args.steps / (e2e_ms_max * 1e-3) / 1e9
+        hbm_peak, hbm_src = load_peaks()
+        # --- roofline of the dominant kernel (hx_myers_pair_kernel) -------------------------------
+        # algorithmic work per launch: the launch scans every base of this rank
+        # against the 15 unique built-in patterns (20 searches/base in the reference's count);
+        # one word-step = INT_OPS_PER_STEP integer instructions (SASS of the hot loop).
+        uniq = len({p for f, r in pairs for p in (("f", f), ("r", r))})
+        int_ops_per_step = 12.5
+        per_launch_ms = myers_ms_max / max(1, myers_launches)
+        steps_exec = bases * uniq
+        achieved_tops = steps_exec * int_ops_per_step / (per_launch_ms * 1e-3) / 1e12
+        peak = {}
+        for name, var in (("lop3", 0), ("imad", 3), ("lop3_imad", 4), ("myers_step", 10)):
+            try:
+                peak[name] = hx.int_peak(var, 1500, local) / 1e3  # Tops/s
+            except Exception as e:  # pragma: no cover
+                peak[name] = None
+                peak["error"] = str(e)
+        alu_peak = peak.get("lop3") or float("nan")
+        roofline = {"bound": "int_alu", "kernel": "hx_myers_pair_kernel<u32,15>",
+                    "achieved": achieved_tops, "peak": alu_peak, "unit": "Tint-op/s",
+                    "frac": achieved_tops / alu_peak,
+                    "peak_source": "hx_int_peak LOP3 stream measured in this run (ALU pipe; no integer figure in "
+                                   "MEASURED_PEAKS.json)",
+                    "word_steps_per_s": steps_exec / (per_launch_ms * 1e-3),
+                    "int_ops_per_word_step": int_ops_per_step, "kernel_ms_per_launch": per_launch_ms,
+                    "kernel_share_of_step": myers_ms_max / dev_ms_max,
+                    "dual_pipe_peak": peak.get("lop3_imad"), "frac_of_dual_pipe": (achieved_tops / peak["lop3_imad"])
+                    if peak.get("lop3_imad") else None, "bare_step_peak_gsteps": (peak.get("myers_step") or 0) * 1e3,
+                    "traffic": None,
+                    "hbm": {"achieved": bases / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": bases / (per_launch_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                            "algorithmic_bytes_per_launch": bases}}
+        line = {"metric": "Gbases/s", "value": value, "unit": "Gbases/s", "gcups": value * cells,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": "c2: 1M synthetic full-length 16S reads ~1.5 kb per GPU, 10 built-in "
+                                       "regions (20 searches/base, 393 cells/base), -m 0", "records_per_gpu": n,
+                           "bases_per_gpu": bases, "pairs": npairs, "k": args.k, "regions_found": found,
+                           "l2": "inputs (1.5 GB/GPU) larger than the 126 MB L2; no flush needed",
+                           "parallelism": f"records sharded over {world} GPU(s), no collective"},
+                "e2e": {"value": e2e, "unit": "Gbases/s", "gcups": e2e * cells, "ms_per_step": e2e_ms_max / args.steps,
+                        "h2d_bytes_per_step": int(bases + offsets.nbytes), "d2h_bytes_per_step": int(n * npairs * 12),
+                        "timer": "host wall clock around hx_run_batch (synchronous), max over ranks"},
+                "gpu_launches": int(total_launches), "roofline": roofline, "clocks": clocks}
+        if not args.no_cpu_baseline:
+            ns = min(args.cpu_sample, n)
+            cb, cdt = cpu_port_run(arena, offsets, ns, pairs, args.k, 1)
+            line["cpu_baseline"] = {"value": cb / cdt / 1e9, "unit": "Gbases/s", "gcups": cb / cdt / 1e9 * cells,
+                                    "cores": 1, "kind": "port",
+                                    "sample": f"first {ns} records ({cb} bases) of the same workload, 1 thread (the "
+                                              "reference is single-threaded); C port of utils.rs:270-351 + rust-bio "
+                                              f"Myers, {cdt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    hx.pinned_free(h_arena)
+    hx.pinned_free(h_out_raw)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

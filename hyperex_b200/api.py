@@ -1,0 +1,258 @@
+"""Host-side mirror of the reference's interface for the primer-search-and-extract path.
+
+Names, argument meaning and error behaviour follow Ebedthan/hyperex v0.2.0 `src/utils.rs`
+(region_to_primer 112-131, file_to_vec 134-145, primers_to_region 157-166, to_complement 169-194,
+to_reverse_complement 197-199, sequence_type 207-228, get_hypervar_regions 231-414) so the parity
+tests read like the reference's own unit tests (src/utils.rs:585-749).  Everything is a thin
+ctypes call into the C ABI; the compute runs on the GPU or fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+
+RESULT_DTYPE = np.dtype([("f_start", "<u4"), ("r_end", "<u4"), ("flags", "u1"), ("combined", "u1"),
+                         ("reserved", "<u2")])
+FWD_ANY, REV_ANY, PAIR_VALID, ALPHABET_NONE, RNA = 1, 2, 4, 8, 16
+
+SUPPORTED_REGIONS = ["v1v2", "v1v3", "v1v9", "v3v4", "v3v5", "v4", "v4v5", "v5v7", "v6v9", "v7v9"]
+
+
+class HyperexError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"hx error {code}: {msg}")
+        self.code = code
+
+
+class Alphabet:
+    Dna = 0
+    Rna = 1
+
+
+def _b(s) -> bytes:
+    return s.encode() if isinstance(s, str) else bytes(s)
+
+
+def _cstrs(strs: Sequence):
+    return (C.c_char_p * max(1, len(strs)))(*[_b(s) for s in strs])
+
+
+# ---- pure host helpers (utils.rs string functions) ---------------------------------------
+def sequence_type(sequence):
+    """utils.rs:207-228 -> Alphabet.Dna / Alphabet.Rna / None"""
+    s = _b(sequence)
+    r = _lib.load().hx_sequence_type(s, len(s))
+    return None if r == 2 else r
+
+
+def to_complement(primer, alphabet: str) -> str:
+    p = _b(primer)
+    out = C.create_string_buffer(len(p) + 1)
+    _lib.load().hx_to_complement(p, len(p), {"dna": 0, "rna": 1}.get(alphabet, 2), out)
+    return out.raw[:len(p)].decode()
+
+
+def to_reverse_complement(primer, alphabet: str) -> str:
+    p = _b(primer)
+    out = C.create_string_buffer(len(p) + 1)
+    _lib.load().hx_to_reverse_complement(p, len(p), {"dna": 0, "rna": 1}.get(alphabet, 2), out)
+    return out.raw[:len(p)].decode()
+
+
+def primers_to_region(primers: Sequence[str]) -> str:
+    out = C.create_string_buffer(16)
+    _lib.load().hx_primers_to_region(_b(primers[0]), _b(primers[1]), out)
+    return out.value.decode()
+
+
+def region_to_primer(region: str):
+    """utils.rs:112-131: [forward, reverse] or [] for an unsupported name"""
+    f, r = C.c_char_p(), C.c_char_p()
+    if _lib.load().hx_region_to_primer(_b(region), C.byref(f), C.byref(r)) != 0:
+        return []
+    return [f.value.decode(), r.value.decode()]
+
+
+def supported_regions():
+    n = C.c_uint32()
+    p = _lib.load().hx_supported_regions(C.byref(n))
+    return [p[i].decode() for i in range(n.value)]
+
+
+def default_primers():
+    """utils.rs:513-518: all built-in regions in SUPPORTED_REGIONS order"""
+    return [region_to_primer(r) for r in supported_regions()]
+
+
+def file_to_vec(filename: str):
+    """utils.rs:134-145; raises ValueError('Primer file must be comma-separated')"""
+    L = _lib.load()
+    f, r = C.POINTER(C.c_char_p)(), C.POINTER(C.c_char_p)()
+    n = L.hx_file_to_vec(_b(filename), C.byref(f), C.byref(r))
+    if n == -5:
+        raise FileNotFoundError(filename)
+    if n < 0:
+        raise ValueError("Primer file must be comma-separated")
+    out = [[f[i].decode(), r[i].decode()] for i in range(n)]
+    L.hx_free_primer_file(f, r, n)
+    return out
+
+
+def read_fasta(path: str, max_bytes: int = 0):
+    """fasta::Reader::new(read_file(path)).records() (utils.rs:237-238) -> iterator of
+    (arena u8[], offsets u64[n+1], ids [str]) batches; arrays are copies"""
+    L = _lib.load()
+    h = C.c_void_p()
+    rc = L.hx_fasta_open(_b(path), C.byref(h))
+    if rc != 0:
+        raise HyperexError(rc, f"cannot open {path}")
+    try:
+        while True:
+            a, o, ids = C.c_void_p(), C.c_void_p(), C.POINTER(C.c_char_p)()
+            n = L.hx_fasta_next(h, max_bytes, C.byref(a), C.byref(o), C.byref(ids))
+            if n < 0:
+                raise HyperexError(int(n), "read error")
+            if n == 0:
+                return
+            offsets = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+            total = int(offsets[-1])
+            arena = np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_uint8)), shape=(max(total, 1),)).copy()[:total]
+            yield arena, offsets, [ids[i].decode("utf-8", "replace") for i in range(n)]
+    finally:
+        L.hx_fasta_close(h)
+
+
+# ---- device path -------------------------------------------------------------------------
+class Context:
+    """Owns an hx_ctx (streams, device buffers, Peq tables) on one or more GPUs."""
+
+    def __init__(self, devices: Iterable[int] = (0,)):
+        self._L = _lib.load()
+        devs = list(devices)
+        arr = (C.c_int * len(devs))(*devs)
+        self._h = C.c_void_p()
+        rc = self._L.hx_create(C.byref(self._h), arr, len(devs))
+        if rc != 0:
+            raise HyperexError(rc, self._L.hx_last_error(None).decode())
+        self.n_pairs = 0
+        self.pairs = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.hx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HyperexError(rc, self._L.hx_last_error(self._h).decode())
+
+    def set_option(self, name: str, value: int):
+        self._check(self._L.hx_set_option(self._h, _b(name), int(value)))
+
+    def set_primers(self, primers: Sequence[Sequence[str]], mismatch: int):
+        fw = [_b(p[0]) for p in primers]
+        rv = [_b(p[1]) for p in primers]
+        fl = (C.c_uint32 * max(1, len(fw)))(*[len(x) for x in fw])
+        rl = (C.c_uint32 * max(1, len(rv)))(*[len(x) for x in rv])
+        self._check(self._L.hx_set_primers(self._h, len(primers), _cstrs(fw), fl, _cstrs(rv), rl, mismatch))
+        self.n_pairs = len(primers)
+        self.pairs = [list(p) for p in primers]
+
+    def run_batch(self, arena: np.ndarray, offsets: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """hx_run_batch on HOST buffers -> (n_records, n_pairs) structured array"""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        if out is None:
+            out = np.zeros((n, self.n_pairs), dtype=RESULT_DTYPE)
+        ap = arena.ctypes.data if arena is not None and arena.size else None
+        self._check(self._L.hx_run_batch(self._h, ap, offsets.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def run_batch_device(self, d_arena: int, d_offsets: int, n_records: int, arena_bytes: int, d_out: int,
+                         stream: int = 0, dev_slot: int = 0):
+        """hx_run_batch_device on raw device pointers (ints); asynchronous when stream != 0"""
+        self._check(self._L.hx_run_batch_device(self._h, dev_slot, d_arena, d_offsets, n_records, arena_bytes, d_out,
+                                                stream if stream else None))
+
+    def find_all_end(self, pattern, text, k: int, fold_case: bool = False):
+        """Myers::find_all_lazy(text, k).collect() on the GPU -> [(end, dist)]"""
+        pattern, text = _b(pattern), _b(text)
+        n = len(text)
+        ends = np.empty(max(n, 1), dtype=np.uint64)
+        dists = np.empty(max(n, 1), dtype=np.uint8)
+        tb = np.frombuffer(text, dtype=np.uint8) if n else np.zeros(1, np.uint8)
+        cnt = self._L.hx_find_all_end(self._h, pattern, len(pattern), tb.ctypes.data, n, k, 1 if fold_case else 0,
+                                      ends.ctypes.data, dists.ctypes.data, n)
+        if cnt < 0:
+            raise HyperexError(int(cnt), self._L.hx_last_error(self._h).decode())
+        return [(int(ends[i]), int(dists[i])) for i in range(cnt)]
+
+    def launch_count(self) -> int:
+        return int(self._L.hx_launch_count(self._h))
+
+    def kernel_time(self, reset: bool = True):
+        ms, n = C.c_double(), C.c_uint64()
+        self._check(self._L.hx_kernel_time(self._h, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, n.value
+
+    def get_hypervar_regions(self, file: str, primers: Sequence[Sequence[str]], prefix: str, mismatch: int,
+                             log=None):
+        """utils.rs:231-414: writes <prefix>.fa and <prefix>.gff; log(level, msg) gets warn!/error! lines"""
+        cb = _lib.LOG_FN((lambda lvl, msg, _u: log(lvl, msg.decode("utf-8", "replace"))) if log
+                         else (lambda lvl, msg, _u: None))
+        fw = _cstrs([p[0] for p in primers])
+        rv = _cstrs([p[1] for p in primers])
+        self._check(self._L.hx_get_hypervar_regions(self._h, _b(file), len(primers), fw, rv, _b(prefix), mismatch, cb,
+                                                    None))
+
+
+def get_hypervar_regions(file: str, primers, prefix: str, mismatch: int, devices=(0,), log=None):
+    """Drop-in for utils::get_hypervar_regions(file, primers, prefix, mismatch) (src/utils.rs:231-236)."""
+    with Context(devices) as ctx:
+        ctx.get_hypervar_regions(file, primers, prefix, mismatch, log=log)
+
+
+def int_peak(variant: int, iters: int = 2000, device: int = 0) -> float:
+    """measured integer throughput (1e9 lane-ops/s) of one instruction class; see hx_int_peak"""
+    g = C.c_double()
+    rc = _lib.load().hx_int_peak(device, variant, iters, C.byref(g))
+    if rc != 0:
+        raise HyperexError(rc, "hx_int_peak failed")
+    return g.value
+
+
+def pinned_empty(nbytes: int) -> np.ndarray:
+    """uint8 numpy view of cudaHostAlloc'd memory (hx_alloc_pinned); keep the array alive while in use"""
+    L = _lib.load()
+    p = L.hx_alloc_pinned(max(nbytes, 1))
+    if not p:
+        raise MemoryError("hx_alloc_pinned failed")
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+    _PINNED[arr.ctypes.data] = p
+    return arr
+
+
+_PINNED: dict = {}
+
+
+def pinned_free(arr: np.ndarray):
+    p = _PINNED.pop(arr.ctypes.data, None)
+    if p:
+        _lib.load().hx_free_pinned(p)

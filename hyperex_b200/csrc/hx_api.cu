@@ -1,0 +1,658 @@
+// hx_api.cu — C ABI runtime of the B200-native HyperEx hot path (include/hyperex_b200.h).
+//
+// Host side of the device path: primer set -> pattern groups + IUPAC Peq tables
+// (replaces MyersBuilder, utils.rs:251-268,299-302), and the batch pipeline that shards a
+// host arena into slabs, copies them host->device on alternating streams, runs
+// tile build -> classify -> Myers+pairing scan -> combine, and copies the result table back
+// in input order (replaces the record loop utils.rs:270-351).  No CPU fallback exists: all
+// compute entry points fail with HX_ERR_CUDA when CUDA is unusable.
+#include "../../include/hyperex_b200.h"
+#include "hx_device.h"
+#include "hx_host.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+static_assert(sizeof(hx_result) == 12, "hx_result must be 12 bytes");
+
+namespace {
+
+constexpr int HX_NSLOT = 3;  // pipeline depth per device (H2D / scan / D2H overlap)
+
+std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) {
+            cudaError_t e = cudaFree(p);  // synchronises the device: safe to regrow
+            p = nullptr;
+            cap = 0;
+            if (e != cudaSuccess) return e;
+        }
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e != cudaSuccess) return e;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf<uint8_t> arena;
+    DevBuf<uint64_t> offsets;
+    DevBuf<uint32_t> rec_u32;  // rec_raw | tile_first | tile_cnt   (3 x rec_cap)
+    DevBuf<uint32_t> scratch;  // ntiles, overflow, pad[2], hist[NB], cursor[NB]
+    DevBuf<HxTile> tiles;
+    DevBuf<uint32_t> order;
+    DevBuf<uint64_t> sum_f, sum_r, pair_hi;
+    DevBuf<uint32_t> pair_lo;
+    DevBuf<hx_result> out;
+    uint32_t *h_status = nullptr;  // pinned: [0] ntiles, [1] overflow
+    void release() {
+        arena.release(); offsets.release(); rec_u32.release(); scratch.release(); tiles.release();
+        order.release(); sum_f.release(); sum_r.release(); pair_hi.release(); pair_lo.release(); out.release();
+        if (h_status) cudaFreeHost(h_status);
+        if (stream) cudaStreamDestroy(stream);
+        h_status = nullptr;
+        stream = nullptr;
+    }
+};
+
+struct Device {
+    int dev = 0;
+    Slot slots[HX_NSLOT];
+    uint8_t *d_tables = nullptr;
+    HxGroup *d_groups = nullptr;
+    HxPairRef *d_pairs = nullptr;
+};
+
+struct TimedLaunch {
+    cudaEvent_t a, b;
+    int dev;
+};
+
+}  // namespace
+
+struct hx_ctx {
+    std::vector<Device> devs;
+    std::string err;
+    // primer set
+    uint32_t n_pairs = 0;
+    uint8_t k = 0;
+    uint32_t m_max = 0;
+    uint32_t n_slots = 0;  // per-pattern summary slots over all groups
+    std::vector<HxGroup> groups;
+    std::vector<HxPairRef> pair_refs;
+    std::vector<uint8_t> tables;
+    bool primers_set = false;
+    // options
+    int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_variant = 0, opt_time = 0;
+    uint64_t launches = 0;
+    std::vector<TimedLaunch> timed;
+    double myers_ms = 0;
+    uint64_t myers_launches = 0;
+};
+
+namespace {
+
+int fail(hx_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define HX_CUDA(ctx, call)                                                                              \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? HX_ERR_NOMEM : HX_ERR_CUDA, "%s: %s",  \
+                        #call, cudaGetErrorString(e__));                                                \
+    } while (0)
+
+// Top-aligned Peq word of `pat` for text byte b (IUPAC table of utils.rs:251-263 through
+// hxh_symbol_matches; build_64 semantics: bit i set iff pattern[i] matches b).
+uint64_t peq_word(const std::string &pat, uint8_t b, int bits) {
+    uint64_t w = 0;
+    const int m = (int)pat.size();
+    for (int i = 0; i < m; ++i)
+        if (hxh_symbol_matches((uint8_t)pat[i], b)) w |= 1ull << (i + bits - m);
+    return w;
+}
+
+struct PatternKey {
+    std::string dna, rna;
+    bool operator==(const PatternKey &o) const { return dna == o.dna && rna == o.rna; }
+};
+
+void sync_timed(hx_ctx *ctx) {
+    for (auto &t : ctx->timed) {
+        cudaSetDevice(t.dev);
+        cudaEventSynchronize(t.b);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            ctx->myers_ms += ms;
+            ctx->myers_launches += 1;
+        }
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    ctx->timed.clear();
+}
+
+struct SlabPlan {
+    uint32_t tile_len, single_max, warm, gran, tile_cap;
+};
+
+SlabPlan plan_slab(const hx_ctx *ctx, uint32_t n_records, uint64_t bytes) {
+    SlabPlan p;
+    const uint64_t target = 148ull * 1024;  // ~2 resident waves of scan threads
+    uint64_t tile_len, single_max;
+    if (n_records >= target / 4) {
+        tile_len = 2048;
+        single_max = 4096;
+    } else {
+        tile_len = ((bytes / target + 15) / 16) * 16;
+        tile_len = std::min<uint64_t>(std::max<uint64_t>(tile_len, 256), 2048);
+        single_max = tile_len + tile_len / 2;
+    }
+    if (ctx->opt_tile_len > 0) tile_len = (uint64_t)((ctx->opt_tile_len + 15) / 16 * 16);
+    if (ctx->opt_single_max > 0) single_max = (uint64_t)ctx->opt_single_max;
+    if (single_max < tile_len) single_max = tile_len;
+    p.tile_len = (uint32_t)tile_len;
+    p.single_max = (uint32_t)single_max;
+    p.warm = ctx->m_max + ctx->k - 1;  // a hit with dist <= k spans <= m + k text bytes
+    const uint64_t maxspan = std::max<uint64_t>(single_max, tile_len + 16) + p.warm;
+    uint64_t gran = (maxspan + HX_NBUCKETS - 1) / HX_NBUCKETS;
+    p.gran = (uint32_t)std::max<uint64_t>(16, (gran + 15) / 16 * 16);
+    p.tile_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)n_records + bytes / tile_len + 1);
+    return p;
+}
+
+// Enqueue the whole device path for one slab on `st`.  d_out receives n_records x n_pairs results.
+int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const uint64_t *d_offsets, uint64_t off_base,
+                 uint32_t n_records, uint64_t bytes, hx_result *d_out, cudaStream_t st) {
+    if (n_records == 0) return HX_OK;
+    const SlabPlan pl = plan_slab(ctx, n_records, bytes);
+    HX_CUDA(ctx, S.rec_u32.reserve((size_t)n_records * 3));
+    HX_CUDA(ctx, S.scratch.reserve(4 + 2 * HX_NBUCKETS));
+    HX_CUDA(ctx, S.tiles.reserve(pl.tile_cap));
+    HX_CUDA(ctx, S.order.reserve(pl.tile_cap));
+    HX_CUDA(ctx, S.sum_f.reserve((size_t)ctx->n_slots * pl.tile_cap));
+    HX_CUDA(ctx, S.sum_r.reserve((size_t)ctx->n_slots * pl.tile_cap));
+    HX_CUDA(ctx, S.pair_hi.reserve((size_t)ctx->n_pairs * pl.tile_cap));
+    HX_CUDA(ctx, S.pair_lo.reserve((size_t)ctx->n_pairs * pl.tile_cap));
+
+    uint32_t *rec_raw = S.rec_u32.p, *tile_first = rec_raw + n_records, *tile_cnt = tile_first + n_records;
+    uint32_t *ntiles = S.scratch.p, *overflow = ntiles + 1, *hist = ntiles + 4, *cursor = hist + HX_NBUCKETS;
+    HX_CUDA(ctx, cudaMemsetAsync(S.scratch.p, 0, (4 + 2 * HX_NBUCKETS) * sizeof(uint32_t), st));
+    HX_CUDA(ctx, cudaMemsetAsync(rec_raw, 0, (size_t)n_records * sizeof(uint32_t), st));
+
+    HxBuildArgs b;
+    b.offsets = d_offsets;
+    b.n_records = n_records;
+    b.single_max = pl.single_max;
+    b.tile_len = pl.tile_len;
+    b.warm = pl.warm;
+    b.bucket_gran = pl.gran;
+    b.tile_cap = pl.tile_cap;
+    b.tiles = S.tiles.p;
+    b.tile_first = tile_first;
+    b.tile_cnt = tile_cnt;
+    b.ntiles = ntiles;
+    b.hist = hist;
+    b.overflow = overflow;
+    ctx->launches += hx_launch_tile_build(b, cursor, S.order.p, st);
+    ctx->launches += hx_launch_classify(d_arena, d_offsets, off_base, S.tiles.p, ntiles, pl.tile_cap, rec_raw, st);
+
+    for (size_t gi = 0; gi < ctx->groups.size(); ++gi) {
+        const HxGroup &hg = ctx->groups[gi];
+        HxScanArgs a;
+        a.arena = d_arena;
+        a.offsets = d_offsets;
+        a.off_base = off_base;
+        a.tiles = S.tiles.p;
+        a.order = S.order.p;
+        a.ntiles = ntiles;
+        a.rec_raw = rec_raw;
+        a.tables = D.d_tables + hg.table_off;
+        a.group = D.d_groups + gi;
+        a.sum_f = S.sum_f.p;
+        a.sum_r = S.sum_r.p;
+        a.pair_hi = S.pair_hi.p;
+        a.pair_lo = S.pair_lo.p;
+        a.tile_stride = pl.tile_cap;
+        a.k = ctx->k;
+        a.variant = (int)ctx->opt_variant;
+        a.two = 2;
+        TimedLaunch tl;
+        if (ctx->opt_time) {
+            tl.dev = D.dev;
+            cudaEventCreate(&tl.a);
+            cudaEventCreate(&tl.b);
+            cudaEventRecord(tl.a, st);
+        }
+        int nl = hx_launch_scan(a, hg, pl.tile_cap, st);
+        if (nl < 0) return fail(ctx, HX_ERR_STATE, "no scan kernel for group of %d patterns", hg.np);
+        ctx->launches += nl;
+        if (ctx->opt_time) {
+            cudaEventRecord(tl.b, st);
+            ctx->timed.push_back(tl);
+        }
+    }
+    ctx->launches += hx_launch_combine(tile_first, tile_cnt, rec_raw, D.d_pairs, ctx->n_pairs, n_records, S.sum_f.p,
+                                       S.sum_r.p, S.pair_hi.p, S.pair_lo.p, pl.tile_cap, d_out, st);
+    HX_CUDA(ctx, cudaMemcpyAsync(S.h_status, S.scratch.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    HX_CUDA(ctx, cudaGetLastError());
+    return HX_OK;
+}
+
+int check_status(hx_ctx *ctx, const Slot &S) {
+    if (S.h_status[1] == 2) return fail(ctx, HX_ERR_ARG, "a record is longer than 2^32-257 bytes");
+    if (S.h_status[1]) return fail(ctx, HX_ERR_CAPACITY, "internal tile capacity exceeded");
+    return HX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hx_abi_version(void) { return HX_ABI_VERSION; }
+
+const char *hx_last_error(const hx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hx_create(hx_ctx **out, const int *dev_ids, int n_dev) {
+    if (!out || n_dev < 1) return fail(nullptr, HX_ERR_ARG, "hx_create: bad arguments");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, HX_ERR_CUDA, "hx_create: no CUDA device (%s); there is no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    hx_ctx *ctx = new (std::nothrow) hx_ctx();
+    if (!ctx) return fail(nullptr, HX_ERR_NOMEM, "hx_create: out of memory");
+    ctx->devs.resize(n_dev);
+    for (int i = 0; i < n_dev; ++i) {
+        Device &D = ctx->devs[i];
+        D.dev = dev_ids ? dev_ids[i] : i;
+        if (D.dev < 0 || D.dev >= count) {
+            fail(nullptr, HX_ERR_ARG, "hx_create: device %d not present (count %d)", D.dev, count);
+            hx_destroy(ctx);
+            return HX_ERR_ARG;
+        }
+        cudaError_t ce = cudaSetDevice(D.dev);
+        for (int s = 0; s < HX_NSLOT && ce == cudaSuccess; ++s) {
+            ce = cudaStreamCreateWithFlags(&D.slots[s].stream, cudaStreamNonBlocking);
+            if (ce == cudaSuccess) ce = cudaHostAlloc((void **)&D.slots[s].h_status, 16, cudaHostAllocDefault);
+            if (ce == cudaSuccess) memset(D.slots[s].h_status, 0, 16);
+        }
+        if (ce != cudaSuccess) {
+            fail(nullptr, HX_ERR_CUDA, "hx_create: device %d: %s", D.dev, cudaGetErrorString(ce));
+            hx_destroy(ctx);
+            return HX_ERR_CUDA;
+        }
+    }
+    *out = ctx;
+    return HX_OK;
+}
+
+void hx_destroy(hx_ctx *ctx) {
+    if (!ctx) return;
+    sync_timed(ctx);
+    for (Device &D : ctx->devs) {
+        cudaSetDevice(D.dev);
+        cudaDeviceSynchronize();
+        for (Slot &S : D.slots) S.release();
+        if (D.d_tables) cudaFree(D.d_tables);
+        if (D.d_groups) cudaFree(D.d_groups);
+        if (D.d_pairs) cudaFree(D.d_pairs);
+    }
+    delete ctx;
+}
+
+int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
+    if (!ctx || !name) return HX_ERR_ARG;
+    const std::string n(name);
+    if (n == "tile_len") ctx->opt_tile_len = value;
+    else if (n == "single_max") ctx->opt_single_max = value;
+    else if (n == "slab_bytes") ctx->opt_slab_bytes = std::max<int64_t>(value, 1);
+    else if (n == "step_variant") ctx->opt_variant = value;
+    else if (n == "time_kernels") ctx->opt_time = value;
+    else return fail(ctx, HX_ERR_ARG, "unknown option %s", name);
+    return HX_OK;
+}
+
+int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len,
+                   const char *const *rev, const uint32_t *rev_len, uint8_t k) {
+    if (!ctx) return HX_ERR_ARG;
+    if (n_pairs == 0 || n_pairs > 65535 || !fwd || !rev)
+        return fail(ctx, HX_ERR_ARG, "hx_set_primers: need 1..65535 primer pairs");
+    ctx->primers_set = false;
+    std::vector<std::string> F(n_pairs), R(n_pairs);
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        if (!fwd[i] || !rev[i]) return fail(ctx, HX_ERR_ARG, "hx_set_primers: NULL primer in pair %u", i);
+        const size_t lf = fwd_len ? fwd_len[i] : strlen(fwd[i]);
+        const size_t lr = rev_len ? rev_len[i] : strlen(rev[i]);
+        // rust-bio build_64 asserts 0 < m <= 64 (call sites utils.rs:301-302)
+        if (lf == 0 || lf > 64 || lr == 0 || lr > 64)
+            return fail(ctx, HX_ERR_ARG, "hx_set_primers: pair %u: primer length must be 1..64 (got %zu, %zu)", i, lf,
+                        lr);
+        F[i].assign(fwd[i], lf);
+        R[i].assign(rev[i], lr);
+        if (memchr(F[i].data(), 0, lf) || memchr(R[i].data(), 0, lr))
+            return fail(ctx, HX_ERR_ARG, "hx_set_primers: pair %u: NUL byte inside a primer", i);
+    }
+    // unique patterns per pair: forward as given; reverse = reverse complement per alphabet (utils.rs:299)
+    struct PairPat { PatternKey f, r; bool is_long; };
+    std::vector<PairPat> pp(n_pairs);
+    uint32_t m_max = 0;
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        pp[i].f = PatternKey{F[i], F[i]};
+        std::string rd(R[i].size(), '\0'), rr(R[i].size(), '\0');
+        hx_to_reverse_complement(R[i].data(), R[i].size(), 0, &rd[0]);
+        hx_to_reverse_complement(R[i].data(), R[i].size(), 1, &rr[0]);
+        pp[i].r = PatternKey{rd, rr};
+        pp[i].is_long = F[i].size() > 32 || R[i].size() > 32;
+        m_max = std::max<uint32_t>(m_max, (uint32_t)std::max(F[i].size(), R[i].size()));
+    }
+    // greedy grouping, short (32-bit words) and long (64-bit words) pairs separately
+    std::vector<HxGroup> groups;
+    std::vector<std::vector<PatternKey>> gpats;
+    std::vector<HxPairRef> refs(n_pairs);
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool want_long = pass == 1;
+        const int np_max = want_long ? HX_MAX_NP64 : HX_MAX_NP32;
+        int cur = -1;
+        for (uint32_t i = 0; i < n_pairs; ++i) {
+            if (pp[i].is_long != want_long) continue;
+            auto find_in = [&](int gidx, const PatternKey &key) -> int {
+                for (size_t j = 0; j < gpats[gidx].size(); ++j)
+                    if (gpats[gidx][j] == key) return (int)j;
+                return -1;
+            };
+            int fi = -1, ri = -1, need = 0;
+            if (cur >= 0) {
+                fi = find_in(cur, pp[i].f);
+                ri = find_in(cur, pp[i].r);
+                need = (fi < 0 ? 1 : 0) + ((ri < 0 && !(pp[i].r == pp[i].f)) ? 1 : 0);
+            }
+            if (cur < 0 || (int)gpats[cur].size() + need > np_max || groups[cur].npairs >= HX_MAX_GROUP_PAIRS) {
+                HxGroup g;
+                memset(&g, 0, sizeof g);
+                g.word64 = want_long ? 1 : 0;
+                groups.push_back(g);
+                gpats.emplace_back();
+                cur = (int)groups.size() - 1;
+                fi = ri = -1;
+            }
+            if (fi < 0) {
+                gpats[cur].push_back(pp[i].f);
+                fi = (int)gpats[cur].size() - 1;
+            }
+            ri = find_in(cur, pp[i].r);
+            if (ri < 0) {
+                gpats[cur].push_back(pp[i].r);
+                ri = (int)gpats[cur].size() - 1;
+            }
+            HxGroup &g = groups[cur];
+            g.pair_f[g.npairs] = (uint8_t)fi;
+            g.pair_r[g.npairs] = (uint8_t)ri;
+            g.pair_global[g.npairs] = (uint16_t)i;
+            g.npairs++;
+            refs[i].len_f = (uint32_t)F[i].size();  // utils.rs:327 forward_len
+            refs[i].pad = (uint32_t)cur;            // group index for now, slots resolved below
+            refs[i].f_slot = (uint32_t)fi;
+            refs[i].r_slot = (uint32_t)ri;
+        }
+    }
+    // tables: [group][alphabet dna|rna][256 rows][row stride]; text bytes are case-folded
+    // here (utils.rs:295) so the kernel indexes rows with the raw byte.
+    std::vector<uint8_t> blob;
+    uint32_t slot_base = 0;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        HxGroup &g = groups[gi];
+        g.np = (int)gpats[gi].size();
+        g.slot_base = slot_base;
+        slot_base += (uint32_t)g.np;
+        const int wb = g.word64 ? 8 : 4, bits = wb * 8;
+        const int stride = hx_row_stride(g.np, wb);
+        g.table_off = (uint32_t)blob.size();
+        blob.resize(blob.size() + 2 * (size_t)hx_table_bytes(g.np, wb), 0);
+        for (int p = 0; p < g.np; ++p) g.m[p] = (uint8_t)gpats[gi][p].dna.size();
+        for (int alpha = 0; alpha < 2; ++alpha) {
+            uint8_t *tab = blob.data() + g.table_off + (size_t)alpha * hx_table_bytes(g.np, wb);
+            for (int b = 1; b < 256; ++b) {  // row 0 stays all-zero: the "null" byte
+                const uint8_t u = (b >= 'a' && b <= 'z') ? (uint8_t)(b - 32) : (uint8_t)b;
+                for (int p = 0; p < g.np; ++p) {
+                    const std::string &pat = alpha ? gpats[gi][p].rna : gpats[gi][p].dna;
+                    const uint64_t w = peq_word(pat, u, bits);
+                    memcpy(tab + (size_t)b * stride + (size_t)p * wb, &w, wb);  // little endian: low bytes first
+                }
+            }
+        }
+    }
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        const HxGroup &g = groups[refs[i].pad];
+        refs[i].f_slot += g.slot_base;
+        refs[i].r_slot += g.slot_base;
+        refs[i].pad = 0;
+    }
+    // upload to every device
+    for (Device &D : ctx->devs) {
+        HX_CUDA(ctx, cudaSetDevice(D.dev));
+        HX_CUDA(ctx, cudaDeviceSynchronize());
+        if (D.d_tables) cudaFree(D.d_tables);
+        if (D.d_groups) cudaFree(D.d_groups);
+        if (D.d_pairs) cudaFree(D.d_pairs);
+        D.d_tables = nullptr; D.d_groups = nullptr; D.d_pairs = nullptr;
+        HX_CUDA(ctx, cudaMalloc((void **)&D.d_tables, blob.size()));
+        HX_CUDA(ctx, cudaMalloc((void **)&D.d_groups, groups.size() * sizeof(HxGroup)));
+        HX_CUDA(ctx, cudaMalloc((void **)&D.d_pairs, refs.size() * sizeof(HxPairRef)));
+        HX_CUDA(ctx, cudaMemcpy(D.d_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+        HX_CUDA(ctx, cudaMemcpy(D.d_groups, groups.data(), groups.size() * sizeof(HxGroup), cudaMemcpyHostToDevice));
+        HX_CUDA(ctx, cudaMemcpy(D.d_pairs, refs.data(), refs.size() * sizeof(HxPairRef), cudaMemcpyHostToDevice));
+    }
+    ctx->n_pairs = n_pairs;
+    ctx->k = k;
+    ctx->m_max = m_max;
+    ctx->n_slots = slot_base;
+    ctx->groups.swap(groups);
+    ctx->pair_refs.swap(refs);
+    ctx->tables.swap(blob);
+    ctx->primers_set = true;
+    return HX_OK;
+}
+
+int hx_run_batch_device(hx_ctx *ctx, int dev_slot, const uint8_t *d_arena, const uint64_t *d_offsets,
+                        uint32_t n_records, uint64_t arena_bytes, hx_result *d_out, void *stream) {
+    if (!ctx) return HX_ERR_ARG;
+    if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch_device: call hx_set_primers first");
+    if (dev_slot < 0 || dev_slot >= (int)ctx->devs.size() || (n_records && (!d_arena || !d_offsets || !d_out)))
+        return fail(ctx, HX_ERR_ARG, "hx_run_batch_device: bad arguments");
+    if (((uintptr_t)d_arena & 15u) != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_device: d_arena must be 16-byte aligned");
+    Device &D = ctx->devs[dev_slot];
+    HX_CUDA(ctx, cudaSetDevice(D.dev));
+    Slot &S = D.slots[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : S.stream;
+    int rc = enqueue_slab(ctx, D, S, d_arena, d_offsets, 0, n_records, arena_bytes, d_out, st);
+    if (rc != HX_OK) return rc;
+    if (!stream) {
+        HX_CUDA(ctx, cudaStreamSynchronize(st));
+        if (n_records) {
+            rc = check_status(ctx, S);
+            if (rc != HX_OK) return rc;
+        }
+        sync_timed(ctx);
+    }
+    return HX_OK;
+}
+
+int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out) {
+    if (!ctx) return HX_ERR_ARG;
+    if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch: call hx_set_primers first");
+    if (n_records == 0) return HX_OK;
+    if (!offsets || !out) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL offsets/out");
+    if (offsets[n_records] < offsets[0]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
+    if (offsets[n_records] > offsets[0] && !arena) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL arena");
+    const uint64_t slab_bytes = (uint64_t)ctx->opt_slab_bytes;
+    const size_t np = ctx->n_pairs;
+    const int ndev = (int)ctx->devs.size();
+    // per (device, slot): the slab it last ran, so its status word can be checked before reuse
+    std::vector<int> used(ndev * HX_NSLOT, 0);
+    uint32_t r0 = 0;
+    uint64_t slab_idx = 0;
+    int rc = HX_OK;
+    while (r0 < n_records && rc == HX_OK) {
+        // largest r1 with offsets[r1] - offsets[r0] <= slab_bytes (at least one record)
+        const uint64_t limit = offsets[r0] + slab_bytes;
+        uint32_t r1 = (uint32_t)(std::upper_bound(offsets + r0 + 1, offsets + n_records + 1, limit) - offsets) - 1;
+        if (r1 <= r0) r1 = r0 + 1;
+        for (uint32_t i = r0; i < r1; ++i)  // cheap sanity: monotone offsets inside the slab edges
+            if (offsets[i + 1] < offsets[i]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
+        const uint32_t n = r1 - r0;
+        const uint64_t bytes = offsets[r1] - offsets[r0];
+        const int di = (int)(slab_idx % ndev);
+        const int si = (int)((slab_idx / ndev) % HX_NSLOT);
+        Device &D = ctx->devs[di];
+        Slot &S = D.slots[si];
+        HX_CUDA(ctx, cudaSetDevice(D.dev));
+        if (used[di * HX_NSLOT + si]) {
+            // buffers of this slot may be regrown below: wait for its previous slab and check it
+            HX_CUDA(ctx, cudaStreamSynchronize(S.stream));
+            rc = check_status(ctx, S);
+            if (rc != HX_OK) break;
+        }
+        // the host arena slice is copied with its 16-byte phase preserved so that device
+        // addresses keep the alignment of the arena offsets
+        const uint64_t base = offsets[r0] & ~15ull;
+        const uint64_t copy_bytes = offsets[r1] - base;
+        HX_CUDA(ctx, S.arena.reserve(copy_bytes + 64));
+        HX_CUDA(ctx, S.offsets.reserve((size_t)n + 1));
+        HX_CUDA(ctx, S.out.reserve((size_t)n * np));
+        if (copy_bytes)
+            HX_CUDA(ctx, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, S.stream));
+        HX_CUDA(ctx, cudaMemcpyAsync(S.offsets.p, offsets + r0, ((size_t)n + 1) * sizeof(uint64_t),
+                                     cudaMemcpyHostToDevice, S.stream));
+        rc = enqueue_slab(ctx, D, S, S.arena.p, S.offsets.p, base, n, bytes, S.out.p, S.stream);
+        if (rc != HX_OK) break;
+        HX_CUDA(ctx, cudaMemcpyAsync(out + (size_t)r0 * np, S.out.p, (size_t)n * np * sizeof(hx_result),
+                                     cudaMemcpyDeviceToHost, S.stream));
+        used[di * HX_NSLOT + si] = 1;
+        r0 = r1;
+        ++slab_idx;
+    }
+    for (int di = 0; di < ndev; ++di) {
+        cudaSetDevice(ctx->devs[di].dev);
+        for (int si = 0; si < HX_NSLOT; ++si) {
+            if (!used[di * HX_NSLOT + si]) continue;
+            cudaError_t e = cudaStreamSynchronize(ctx->devs[di].slots[si].stream);
+            if (e != cudaSuccess && rc == HX_OK) rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: %s", cudaGetErrorString(e));
+            if (rc == HX_OK) rc = check_status(ctx, ctx->devs[di].slots[si]);
+        }
+    }
+    sync_timed(ctx);
+    return rc;
+}
+
+int64_t hx_find_all_end(hx_ctx *ctx, const char *pattern, uint32_t pattern_len, const uint8_t *text, uint64_t text_len,
+                        uint8_t k, int fold_case, uint64_t *out_end, uint8_t *out_dist, uint64_t cap) {
+    if (!ctx) return HX_ERR_ARG;
+    if (!pattern || pattern_len == 0 || pattern_len > 64)
+        return fail(ctx, HX_ERR_ARG, "hx_find_all_end: pattern length must be 1..64");
+    if (text_len && !text) return fail(ctx, HX_ERR_ARG, "hx_find_all_end: NULL text");
+    if (cap && (!out_end || !out_dist)) return fail(ctx, HX_ERR_ARG, "hx_find_all_end: NULL output");
+    if (text_len == 0) return 0;
+    Device &D = ctx->devs[0];
+    HX_CUDA(ctx, cudaSetDevice(D.dev));
+    cudaStream_t st = D.slots[0].stream;
+    const std::string pat(pattern, pattern_len);
+    std::vector<uint64_t> table(256, 0);
+    for (int b = 0; b < 256; ++b) {
+        const uint8_t u = (fold_case && b >= 'a' && b <= 'z') ? (uint8_t)(b - 32) : (uint8_t)b;
+        table[b] = peq_word(pat, u, 64);
+    }
+    const uint32_t tile_len = ctx->opt_tile_len > 0 ? (uint32_t)ctx->opt_tile_len : 1024u;
+    const uint64_t ntiles64 = (text_len + tile_len - 1) / tile_len;
+    if (ntiles64 > 0x7fffffffull) return fail(ctx, HX_ERR_ARG, "hx_find_all_end: text too long");
+    const uint32_t ntiles = (uint32_t)ntiles64;
+    uint8_t *d_text = nullptr, *d_dist = nullptr;
+    uint64_t *d_table = nullptr, *d_counts = nullptr, *d_end = nullptr;
+    int64_t result = HX_ERR_CUDA;
+    uint64_t total = 0;
+    const uint64_t ocap = std::min<uint64_t>(cap, text_len);
+    cudaError_t e = cudaMalloc((void **)&d_text, text_len);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_table, 256 * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_counts, ((size_t)ntiles + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_end, std::max<uint64_t>(ocap, 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_dist, std::max<uint64_t>(ocap, 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_text, text, text_len, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_table, table.data(), 256 * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        ctx->launches += hx_launch_find(d_text, text_len, (const uint8_t *)d_table, pattern_len, k, tile_len, ntiles,
+                                        d_counts, d_end, d_dist, ocap, 0, st);
+        ctx->launches += hx_launch_find(d_text, text_len, (const uint8_t *)d_table, pattern_len, k, tile_len, ntiles,
+                                        d_counts, d_end, d_dist, ocap, 1, st);
+        e = cudaMemcpyAsync(&total, d_counts + ntiles, 8, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) {
+        const uint64_t ncopy = std::min<uint64_t>(total, ocap);
+        if (ncopy) {
+            e = cudaMemcpy(out_end, d_end, ncopy * 8, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(out_dist, d_dist, ncopy, cudaMemcpyDeviceToHost);
+        }
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) result = (int64_t)total;
+    else fail(ctx, HX_ERR_CUDA, "hx_find_all_end: %s", cudaGetErrorString(e));
+    cudaFree(d_text); cudaFree(d_table); cudaFree(d_counts); cudaFree(d_end); cudaFree(d_dist);
+    return result;
+}
+
+void *hx_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void hx_free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+uint64_t hx_launch_count(const hx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int hx_kernel_time(hx_ctx *ctx, double *myers_ms, uint64_t *myers_launches, int reset) {
+    if (!ctx) return HX_ERR_ARG;
+    sync_timed(ctx);
+    if (myers_ms) *myers_ms = ctx->myers_ms;
+    if (myers_launches) *myers_launches = ctx->myers_launches;
+    if (reset) {
+        ctx->myers_ms = 0;
+        ctx->myers_launches = 0;
+    }
+    return HX_OK;
+}
+
+}  // extern "C"
+
+// used by hx_host.cpp (the file-level driver) to reach the batch path without the C structs
+int hx_internal_pairs(const hx_ctx *ctx) { return ctx ? (int)ctx->n_pairs : 0; }

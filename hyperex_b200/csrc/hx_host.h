@@ -1,0 +1,46 @@
+// hx_host.h — host-side pieces of the product that are not device code: the reference's
+// primer/region tables, IUPAC match predicate, FASTA ingest and the FASTA/GFF3 writers.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+// utils.rs:251-263 + rust-bio build_64: does pattern symbol p match text byte b?
+bool hxh_symbol_matches(uint8_t p, uint8_t b);
+
+// rust-bio fasta::Reader rules (call sites utils.rs:238,270) over a decompressed stream.
+struct HxhRecordBatch {
+    uint8_t *arena = nullptr;      // pinned when possible (hx_alloc_pinned), else malloc
+    size_t arena_cap = 0;
+    bool pinned = false;
+    std::vector<uint64_t> offsets; // n + 1
+    std::vector<std::string> ids;
+    void clear();
+    ~HxhRecordBatch();
+};
+
+class HxhByteSource;  // plain / gzip / bzip2 / xz / zstd byte stream (utils.rs:148-154)
+
+class HxhFastaReader {
+  public:
+    HxhFastaReader();
+    ~HxhFastaReader();
+    // returns 0 or a negative hx_status; err receives the message
+    int open(const char *path, std::string &err);
+    // appends records until the arena holds >= max_bytes or max_records; returns the number of
+    // records appended, 0 at the end of the input.
+    size_t next_batch(HxhRecordBatch &batch, size_t max_bytes, size_t max_records);
+
+  private:
+    bool fill();
+    bool read_line(std::string &line);  // includes the trailing '\n' when present
+    HxhByteSource *src_ = nullptr;
+    std::vector<uint8_t> buf_;
+    size_t pos_ = 0, end_ = 0;
+    bool eof_ = false;
+    std::string line_;   // look-ahead line (rust-bio keeps the next header in self.line)
+    bool have_line_ = false;
+    bool finished_ = false;
+};

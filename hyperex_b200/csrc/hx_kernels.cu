@@ -1,0 +1,635 @@
+// hx_kernels.cu — hand-written sm_100a kernels of the HyperEx primer-search hot path.
+//
+//   hx_tile_build_kernel / hx_bucket_scan_kernel / hx_tile_scatter_kernel
+//       records -> tiles (whole short record, or overlapped window of a long one), ordered
+//       longest-first so the lanes of a warp finish together.
+//   hx_classify_kernel        utils.rs:207-228 sequence_type (HBM-bound byte reduction)
+//   hx_myers_pair_kernel      utils.rs:301-351: the Myers Pv/Mv/score recurrence of rust-bio
+//                             Myers<u64>::find_all_lazy for ALL patterns of a group per text
+//                             byte, fused with the reference's hit-selection rule evaluated
+//                             as a streaming arg-min (no hit lists are materialised)
+//   hx_combine_kernel         joins the per-tile summaries of a record into hx_result
+//   hx_find_kernel            known-answer mirror of find_all_lazy (count / scan / write)
+//
+// Integer bit-parallel work: no tensor cores by design (BASELINE.json north_star).
+#include "hx_device.h"
+
+#include <stdio.h>
+
+// ------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int hx_alpha_of(uint32_t raw) {
+    // utils.rs:211-227: 0 dna, 1 rna, 2 none
+    const bool u = raw & HX_RAW_U, t = raw & HX_RAW_T;
+    if (u && !t) return 1;
+    if (t && !u) return 0;
+    if (!u && !t) return (raw & HX_RAW_NONIUPAC) ? 2 : 0;
+    return 2;
+}
+
+__device__ __forceinline__ uint32_t hx_w32(const uint4 &v, int i) {
+    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+}
+
+__device__ __forceinline__ uint4 hx_ldg16(const uint8_t *p) {
+    return __ldg(reinterpret_cast<const uint4 *>(p));
+}
+
+// ------------------------------------------------------------------------------------
+// tile construction
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hx_bucket_of(uint32_t span, uint32_t gran) {
+    uint32_t b = span / gran;
+    return b < HX_NBUCKETS ? b : HX_NBUCKETS - 1;
+}
+
+__global__ void __launch_bounds__(256) hx_tile_build_kernel(const HxBuildArgs a) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_records) return;
+    const uint64_t len64 = a.offsets[r + 1] - a.offsets[r];
+    if (len64 > 0xFFFFFF00ull) {  // record positions are 32-bit (hx_result.f_start / r_end)
+        *a.overflow = 2;
+        a.tile_cnt[r] = 0;
+        a.tile_first[r] = 0;
+        return;
+    }
+    const uint32_t len = (uint32_t)len64;
+    uint32_t nt = 0, tl = 0;
+    if (len == 0) {
+        nt = 0;
+    } else if (len <= a.single_max) {
+        nt = 1;
+        tl = len;
+    } else {
+        nt = (len + a.tile_len - 1) / a.tile_len;
+        tl = ((len + nt - 1) / nt + 15u) & ~15u;  // equal-sized windows, 16-byte granular
+        nt = (len + tl - 1) / tl;
+    }
+    const uint32_t base = nt ? atomicAdd(a.ntiles, nt) : 0u;
+    if (base + nt > a.tile_cap) {
+        *a.overflow = 1;
+        a.tile_cnt[r] = 0;
+        a.tile_first[r] = 0;
+        return;
+    }
+    a.tile_first[r] = base;
+    a.tile_cnt[r] = nt;
+    for (uint32_t i = 0; i < nt; ++i) {
+        HxTile t;
+        t.rec = r;
+        t.own_start = i * tl;
+        t.own_len = min(tl, len - t.own_start);
+        t.warm = min(a.warm, t.own_start);
+        a.tiles[base + i] = t;
+        atomicAdd(&a.hist[hx_bucket_of(t.warm + t.own_len, a.bucket_gran)], 1u);
+    }
+}
+
+// cursor[b] = number of tiles in buckets longer than b (longest bucket is processed first)
+__global__ void __launch_bounds__(HX_NBUCKETS) hx_bucket_scan_kernel(const uint32_t *hist, uint32_t *cursor) {
+    __shared__ uint32_t warp_sum[32];
+    const int i = threadIdx.x;
+    const int b = HX_NBUCKETS - 1 - i;
+    const uint32_t own = hist[b];
+    uint32_t x = own;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if ((i & 31) >= d) x += y;
+    }
+    if ((i & 31) == 31) warp_sum[i >> 5] = x;
+    __syncthreads();
+    if (i < 32) {
+        uint32_t w = warp_sum[i];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+            if (i >= d) w += y;
+        }
+        warp_sum[i] = w;
+    }
+    __syncthreads();
+    const uint32_t before = (i >> 5) ? warp_sum[(i >> 5) - 1] : 0u;
+    cursor[b] = before + x - own;
+}
+
+__global__ void __launch_bounds__(256) hx_tile_scatter_kernel(const HxTile *tiles, const uint32_t *ntiles,
+                                                              uint32_t tile_cap, uint32_t gran, uint32_t *cursor,
+                                                              uint32_t *order) {
+    const uint32_t n = min(*ntiles, tile_cap);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const HxTile tl = tiles[t];
+        const uint32_t pos = atomicAdd(&cursor[hx_bucket_of(tl.warm + tl.own_len, gran)], 1u);
+        order[pos] = t;
+    }
+}
+
+int hx_launch_tile_build(const HxBuildArgs &a, uint32_t *cursor, uint32_t *order, cudaStream_t st) {
+    if (a.n_records == 0) return 0;
+    hx_tile_build_kernel<<<(a.n_records + 255) / 256, 256, 0, st>>>(a);
+    hx_bucket_scan_kernel<<<1, HX_NBUCKETS, 0, st>>>(a.hist, cursor);
+    uint32_t blocks = (a.tile_cap + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    hx_tile_scatter_kernel<<<blocks, 256, 0, st>>>(a.tiles, a.ntiles, a.tile_cap, a.bucket_gran, cursor, order);
+    return 3;
+}
+
+// ------------------------------------------------------------------------------------
+// utils.rs:207-228 sequence_type: per record, does the upper-cased text contain 'U', 'T',
+// or a byte outside "ACGTRYSWKMBDHVN"?  One warp per tile, 16-byte coalesced loads.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hx_classify_kernel(const uint8_t *__restrict__ arena,
+                                                          const uint64_t *__restrict__ offsets,
+                                                          const uint64_t off_base,
+                                                          const HxTile *__restrict__ tiles,
+                                                          const uint32_t *__restrict__ ntiles_p, uint32_t tile_cap,
+                                                          uint32_t *__restrict__ rec_raw) {
+    __shared__ uint8_t cls[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int u = (i >= 'a' && i <= 'z') ? i - 32 : i;  // to_ascii_uppercase (utils.rs:210)
+        uint32_t f = 0;
+        if (u == 'U') f |= HX_RAW_U;
+        if (u == 'T') f |= HX_RAW_T;
+        const bool iupac = u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'R' || u == 'Y' || u == 'S' ||
+                           u == 'W' || u == 'K' || u == 'M' || u == 'B' || u == 'D' || u == 'H' || u == 'V' ||
+                           u == 'N';
+        if (!iupac) f |= HX_RAW_NONIUPAC;
+        cls[i] = (uint8_t)f;
+    }
+    __syncthreads();
+    const uint32_t ntiles = min(*ntiles_p, tile_cap);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += warps) {
+        const HxTile tl = tiles[t];
+        const uint64_t s = offsets[tl.rec] - off_base + tl.own_start;
+        const uint64_t e = s + tl.own_len;
+        uint32_t f = 0;
+        for (uint64_t A = (s & ~15ull) + lane * 16ull; A < e; A += 512ull) {
+            const uint4 v = hx_ldg16(arena + A);
+            const bool full = A >= s && A + 16 <= e;
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                const uint32_t w = hx_w32(v, wi);
+#pragma unroll
+                for (int bi = 0; bi < 4; ++bi) {
+                    const uint64_t pos = A + wi * 4 + bi;
+                    if (full || (pos >= s && pos < e)) f |= cls[(w >> (8 * bi)) & 0xffu];
+                }
+            }
+        }
+        f = __reduce_or_sync(0xffffffffu, f);
+        if (lane == 0 && f) atomicOr(&rec_raw[tl.rec], f);
+    }
+}
+
+int hx_launch_classify(const uint8_t *arena, const uint64_t *offsets, uint64_t off_base, const HxTile *tiles,
+                       const uint32_t *ntiles, uint32_t tile_cap, uint32_t *rec_raw, cudaStream_t st) {
+    if (tile_cap == 0) return 0;
+    uint64_t blocks = ((uint64_t)tile_cap * 32 + 255) / 256;
+    if (blocks > 148 * 8 * 4) blocks = 148 * 8 * 4;
+    hx_classify_kernel<<<(uint32_t)blocks, 256, 0, st>>>(arena, offsets, off_base, tiles, ntiles, tile_cap, rec_raw);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------
+// The Myers step (rust-bio 1.6.0 Myers::step).  The pattern is
+// TOP-ALIGNED in the word: bit (i + BITS - m) belongs to pattern position i, so `bound` is
+// the sign bit and the score update needs no per-pattern mask.  The unused low bits keep
+// pv = 1, mv = 0 and eq = 0, which makes them feed ph = mh = 0 into pattern bit 0 exactly
+// like the `<< 1` of the reference feeds a 0 (free start in the text).
+// The score is kept biased: s = dist - (k + 1), so "dist <= k" is the sign bit of s.
+//   V = 0  plain C (shifts)            V = 1  score via mad.hi (FMA pipe)
+//   V = 2  shifts via add-with-carry, score via addc/subc
+//   V = 3  score via IMAD.HI with a runtime multiplier (FMA pipe)
+// ------------------------------------------------------------------------------------
+template <int V>
+__device__ __forceinline__ void hx_step(const uint32_t eq, uint32_t &pv, uint32_t &mv, int &s, const uint32_t two) {
+    const uint32_t xv = eq | mv;
+    const uint32_t xh = (((eq & pv) + pv) ^ pv) | eq;
+    uint32_t ph = mv | ~(xh | pv);
+    uint32_t mh = pv & xh;
+    if (V == 3) {
+        // `two` is a kernel argument (== 2): ptxas cannot strength-reduce the multiply, so both
+        // score updates issue as IMAD.HI on the FMA pipe instead of LEA.HI on the ALU pipe.
+        asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(s) : "r"(ph), "r"(two));  // s += ph >> 31
+        asm("mad.hi.s32 %0, %1, %2, %0;" : "+r"(s) : "r"(mh), "r"(two));  // s -= mh >> 31
+        ph <<= 1;
+        mh <<= 1;
+    } else if (V == 1) {
+        asm("mad.hi.u32 %0, %1, 2, %0;" : "+r"(s) : "r"(ph));  // s += ph >> 31
+        asm("mad.hi.s32 %0, %1, 2, %0;" : "+r"(s) : "r"(mh));  // s -= mh >> 31
+        ph <<= 1;
+        mh <<= 1;
+    } else if (V == 2) {
+        asm("add.cc.u32 %0, %0, %0;\n\taddc.s32 %1, %1, 0;" : "+r"(ph), "+r"(s));
+        asm("add.cc.u32 %0, %0, %0;\n\tsubc.s32 %1, %1, 0;" : "+r"(mh), "+r"(s));
+    } else {
+        s += (int)(ph >> 31) - (int)(mh >> 31);
+        ph <<= 1;
+        mh <<= 1;
+    }
+    pv = mh | ~(xv | ph);
+    mv = ph & xv;
+}
+
+template <int V>
+__device__ __forceinline__ void hx_step(const uint64_t eq, uint64_t &pv, uint64_t &mv, int &s, const uint32_t) {
+    const uint64_t xv = eq | mv;
+    const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
+    uint64_t ph = mv | ~(xh | pv);
+    uint64_t mh = pv & xh;
+    s += (int)(ph >> 63) - (int)(mh >> 63);
+    ph <<= 1;
+    mh <<= 1;
+    pv = mh | ~(xv | ph);
+    mv = ph & xv;
+}
+
+template <typename W, int NP>
+struct HxRow {
+    static constexpr int WB = sizeof(W);
+    static constexpr int NV = (NP * WB + 15) / 16;
+    uint4 v[NV];
+    __device__ __forceinline__ void load(const uint8_t *row) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(row);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = p[i];
+    }
+    __device__ __forceinline__ W eq(int p) const {
+        if (WB == 4) return (W)hx_w32(v[p >> 2], p & 3);
+        const uint4 &q = v[p >> 1];
+        return (p & 1) ? (W)(((uint64_t)q.w << 32) | q.z) : (W)(((uint64_t)q.y << 32) | q.x);
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// hx_myers_pair_kernel<W, NP, V>
+//   one thread = one tile; per text byte the thread loads one Peq row (all NP patterns of the
+//   group, shared memory, 16-byte LDS) and advances NP independent automata held in registers.
+//   A hit (sign bit of any biased score) is rare and handled out of line: it updates
+//     bestR[p]  = lexicographic min (dist, end) over all hits of pattern p in the tile
+//     bestF[p]  = same, restricted to hits usable as a forward primer (end >= m_p - 1,
+//                 utils.rs:334)
+//     pair[q]   = arg-min of (f_dist + r_dist, f_end, r_end) over pairs with r_end > f_end
+//                 (utils.rs:338-349), evaluated as a stream: at a reverse hit the only forward
+//                 candidate that can win is bestF (DESIGN.md §pairing proves the equivalence).
+//   Text is read with 16-byte vector loads, one ahead (software prefetch).
+// ------------------------------------------------------------------------------------
+template <typename W, int NP, int V>
+__global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((sizeof(W) * NP <= 32) ? 5 : 4))
+    hx_myers_pair_kernel(const HxScanArgs a) {
+    constexpr int WB = sizeof(W);
+    constexpr int STRIDE = hx_row_stride(NP, WB);
+    constexpr int TBYTES = 256 * STRIDE;
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ HxGroup g;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.tables);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int i = threadIdx.x; i < 2 * TBYTES / 16; i += HX_THREADS) dst[i] = __ldg(src + i);
+        if (threadIdx.x < sizeof(HxGroup) / 4)
+            reinterpret_cast<uint32_t *>(&g)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.group)[threadIdx.x];
+    }
+    __syncthreads();
+
+    const uint32_t ntiles = min(*a.ntiles, a.tile_stride);
+    const uint32_t t = blockIdx.x * HX_THREADS + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t tile_id = a.order[t];
+    const HxTile tl = a.tiles[tile_id];
+    const int alpha = hx_alpha_of(a.rec_raw[tl.rec]);
+    if (alpha == 2) return;  // utils.rs:276-279: record skipped
+    const uint8_t *tab = smem + (alpha == 1 ? TBYTES : 0);
+
+    W pv[NP], mv[NP];
+    int s[NP];
+    uint64_t bestF[NP], bestR[NP];
+    uint64_t phi[HX_MAX_GROUP_PAIRS];
+    uint32_t plo[HX_MAX_GROUP_PAIRS];
+    const int bias = (int)a.k + 1;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        pv[p] = ~(W)0;
+        mv[p] = 0;
+        s[p] = (int)g.m[p] - bias;
+        bestF[p] = HX_NONE64;
+        bestR[p] = HX_NONE64;
+    }
+    for (int q = 0; q < HX_MAX_GROUP_PAIRS; ++q) {
+        phi[q] = HX_NONE64;
+        plo[q] = 0;
+    }
+
+    const uint64_t a0 = a.offsets[tl.rec] - a.off_base + tl.own_start - tl.warm;
+    const uint64_t ab = a0 & ~15ull;
+    const uint32_t lead = (uint32_t)(a0 - ab);
+    const uint32_t nchunks = (lead + tl.warm + tl.own_len + 15u) >> 4;
+    const uint32_t pos0 = tl.own_start - tl.warm - lead;  // record position of chunk 0 byte 0 (may wrap)
+    const uint8_t *src = a.arena + ab;
+
+    uint4 cur = hx_ldg16(src);
+    if (tl.own_start == tl.warm && lead) {
+        // The scan starts at the record start: bytes before it belong to the previous record.
+        // Byte 0 selects the all-zero Peq row, under which a fresh automaton stays fresh.
+        uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+            const int z = (int)lead - 4 * wi;  // bytes of this word to clear
+            if (z >= 4) w[wi] = 0;
+            else if (z > 0) w[wi] &= 0xffffffffu << (8 * z);
+        }
+        cur = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+
+    // UB text bytes are processed per trip of the innermost loop.  Wide groups keep UB = 1 so that
+    // the (large) rare path exists once and the hot loop stays inside the instruction cache.
+    constexpr int UB = (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
+    const uint32_t two = a.two;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint4 nxt = (c + 1 < nchunks) ? hx_ldg16(src + 16ull * (c + 1)) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (int wi = 0; wi < 4; ++wi) {
+            uint32_t w = cur.x;
+            cur.x = cur.y;
+            cur.y = cur.z;
+            cur.z = cur.w;
+#pragma unroll 1
+            for (int b0 = 0; b0 < 4; b0 += UB) {
+#pragma unroll
+                for (int bi = 0; bi < UB; ++bi) {
+                    const uint32_t byte = w & 0xffu;
+                    w >>= 8;
+                    HxRow<W, NP> row;
+                    row.load(tab + byte * STRIDE);
+                    int any = 0;
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        hx_step<V>(row.eq(p), pv[p], mv[p], s[p], two);
+                        any |= s[p];
+                    }
+                    if (any < 0) {
+                        // ---- rare path: at least one pattern has dist <= k at this position ----
+                        const uint32_t pos = pos0 + (c << 4) + (wi << 2) + b0 + bi;
+                        if (pos - tl.own_start < tl.own_len) {
+                            uint32_t hm = 0;
+                            uint8_t dl[NP];
+#pragma unroll
+                            for (int p = 0; p < NP; ++p) {
+                                dl[p] = (uint8_t)(s[p] + bias);
+                                hm |= (s[p] < 0 ? 1u : 0u) << p;
+                            }
+                            // reverse role first: forward candidates must end strictly before pos
+#pragma unroll 1
+                            for (int q = 0; q < g.npairs; ++q) {
+                                const int r = g.pair_r[q];
+                                if ((hm >> r) & 1u) {
+                                    const uint64_t bf = bestF[g.pair_f[q]];
+                                    if (bf != HX_NONE64) {
+                                        const uint32_t comb = (uint32_t)(bf >> 32) + dl[r];
+                                        if (comb < (uint32_t)(phi[q] >> 32)) {
+                                            phi[q] = ((uint64_t)comb << 32) | (uint32_t)bf;
+                                            plo[q] = pos;
+                                        }
+                                    }
+                                }
+                            }
+#pragma unroll 1
+                            for (int p = 0; p < NP; ++p) {
+                                if ((hm >> p) & 1u) {
+                                    const uint64_t key = ((uint64_t)dl[p] << 32) | pos;
+                                    if (key < bestR[p]) bestR[p] = key;
+                                    if (pos + 1 >= g.m[p] && key < bestF[p]) bestF[p] = key;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        cur = nxt;
+    }
+
+    const size_t ts = a.tile_stride;
+    for (int p = 0; p < NP; ++p) {
+        a.sum_f[(size_t)(g.slot_base + p) * ts + tile_id] = bestF[p];
+        a.sum_r[(size_t)(g.slot_base + p) * ts + tile_id] = bestR[p];
+    }
+    for (int q = 0; q < g.npairs; ++q) {
+        a.pair_hi[(size_t)g.pair_global[q] * ts + tile_id] = phi[q];
+        a.pair_lo[(size_t)g.pair_global[q] * ts + tile_id] = plo[q];
+    }
+}
+
+template <typename W, int NP, int V>
+static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
+    const int smem = 2 * hx_table_bytes(NP, sizeof(W));
+    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 8 && !attr_done[dev]) {
+        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        attr_done[dev] = true;
+    } else if (dev >= 8) {
+        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
+    const uint32_t blocks = (tile_cap + HX_THREADS - 1) / HX_THREADS;
+    hx_myers_pair_kernel<W, NP, V><<<blocks, HX_THREADS, smem, st>>>(a);
+    return 1;
+}
+
+template <typename W, int V, int NP>
+struct HxDispatch {
+    static int run(int np, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
+        if (np == NP) return hx_scan_launch_one<W, NP, V>(a, cap, st);
+        return HxDispatch<W, V, NP - 1>::run(np, a, cap, st);
+    }
+};
+template <typename W, int V>
+struct HxDispatch<W, V, 0> {
+    static int run(int, const HxScanArgs &, uint32_t, cudaStream_t) { return -1; }
+};
+
+int hx_launch_scan(const HxScanArgs &a, const HxGroup &hg, uint32_t tile_cap, cudaStream_t st) {
+    if (tile_cap == 0) return 0;
+    if (hg.word64) return HxDispatch<uint64_t, 0, HX_MAX_NP64>::run(hg.np, a, tile_cap, st);
+    switch (a.variant) {
+    case 1: return HxDispatch<uint32_t, 1, HX_MAX_NP32>::run(hg.np, a, tile_cap, st);
+    case 2: return HxDispatch<uint32_t, 2, HX_MAX_NP32>::run(hg.np, a, tile_cap, st);
+    case 3: return HxDispatch<uint32_t, 3, HX_MAX_NP32>::run(hg.np, a, tile_cap, st);
+    default: return HxDispatch<uint32_t, 0, HX_MAX_NP32>::run(hg.np, a, tile_cap, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// hx_combine_kernel: one thread per (pair, record).  Walks the record's tiles left to right
+// and joins their summaries with the same streaming rule, at tile granularity:
+//   cross candidates  (forward hit in an earlier tile, reverse hit in this tile) = bestF so far
+//                     + this tile's bestR;  within-tile candidates come from the scan kernel.
+// Result = lexicographic min of (combined, f_end, r_end)  ==  utils.rs:327-351.
+// ------------------------------------------------------------------------------------
+struct HxResultDev {
+    uint32_t f_start, r_end, meta;
+};
+
+__global__ void __launch_bounds__(256)
+    hx_combine_kernel(const uint32_t *__restrict__ tile_first, const uint32_t *__restrict__ tile_cnt,
+                      const uint32_t *__restrict__ rec_raw, const HxPairRef *__restrict__ pairs, uint32_t n_pairs,
+                      uint32_t n_records, const uint64_t *__restrict__ sum_f, const uint64_t *__restrict__ sum_r,
+                      const uint64_t *__restrict__ pair_hi, const uint32_t *__restrict__ pair_lo, uint32_t ts,
+                      HxResultDev *__restrict__ out) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)n_pairs * n_records) return;
+    const uint32_t q = (uint32_t)(idx / n_records);
+    const uint32_t r = (uint32_t)(idx % n_records);
+    const int alpha = hx_alpha_of(rec_raw[r]);
+    HxResultDev res = {0u, 0u, 0u};
+    if (alpha == 2) {
+        res.meta = 8u;
+        out[(size_t)r * n_pairs + q] = res;
+        return;
+    }
+    const HxPairRef pr = pairs[q];
+    const uint32_t t0 = tile_first[r], nt = tile_cnt[r];
+    uint64_t bestF = HX_NONE64;          // (dist<<32 | end) of the best valid forward hit so far
+    uint64_t bhi = HX_NONE64;            // combined<<32 | f_end
+    uint32_t blo = 0;                    // r_end
+    bool fany = false, rany = false;
+    for (uint32_t i = 0; i < nt; ++i) {
+        const size_t t = t0 + i;
+        const uint64_t tf = sum_f[(size_t)pr.f_slot * ts + t];
+        const uint64_t tfr = sum_r[(size_t)pr.f_slot * ts + t];
+        const uint64_t tr = sum_r[(size_t)pr.r_slot * ts + t];
+        fany |= tfr != HX_NONE64;
+        rany |= tr != HX_NONE64;
+        if (bestF != HX_NONE64 && tr != HX_NONE64) {
+            const uint64_t chi = (((bestF >> 32) + (tr >> 32)) << 32) | (uint32_t)bestF;
+            const uint32_t clo = (uint32_t)tr;
+            if (chi < bhi || (chi == bhi && clo < blo)) {
+                bhi = chi;
+                blo = clo;
+            }
+        }
+        const uint64_t whi = pair_hi[(size_t)q * ts + t];
+        if (whi != HX_NONE64) {
+            const uint32_t wlo = pair_lo[(size_t)q * ts + t];
+            if (whi < bhi || (whi == bhi && wlo < blo)) {
+                bhi = whi;
+                blo = wlo;
+            }
+        }
+        if (tf < bestF) bestF = tf;
+    }
+    uint32_t flags = (fany ? 1u : 0u) | (rany ? 2u : 0u) | (alpha == 1 ? 16u : 0u);
+    if (bhi != HX_NONE64) {
+        flags |= 4u;
+        res.f_start = (uint32_t)bhi - (pr.len_f - 1u);
+        res.r_end = blo;
+        res.meta = flags | (uint32_t)((bhi >> 32) & 0xffu) << 8;
+    } else {
+        res.meta = flags;
+    }
+    out[(size_t)r * n_pairs + q] = res;
+}
+
+int hx_launch_combine(const uint32_t *tile_first, const uint32_t *tile_cnt, const uint32_t *rec_raw,
+                      const HxPairRef *pairs, uint32_t n_pairs, uint32_t n_records, const uint64_t *sum_f,
+                      const uint64_t *sum_r, const uint64_t *pair_hi, const uint32_t *pair_lo, uint32_t tile_stride,
+                      void *out, cudaStream_t st) {
+    const uint64_t total = (uint64_t)n_pairs * n_records;
+    if (total == 0) return 0;
+    hx_combine_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, st>>>(tile_first, tile_cnt, rec_raw, pairs, n_pairs,
+                                                                      n_records, sum_f, sum_r, pair_hi, pair_lo,
+                                                                      tile_stride, (HxResultDev *)out);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------
+// Known-answer mirror of Myers<u64>::find_all_lazy(text, k).collect() (utils.rs:305-309).
+// pass 0 counts the hits of every window, hx_scan_u64_kernel turns the counts into write
+// offsets, pass 1 writes (end, dist) in ascending text order.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    hx_find_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__restrict__ table, uint32_t m,
+                   uint32_t k, uint32_t tile_len, uint32_t ntiles, uint64_t *__restrict__ counts,
+                   uint64_t *__restrict__ out_end, uint8_t *__restrict__ out_dist, uint64_t cap, int pass) {
+    __shared__ uint64_t peq[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) peq[i] = table[i];
+    __syncthreads();
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint64_t own_start = (uint64_t)t * tile_len;
+    const uint64_t own_end = min(own_start + tile_len, n);
+    const uint64_t warm = min((uint64_t)(m + k - 1), own_start);
+    uint64_t pv = ~0ull, mv = 0;
+    int s = (int)m - (int)k - 1;
+    uint64_t cnt = 0;
+    const uint64_t base = pass ? counts[t] : 0;
+    for (uint64_t i = own_start - warm; i < own_end; ++i) {
+        hx_step<0>(peq[text[i]], pv, mv, s, 2u);
+        if (s < 0 && i >= own_start) {
+            if (pass) {
+                const uint64_t o = base + cnt;
+                if (o < cap) {
+                    out_end[o] = i;
+                    out_dist[o] = (uint8_t)(s + (int)k + 1);
+                }
+            }
+            ++cnt;
+        }
+    }
+    if (!pass) counts[t] = cnt;
+}
+
+// exclusive scan of counts[0..n) in place, total written to counts[n]; single CTA
+__global__ void __launch_bounds__(1024) hx_scan_u64_kernel(uint64_t *counts, uint32_t n) {
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t own = i < n ? counts[i] : 0;
+        uint64_t x = own;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_sum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t w = warp_sum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t y = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += y;
+            }
+            warp_sum[lane] = w;
+        }
+        __syncthreads();
+        const uint64_t carry = carry_s;
+        const uint64_t before = wid ? warp_sum[wid - 1] : 0;
+        if (i < n) counts[i] = carry + before + x - own;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[n] = carry_s;
+}
+
+int hx_launch_find(const uint8_t *text, uint64_t n, const uint8_t *table, uint32_t m, uint32_t k, uint32_t tile_len,
+                   uint32_t ntiles, uint64_t *counts, uint64_t *out_end, uint8_t *out_dist, uint64_t cap, int pass,
+                   cudaStream_t st) {
+    if (ntiles == 0) return 0;
+    hx_find_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(text, n, (const uint64_t *)table, m, k, tile_len, ntiles,
+                                                        counts, out_end, out_dist, cap, pass);
+    if (pass == 0) {
+        hx_scan_u64_kernel<<<1, 1024, 0, st>>>(counts, ntiles);
+        return 2;
+    }
+    return 1;
+}

@@ -1,0 +1,163 @@
+/*
+ * hyperex_b200.h — C ABI of the B200-native HyperEx primer-search-and-extract hot path.
+ *
+ * Drop-in boundary.  The reference (Ebedthan/hyperex v0.2.0) has no FFI;
+ * its seam is the Rust call
+ *     utils::get_hypervar_regions(file, primers, prefix, mismatch)     src/utils.rs:231-236
+ * (called once from src/main.rs:38) and, inside it, the rust-bio 1.6.0 operator API
+ *     MyersBuilder::new/.ambig/.build_64        src/utils.rs:265-268, 301-302
+ *     Myers<u64>::find_all_lazy(text, k)        src/utils.rs:305-309
+ * Every entry point below names the reference lines it replaces.  All functions are
+ * `extern "C"`, take plain pointers and sizes, never throw or unwind, and return 0 (HX_OK)
+ * or a negative hx_status; hx_last_error() gives the message.  There is NO CPU fallback:
+ * every compute entry point fails with HX_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef HYPEREX_B200_H
+#define HYPEREX_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HX_ABI_VERSION 1
+
+typedef enum {
+    HX_OK = 0,
+    HX_ERR_ARG = -1,      /* bad argument (NULL, zero-length / >64-nt primer, unsorted offsets ...) */
+    HX_ERR_CUDA = -2,     /* CUDA runtime error or no device */
+    HX_ERR_NOMEM = -3,    /* host or device allocation failed */
+    HX_ERR_STATE = -4,    /* call order (no primers set, ...) */
+    HX_ERR_IO = -5,       /* file errors in the host driver */
+    HX_ERR_CAPACITY = -6  /* an output buffer was too small; never silently truncates */
+} hx_status;
+
+/* flags of hx_result */
+#define HX_FWD_ANY 1u        /* forward_matches non-empty           (utils.rs:312) */
+#define HX_REV_ANY 2u        /* reverse_matches non-empty           (utils.rs:313) */
+#define HX_PAIR_VALID 4u     /* best_pair is Some                   (utils.rs:328-351) */
+#define HX_ALPHABET_NONE 8u  /* sequence_type == None, record skipped (utils.rs:273-280) */
+#define HX_RNA 16u           /* record classified as RNA            (utils.rs:214-215) */
+
+/* One (record, primer pair) outcome: everything utils.rs:353-409 needs to write the FASTA
+ * record, the GFF line or one of the four warnings. */
+typedef struct hx_result {
+    uint32_t f_start;  /* 0-based region start = f_end - (len(forward)-1)   (utils.rs:334) */
+    uint32_t r_end;    /* 0-based inclusive region end                      (utils.rs:348) */
+    uint8_t flags;     /* HX_* bits above */
+    uint8_t combined;  /* f_dist + r_dist of the chosen pair                (utils.rs:342) */
+    uint16_t reserved; /* 0 */
+} hx_result;
+
+typedef struct hx_ctx hx_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+/* Creates a context driving n_dev CUDA devices (dev_ids may be NULL => devices 0..n_dev-1).
+ * Records of a batch are sharded over the devices with no collective. */
+int hx_create(hx_ctx **out, const int *dev_ids, int n_dev);
+void hx_destroy(hx_ctx *ctx);
+const char *hx_last_error(const hx_ctx *ctx); /* ctx may be NULL: last creation error */
+int hx_abi_version(void);
+
+/* Replaces MyersBuilder::new + .ambig x11 (utils.rs:251-268), to_reverse_complement
+ * (utils.rs:299) and build_64 x2 (utils.rs:301-302) for every primer pair, once per run
+ * instead of once per record x pair.  Builds IUPAC Peq tables for fwd, rc_dna(rev) and
+ * rc_rna(rev).  A primer of length 0 or > 64 is HX_ERR_ARG (the reference aborts inside
+ * rust-bio).  k is `mismatch` of utils.rs:235 (unit-cost edit distance bound). */
+int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len,
+                   const char *const *rev, const uint32_t *rev_len, uint8_t k);
+
+/* Tuning knobs (tests use them to force window seams). name: "tile_len" (owned bytes per
+ * window of a long record), "single_max" (records up to this length are one tile),
+ * "slab_bytes" (host->device pipeline granule), "step_variant". */
+int hx_set_option(hx_ctx *ctx, const char *name, int64_t value);
+
+/* Replaces the record loop body utils.rs:270-351 (sequence_type, to_ascii_uppercase, both
+ * find_all_lazy scans and the pairing loop) for a batch of records held in HOST memory:
+ * record i = arena[offsets[i] .. offsets[i+1]).  out has n_records * n_pairs entries,
+ * record-major, pairs in hx_set_primers order (== the reference's output order).
+ * Internally: slabs are copied host->device on alternating streams while the previous slab
+ * is being scanned; results are copied back in input order.  Synchronous for the caller. */
+int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                 hx_result *out);
+
+/* Same, for an arena already resident in device memory of the context's device `dev_slot`
+ * (index into dev_ids).  d_arena must be 16-byte aligned and readable up to the next
+ * multiple of 16 bytes past offsets[n_records]; d_out is device memory.  Work is enqueued on
+ * `stream` (a cudaStream_t, may be NULL for the context's own stream) and is asynchronous
+ * unless stream is NULL. */
+int hx_run_batch_device(hx_ctx *ctx, int dev_slot, const uint8_t *d_arena, const uint64_t *d_offsets,
+                        uint32_t n_records, uint64_t arena_bytes, hx_result *d_out, void *stream);
+
+/* Known-answer entry point mirroring Myers<u64>::find_all_lazy(text, k).collect()
+ * (utils.rs:305-309) 1:1 on the GPU: every (end 0-based inclusive, dist) with dist <= k,
+ * ascending.  The pattern is used as given (no reverse complement); IUPAC table of
+ * utils.rs:251-263; text bytes are matched as given when fold_case == 0 and upper-cased
+ * (utils.rs:295) otherwise.  Returns the total number of hits (>= 0) or a negative
+ * hx_status; if the total exceeds cap only the first cap hits are stored. */
+int64_t hx_find_all_end(hx_ctx *ctx, const char *pattern, uint32_t pattern_len, const uint8_t *text,
+                        uint64_t text_len, uint8_t k, int fold_case, uint64_t *out_end, uint8_t *out_dist,
+                        uint64_t cap);
+
+/* pinned host memory for arenas / result tables (cudaHostAlloc) */
+void *hx_alloc_pinned(size_t bytes);
+void hx_free_pinned(void *p);
+
+/* number of kernels the context has launched so far (bench.py's gpu_launches) */
+uint64_t hx_launch_count(const hx_ctx *ctx);
+/* device time (ms) of the dominant kernel (hx_myers_pair_kernel) accumulated by CUDA events
+ * on the launching stream since the last reset, and the number of launches timed; only
+ * collected after hx_set_option(ctx, "time_kernels", 1). */
+int hx_kernel_time(hx_ctx *ctx, double *myers_ms, uint64_t *myers_launches, int reset);
+
+/* Measurement helper (hx_intpeak.cu): measured throughput, in 1e9 lane-operations per second, of one
+ * integer instruction class on `device` (variant 0 LOP3, 1 IADD3, 2 SHF, 3 IMAD, 4 LOP3+IMAD 1:1,
+ * 5 IMAD.HI, 6 LOP3+IADD3, 7 LOP3+IMAD 2:1) or of the bare Myers step on register operands (10-12:
+ * step variants 0-2, in word-steps).  This is the integer-ALU roofline denominator of bench.py. */
+int hx_int_peak(int device, int variant, int iters, double *gops);
+
+/* ---- host helpers that shape the output bytes (pure host code) ---------------------- */
+/* utils.rs:207-228: 0 dna, 1 rna, 2 none */
+int hx_sequence_type(const uint8_t *seq, size_t n);
+/* utils.rs:169-199: alphabet 0 dna / 1 rna; out holds n bytes */
+void hx_to_complement(const char *primer, size_t n, int alphabet, char *out);
+void hx_to_reverse_complement(const char *primer, size_t n, int alphabet, char *out);
+/* utils.rs:157-166 (+29-45): label of a primer pair, "" when unknown; out holds >= 8 bytes */
+void hx_primers_to_region(const char *fwd, const char *rev, char *out);
+/* utils.rs:112-131: 0 and the two primers, or HX_ERR_ARG for an unsupported name */
+int hx_region_to_primer(const char *region, const char **fwd, const char **rev);
+/* utils.rs:23-25 */
+const char *const *hx_supported_regions(uint32_t *n);
+/* utils.rs:134-145: parses a primer CSV; returns n_pairs >= 0 or HX_ERR_IO / HX_ERR_ARG
+ * ("Primer file must be comma-separated").  Strings are owned by the library until
+ * hx_free_primer_file. */
+int hx_file_to_vec(const char *path, char ***fwd, char ***rev);
+void hx_free_primer_file(char **fwd, char **rev, int n);
+
+/* ---- FASTA ingest -> arena packer (replaces fasta::Reader::new(reader).records(), utils.rs:237-238,270)
+ * rust-bio reader rules: id = header up to the first whitespace, sequence lines joined with
+ * trim_end(), iteration stops at the first malformed or empty record; input may be plain, gzip,
+ * bzip2, xz or zstd (niffler sniffing, utils.rs:148-154).  hx_fasta_next packs up to max_bytes of
+ * sequence into a pinned arena owned by the reader (valid until the next call / close) and returns
+ * the number of records (0 at the end of the input, negative hx_status on error). */
+typedef struct hx_fasta hx_fasta;
+int hx_fasta_open(const char *path, hx_fasta **out);
+int64_t hx_fasta_next(hx_fasta *r, size_t max_bytes, const uint8_t **arena, const uint64_t **offsets,
+                      const char *const **ids);
+void hx_fasta_close(hx_fasta *r);
+
+/* ---- the reference's seam itself ----------------------------------------------------- */
+/* utils.rs:231-414 get_hypervar_regions(file, primers, prefix, mismatch): reads FASTA
+ * (plain / gzip / bzip2 / xz, utils.rs:148-154), runs the batch path on the GPU(s) of ctx,
+ * writes <prefix>.fa and <prefix>.gff byte-identically to the reference.  log_fn (may be
+ * NULL) receives the reference's warn!/error! messages (level 1 = WARN, 2 = ERROR). */
+typedef void (*hx_log_fn)(int level, const char *msg, void *user);
+int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n_pairs, const char *const *fwd,
+                            const char *const *rev, const char *prefix, uint8_t mismatch, hx_log_fn log_fn,
+                            void *user);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPEREX_B200_H */

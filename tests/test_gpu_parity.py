@@ -1,0 +1,259 @@
+"""GPU parity suite (`-m gpu`): the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs — bit-exact (integer work: hit coordinates, distances, flags, FASTA/GFF bytes)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import hx_synth
+import hyperex_b200 as hx
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(res, ref, arena=None, offsets=None, pairs=None, k=None):
+    if res.tobytes() == ref.tobytes():
+        return
+    bad = np.argwhere((res["f_start"] != ref["f_start"]) | (res["r_end"] != ref["r_end"]) |
+                      (res["flags"] != ref["flags"]) | (res["combined"] != ref["combined"]))
+    r, p = bad[0]
+    raise AssertionError(f"{len(bad)} mismatching (record, pair) cells; first at record {r} pair {p}: "
+                         f"gpu={res[r, p]} oracle={ref[r, p]} k={k} pair={pairs[p] if pairs else None} "
+                         f"len={int(offsets[r + 1] - offsets[r]) if offsets is not None else None}")
+
+
+def _run(ctx, arena, offsets, pairs, k, **opts):
+    for name in ("tile_len", "single_max"):
+        ctx.set_option(name, opts.get(name, 0))
+    ctx.set_option("slab_bytes", opts.get("slab_bytes", 128 << 20))
+    ctx.set_option("step_variant", opts.get("step_variant", 0))
+    ctx.set_primers(pairs, k)
+    return ctx.run_batch(arena, offsets)
+
+
+# ---- find_all_lazy mirror ------------------------------------------------------------------------
+def test_find_all_end_rustbio_vectors(ctx):
+    assert ctx.find_all_end("TCCTAGGGC", "CGGTCCTGAGGGATTAGCAC", 2) == [(11, 2), (12, 2)]
+    assert ctx.find_all_end("TGAGCGT", "ACCGTGGATGAGCGCCATAG", 1) == [(13, 1), (14, 1)]
+    assert min(d for _, d in ctx.find_all_end("TGAGCGT", "TGAGCNTA", 7)) == 1
+
+
+@pytest.mark.parametrize("tile_len", [0, 16, 48])
+def test_find_all_end_random_vs_oracle(ctx, tile_len):
+    rng = np.random.default_rng(1 + tile_len)
+    ctx.set_option("tile_len", tile_len)
+    try:
+        for _ in range(120):
+            m = int(rng.integers(1, 65))
+            n = int(rng.integers(0, 600))
+            k = int(rng.integers(0, min(m, 5) + 1)) if rng.random() < 0.85 else int(rng.integers(0, m + 3))
+            pat = "".join("ACGTACGTMRWSYKVHDBNU"[i] for i in rng.integers(0, 20, m))
+            txt = "".join("ACGTACGTACGTNRYUacgtn"[i] for i in rng.integers(0, 21, n))
+            fold = bool(rng.integers(0, 2))
+            ref = O.find_all_end(pat, txt.upper() if fold else txt, k)
+            assert ctx.find_all_end(pat, txt, k, fold_case=fold) == ref, (pat, txt, k, fold)
+    finally:
+        ctx.set_option("tile_len", 0)
+
+
+def test_find_all_end_capacity_is_reported_not_truncated_silently(ctx):
+    import ctypes as C
+    L = hx._lib.load()
+    ends = np.zeros(4, np.uint64)
+    dists = np.zeros(4, np.uint8)
+    text = b"ACGT" * 50
+    total = L.hx_find_all_end(ctx._h, b"AC", 2, text, len(text), 2, 0, ends.ctypes.data, dists.ctypes.data, 4)
+    assert total == len(text)  # k >= m: every position is a hit
+    assert list(ends) == [0, 1, 2, 3]
+
+
+# ---- config 1: the reference's own CPU-runnable case ----------------------------------------------
+@pytest.mark.parametrize("k", [0, 2])
+def test_config1_bytes(ctx, golden_dir, tmp_path, k):
+    prefix = str(tmp_path / "hyperex_out")
+    logs = []
+    for f in ("test.fa", "test.fa.gz"):
+        for ext in (".fa", ".gff"):
+            if os.path.exists(prefix + ext):
+                os.remove(prefix + ext)
+        ctx.get_hypervar_regions(os.path.join(golden_dir, f), hx.default_primers(), prefix, k,
+                                 log=lambda lvl, msg: logs.append((lvl, msg)))
+        fa, gff = open(prefix + ".fa", "rb").read(), open(prefix + ".gff", "rb").read()
+        assert fa == open(os.path.join(golden_dir, f"config1_k{k}.fa"), "rb").read()
+        assert gff == open(os.path.join(golden_dir, f"config1_k{k}.gff"), "rb").read()
+        assert hashlib.sha256(fa).hexdigest() == "7c8b0083b64b8dbed0cafe64048e64ab1e9981c4f00b854e2ecb245a471d214c"
+        assert hashlib.sha256(gff).hexdigest() == "885ab68f83df0940714a9f9ca25ab01c1e23962f5bab05a54a5c918b348df043"
+    if k == 0:
+        msgs = [m for _, m in logs[:6]]
+        assert msgs[0] == "Sequence Allorhizobium_borbori__DN316__EF125187 is short (1353 bp). Some regions may not be found."
+        assert msgs[1] == "Both primers not found for region v1v2 in sequence Allorhizobium_borbori__DN316__EF125187"
+        assert msgs[2] == ("Forward primer AGAGTTTGATCMTGGCTCAG not found for region v1v3 in sequence "
+                           "Allorhizobium_borbori__DN316__EF125187")
+        assert msgs[4] == ("Reverse primer TACGGYTACCTTGTTAYGACTT not found for region v6v9 in sequence "
+                           "Allorhizobium_borbori__DN316__EF125187")
+
+
+@pytest.mark.parametrize("name", ["c2_small", "c3_small", "mixed_small"])
+def test_golden_batches(ctx, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    pairs = [list(p) for p in z["pairs"]]
+    for variant in (0, 1, 2):
+        res = _run(ctx, z["arena"], z["offsets"], pairs, int(z["k"]), step_variant=variant)
+        _cmp(res, z["res"], z["arena"], z["offsets"], pairs, int(z["k"]))
+
+
+# ---- seeded batches of the BASELINE.json shapes at oracle-friendly sizes -----------------------------
+def test_c2_reads_all_regions_k0(ctx):
+    a, o = hx_synth.gen_reads(3000, seed=22)
+    res = _run(ctx, a, o, hx.default_primers(), 0)
+    _cmp(res, O.run_batch(a, o, O.default_pairs(), 0, nthreads=8), a, o, O.default_pairs(), 0)
+    assert (res["flags"] & 7 == 7).all()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_c3_degenerate_primers_both_strands(ctx, k):
+    a, o = hx_synth.gen_reads_mutated(1500, seed=30 + k, max_edits=3, revcomp_frac=0.5)
+    pairs = [hx.region_to_primer("v3v4"), hx.region_to_primer("v4v5")]
+    _cmp(_run(ctx, a, o, pairs, k), O.run_batch(a, o, pairs, k, nthreads=8), a, o, pairs, k)
+
+
+@pytest.mark.parametrize("tile_len,single_max", [(0, 0), (256, 256), (64, 64), (1024, 1500)])
+def test_c4_softmasked_contigs_windows(ctx, tile_len, single_max):
+    a, o = hx_synth.gen_contigs(3, seed=41, length=60_000, copies=(3, 6), n_runs=3)
+    pairs = hx.default_primers()
+    ref = O.run_batch(a, o, pairs, 3, nthreads=8)
+    _cmp(_run(ctx, a, o, pairs, 3, tile_len=tile_len, single_max=single_max), ref, a, o, pairs, 3)
+
+
+def test_c5_primer_csv_64_pairs(ctx):
+    pairs = hx_synth.gen_primer_pairs(54, seed=5, builtins=O.default_pairs())
+    assert len(pairs) == 64 and any(len(p[0]) > 32 or len(p[1]) > 32 for p in pairs)
+    a, o = hx_synth.gen_reads_mutated(300, seed=51, max_edits=2, revcomp_frac=0.3)
+    # plant some of the random primers so that the long-pattern (64-bit) path reports hits
+    rng = np.random.default_rng(52)
+    a = a.copy()
+    for r in range(0, 300, 3):
+        f, rv = pairs[10 + (r // 3) % 54]
+        s = int(o[r])
+        fs = hx_synth._resolve(rng, f, 1)[0]
+        rs = hx_synth._resolve(rng, O.to_reverse_complement(rv, O.DNA).decode(), 1)[0]
+        a[s + 100:s + 100 + len(fs)] = fs
+        a[s + 700:s + 700 + len(rs)] = rs
+    ref = O.run_batch(a, o, pairs, 2, nthreads=8)
+    assert (ref[:, 10:]["flags"] & 4).any()
+    _cmp(_run(ctx, a, o, pairs, 2), ref, a, o, pairs, 2)
+
+
+# ---- edge cases the domain has -------------------------------------------------------------------------
+def test_edge_records(ctx):
+    recs = [b"", b"A", b"T", b"U", b"X", b"acgtn", b"ACGU" * 10 + b"T", b"N" * 50,
+            b"GTGCCAGCMGCCGCGGTAA", b"GTGCCAGCAGCCGCGGTAA" + b"ATTAGAAACCCTTGTAGTCC",
+            b"ccagcagccgcggtaat" + b"ACGT" * 30 + b"CCTACGGGAGGCAGCAG",  # reverse hit before forward hit
+            b"CCTACGGGAGGCAGCAG", b"CTACGGGAGGCAGCAG" + b"A" * 40 + b"GGATTAGATACCCTGGTAGTC",
+            b"CCUACGGGAGGCAGCAG" + b"ACGU" * 20 + b"GGAUUAGAUACCCUGGUAGUC",  # RNA record
+            b""]
+    a, o = hx_synth.pack(recs)
+    for k in (0, 1, 3, 17, 24):
+        pairs = hx.default_primers()
+        _cmp(_run(ctx, a, o, pairs, k), O.run_batch(a, o, pairs, k), a, o, pairs, k)
+
+
+def test_k_at_least_pattern_length_every_position_hits(ctx):
+    # README example `-f ATCG -r GGCC -m 1` style: tiny primers, k close to / above m
+    a, o = hx_synth.gen_reads_mutated(40, seed=61, lmin=5, lmax=300, sites=[])
+    for pairs, k in (([["ATCG", "GGCC"]], 1), ([["ATCG", "GGCC"]], 4), ([["AC", "GTTGCA"]], 3),
+                     ([["A", "C"], ["ACGTN", "T"]], 1)):
+        _cmp(_run(ctx, a, o, pairs, k, tile_len=32, single_max=48), O.run_batch(a, o, pairs, k), a, o, pairs, k)
+
+
+def test_rna_records_use_rna_reverse_complement(ctx):
+    a, o = hx_synth.gen_reads_mutated(200, seed=71, max_edits=1, revcomp_frac=0.0, rna_frac=0.6)
+    pairs = hx.default_primers()
+    ref = O.run_batch(a, o, pairs, 2, nthreads=8)
+    assert (ref["flags"] & 16).any() and not (ref["flags"] & 16).all()
+    _cmp(_run(ctx, a, o, pairs, 2), ref, a, o, pairs, 2)
+
+
+def test_primer_validation_errors(ctx):
+    for bad in ([["", "ACGT"]], [["A" * 65, "ACGT"]], [["ACGT", "C" * 70]]):
+        with pytest.raises(hx.HyperexError) as e:
+            ctx.set_primers(bad, 0)
+        assert e.value.code == -1
+    ctx.set_primers([["A" * 64, "C" * 64]], 0)  # 64 is allowed (rust-bio: 0 < m <= 64)
+
+
+def test_slab_pipeline_and_unaligned_offsets(ctx):
+    a, o = hx_synth.gen_reads_mutated(700, seed=81, max_edits=2, lmin=1, lmax=900)
+    pairs = hx.default_primers()
+    ref = O.run_batch(a, o, pairs, 2, nthreads=8)
+    for slab in (1, 4096, 50_000, 1 << 20):
+        _cmp(_run(ctx, a, o, pairs, 2, slab_bytes=slab), ref, a, o, pairs, 2)
+    # an arena whose first record does not start at offset 0
+    pad = 7
+    a2 = np.concatenate([np.frombuffer(b"GTGCCAG", np.uint8), a])
+    o2 = o + np.uint64(pad)
+    _cmp(_run(ctx, a2, o2, pairs, 2, slab_bytes=30_000), ref, a2, o2, pairs, 2)
+
+
+def test_device_resident_entry_point(ctx):
+    import torch
+    a, o = hx_synth.gen_reads(2000, seed=91)
+    pairs = hx.default_primers()
+    ref = O.run_batch(a, o, pairs, 0, nthreads=8)
+    ctx.set_option("tile_len", 0)
+    ctx.set_option("single_max", 0)
+    ctx.set_primers(pairs, 0)
+    pad = (-len(a)) % 16 + 16
+    d_arena = torch.from_numpy(np.concatenate([a, np.zeros(pad, np.uint8)])).cuda()
+    d_off = torch.from_numpy(o.view(np.int64)).cuda()
+    d_out = torch.zeros(len(o) - 1, len(pairs) * 12, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.run_batch_device(d_arena.data_ptr(), d_off.data_ptr(), len(o) - 1, len(a), d_out.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    res = d_out.cpu().numpy().view(hx.RESULT_DTYPE).reshape(len(o) - 1, len(pairs))
+    _cmp(res, ref, a, o, pairs, 0)
+
+
+# ---- file-level seam: FASTA in, FASTA + GFF3 bytes out ---------------------------------------------------
+@pytest.mark.parametrize("k,codec", [(0, "plain"), (2, "gz"), (3, "xz")])
+def test_get_hypervar_regions_bytes(ctx, tmp_path, k, codec):
+    import gzip
+    import lzma
+    a, o = hx_synth.gen_reads_mutated(400, seed=95 + k, max_edits=2, revcomp_frac=0.3, lower_frac=0.4, rna_frac=0.1)
+    ids = [f"seq{i}" if i % 2 else f"seq{i} len={int(o[i + 1] - o[i])}" for i in range(400)]
+    buf = hx_synth.to_fasta(a, o, ids, width=70 if k else 0, crlf=bool(k == 2))
+    path = tmp_path / "in.fa"
+    path.write_bytes({"plain": lambda b: b, "gz": gzip.compress, "xz": lzma.compress}[codec](buf))
+    pairs = hx.default_primers() + [["ACGTACGTAC", "TTGACA"]]  # one pair without a region label
+    prefix = str(tmp_path / "out")
+    ctx.set_option("tile_len", 0)
+    ctx.set_option("single_max", 0)
+    ctx.get_hypervar_regions(str(path), pairs, prefix, k)
+    fa, gff, _ = O.get_hypervar_regions(buf, pairs, k)
+    assert open(prefix + ".fa", "rb").read() == fa
+    assert open(prefix + ".gff", "rb").read() == gff
+
+
+# ---- full-size properties (BASELINE.json config 2 shape; the oracle is too slow at this size) -------------
+def test_full_size_properties(ctx):
+    n = 200_000
+    a, o = hx_synth.gen_reads(n, seed=2)
+    pairs = hx.default_primers()
+    res = _run(ctx, a, o, pairs, 0)
+    # every planted site is found exactly, in gene order, inside the record
+    assert (res["flags"] == 7).all() and (res["combined"] == 0).all()
+    lens = np.diff(o.astype(np.int64))
+    assert (res["r_end"] < lens[:, None]).all() and (res["f_start"] < res["r_end"]).all()
+    # idempotence / order independence: a permuted batch gives the permuted table
+    perm = np.random.default_rng(3).permutation(n)[:20000]
+    recs = [a[int(o[i]):int(o[i + 1])] for i in perm]
+    a2, o2 = hx_synth.pack(recs)
+    res2 = _run(ctx, a2, o2, pairs, 0, slab_bytes=8 << 20)
+    assert res2.tobytes() == res[perm].tobytes()
+    # and a sample agrees with the oracle
+    samp = np.arange(0, n, 97)
+    a3, o3 = hx_synth.pack([a[int(o[i]):int(o[i + 1])] for i in samp])
+    assert O.run_batch(a3, o3, pairs, 0, nthreads=8).tobytes() == res[samp].tobytes()

@@ -1,0 +1,162 @@
+"""CPU suite for the product's host side: the C ABI loads and exports every declared symbol, and the
+host helpers behave like the reference's (the cases mirror src/utils.rs:593-748).  No compute calls:
+without a GPU the compute entry points must fail loudly, never fall back."""
+import bz2
+import ctypes
+import gzip
+import lzma
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hx_synth
+import hyperex_b200 as hx
+from hyperex_b200 import _lib
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "hyperex_b200.h")).read()
+    declared = set(re.findall(r"\b(hx_[a-z_0-9]+)\s*\(", header)) - {"hx_log_fn"}
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/hyperex_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS)
+    assert lib.hx_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(hx.HyperexError) as e:
+        hx.Context((0,))
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "hyperex_b200")
+    for dp, _dn, fn in os.walk(pkg):
+        for f in fn:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "oracle" not in txt.lower() or f == "_never_", f"{f} mentions the oracle"
+
+
+# ---- mirrors of the reference unit tests (src/utils.rs:593-683) ------------------------------
+def test_complement_dna():
+    assert hx.to_complement("ATCGATCGATCGATCGRYKBVDHX", "dna") == "TAGCTAGCTAGCTAGCYRMVBHDX"
+
+
+def test_complement_rna():
+    assert hx.to_complement("AUCGAUCGAUCGAUCGRYKBVDHMXN", "rna") == "UAGCUAGCUAGCUAGCYRMVBHDKXN"
+
+
+def test_reverse_complement():
+    assert hx.to_reverse_complement("GTGCCAGCMGCCGCGGTAAN", "dna") == "NTTACCGCGGCKGCTGGCAC"
+
+
+def test_sequence_type_dna_ok():
+    assert hx.sequence_type("ATCGATCGATCG") == hx.Alphabet.Dna
+
+
+def test_sequence_type_dna_ok2():
+    assert hx.sequence_type("ATCGMTGCAATCG") == hx.Alphabet.Dna
+
+
+def test_sequence_type_rna_ok():
+    assert hx.sequence_type("AGCUUUGCA") == hx.Alphabet.Rna
+
+
+def test_sequence_type_rna_ok2():
+    assert hx.sequence_type("GUUUUAACCCAAM") == hx.Alphabet.Rna
+
+
+def test_sequence_type_none():
+    assert hx.sequence_type("ATCXXXRMGU") is None
+
+
+def test_region_to_primer_ok():
+    for r in O.supported_regions():
+        assert hx.region_to_primer(r) == O.region_to_primer(r)
+    assert hx.region_to_primer("v9v9") == []
+    assert hx.supported_regions() == O.supported_regions() == hx.SUPPORTED_REGIONS
+    assert hx.default_primers() == O.default_pairs()
+
+
+def test_helpers_agree_with_oracle_on_random_strings():
+    rng = np.random.default_rng(5)
+    alpha = "ACGTUMRWSYKVHDBNXacgtn-"
+    prim = O.default_pairs()
+    for _ in range(300):
+        s = "".join(alpha[i] for i in rng.integers(0, len(alpha), int(rng.integers(0, 40))))
+        st = hx.sequence_type(s)
+        assert (2 if st is None else st) == O.sequence_type(s)
+        for name, a in (("dna", O.DNA), ("rna", O.RNA)):
+            assert hx.to_complement(s, name).encode() == O.to_complement(s, a)
+            assert hx.to_reverse_complement(s, name).encode() == O.to_reverse_complement(s, a)
+    for f, _ in prim:
+        for _, r in prim:
+            assert hx.primers_to_region([f, r]) == O.primers_to_region(f, r)
+    assert hx.primers_to_region(["AAA", "CCC"]) == ""
+
+
+def test_file_to_vec(golden_dir, tmp_path):
+    assert hx.file_to_vec(os.path.join(golden_dir, "primers.txt")) == [
+        ["CCTACGGGNGGCWGCAG", "ATTACCGCGGCTGCTGG"], ["GTGCCAGCMGCCGCGGTAA", "GACTACHVGGGTATCTAATCC"]]
+    bad = tmp_path / "bad.txt"
+    bad.write_text("ACGT TTTT\n")
+    with pytest.raises(ValueError, match="comma-separated"):  # utils.rs:141 / test_file_to_vec_no_ok
+        hx.file_to_vec(str(bad))
+    with pytest.raises(FileNotFoundError):
+        hx.file_to_vec(str(tmp_path / "missing.txt"))
+    crlf = tmp_path / "crlf.csv"
+    crlf.write_bytes(b"AC,GT,extra\r\nTT,GG\r\n")
+    assert hx.file_to_vec(str(crlf)) == [["AC", "GT"], ["TT", "GG"]]
+
+
+# ---- FASTA ingest (rust-bio reader rules + niffler sniffing) ------------------------------------
+def _read_all(path, max_bytes=0):
+    arenas, ids, lens = [], [], []
+    for a, o, i in hx.read_fasta(path, max_bytes):
+        arenas.append(a)
+        ids += i
+        lens += list(np.diff(o.astype(np.int64)))
+    return (np.concatenate(arenas) if arenas else np.zeros(0, np.uint8)), ids, lens
+
+
+def test_read_fasta_fixture_plain_and_gz(golden_dir):
+    for name in ("test.fa", "test.fa.gz"):
+        arena, ids, lens = _read_all(os.path.join(golden_dir, name))
+        assert ids == ["Allorhizobium_borbori__DN316__EF125187"] and lens == [1353]
+        oa, _oo, oi = O.parse_fasta(open(os.path.join(golden_dir, "test.fa"), "rb").read())
+        assert arena.tobytes() == oa.tobytes() and ids == oi
+
+
+@pytest.mark.parametrize("codec", ["plain", "gz", "bz2", "xz"])
+def test_read_fasta_matches_oracle_reader(tmp_path, codec):
+    a, o = hx_synth.gen_reads_mutated(40, seed=9, lower_frac=0.5, lmin=10, lmax=700)
+    ids = [f"r{i}_x" if i % 3 else f"r{i} some description" for i in range(40)]
+    buf = hx_synth.to_fasta(a, o, ids, width=60, crlf=True) + b">last\nAC GT\t\n\n>\n>never\nAA\n"
+    path = tmp_path / f"in.fa.{codec}"
+    path.write_bytes({"plain": lambda b: b, "gz": gzip.compress, "bz2": bz2.compress, "xz": lzma.compress}[codec](buf))
+    oa, oo, oi = O.parse_fasta(buf)
+    for mb in (0, 1000):  # whole file / many small batches
+        arena, rid, lens = _read_all(str(path), mb)
+        assert rid == oi and lens == list(np.diff(oo.astype(np.int64))) and arena.tobytes() == oa.tobytes()
+
+
+def test_read_fasta_errors(tmp_path):
+    with pytest.raises(hx.HyperexError):
+        list(hx.read_fasta(str(tmp_path / "missing.fa")))
+    short = tmp_path / "short.fa"
+    short.write_bytes(b">a\n")  # niffler: file too short to sniff
+    with pytest.raises(hx.HyperexError):
+        list(hx.read_fasta(str(short)))
+    notfa = tmp_path / "not.fa"
+    notfa.write_bytes(b"ACGTACGT\n>x\nAC\n")
+    assert list(hx.read_fasta(str(notfa))) == []
