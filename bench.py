@@ -51,7 +51,6 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--records", type=int, default=1_000_000, help="records per GPU")
     ap.add_argument("--k", type=int, default=0)
-    ap.add_argument("--variant", type=int, default=-1, help="Myers step variant (-1: library default)")
     ap.add_argument("--cpu-sample", type=int, default=60_000, help="records of the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=0, help="records per step of the reference arm (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -197,8 +196,6 @@ def main():
     npairs = len(pairs)
 
     ctx = hx.Context((local,))
-    if args.variant >= 0:
-        ctx.set_option("step_variant", args.variant)
     ctx.set_primers(pairs, args.k)
 
     # ---- device-resident leg ("value") -------------------------------------------------------

@@ -101,7 +101,7 @@ struct hx_ctx {
     std::vector<uint8_t> tables;
     bool primers_set = false;
     // options
-    int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_variant = 0, opt_time = 0;
+    int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0;
     uint64_t launches = 0;
     std::vector<TimedLaunch> timed;
     double myers_ms = 0;
@@ -234,6 +234,9 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const 
         a.order = S.order.p;
         a.ntiles = ntiles;
         a.rec_raw = rec_raw;
+        a.tile_cnt = tile_cnt;
+        a.out = d_out;
+        a.n_pairs_total = ctx->n_pairs;
         a.tables = D.d_tables + hg.table_off;
         a.group = D.d_groups + gi;
         a.sum_f = S.sum_f.p;
@@ -242,7 +245,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const 
         a.pair_lo = S.pair_lo.p;
         a.tile_stride = pl.tile_cap;
         a.k = ctx->k;
-        a.variant = (int)ctx->opt_variant;
+        a.variant = 0;
         a.two = 2;
         TimedLaunch tl;
         if (ctx->opt_time) {
@@ -335,7 +338,6 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     if (n == "tile_len") ctx->opt_tile_len = value;
     else if (n == "single_max") ctx->opt_single_max = value;
     else if (n == "slab_bytes") ctx->opt_slab_bytes = std::max<int64_t>(value, 1);
-    else if (n == "step_variant") ctx->opt_variant = value;
     else if (n == "time_kernels") ctx->opt_time = value;
     else return fail(ctx, HX_ERR_ARG, "unknown option %s", name);
     return HX_OK;
@@ -417,6 +419,7 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
             g.pair_f[g.npairs] = (uint8_t)fi;
             g.pair_r[g.npairs] = (uint8_t)ri;
             g.pair_global[g.npairs] = (uint16_t)i;
+            g.rmask[ri] |= (uint16_t)(1u << g.npairs);
             g.npairs++;
             refs[i].len_f = (uint32_t)F[i].size();  // utils.rs:327 forward_len
             refs[i].pad = (uint32_t)cur;            // group index for now, slots resolved below
@@ -472,7 +475,7 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
         HX_CUDA(ctx, cudaMemcpy(D.d_pairs, refs.data(), refs.size() * sizeof(HxPairRef), cudaMemcpyHostToDevice));
     }
     ctx->n_pairs = n_pairs;
-    ctx->k = k;
+    ctx->k = k > 64 ? 64 : k;  // dist <= m <= 64: any larger bound accepts exactly the same hits
     ctx->m_max = m_max;
     ctx->n_slots = slot_base;
     ctx->groups.swap(groups);

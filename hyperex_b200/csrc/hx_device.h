@@ -40,6 +40,7 @@ struct HxGroup {
     uint8_t pair_f[HX_MAX_GROUP_PAIRS];       // group-local forward pattern of each pair
     uint8_t pair_r[HX_MAX_GROUP_PAIRS];       // group-local reverse pattern of each pair
     uint16_t pair_global[HX_MAX_GROUP_PAIRS]; // index of the pair in hx_set_primers order
+    uint16_t rmask[HX_MAX_NP32];              // bit q set: pair q of the group has this pattern as reverse
 };
 
 // global pair -> where its summaries live (used by the pairing/combine kernel)
@@ -65,6 +66,9 @@ struct HxScanArgs {
     const uint32_t *order;     // processing order (longest tile first)
     const uint32_t *ntiles;    // device-side tile count
     const uint32_t *rec_raw;   // HX_RAW_* per record
+    const uint32_t *tile_cnt;  // tiles per record (1: the scan kernel writes the final result)
+    void *out;                 // hx_result[n_records][n_pairs_total]
+    uint32_t n_pairs_total;
     const uint8_t *tables;     // Peq blob
     const HxGroup *group;      // this launch's group (device memory)
     uint64_t *sum_f;           // [slot][tile] best valid forward hit  key = dist<<32 | end
@@ -74,7 +78,7 @@ struct HxScanArgs {
     uint32_t tile_stride;      // capacity used as the [slot]/[pair] stride
     uint32_t k;
     int32_t variant;
-    uint32_t two;              // == 2, passed at run time (see hx_step variant 3)
+    uint32_t two;              // == 2, passed at run time (a constant ptxas cannot fold)
 };
 
 struct HxBuildArgs {

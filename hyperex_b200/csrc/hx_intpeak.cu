@@ -32,6 +32,10 @@ __device__ __forceinline__ void op(uint32_t &x, const uint32_t y, const uint32_t
     else if (VAR == 6) {
         if (chain & 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(nb));
         else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(y), "r"(z));
+    } else if (VAR == 8) {
+        uint64_t acc = ((uint64_t)z << 32) | x;
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x), "r"(y));
+        x = (uint32_t)acc ^ (uint32_t)(acc >> 32);
     } else if (VAR == 7) {
         if (chain % 3 == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z));
         else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(y), "r"(z));
@@ -85,6 +89,51 @@ __device__ __forceinline__ void step(const uint32_t eq, uint32_t &pv, uint32_t &
 
 constexpr int NPAT = 15;
 
+// Variant 4: `ph << 1` and `score += ph >> 31` in ONE FMA-pipe instruction: the 64-bit multiply-add
+// (0:ph) * one + (sP:ph) = (sP + carry : 2 ph).  Same for mh with its own accumulator sM; a hit is
+// sP - sM < 0 with sP initialised to m - k - 1.
+__device__ __forceinline__ void step_wide(const uint32_t eq, uint32_t &pv, uint32_t &mv, uint32_t &sP, uint32_t &sM,
+                                          const uint32_t one) {
+    const uint32_t xv = eq | mv;
+    const uint32_t xh = (((eq & pv) + pv) ^ pv) | eq;
+    uint32_t ph = mv | ~(xh | pv);
+    uint32_t mh = pv & xh;
+    uint64_t a, b;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(ph), "r"(sP));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a) : "r"(ph), "r"(one));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(ph), "=r"(sP) : "l"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(mh), "r"(sM));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(b) : "r"(mh), "r"(one));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(mh), "=r"(sM) : "l"(b));
+    pv = mh | ~(xv | ph);
+    mv = ph & xv;
+}
+
+__global__ void __launch_bounds__(128, 4) hx_steppeak_wide_kernel(uint32_t *out, int iters, uint32_t seed, uint32_t one) {
+    uint32_t pv[NPAT], mv[NPAT], sP[NPAT], sM[NPAT];
+#pragma unroll
+    for (int p = 0; p < NPAT; ++p) {
+        pv[p] = ~0u;
+        mv[p] = 0;
+        sP[p] = 20;
+        sM[p] = 0;
+    }
+    uint32_t e = seed ^ (threadIdx.x * 2654435761u);
+    int any = 0;
+    for (int it = 0; it < iters; ++it) {
+        e = e * 1664525u + 1013904223u;
+#pragma unroll
+        for (int p = 0; p < NPAT; ++p) {
+            step_wide(e ^ (0x9e3779b9u * (p + 1)), pv[p], mv[p], sP[p], sM[p], one);
+            any |= (int)(sP[p] - sM[p]);
+        }
+    }
+    uint32_t acc = (uint32_t)any;
+#pragma unroll
+    for (int p = 0; p < NPAT; ++p) acc ^= pv[p] ^ mv[p];
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
 template <int V>
 __global__ void __launch_bounds__(128, 4) hx_steppeak_kernel(uint32_t *out, int iters, uint32_t seed, uint32_t two) {
     uint32_t pv[NPAT], mv[NPAT];
@@ -134,9 +183,11 @@ cudaError_t run_step(uint32_t *d, int iters, float *ms) {
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     const int blocks = 148 * 4 * 4;
-    hx_steppeak_kernel<V><<<blocks, 128>>>(d, iters / 8, 12345u, 2u);
+    if (V == 4) hx_steppeak_wide_kernel<<<blocks, 128>>>(d, iters / 8, 12345u, 1u);
+    else hx_steppeak_kernel<V><<<blocks, 128>>>(d, iters / 8, 12345u, 2u);
     cudaEventRecord(a);
-    hx_steppeak_kernel<V><<<blocks, 128>>>(d, iters, 12345u, 2u);
+    if (V == 4) hx_steppeak_wide_kernel<<<blocks, 128>>>(d, iters, 12345u, 1u);
+    else hx_steppeak_kernel<V><<<blocks, 128>>>(d, iters, 12345u, 2u);
     cudaEventRecord(b);
     cudaError_t e = cudaEventSynchronize(b);
     cudaEventElapsedTime(ms, a, b);
@@ -166,10 +217,12 @@ extern "C" int hx_int_peak(int device, int variant, int iters, double *gops) {
     case 5: e = run_peak<5>(d, iters, &ms); break;
     case 6: e = run_peak<6>(d, iters, &ms); break;
     case 7: e = run_peak<7>(d, iters, &ms); break;
+    case 8: e = run_peak<8>(d, iters, &ms); break;
     case 10: e = run_step<0>(d, iters, &ms); break;
     case 11: e = run_step<1>(d, iters, &ms); break;
     case 12: e = run_step<2>(d, iters, &ms); break;
     case 13: e = run_step<3>(d, iters, &ms); break;
+    case 14: e = run_step<4>(d, iters, &ms); break;
     default: cudaFree(d); return HX_ERR_ARG;
     }
     if (variant < 10) ops = (double)148 * 8 * 256 * (double)iters * UNROLL * CHAINS;

@@ -200,42 +200,22 @@ int hx_launch_classify(const uint8_t *arena, const uint64_t *offsets, uint64_t o
 // pv = 1, mv = 0 and eq = 0, which makes them feed ph = mh = 0 into pattern bit 0 exactly
 // like the `<< 1` of the reference feeds a 0 (free start in the text).
 // The score is kept biased: s = dist - (k + 1), so "dist <= k" is the sign bit of s.
-//   V = 0  plain C (shifts)            V = 1  score via mad.hi (FMA pipe)
-//   V = 2  shifts via add-with-carry, score via addc/subc
-//   V = 3  score via IMAD.HI with a runtime multiplier (FMA pipe)
+// (Measured on B200, profiles/int_peak_r01.json: moving the score update to IMAD.HI or to a carry chain is
+// slower than what ptxas emits for the plain C below, so there is a single step variant.)
 // ------------------------------------------------------------------------------------
-template <int V>
-__device__ __forceinline__ void hx_step(const uint32_t eq, uint32_t &pv, uint32_t &mv, int &s, const uint32_t two) {
+__device__ __forceinline__ void hx_step(const uint32_t eq, uint32_t &pv, uint32_t &mv, int &s) {
     const uint32_t xv = eq | mv;
     const uint32_t xh = (((eq & pv) + pv) ^ pv) | eq;
     uint32_t ph = mv | ~(xh | pv);
     uint32_t mh = pv & xh;
-    if (V == 3) {
-        // `two` is a kernel argument (== 2): ptxas cannot strength-reduce the multiply, so both
-        // score updates issue as IMAD.HI on the FMA pipe instead of LEA.HI on the ALU pipe.
-        asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(s) : "r"(ph), "r"(two));  // s += ph >> 31
-        asm("mad.hi.s32 %0, %1, %2, %0;" : "+r"(s) : "r"(mh), "r"(two));  // s -= mh >> 31
-        ph <<= 1;
-        mh <<= 1;
-    } else if (V == 1) {
-        asm("mad.hi.u32 %0, %1, 2, %0;" : "+r"(s) : "r"(ph));  // s += ph >> 31
-        asm("mad.hi.s32 %0, %1, 2, %0;" : "+r"(s) : "r"(mh));  // s -= mh >> 31
-        ph <<= 1;
-        mh <<= 1;
-    } else if (V == 2) {
-        asm("add.cc.u32 %0, %0, %0;\n\taddc.s32 %1, %1, 0;" : "+r"(ph), "+r"(s));
-        asm("add.cc.u32 %0, %0, %0;\n\tsubc.s32 %1, %1, 0;" : "+r"(mh), "+r"(s));
-    } else {
-        s += (int)(ph >> 31) - (int)(mh >> 31);
-        ph <<= 1;
-        mh <<= 1;
-    }
+    s += (int)(ph >> 31) - (int)(mh >> 31);  // ptxas: LEA.HI + LEA.HI.SX32 (one ALU op per sign bit)
+    ph <<= 1;                                // ptxas: IMAD.IADD x+x on the FMA pipe
+    mh <<= 1;
     pv = mh | ~(xv | ph);
     mv = ph & xv;
 }
 
-template <int V>
-__device__ __forceinline__ void hx_step(const uint64_t eq, uint64_t &pv, uint64_t &mv, int &s, const uint32_t) {
+__device__ __forceinline__ void hx_step(const uint64_t eq, uint64_t &pv, uint64_t &mv, int &s) {
     const uint64_t xv = eq | mv;
     const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
     uint64_t ph = mv | ~(xh | pv);
@@ -265,43 +245,56 @@ struct HxRow {
 };
 
 // ------------------------------------------------------------------------------------
-// hx_myers_pair_kernel<W, NP, V>
+// hx_myers_pair_kernel<W, NP>
 //   one thread = one tile; per text byte the thread loads one Peq row (all NP patterns of the
 //   group, shared memory, 16-byte LDS) and advances NP independent automata held in registers.
-//   A hit (sign bit of any biased score) is rare and handled out of line: it updates
+//
+//   A hit (sign bit of any biased score) is rare.  The lane that sees it only PUSHES a compact
+//   event record {position, the NP biased scores as bytes} into its private shared-memory queue
+//   (a few PRMT + STS, no long-latency operation while the other 31 lanes wait).  Queues are
+//   DRAINED warp-synchronously — all lanes together, whenever any lane's queue is nearly full and
+//   at the last word of the warp's scan — so the pairing logic below runs with full lanes:
 //     bestR[p]  = lexicographic min (dist, end) over all hits of pattern p in the tile
 //     bestF[p]  = same, restricted to hits usable as a forward primer (end >= m_p - 1,
 //                 utils.rs:334)
 //     pair[q]   = arg-min of (f_dist + r_dist, f_end, r_end) over pairs with r_end > f_end
 //                 (utils.rs:338-349), evaluated as a stream: at a reverse hit the only forward
-//                 candidate that can win is bestF (DESIGN.md §pairing proves the equivalence).
-//   Text is read with 16-byte vector loads, one ahead (software prefetch).
+//                 candidate that can win is bestF (DESIGN.md §3.2 proves the equivalence).
+//   All loops are warp-uniform (trip count = the warp's longest tile; lanes past their own end
+//   scan null bytes, whose all-zero Peq row cannot produce an owned hit).
+//   The CTA stages the Peq table of ONE alphabet at a time; a CTA that holds both DNA and RNA
+//   records (rare) runs the scan twice.
+//   Records that consist of a single tile get their final hx_result written here; windows of
+//   longer records write summaries for hx_combine_kernel.
 // ------------------------------------------------------------------------------------
-template <typename W, int NP, int V>
+#define HX_QCAP 8  // event records per thread queue
+
+template <typename W, int NP>
 __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((sizeof(W) * NP <= 32) ? 5 : 4))
     hx_myers_pair_kernel(const HxScanArgs a) {
     constexpr int WB = sizeof(W);
     constexpr int STRIDE = hx_row_stride(NP, WB);
     constexpr int TBYTES = 256 * STRIDE;
+    constexpr int SW = (NP + 3) / 4;  // score words of an event record
+    constexpr int RW = 1 + SW;        // words of an event record: position + scores
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ HxGroup g;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.tables);
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (int i = threadIdx.x; i < 2 * TBYTES / 16; i += HX_THREADS) dst[i] = __ldg(src + i);
-        if (threadIdx.x < sizeof(HxGroup) / 4)
-            reinterpret_cast<uint32_t *>(&g)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.group)[threadIdx.x];
-    }
-    __syncthreads();
+    uint32_t *const queue = reinterpret_cast<uint32_t *>(smem + TBYTES) + threadIdx.x;  // [record][word][thread]
+    if (threadIdx.x < sizeof(HxGroup) / 4)
+        reinterpret_cast<uint32_t *>(&g)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.group)[threadIdx.x];
 
     const uint32_t ntiles = min(*a.ntiles, a.tile_stride);
     const uint32_t t = blockIdx.x * HX_THREADS + threadIdx.x;
-    if (t >= ntiles) return;
-    const uint32_t tile_id = a.order[t];
-    const HxTile tl = a.tiles[tile_id];
-    const int alpha = hx_alpha_of(a.rec_raw[tl.rec]);
-    if (alpha == 2) return;  // utils.rs:276-279: record skipped
-    const uint8_t *tab = smem + (alpha == 1 ? TBYTES : 0);
+    const bool have = t < ntiles;
+    const uint32_t tile_id = have ? a.order[t] : 0u;
+    HxTile tl = {0u, 0u, 0u, 0u};
+    int alpha = 2;
+    bool single = false;
+    if (have) {
+        tl = a.tiles[tile_id];
+        alpha = hx_alpha_of(a.rec_raw[tl.rec]);  // 2: utils.rs:276-279, record skipped
+        single = a.tile_cnt[tl.rec] == 1u;
+    }
 
     W pv[NP], mv[NP];
     int s[NP];
@@ -309,6 +302,7 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
     uint64_t phi[HX_MAX_GROUP_PAIRS];
     uint32_t plo[HX_MAX_GROUP_PAIRS];
     const int bias = (int)a.k + 1;
+    __syncthreads();  // g is visible
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         pv[p] = ~(W)0;
@@ -321,146 +315,214 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
         phi[q] = HX_NONE64;
         plo[q] = 0;
     }
+    const int dz = (int)a.two - 2;  // run-time zero: keeps the pairing state in local memory, not registers
 
-    const uint64_t a0 = a.offsets[tl.rec] - a.off_base + tl.own_start - tl.warm;
+    const uint64_t a0 = have ? a.offsets[tl.rec] - a.off_base + tl.own_start - tl.warm : 0ull;
     const uint64_t ab = a0 & ~15ull;
     const uint32_t lead = (uint32_t)(a0 - ab);
-    const uint32_t nchunks = (lead + tl.warm + tl.own_len + 15u) >> 4;
     const uint32_t pos0 = tl.own_start - tl.warm - lead;  // record position of chunk 0 byte 0 (may wrap)
     const uint8_t *src = a.arena + ab;
-
-    uint4 cur = hx_ldg16(src);
-    if (tl.own_start == tl.warm && lead) {
-        // The scan starts at the record start: bytes before it belong to the previous record.
-        // Byte 0 selects the all-zero Peq row, under which a fresh automaton stays fresh.
-        uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-        for (int wi = 0; wi < 4; ++wi) {
-            const int z = (int)lead - 4 * wi;  // bytes of this word to clear
-            if (z >= 4) w[wi] = 0;
-            else if (z > 0) w[wi] &= 0xffffffffu << (8 * z);
-        }
-        cur = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-
-    // UB text bytes are processed per trip of the innermost loop.  Wide groups keep UB = 1 so that
-    // the (large) rare path exists once and the hot loop stays inside the instruction cache.
+    // UB text bytes are processed per trip of the innermost loop (narrow groups amortise the loop
+    // overhead over more bytes; wide groups keep the hot loop small).
     constexpr int UB = (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
-    const uint32_t two = a.two;
-    for (uint32_t c = 0; c < nchunks; ++c) {
-        const uint4 nxt = (c + 1 < nchunks) ? hx_ldg16(src + 16ull * (c + 1)) : make_uint4(0, 0, 0, 0);
-#pragma unroll 1
-        for (int wi = 0; wi < 4; ++wi) {
-            uint32_t w = cur.x;
-            cur.x = cur.y;
-            cur.y = cur.z;
-            cur.z = cur.w;
-#pragma unroll 1
-            for (int b0 = 0; b0 < 4; b0 += UB) {
+    uint32_t cnt = 0;  // records in this lane's queue
+
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool mine = alpha == pass;
+        if (!__syncthreads_or(mine ? 1 : 0)) continue;  // no record of this alphabet in the CTA
+        {
+            const uint4 *tsrc = reinterpret_cast<const uint4 *>(a.tables) + (size_t)pass * (TBYTES / 16);
+            uint4 *dst = reinterpret_cast<uint4 *>(smem);
+            for (int i = threadIdx.x; i < TBYTES / 16; i += HX_THREADS) dst[i] = __ldg(tsrc + i);
+        }
+        __syncthreads();
+        const uint8_t *tab = smem;
+        const uint32_t own_len = mine ? tl.own_len : 0u;  // a lane that is not scanning owns nothing
+        const uint32_t nchunks = mine ? (lead + tl.warm + tl.own_len + 15u) >> 4 : 0u;
+        const uint32_t nchunks_w = __reduce_max_sync(0xffffffffu, nchunks);
+
+        uint4 cur = make_uint4(0, 0, 0, 0);
+        if (nchunks) {
+            cur = hx_ldg16(src);
+            if (tl.own_start == tl.warm && lead) {
+                // The scan starts at the record start: bytes before it belong to the previous record.
+                // Byte 0 selects the all-zero Peq row, under which a fresh automaton stays fresh.
+                uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-                for (int bi = 0; bi < UB; ++bi) {
-                    const uint32_t byte = w & 0xffu;
-                    w >>= 8;
-                    HxRow<W, NP> row;
-                    row.load(tab + byte * STRIDE);
-                    int any = 0;
-#pragma unroll
-                    for (int p = 0; p < NP; ++p) {
-                        hx_step<V>(row.eq(p), pv[p], mv[p], s[p], two);
-                        any |= s[p];
-                    }
-                    if (any < 0) {
-                        // ---- rare path: at least one pattern has dist <= k at this position ----
-                        const uint32_t pos = pos0 + (c << 4) + (wi << 2) + b0 + bi;
-                        if (pos - tl.own_start < tl.own_len) {
-                            uint32_t hm = 0;
-                            uint8_t dl[NP];
-#pragma unroll
-                            for (int p = 0; p < NP; ++p) {
-                                dl[p] = (uint8_t)(s[p] + bias);
-                                hm |= (s[p] < 0 ? 1u : 0u) << p;
-                            }
-                            // reverse role first: forward candidates must end strictly before pos
+                for (int wi = 0; wi < 4; ++wi) {
+                    const int z = (int)lead - 4 * wi;  // bytes of this word to clear
+                    if (z >= 4) w[wi] = 0;
+                    else if (z > 0) w[wi] &= 0xffffffffu << (8 * z);
+                }
+                cur = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+
+        for (uint32_t c = 0; c < nchunks_w; ++c) {
+            const uint4 nxt = (c + 1 < nchunks) ? hx_ldg16(src + 16ull * (c + 1)) : make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-                            for (int q = 0; q < g.npairs; ++q) {
-                                const int r = g.pair_r[q];
-                                if ((hm >> r) & 1u) {
-                                    const uint64_t bf = bestF[g.pair_f[q]];
-                                    if (bf != HX_NONE64) {
-                                        const uint32_t comb = (uint32_t)(bf >> 32) + dl[r];
-                                        if (comb < (uint32_t)(phi[q] >> 32)) {
-                                            phi[q] = ((uint64_t)comb << 32) | (uint32_t)bf;
-                                            plo[q] = pos;
-                                        }
-                                    }
+            for (int wi = 0; wi < 4; ++wi) {
+                uint32_t w = cur.x;
+                cur.x = cur.y;
+                cur.y = cur.z;
+                cur.z = cur.w;
+#pragma unroll 1
+                for (int b0 = 0; b0 < 4; b0 += UB) {
+#pragma unroll
+                    for (int bi = 0; bi < UB; ++bi) {
+                        const uint32_t byte = w & 0xffu;
+                        w >>= 8;
+                        HxRow<W, NP> row;
+                        row.load(tab + byte * STRIDE);
+                        int any = 0;
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) {
+                            hx_step(row.eq(p), pv[p], mv[p], s[p]);
+                            any |= s[p];
+                        }
+                        if (any < 0) {
+                            // ---- rare: some pattern has dist <= k here; record the event ----
+                            const uint32_t pos = pos0 + (c << 4) + (wi << 2) + b0 + bi;
+                            if (pos - tl.own_start < own_len) {
+                                uint32_t *r = queue + cnt * (RW * HX_THREADS);
+                                r[0] = pos;
+#pragma unroll
+                                for (int j = 0; j < SW; ++j) {
+                                    const uint32_t b0_ = (uint32_t)s[4 * j];
+                                    const uint32_t b1_ = (4 * j + 1 < NP) ? (uint32_t)s[4 * j + 1] : 0x7fu;
+                                    const uint32_t b2_ = (4 * j + 2 < NP) ? (uint32_t)s[4 * j + 2] : 0x7fu;
+                                    const uint32_t b3_ = (4 * j + 3 < NP) ? (uint32_t)s[4 * j + 3] : 0x7fu;
+                                    r[(1 + j) * HX_THREADS] =
+                                        __byte_perm(__byte_perm(b0_, b1_, 0x0040), __byte_perm(b2_, b3_, 0x0040), 0x5410);
                                 }
-                            }
-#pragma unroll 1
-                            for (int p = 0; p < NP; ++p) {
-                                if ((hm >> p) & 1u) {
-                                    const uint64_t key = ((uint64_t)dl[p] << 32) | pos;
-                                    if (key < bestR[p]) bestR[p] = key;
-                                    if (pos + 1 >= g.m[p] && key < bestF[p]) bestF[p] = key;
-                                }
+                                ++cnt;
                             }
                         }
                     }
                 }
+                // ---- warp-synchronous drain: all lanes process their queued events together ----
+                const bool last_word = (c + 1 == nchunks_w) && wi == 3;
+                if (__any_sync(0xffffffffu, cnt > HX_QCAP - 4 || (last_word && cnt))) {
+                    for (uint32_t i = 0; i < cnt; ++i) {
+                        const uint32_t *r = queue + i * (RW * HX_THREADS);
+                        const uint32_t pos = r[0];
+                        uint32_t sw[SW];
+                        uint32_t hm = 0;  // bit p: pattern p hit (its biased score byte is negative)
+#pragma unroll
+                        for (int j = 0; j < SW; ++j) {
+                            sw[j] = r[(1 + j) * HX_THREADS];
+                            const uint32_t neg = sw[j] & 0x80808080u;
+                            hm |= (((neg >> 7) & 1u) | ((neg >> 14) & 2u) | ((neg >> 21) & 4u) | ((neg >> 28) & 8u)) << (4 * j);
+                        }
+                        // reverse roles first: forward candidates must end strictly before pos
+                        uint32_t m1 = hm;
+                        while (m1) {
+                            const int p = __ffs((int)m1) - 1;
+                            m1 &= m1 - 1;
+                            uint32_t word = sw[0];
+#pragma unroll
+                            for (int j = 1; j < SW; ++j) word = (p >> 2) == j ? sw[j] : word;
+                            const uint32_t d = (uint32_t)((int)(int8_t)(word >> (8 * (p & 3))) + bias);
+                            uint32_t rm = g.rmask[p];  // pairs whose reverse pattern is p
+                            while (rm) {
+                                const int q = __ffs((int)rm) - 1;
+                                rm &= rm - 1;
+                                const uint64_t bf = bestF[g.pair_f[q] + dz];
+                                if (bf != HX_NONE64) {
+                                    const uint32_t comb = (uint32_t)(bf >> 32) + d;
+                                    if (comb < (uint32_t)(phi[q + dz] >> 32)) {
+                                        phi[q + dz] = ((uint64_t)comb << 32) | (uint32_t)bf;
+                                        plo[q + dz] = pos;
+                                    }
+                                }
+                            }
+                        }
+                        uint32_t m2 = hm;
+                        while (m2) {
+                            const int p = __ffs((int)m2) - 1;
+                            m2 &= m2 - 1;
+                            uint32_t word = sw[0];
+#pragma unroll
+                            for (int j = 1; j < SW; ++j) word = (p >> 2) == j ? sw[j] : word;
+                            const uint32_t d = (uint32_t)((int)(int8_t)(word >> (8 * (p & 3))) + bias);
+                            const uint64_t key = ((uint64_t)d << 32) | pos;
+                            if (key < bestR[p + dz]) bestR[p + dz] = key;
+                            if (pos + 1 >= g.m[p] && key < bestF[p + dz]) bestF[p + dz] = key;
+                        }
+                    }
+                    cnt = 0;
+                }
             }
+            cur = nxt;
         }
-        cur = nxt;
+        __syncthreads();  // the table may be replaced by the next pass
     }
 
+    if (!have || alpha == 2) return;
+    if (single) {
+        // the tile is the whole record: final result of utils.rs:312-351 for every pair of the group
+        uint32_t *out = reinterpret_cast<uint32_t *>(a.out) + (size_t)tl.rec * a.n_pairs_total * 3;
+        for (int q = 0; q < g.npairs; ++q) {
+            const int f = g.pair_f[q], r = g.pair_r[q];
+            uint32_t flags = (bestR[f + dz] != HX_NONE64 ? 1u : 0u) | (bestR[r + dz] != HX_NONE64 ? 2u : 0u) |
+                             (alpha == 1 ? 16u : 0u);
+            uint32_t f_start = 0, r_end = 0, comb = 0;
+            const uint64_t hi = phi[q + dz];
+            if (hi != HX_NONE64) {
+                flags |= 4u;
+                f_start = (uint32_t)hi - ((uint32_t)g.m[f] - 1u);
+                r_end = plo[q + dz];
+                comb = (uint32_t)(hi >> 32) & 0xffu;
+            }
+            uint32_t *o = out + (size_t)g.pair_global[q] * 3;
+            o[0] = f_start;
+            o[1] = r_end;
+            o[2] = flags | (comb << 8);
+        }
+        return;
+    }
     const size_t ts = a.tile_stride;
     for (int p = 0; p < NP; ++p) {
-        a.sum_f[(size_t)(g.slot_base + p) * ts + tile_id] = bestF[p];
-        a.sum_r[(size_t)(g.slot_base + p) * ts + tile_id] = bestR[p];
+        a.sum_f[(size_t)(g.slot_base + p) * ts + tile_id] = bestF[p + dz];
+        a.sum_r[(size_t)(g.slot_base + p) * ts + tile_id] = bestR[p + dz];
     }
     for (int q = 0; q < g.npairs; ++q) {
-        a.pair_hi[(size_t)g.pair_global[q] * ts + tile_id] = phi[q];
-        a.pair_lo[(size_t)g.pair_global[q] * ts + tile_id] = plo[q];
+        a.pair_hi[(size_t)g.pair_global[q] * ts + tile_id] = phi[q + dz];
+        a.pair_lo[(size_t)g.pair_global[q] * ts + tile_id] = plo[q + dz];
     }
 }
 
-template <typename W, int NP, int V>
+template <typename W, int NP>
 static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
-    const int smem = 2 * hx_table_bytes(NP, sizeof(W));
+    const int smem = hx_table_bytes(NP, sizeof(W)) + HX_QCAP * (1 + (NP + 3) / 4) * HX_THREADS * 4;
     static bool attr_done[8] = {false, false, false, false, false, false, false, false};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 8 && !attr_done[dev]) {
-        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr_done[dev] = true;
-    } else if (dev >= 8) {
-        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (dev >= 8 || !attr_done[dev]) {
+        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (dev < 8) attr_done[dev] = true;
     }
     const uint32_t blocks = (tile_cap + HX_THREADS - 1) / HX_THREADS;
-    hx_myers_pair_kernel<W, NP, V><<<blocks, HX_THREADS, smem, st>>>(a);
+    hx_myers_pair_kernel<W, NP><<<blocks, HX_THREADS, smem, st>>>(a);
     return 1;
 }
 
-template <typename W, int V, int NP>
+template <typename W, int NP>
 struct HxDispatch {
     static int run(int np, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
-        if (np == NP) return hx_scan_launch_one<W, NP, V>(a, cap, st);
-        return HxDispatch<W, V, NP - 1>::run(np, a, cap, st);
+        if (np == NP) return hx_scan_launch_one<W, NP>(a, cap, st);
+        return HxDispatch<W, NP - 1>::run(np, a, cap, st);
     }
 };
-template <typename W, int V>
-struct HxDispatch<W, V, 0> {
+template <typename W>
+struct HxDispatch<W, 0> {
     static int run(int, const HxScanArgs &, uint32_t, cudaStream_t) { return -1; }
 };
 
 int hx_launch_scan(const HxScanArgs &a, const HxGroup &hg, uint32_t tile_cap, cudaStream_t st) {
     if (tile_cap == 0) return 0;
-    if (hg.word64) return HxDispatch<uint64_t, 0, HX_MAX_NP64>::run(hg.np, a, tile_cap, st);
-    switch (a.variant) {
-    case 1: return HxDispatch<uint32_t, 1, HX_MAX_NP32>::run(hg.np, a, tile_cap, st);
-    case 2: return HxDispatch<uint32_t, 2, HX_MAX_NP32>::run(hg.np, a, tile_cap, st);
-    case 3: return HxDispatch<uint32_t, 3, HX_MAX_NP32>::run(hg.np, a, tile_cap, st);
-    default: return HxDispatch<uint32_t, 0, HX_MAX_NP32>::run(hg.np, a, tile_cap, st);
-    }
+    if (hg.word64) return HxDispatch<uint64_t, HX_MAX_NP64>::run(hg.np, a, tile_cap, st);
+    return HxDispatch<uint32_t, HX_MAX_NP32>::run(hg.np, a, tile_cap, st);
 }
 
 // ------------------------------------------------------------------------------------
@@ -493,6 +555,7 @@ __global__ void __launch_bounds__(256)
     }
     const HxPairRef pr = pairs[q];
     const uint32_t t0 = tile_first[r], nt = tile_cnt[r];
+    if (nt == 1u) return;  // single-tile record: hx_myers_pair_kernel wrote the final result
     uint64_t bestF = HX_NONE64;          // (dist<<32 | end) of the best valid forward hit so far
     uint64_t bhi = HX_NONE64;            // combined<<32 | f_end
     uint32_t blo = 0;                    // r_end
@@ -568,7 +631,7 @@ __global__ void __launch_bounds__(128)
     uint64_t cnt = 0;
     const uint64_t base = pass ? counts[t] : 0;
     for (uint64_t i = own_start - warm; i < own_end; ++i) {
-        hx_step<0>(peq[text[i]], pv, mv, s, 2u);
+        hx_step(peq[text[i]], pv, mv, s);
         if (s < 0 && i >= own_start) {
             if (pass) {
                 const uint64_t o = base + cnt;

@@ -28,7 +28,6 @@ def _run(ctx, arena, offsets, pairs, k, **opts):
     for name in ("tile_len", "single_max"):
         ctx.set_option(name, opts.get(name, 0))
     ctx.set_option("slab_bytes", opts.get("slab_bytes", 128 << 20))
-    ctx.set_option("step_variant", opts.get("step_variant", 0))
     ctx.set_primers(pairs, k)
     return ctx.run_batch(arena, offsets)
 
@@ -99,9 +98,8 @@ def test_config1_bytes(ctx, golden_dir, tmp_path, k):
 def test_golden_batches(ctx, golden_dir, name):
     z = np.load(os.path.join(golden_dir, name + ".npz"))
     pairs = [list(p) for p in z["pairs"]]
-    for variant in (0, 1, 2):
-        res = _run(ctx, z["arena"], z["offsets"], pairs, int(z["k"]), step_variant=variant)
-        _cmp(res, z["res"], z["arena"], z["offsets"], pairs, int(z["k"]))
+    res = _run(ctx, z["arena"], z["offsets"], pairs, int(z["k"]))
+    _cmp(res, z["res"], z["arena"], z["offsets"], pairs, int(z["k"]))
 
 
 # ---- seeded batches of the BASELINE.json shapes at oracle-friendly sizes -----------------------------
