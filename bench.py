@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=60_000, help="records of the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=0, help="records per step of the reference arm (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ab", action="store_true", help="skip the TMA / LDG text-path A/B")
     return ap.parse_args()
 
 
@@ -124,6 +125,21 @@ def load_peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(bases):
+    """dram__bytes_read.sum + dram__bytes_write.sum of hx_myers_pair_kernel from the committed ncu capture of
+    this same command (profiles/r01_ncu_traffic.json, written from the .ncu-rep by tools/ncu_summary.py); only
+    reported when the capture was taken on the same number of bases per launch."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if int(t["bases_per_launch"]) == int(bases):
+            return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "dram_bytes_read": t["dram_bytes_read"],
+                    "dram_bytes_write": t["dram_bytes_write"], "algorithmic_bytes": int(bases),
+                    "source": t.get("source", "profiles/r01_ncu_traffic.json")}
+    except Exception:
+        pass
+    return None
 
 
 def cpu_port_run(arena, offsets, n, pairs, k, nthreads, rebuild=True):
@@ -236,6 +252,21 @@ def main():
     myers_ms, myers_launches = ctx.kernel_time(reset=True)
     ctx.set_option("time_kernels", 0)
 
+    # ---- A/B of the text path (not part of the timed region): TMA bulk-copy staging vs the default ----
+    ab_ms = None
+    if rank == 0 and not args.no_ab:
+        ctx.set_option("text_tma", 1)
+        dev_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(2):
+            dev_step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ab_ms = e0.elapsed_time(e1) / 2
+        ctx.set_option("text_tma", 0)
+
     # ---- end-to-end leg ("e2e"): host arena in, host result table out, every step ----------------
     h_arena = hx.pinned_empty(bases + 64)
     h_arena[:bases] = arena
@@ -274,10 +305,13 @@ def main():
         # against the 15 unique built-in patterns (20 searches/base in the reference's count);
         # one word-step = INT_OPS_PER_STEP integer instructions (SASS of the hot loop).
         uniq = len({p for f, r in pairs for p in (("f", f), ("r", r))})
-        int_ops_per_step = 12.5
+        # Instruction mix of the hot loop per word-step at NP = 15 (cuobjdump -sass + the ncu source page,
+        # profiles/r01_ncu_myers_pair_kernel_u32_15.csv): ALU pipe 10.0 (7 LOP3 + 2 LEA.HI + 0.5 LOP3 hit test +
+        # 0.5 per-byte overhead), FMA pipe 3.1 (IMAD.IADD: the carry add and the two shifts).
+        alu_ops, fma_ops = 10.0, 3.1
         per_launch_ms = myers_ms_max / max(1, myers_launches)
         steps_exec = bases * uniq
-        achieved_tops = steps_exec * int_ops_per_step / (per_launch_ms * 1e-3) / 1e12
+        steps_per_s = steps_exec / (per_launch_ms * 1e-3)
         peak = {}
         for name, var in (("lop3", 0), ("imad", 3), ("lop3_imad", 4), ("myers_step", 10)):
             try:
@@ -286,20 +320,26 @@ def main():
                 peak[name] = None
                 peak["error"] = str(e)
         alu_peak = peak.get("lop3") or float("nan")
+        achieved_alu = steps_per_s * alu_ops / 1e12
         roofline = {"bound": "int_alu", "kernel": "hx_myers_pair_kernel<u32,15>",
-                    "achieved": achieved_tops, "peak": alu_peak, "unit": "Tint-op/s",
-                    "frac": achieved_tops / alu_peak,
-                    "peak_source": "hx_int_peak LOP3 stream measured in this run (ALU pipe; no integer figure in "
-                                   "MEASURED_PEAKS.json)",
-                    "word_steps_per_s": steps_exec / (per_launch_ms * 1e-3),
-                    "int_ops_per_word_step": int_ops_per_step, "kernel_ms_per_launch": per_launch_ms,
+                    "achieved": achieved_alu, "peak": alu_peak, "unit": "Tint-op/s (ALU pipe)",
+                    "frac": achieved_alu / alu_peak,
+                    "peak_source": "of measured: hx_int_peak LOP3 stream in this run (the ALU pipe executes LOP3/LEA/"
+                                   "SHF/IADD3; MEASURED_PEAKS.json has no integer figure)",
+                    "word_steps_per_s": steps_per_s, "alu_ops_per_word_step": alu_ops,
+                    "fma_ops_per_word_step": fma_ops, "kernel_ms_per_launch": per_launch_ms,
                     "kernel_share_of_step": myers_ms_max / dev_ms_max,
-                    "dual_pipe_peak": peak.get("lop3_imad"), "frac_of_dual_pipe": (achieved_tops / peak["lop3_imad"])
-                    if peak.get("lop3_imad") else None, "bare_step_peak_gsteps": (peak.get("myers_step") or 0) * 1e3,
-                    "traffic": None,
+                    "all_int_ops": {"achieved": steps_per_s * (alu_ops + fma_ops) / 1e12,
+                                    "dual_pipe_peak": peak.get("lop3_imad"),
+                                    "frac": (steps_per_s * (alu_ops + fma_ops) / 1e12 / peak["lop3_imad"])
+                                    if peak.get("lop3_imad") else None},
+                    "bare_step_peak_gsteps": (peak.get("myers_step") or 0) * 1e3,
+                    "traffic": load_traffic(bases),
                     "hbm": {"achieved": bases / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": bases / (per_launch_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                             "algorithmic_bytes_per_launch": bases}}
+        if ab_ms is not None:
+            roofline["text_path_ab"] = {"ldg_ms_per_step": dev_ms_max / args.steps, "tma_ms_per_step": ab_ms}
         line = {"metric": "Gbases/s", "value": value, "unit": "Gbases/s", "gcups": value * cells,
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",

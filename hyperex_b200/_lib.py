@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libhyperex_b200.so")
+LIB_PATH = os.environ.get("HYPEREX_B200_LIB") or os.path.join(_HERE, "_lib", "libhyperex_b200.so")
 
 # every symbol include/hyperex_b200.h declares
 EXPORTS = [

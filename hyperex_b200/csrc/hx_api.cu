@@ -101,7 +101,7 @@ struct hx_ctx {
     std::vector<uint8_t> tables;
     bool primers_set = false;
     // options
-    int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0;
+    int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0;
     uint64_t launches = 0;
     std::vector<TimedLaunch> timed;
     double myers_ms = 0;
@@ -245,7 +245,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const 
         a.pair_lo = S.pair_lo.p;
         a.tile_stride = pl.tile_cap;
         a.k = ctx->k;
-        a.variant = 0;
+        a.variant = (int)ctx->opt_text_tma;
         a.two = 2;
         TimedLaunch tl;
         if (ctx->opt_time) {
@@ -339,6 +339,7 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     else if (n == "single_max") ctx->opt_single_max = value;
     else if (n == "slab_bytes") ctx->opt_slab_bytes = std::max<int64_t>(value, 1);
     else if (n == "time_kernels") ctx->opt_time = value;
+    else if (n == "text_tma") ctx->opt_text_tma = value ? 1 : 0;
     else return fail(ctx, HX_ERR_ARG, "unknown option %s", name);
     return HX_OK;
 }

@@ -77,7 +77,7 @@ struct HxScanArgs {
     uint32_t *pair_lo;         // [pair][tile] r_end
     uint32_t tile_stride;      // capacity used as the [slot]/[pair] stride
     uint32_t k;
-    int32_t variant;
+    int32_t variant;           // text path: 0 per-thread LDG.128 + prefetch, 1 TMA bulk copies into shared memory
     uint32_t two;              // == 2, passed at run time (a constant ptxas cannot fold)
 };
 

@@ -203,19 +203,32 @@ int hx_launch_classify(const uint8_t *arena, const uint64_t *offsets, uint64_t o
 // (Measured on B200, profiles/int_peak_r01.json: moving the score update to IMAD.HI or to a carry chain is
 // slower than what ptxas emits for the plain C below, so there is a single step variant.)
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void hx_step(const uint32_t eq, uint32_t &pv, uint32_t &mv, int &s) {
+#ifndef HX_EXP
+#define HX_EXP 0
+#endif
+__device__ __forceinline__ void hx_step(const uint32_t eq, uint32_t &pv, uint32_t &mv, int &s, const uint32_t hx_two = 2u) {
     const uint32_t xv = eq | mv;
     const uint32_t xh = (((eq & pv) + pv) ^ pv) | eq;
     uint32_t ph = mv | ~(xh | pv);
     uint32_t mh = pv & xh;
+#if HX_EXP == 1
+    // experiment: both score updates as IMAD.HI (FMA pipe, half rate) with a run-time multiplier
+    asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(s) : "r"(ph), "r"(hx_two));
+    asm("mad.hi.s32 %0, %1, %2, %0;" : "+r"(s) : "r"(mh), "r"(hx_two));
+#elif HX_EXP == 2
+    // experiment: only the ph update as IMAD.HI
+    asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(s) : "r"(ph), "r"(hx_two));
+    s -= (int)(mh >> 31);
+#else
     s += (int)(ph >> 31) - (int)(mh >> 31);  // ptxas: LEA.HI + LEA.HI.SX32 (one ALU op per sign bit)
+#endif
     ph <<= 1;                                // ptxas: IMAD.IADD x+x on the FMA pipe
     mh <<= 1;
     pv = mh | ~(xv | ph);
     mv = ph & xv;
 }
 
-__device__ __forceinline__ void hx_step(const uint64_t eq, uint64_t &pv, uint64_t &mv, int &s) {
+__device__ __forceinline__ void hx_step(const uint64_t eq, uint64_t &pv, uint64_t &mv, int &s, const uint32_t = 2u) {
     const uint64_t xv = eq | mv;
     const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
     uint64_t ph = mv | ~(xh | pv);
@@ -245,13 +258,14 @@ struct HxRow {
 };
 
 // ------------------------------------------------------------------------------------
-// hx_myers_pair_kernel<W, NP>
+// hx_myers_pair_kernel<W, NP, TMA>
 //   one thread = one tile; per text byte the thread loads one Peq row (all NP patterns of the
 //   group, shared memory, 16-byte LDS) and advances NP independent automata held in registers.
 //
 //   A hit (sign bit of any biased score) is rare.  The lane that sees it only PUSHES a compact
-//   event record {position, the NP biased scores as bytes} into its private shared-memory queue
-//   (a few PRMT + STS, no long-latency operation while the other 31 lanes wait).  Queues are
+//   event record {position, the NP biased scores as bytes} into its private queue in local
+//   memory (a few PRMT + fire-and-forget STL, no long-latency operation while the other 31
+//   lanes wait; with the text staged by TMA the L1 is free to hold this state).  Queues are
 //   DRAINED warp-synchronously — all lanes together, whenever any lane's queue is nearly full and
 //   at the last word of the warp's scan — so the pairing logic below runs with full lanes:
 //     bestR[p]  = lexicographic min (dist, end) over all hits of pattern p in the tile
@@ -267,9 +281,44 @@ struct HxRow {
 //   Records that consist of a single tile get their final hx_result written here; windows of
 //   longer records write summaries for hx_combine_kernel.
 // ------------------------------------------------------------------------------------
-#define HX_QCAP 8  // event records per thread queue
+// The text path is a template switch so that both variants ship, are parity-tested and can be A/B-timed:
+//   TMA = false  per-thread 16-byte LDG.128, one chunk ahead (measured 3 % faster on B200: a bulk
+//                copy is a warp-uniform instruction, so 32 independent per-lane streams issue as 32
+//                serialised UBLKCPs; profiles/r01_text_path_ab.md)
+//   TMA = true   text staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier),
+//                two HX_CH-byte stages per thread; keeps the text out of the L1
+#define HX_QCAP 16  // event records per thread queue (local memory; pushes are fire-and-forget stores)
+#ifndef HX_CH
+#define HX_CH 128   // bytes per text stage of one thread (two stages in flight)
+#endif
+#define HX_CPS (HX_CH / 16)  // 16-byte chunks per stage
 
-template <typename W, int NP>
+// ---- TMA (cp.async.bulk) + mbarrier primitives; SASS: UBLKCP / SYNCS ----
+__device__ __forceinline__ uint32_t hx_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void hx_mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hx_mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hx_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void hx_mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+        if (spin > (1u << 26)) __trap();  // a lost copy must fail loudly, never hang the GPU
+    }
+}
+__device__ __forceinline__ void hx_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename W, int NP, bool TMA>
 __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((sizeof(W) * NP <= 32) ? 5 : 4))
     hx_myers_pair_kernel(const HxScanArgs a) {
     constexpr int WB = sizeof(W);
@@ -279,7 +328,22 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
     constexpr int RW = 1 + SW;        // words of an event record: position + scores
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ HxGroup g;
-    uint32_t *const queue = reinterpret_cast<uint32_t *>(smem + TBYTES) + threadIdx.x;  // [record][word][thread]
+    uint32_t queue[HX_QCAP][RW];  // event records; indexed dynamically => local memory
+    // per-thread text pipeline (TMA variant): two HX_CH-byte stages, each with its own mbarrier
+    // (count 1): the thread arms the barrier with the byte count, issues one TMA bulk copy
+    // global -> shared and later waits for the phase; no cross-thread synchronisation is involved.
+    uint8_t *const txt = smem + TBYTES;
+    const uint32_t stage0 = hx_smem_u32(txt + (size_t)threadIdx.x * HX_CH);
+    const uint32_t stage1 = stage0 + HX_THREADS * HX_CH;
+    const uint32_t mbar0 = hx_smem_u32(txt + 2 * HX_THREADS * HX_CH + (size_t)threadIdx.x * 8);
+    const uint32_t mbar1 = mbar0 + HX_THREADS * 8;
+    uint32_t uses0 = 0, uses1 = 0;  // completed waits per stage => phase parity
+    if constexpr (TMA) {
+        hx_mbar_init(mbar0, 1);
+        hx_mbar_init(mbar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        hx_fence_proxy_async();
+    }
     if (threadIdx.x < sizeof(HxGroup) / 4)
         reinterpret_cast<uint32_t *>(&g)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.group)[threadIdx.x];
 
@@ -324,7 +388,13 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
     const uint8_t *src = a.arena + ab;
     // UB text bytes are processed per trip of the innermost loop (narrow groups amortise the loop
     // overhead over more bytes; wide groups keep the hot loop small).
+#if HX_EXP == 3
+    constexpr int UB = (NP * WB <= 24) ? 4 : 2;
+#elif HX_EXP == 4
+    constexpr int UB = 4;
+#else
     constexpr int UB = (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
+#endif
     uint32_t cnt = 0;  // records in this lane's queue
 
     for (int pass = 0; pass < 2; ++pass) {
@@ -341,10 +411,44 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
         const uint32_t nchunks = mine ? (lead + tl.warm + tl.own_len + 15u) >> 4 : 0u;
         const uint32_t nchunks_w = __reduce_max_sync(0xffffffffu, nchunks);
 
-        uint4 cur = make_uint4(0, 0, 0, 0);
-        if (nchunks) {
-            cur = hx_ldg16(src);
-            if (tl.own_start == tl.warm && lead) {
+        const bool mask_lead = nchunks && tl.own_start == tl.warm && lead;
+        const uint32_t nstages = (nchunks + HX_CPS - 1u) / HX_CPS;
+        auto issue = [&](uint32_t st) {
+            if (st < nstages) {
+                const uint32_t bytes = min((uint32_t)HX_CH, (nchunks - HX_CPS * st) * 16u);
+                const uint32_t mb = (st & 1u) ? mbar1 : mbar0;
+                hx_mbar_expect_tx(mb, bytes);
+                hx_bulk_g2s((st & 1u) ? stage1 : stage0, src + (size_t)st * HX_CH, bytes, mb);
+            }
+        };
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if constexpr (TMA) {
+            issue(0);
+            issue(1);
+        } else {
+            if (nchunks) nxt = hx_ldg16(src);
+        }
+
+        for (uint32_t c = 0; c < nchunks_w; ++c) {
+            uint4 cur = make_uint4(0, 0, 0, 0);
+            const uint32_t st = c / HX_CPS, cc = c % HX_CPS;
+            if constexpr (TMA) {
+                if (c < nchunks) {
+                    if (cc == 0) {
+                        if (st & 1u) hx_mbar_wait(mbar1, uses1++ & 1u);
+                        else hx_mbar_wait(mbar0, uses0++ & 1u);
+                    }
+                    const uint32_t sa = ((st & 1u) ? stage1 : stage0) + cc * 16u;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(cur.x), "=r"(cur.y), "=r"(cur.z), "=r"(cur.w)
+                                 : "r"(sa)
+                                 : "memory");
+                }
+            } else {
+                cur = nxt;
+                nxt = (c + 1 < nchunks) ? hx_ldg16(src + 16ull * (c + 1)) : make_uint4(0, 0, 0, 0);
+            }
+            if (c == 0 && mask_lead) {
                 // The scan starts at the record start: bytes before it belong to the previous record.
                 // Byte 0 selects the all-zero Peq row, under which a fresh automaton stays fresh.
                 uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
@@ -356,10 +460,6 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
                 }
                 cur = make_uint4(w[0], w[1], w[2], w[3]);
             }
-        }
-
-        for (uint32_t c = 0; c < nchunks_w; ++c) {
-            const uint4 nxt = (c + 1 < nchunks) ? hx_ldg16(src + 16ull * (c + 1)) : make_uint4(0, 0, 0, 0);
 #pragma unroll 1
             for (int wi = 0; wi < 4; ++wi) {
                 uint32_t w = cur.x;
@@ -377,14 +477,14 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
                         int any = 0;
 #pragma unroll
                         for (int p = 0; p < NP; ++p) {
-                            hx_step(row.eq(p), pv[p], mv[p], s[p]);
+                            hx_step(row.eq(p), pv[p], mv[p], s[p], a.two);
                             any |= s[p];
                         }
                         if (any < 0) {
                             // ---- rare: some pattern has dist <= k here; record the event ----
                             const uint32_t pos = pos0 + (c << 4) + (wi << 2) + b0 + bi;
                             if (pos - tl.own_start < own_len) {
-                                uint32_t *r = queue + cnt * (RW * HX_THREADS);
+                                uint32_t *r = queue[cnt];
                                 r[0] = pos;
 #pragma unroll
                                 for (int j = 0; j < SW; ++j) {
@@ -392,7 +492,7 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
                                     const uint32_t b1_ = (4 * j + 1 < NP) ? (uint32_t)s[4 * j + 1] : 0x7fu;
                                     const uint32_t b2_ = (4 * j + 2 < NP) ? (uint32_t)s[4 * j + 2] : 0x7fu;
                                     const uint32_t b3_ = (4 * j + 3 < NP) ? (uint32_t)s[4 * j + 3] : 0x7fu;
-                                    r[(1 + j) * HX_THREADS] =
+                                    r[1 + j] =
                                         __byte_perm(__byte_perm(b0_, b1_, 0x0040), __byte_perm(b2_, b3_, 0x0040), 0x5410);
                                 }
                                 ++cnt;
@@ -404,13 +504,13 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
                 const bool last_word = (c + 1 == nchunks_w) && wi == 3;
                 if (__any_sync(0xffffffffu, cnt > HX_QCAP - 4 || (last_word && cnt))) {
                     for (uint32_t i = 0; i < cnt; ++i) {
-                        const uint32_t *r = queue + i * (RW * HX_THREADS);
+                        const uint32_t *r = queue[i];
                         const uint32_t pos = r[0];
                         uint32_t sw[SW];
                         uint32_t hm = 0;  // bit p: pattern p hit (its biased score byte is negative)
 #pragma unroll
                         for (int j = 0; j < SW; ++j) {
-                            sw[j] = r[(1 + j) * HX_THREADS];
+                            sw[j] = r[1 + j];
                             const uint32_t neg = sw[j] & 0x80808080u;
                             hm |= (((neg >> 7) & 1u) | ((neg >> 14) & 2u) | ((neg >> 21) & 4u) | ((neg >> 28) & 8u)) << (4 * j);
                         }
@@ -453,7 +553,12 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
                     cnt = 0;
                 }
             }
-            cur = nxt;
+            if constexpr (TMA) {
+                if (cc == HX_CPS - 1u && c < nchunks) {
+                    hx_fence_proxy_async();  // my reads of this stage precede the TMA write that refills it
+                    issue(st + 2u);
+                }
+            }
         }
         __syncthreads();  // the table may be replaced by the next pass
     }
@@ -492,25 +597,26 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
     }
 }
 
-template <typename W, int NP>
+template <typename W, int NP, bool TMA>
 static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
-    const int smem = hx_table_bytes(NP, sizeof(W)) + HX_QCAP * (1 + (NP + 3) / 4) * HX_THREADS * 4;
+    const int smem = hx_table_bytes(NP, sizeof(W)) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
     static bool attr_done[8] = {false, false, false, false, false, false, false, false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 8 || !attr_done[dev]) {
-        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (dev < 8) attr_done[dev] = true;
     }
     const uint32_t blocks = (tile_cap + HX_THREADS - 1) / HX_THREADS;
-    hx_myers_pair_kernel<W, NP><<<blocks, HX_THREADS, smem, st>>>(a);
+    hx_myers_pair_kernel<W, NP, TMA><<<blocks, HX_THREADS, smem, st>>>(a);
     return 1;
 }
 
 template <typename W, int NP>
 struct HxDispatch {
     static int run(int np, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
-        if (np == NP) return hx_scan_launch_one<W, NP>(a, cap, st);
+        if (np == NP) return a.variant == 1 ? hx_scan_launch_one<W, NP, true>(a, cap, st)
+                                            : hx_scan_launch_one<W, NP, false>(a, cap, st);
         return HxDispatch<W, NP - 1>::run(np, a, cap, st);
     }
 };

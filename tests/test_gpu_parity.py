@@ -28,6 +28,7 @@ def _run(ctx, arena, offsets, pairs, k, **opts):
     for name in ("tile_len", "single_max"):
         ctx.set_option(name, opts.get(name, 0))
     ctx.set_option("slab_bytes", opts.get("slab_bytes", 128 << 20))
+    ctx.set_option("text_tma", opts.get("text_tma", 0))
     ctx.set_primers(pairs, k)
     return ctx.run_batch(arena, offsets)
 
@@ -94,12 +95,15 @@ def test_config1_bytes(ctx, golden_dir, tmp_path, k):
                            "Allorhizobium_borbori__DN316__EF125187")
 
 
+@pytest.mark.parametrize("text_tma", [0, 1])
 @pytest.mark.parametrize("name", ["c2_small", "c3_small", "mixed_small"])
-def test_golden_batches(ctx, golden_dir, name):
+def test_golden_batches(ctx, golden_dir, name, text_tma):
     z = np.load(os.path.join(golden_dir, name + ".npz"))
     pairs = [list(p) for p in z["pairs"]]
-    res = _run(ctx, z["arena"], z["offsets"], pairs, int(z["k"]))
-    _cmp(res, z["res"], z["arena"], z["offsets"], pairs, int(z["k"]))
+    for tile in ((0, 0), (4096, 4096)):  # windows (auto for a small batch) and whole-record tiles
+        res = _run(ctx, z["arena"], z["offsets"], pairs, int(z["k"]), tile_len=tile[0], single_max=tile[1],
+                   text_tma=text_tma)
+        _cmp(res, z["res"], z["arena"], z["offsets"], pairs, int(z["k"]))
 
 
 # ---- seeded batches of the BASELINE.json shapes at oracle-friendly sizes -----------------------------
@@ -117,12 +121,13 @@ def test_c3_degenerate_primers_both_strands(ctx, k):
     _cmp(_run(ctx, a, o, pairs, k), O.run_batch(a, o, pairs, k, nthreads=8), a, o, pairs, k)
 
 
+@pytest.mark.parametrize("text_tma", [0, 1])
 @pytest.mark.parametrize("tile_len,single_max", [(0, 0), (256, 256), (64, 64), (1024, 1500)])
-def test_c4_softmasked_contigs_windows(ctx, tile_len, single_max):
+def test_c4_softmasked_contigs_windows(ctx, tile_len, single_max, text_tma):
     a, o = hx_synth.gen_contigs(3, seed=41, length=60_000, copies=(3, 6), n_runs=3)
     pairs = hx.default_primers()
     ref = O.run_batch(a, o, pairs, 3, nthreads=8)
-    _cmp(_run(ctx, a, o, pairs, 3, tile_len=tile_len, single_max=single_max), ref, a, o, pairs, 3)
+    _cmp(_run(ctx, a, o, pairs, 3, tile_len=tile_len, single_max=single_max, text_tma=text_tma), ref, a, o, pairs, 3)
 
 
 def test_c5_primer_csv_64_pairs(ctx):
@@ -141,7 +146,8 @@ def test_c5_primer_csv_64_pairs(ctx):
         a[s + 700:s + 700 + len(rs)] = rs
     ref = O.run_batch(a, o, pairs, 2, nthreads=8)
     assert (ref[:, 10:]["flags"] & 4).any()
-    _cmp(_run(ctx, a, o, pairs, 2), ref, a, o, pairs, 2)
+    for tma in (0, 1):
+        _cmp(_run(ctx, a, o, pairs, 2, text_tma=tma), ref, a, o, pairs, 2)
 
 
 # ---- edge cases the domain has -------------------------------------------------------------------------
@@ -155,7 +161,10 @@ def test_edge_records(ctx):
     a, o = hx_synth.pack(recs)
     for k in (0, 1, 3, 17, 24):
         pairs = hx.default_primers()
-        _cmp(_run(ctx, a, o, pairs, k), O.run_batch(a, o, pairs, k), a, o, pairs, k)
+        ref = O.run_batch(a, o, pairs, k)
+        for tma in (0, 1):
+            _cmp(_run(ctx, a, o, pairs, k, text_tma=tma), ref, a, o, pairs, k)
+            _cmp(_run(ctx, a, o, pairs, k, tile_len=16, single_max=16, text_tma=tma), ref, a, o, pairs, k)
 
 
 def test_k_at_least_pattern_length_every_position_hits(ctx):
@@ -171,7 +180,8 @@ def test_rna_records_use_rna_reverse_complement(ctx):
     pairs = hx.default_primers()
     ref = O.run_batch(a, o, pairs, 2, nthreads=8)
     assert (ref["flags"] & 16).any() and not (ref["flags"] & 16).all()
-    _cmp(_run(ctx, a, o, pairs, 2), ref, a, o, pairs, 2)
+    for tma in (0, 1):
+        _cmp(_run(ctx, a, o, pairs, 2, text_tma=tma), ref, a, o, pairs, 2)
 
 
 def test_primer_validation_errors(ctx):
