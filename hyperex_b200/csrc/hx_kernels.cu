@@ -36,6 +36,39 @@ __device__ __forceinline__ uint4 hx_ldg16(const uint8_t *p) {
     return __ldg(reinterpret_cast<const uint4 *>(p));
 }
 
+// 16-byte load of record text.  HX_LDPOL selects the cache policy (A/B measured with ncu at the bench size,
+// profiles/r01_text_path_ab.md): 0 default (L1 + L2 normal), 1 no L1 allocation, 2 no L1 allocation +
+// L2 evict-first (harmful: the second 16-byte half of a sector is re-fetched from DRAM).
+#ifndef HX_LDPOL
+#define HX_LDPOL 0
+#endif
+__device__ __forceinline__ uint64_t hx_policy_evict_first() {
+    uint64_t pol = 0;
+#if HX_LDPOL == 2
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    return pol;
+}
+__device__ __forceinline__ uint4 hx_ldg16_stream(const uint8_t *p, uint64_t pol) {
+#if HX_LDPOL == 2
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+#elif HX_LDPOL == 1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    (void)pol;
+    return v;
+#else
+    (void)pol;
+    return hx_ldg16(p);
+#endif
+}
+
 // ------------------------------------------------------------------------------------
 // tile construction
 // ------------------------------------------------------------------------------------
@@ -396,6 +429,7 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
     constexpr int UB = (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
 #endif
     uint32_t cnt = 0;  // records in this lane's queue
+    const uint64_t pol = hx_policy_evict_first();
 
     for (int pass = 0; pass < 2; ++pass) {
         const bool mine = alpha == pass;
@@ -426,7 +460,7 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
             issue(0);
             issue(1);
         } else {
-            if (nchunks) nxt = hx_ldg16(src);
+            if (nchunks) nxt = hx_ldg16_stream(src, pol);
         }
 
         for (uint32_t c = 0; c < nchunks_w; ++c) {
@@ -446,7 +480,7 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
                 }
             } else {
                 cur = nxt;
-                nxt = (c + 1 < nchunks) ? hx_ldg16(src + 16ull * (c + 1)) : make_uint4(0, 0, 0, 0);
+                nxt = (c + 1 < nchunks) ? hx_ldg16_stream(src + 16ull * (c + 1), pol) : make_uint4(0, 0, 0, 0);
             }
             if (c == 0 && mask_lead) {
                 // The scan starts at the record start: bytes before it belong to the previous record.
