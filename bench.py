@@ -50,7 +50,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--records", type=int, default=1_000_000, help="records per GPU")
-    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--k", type=int, default=-1, help="-m value (default: the workload's own)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 is the BASELINE.json metric config; c3/c4/c5 are informational")
     ap.add_argument("--cpu-sample", type=int, default=60_000, help="records of the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=0, help="records per step of the reference arm (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -62,6 +64,37 @@ def pairs_and_cells():
     from oracle import oracle as O  # only for the primer table of the CPU legs; the product has its own
     pairs = O.default_pairs()
     return pairs, sum(len(f) + len(r) for f, r in pairs)
+
+
+def make_workload(name, n, rank, k_arg):
+    """(arena, offsets, pairs, k, description) for one rank; shapes follow BASELINE.json configs[1..4]"""
+    import hx_synth
+    from oracle import oracle as O
+    if name == "c2":
+        a, o = hx_synth.gen_reads(n, seed=2 + 1000 * rank)
+        return a, o, O.default_pairs(), 0 if k_arg < 0 else k_arg, (
+            "c2: 1M synthetic full-length 16S reads ~1.5 kb per GPU, 10 built-in regions (20 searches/base, "
+            "393 cells/base), -m 0")
+    if name == "c3":
+        base_n = min(n, 20000)  # the mutated generator is a Python loop: make 20k reads and repeat them
+        a, o = hx_synth.gen_reads_mutated(base_n, seed=3 + 1000 * rank, max_edits=3, revcomp_frac=0.5)
+        reps = max(1, n // base_n)
+        lens = np.tile(np.diff(o.astype(np.int64)), reps)
+        a = np.tile(a, reps)
+        o = np.zeros(len(lens) + 1, np.uint64)
+        o[1:] = np.cumsum(lens)
+        return a, o, [O.region_to_primer("v3v4"), O.region_to_primer("v4v5")], 2 if k_arg < 0 else k_arg, (
+            f"c3: {len(lens)} reads with IUPAC-degenerate primers v3v4+v4v5, sites with 0-3 edits, half reverse-"
+            "complemented, -m 2")
+    if name == "c4":
+        nc = max(1, n // 15625)  # n = 1M -> 64 contigs of 5 Mb
+        a, o = hx_synth.gen_contigs(nc, seed=4 + 1000 * rank, length=5_000_000)
+        return a, o, O.default_pairs(), 3 if k_arg < 0 else k_arg, (
+            f"c4: {nc} soft-masked 5 Mb contigs with multi-copy rRNA operons, 10 built-in regions, -m 3, windows")
+    a, o = hx_synth.gen_reads(n, seed=5 + 1000 * rank)
+    pairs = hx_synth.gen_primer_pairs(54, seed=5, builtins=O.default_pairs())
+    return a, o, pairs, 2 if k_arg < 0 else k_arg, (
+        f"c5: {n} SILVA-scale 16S records per GPU + 64-pair primer CSV (some primers > 32 nt), -m 2")
 
 
 class ClockSampler:
@@ -204,10 +237,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
-    pairs, cells = pairs_and_cells()
-    n = args.records
     # every rank owns a different shard of the N x records job (weak scaling); seed = config index + rank
-    arena, offsets = hx_synth.gen_reads(n, seed=2 + 1000 * rank)
+    arena, offsets, pairs, k, workload_desc = make_workload(args.workload, args.records, rank, args.k)
+    args.k = k
+    cells = sum(len(f) + len(r) for f, r in pairs)
+    n = len(offsets) - 1
     bases = int(offsets[-1])
     npairs = len(pairs)
 
@@ -304,14 +338,16 @@ def main():
         # algorithmic work per launch: the launch scans every base of this rank
         # against the 15 unique built-in patterns (20 searches/base in the reference's count);
         # one word-step = INT_OPS_PER_STEP integer instructions (SASS of the hot loop).
-        uniq = len({p for f, r in pairs for p in (("f", f), ("r", r))})
+        n_groups, steps32, steps64 = ctx.group_info()
+        uniq = steps32 + steps64  # automata stepped per text byte (15 for the 10 built-in regions)
         # Instruction mix of the hot loop per word-step at NP = 15 (cuobjdump -sass + the ncu source page,
         # profiles/r01_ncu_myers_pair_kernel_u32_15.csv): ALU pipe 10.0 (7 LOP3 + 2 LEA.HI + 0.5 LOP3 hit test +
         # 0.5 per-byte overhead), FMA pipe 3.1 (IMAD.IADD: the carry add and the two shifts).
         alu_ops, fma_ops = 10.0, 3.1
         per_launch_ms = myers_ms_max / max(1, myers_launches)
-        steps_exec = bases * uniq
-        steps_per_s = steps_exec / (per_launch_ms * 1e-3)
+        steps_exec = bases * uniq                       # word-steps of one pass over the batch (all groups)
+        scan_ms = myers_ms_max / args.steps             # all scan launches of one step
+        steps_per_s = steps_exec / (scan_ms * 1e-3)
         peak = {}
         for name, var in (("lop3", 0), ("imad", 3), ("lop3_imad", 4), ("myers_step", 10)):
             try:
@@ -321,7 +357,9 @@ def main():
                 peak["error"] = str(e)
         alu_peak = peak.get("lop3") or float("nan")
         achieved_alu = steps_per_s * alu_ops / 1e12
-        roofline = {"bound": "int_alu", "kernel": "hx_myers_pair_kernel<u32,15>",
+        roofline = {"bound": "int_alu", "kernel": "hx_myers_pair_kernel<u32,15>" if args.workload == "c2" else
+                    f"hx_myers_pair_kernel x {n_groups} groups ({steps32} u32 + {steps64} u64 automata/base; the ALU "
+                    "op counts below are those of the u32 NP=15 kernel)",
                     "achieved": achieved_alu, "peak": alu_peak, "unit": "Tint-op/s (ALU pipe)",
                     "frac": achieved_alu / alu_peak,
                     "peak_source": "of measured: hx_int_peak LOP3 stream in this run (the ALU pipe executes LOP3/LEA/"
@@ -334,9 +372,9 @@ def main():
                                     "frac": (steps_per_s * (alu_ops + fma_ops) / 1e12 / peak["lop3_imad"])
                                     if peak.get("lop3_imad") else None},
                     "bare_step_peak_gsteps": (peak.get("myers_step") or 0) * 1e3,
-                    "traffic": load_traffic(bases),
-                    "hbm": {"achieved": bases / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": bases / (per_launch_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                    "traffic": load_traffic(bases) if args.workload == "c2" else None,
+                    "hbm": {"achieved": bases * n_groups / (scan_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": bases * n_groups / (scan_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                             "algorithmic_bytes_per_launch": bases}}
         if ab_ms is not None:
             roofline["text_path_ab"] = {"ldg_ms_per_step": dev_ms_max / args.steps, "tma_ms_per_step": ab_ms}
@@ -344,10 +382,9 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": "c2: 1M synthetic full-length 16S reads ~1.5 kb per GPU, 10 built-in "
-                                       "regions (20 searches/base, 393 cells/base), -m 0", "records_per_gpu": n,
+                "config": {"workload": workload_desc, "records_per_gpu": n,
                            "bases_per_gpu": bases, "pairs": npairs, "k": args.k, "regions_found": found,
-                           "l2": "inputs (1.5 GB/GPU) larger than the 126 MB L2; no flush needed",
+                           "l2": f"inputs ({bases / 1e9:.2f} GB/GPU) larger than the 126 MB L2; no flush needed",
                            "parallelism": f"records sharded over {world} GPU(s), no collective"},
                 "e2e": {"value": e2e, "unit": "Gbases/s", "gcups": e2e * cells, "ms_per_step": e2e_ms_max / args.steps,
                         "h2d_bytes_per_step": int(bases + offsets.nbytes), "d2h_bytes_per_step": int(n * npairs * 12),

@@ -203,6 +203,12 @@ class Context:
             raise HyperexError(int(cnt), self._L.hx_last_error(self._h).decode())
         return [(int(ends[i]), int(dists[i])) for i in range(cnt)]
 
+    def group_info(self):
+        """(n_groups, 32-bit automata per base, 64-bit automata per base) of the current primer set"""
+        g, a, b = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self._L.hx_group_info(self._h, C.byref(g), C.byref(a), C.byref(b)))
+        return g.value, a.value, b.value
+
     def launch_count(self) -> int:
         return int(self._L.hx_launch_count(self._h))
 

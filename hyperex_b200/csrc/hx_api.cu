@@ -55,8 +55,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf<uint8_t> arena;
     DevBuf<uint64_t> offsets;
-    DevBuf<uint32_t> rec_u32;  // rec_raw | tile_first | tile_cnt   (3 x rec_cap)
-    DevBuf<uint32_t> scratch;  // ntiles, overflow, pad[2], hist[NB], cursor[NB]
+    DevBuf<uint32_t> rec_u32;  // rec_raw | tile_first | tile_cnt | long_list   (4 x rec_cap)
+    DevBuf<uint32_t> scratch;  // ntiles, overflow, n_long, pad, hist[NB], cursor[NB]
     DevBuf<HxTile> tiles;
     DevBuf<uint32_t> order;
     DevBuf<uint64_t> sum_f, sum_r, pair_hi;
@@ -193,7 +193,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const 
                  uint32_t n_records, uint64_t bytes, hx_result *d_out, cudaStream_t st) {
     if (n_records == 0) return HX_OK;
     const SlabPlan pl = plan_slab(ctx, n_records, bytes);
-    HX_CUDA(ctx, S.rec_u32.reserve((size_t)n_records * 3));
+    HX_CUDA(ctx, S.rec_u32.reserve((size_t)n_records * 4));
     HX_CUDA(ctx, S.scratch.reserve(4 + 2 * HX_NBUCKETS));
     HX_CUDA(ctx, S.tiles.reserve(pl.tile_cap));
     HX_CUDA(ctx, S.order.reserve(pl.tile_cap));
@@ -203,7 +203,8 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const 
     HX_CUDA(ctx, S.pair_lo.reserve((size_t)ctx->n_pairs * pl.tile_cap));
 
     uint32_t *rec_raw = S.rec_u32.p, *tile_first = rec_raw + n_records, *tile_cnt = tile_first + n_records;
-    uint32_t *ntiles = S.scratch.p, *overflow = ntiles + 1, *hist = ntiles + 4, *cursor = hist + HX_NBUCKETS;
+    uint32_t *long_list = tile_cnt + n_records;
+    uint32_t *ntiles = S.scratch.p, *overflow = ntiles + 1, *n_long = ntiles + 2, *hist = ntiles + 4, *cursor = hist + HX_NBUCKETS;
     HX_CUDA(ctx, cudaMemsetAsync(S.scratch.p, 0, (4 + 2 * HX_NBUCKETS) * sizeof(uint32_t), st));
     HX_CUDA(ctx, cudaMemsetAsync(rec_raw, 0, (size_t)n_records * sizeof(uint32_t), st));
 
@@ -221,6 +222,8 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const 
     b.ntiles = ntiles;
     b.hist = hist;
     b.overflow = overflow;
+    b.long_list = long_list;
+    b.n_long = n_long;
     ctx->launches += hx_launch_tile_build(b, cursor, S.order.p, st);
     ctx->launches += hx_launch_classify(d_arena, d_offsets, off_base, S.tiles.p, ntiles, pl.tile_cap, rec_raw, st);
 
@@ -263,7 +266,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const 
         }
     }
     ctx->launches += hx_launch_combine(tile_first, tile_cnt, rec_raw, D.d_pairs, ctx->n_pairs, n_records, S.sum_f.p,
-                                       S.sum_r.p, S.pair_hi.p, S.pair_lo.p, pl.tile_cap, d_out, st);
+                                       S.sum_r.p, S.pair_hi.p, S.pair_lo.p, pl.tile_cap, long_list, n_long, d_out, st);
     HX_CUDA(ctx, cudaMemcpyAsync(S.h_status, S.scratch.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     HX_CUDA(ctx, cudaGetLastError());
     return HX_OK;
@@ -643,6 +646,16 @@ void hx_free_pinned(void *p) {
 }
 
 uint64_t hx_launch_count(const hx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int hx_group_info(const hx_ctx *ctx, uint32_t *n_groups, uint32_t *steps32_per_base, uint32_t *steps64_per_base) {
+    if (!ctx || !ctx->primers_set) return HX_ERR_STATE;
+    uint32_t s32 = 0, s64 = 0;
+    for (const HxGroup &g : ctx->groups) (g.word64 ? s64 : s32) += (uint32_t)g.np;
+    if (n_groups) *n_groups = (uint32_t)ctx->groups.size();
+    if (steps32_per_base) *steps32_per_base = s32;
+    if (steps64_per_base) *steps64_per_base = s64;
+    return HX_OK;
+}
 
 int hx_kernel_time(hx_ctx *ctx, double *myers_ms, uint64_t *myers_launches, int reset) {
     if (!ctx) return HX_ERR_ARG;

@@ -11,6 +11,7 @@
 #define HX_THREADS 128     // threads per CTA of the scan kernel
 #define HX_NBUCKETS 1024   // length buckets of the tile ordering
 #define HX_NONE64 0xFFFFFFFFFFFFFFFFull
+#define HX_LONG_TILES 64u  // records with more windows than this are joined by a whole warp
 
 // raw per-record alphabet evidence gathered by hx_classify_kernel (utils.rs:207-228)
 #define HX_RAW_U 1u
@@ -95,6 +96,8 @@ struct HxBuildArgs {
     uint32_t *ntiles;       // counter (zeroed)
     uint32_t *hist;         // HX_NBUCKETS (zeroed)
     uint32_t *overflow;     // set to 1 when tile_cap would be exceeded
+    uint32_t *long_list;    // records with more than HX_LONG_TILES windows
+    uint32_t *n_long;       // counter (zeroed)
 };
 
 // launchers (hx_kernels.cu); each returns the number of kernels it launched
@@ -105,7 +108,7 @@ int hx_launch_scan(const HxScanArgs &a, const HxGroup &hostgroup, uint32_t tile_
 int hx_launch_combine(const uint32_t *tile_first, const uint32_t *tile_cnt, const uint32_t *rec_raw,
                       const HxPairRef *pairs, uint32_t n_pairs, uint32_t n_records, const uint64_t *sum_f,
                       const uint64_t *sum_r, const uint64_t *pair_hi, const uint32_t *pair_lo, uint32_t tile_stride,
-                      void *out, cudaStream_t st);
+                      const uint32_t *long_list, const uint32_t *n_long, void *out, cudaStream_t st);
 int hx_launch_find(const uint8_t *text, uint64_t n, const uint8_t *table /*256 x u64*/, uint32_t m, uint32_t k,
                    uint32_t tile_len, uint32_t ntiles, uint64_t *counts /*ntiles+1*/, uint64_t *out_end,
                    uint8_t *out_dist, uint64_t cap, int pass, cudaStream_t st);

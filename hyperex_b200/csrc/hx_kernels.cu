@@ -3,7 +3,8 @@
 //   hx_tile_build_kernel / hx_bucket_scan_kernel / hx_tile_scatter_kernel
 //       records -> tiles (whole short record, or overlapped window of a long one), ordered
 //       longest-first so the lanes of a warp finish together.
-//   hx_classify_kernel        utils.rs:207-228 sequence_type (HBM-bound byte reduction)
+//   hx_classify_kernel, hx_classify_iupac_kernel
+//                             utils.rs:207-228 sequence_type (HBM-bound byte reduction)
 //   hx_myers_pair_kernel      utils.rs:301-351: the Myers Pv/Mv/score recurrence of rust-bio
 //                             Myers<u64>::find_all_lazy for ALL patterns of a group per text
 //                             byte, fused with the reference's hit-selection rule evaluated
@@ -77,46 +78,70 @@ __device__ __forceinline__ uint32_t hx_bucket_of(uint32_t span, uint32_t gran) {
     return b < HX_NBUCKETS ? b : HX_NBUCKETS - 1;
 }
 
+__device__ __forceinline__ void hx_emit_tile(const HxBuildArgs &a, uint32_t *sh_hist, uint32_t r, uint32_t len, uint32_t tl,
+                                             uint32_t base, uint32_t i) {
+    HxTile t;
+    t.rec = r;
+    t.own_start = i * tl;
+    t.own_len = min(tl, len - t.own_start);
+    t.warm = min(a.warm, t.own_start);
+    a.tiles[base + i] = t;
+    atomicAdd(&sh_hist[hx_bucket_of(t.warm + t.own_len, a.bucket_gran)], 1u);  // CTA-private, flushed once
+}
+
+// One thread per record decides the tiling and reserves a contiguous tile range with one atomicAdd (no scan).
+// Short records are written by their own thread; a record with many windows (a contig) is written by the
+// whole warp, and is also appended to the long-record list consumed by hx_combine_long_kernel.
 __global__ void __launch_bounds__(256) hx_tile_build_kernel(const HxBuildArgs a) {
+    __shared__ uint32_t sh_hist[HX_NBUCKETS];
+    for (int i = threadIdx.x; i < HX_NBUCKETS; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n_records) return;
-    const uint64_t len64 = a.offsets[r + 1] - a.offsets[r];
-    if (len64 > 0xFFFFFF00ull) {  // record positions are 32-bit (hx_result.f_start / r_end)
-        *a.overflow = 2;
-        a.tile_cnt[r] = 0;
-        a.tile_first[r] = 0;
-        return;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t len = 0, nt = 0, tl = 0, base = 0;
+    bool ok = false;
+    if (r < a.n_records) {
+        const uint64_t len64 = a.offsets[r + 1] - a.offsets[r];
+        if (len64 > 0xFFFFFF00ull) {  // record positions are 32-bit (hx_result.f_start / r_end)
+            *a.overflow = 2;
+        } else {
+            len = (uint32_t)len64;
+            if (len == 0) {
+                nt = 0;
+            } else if (len <= a.single_max) {
+                nt = 1;
+                tl = len;
+            } else {
+                nt = (len + a.tile_len - 1) / a.tile_len;
+                tl = ((len + nt - 1) / nt + 15u) & ~15u;  // equal-sized windows, 16-byte granular
+                nt = (len + tl - 1) / tl;
+            }
+            base = nt ? atomicAdd(a.ntiles, nt) : 0u;
+            if (base + nt > a.tile_cap) {
+                *a.overflow = 1;
+                nt = 0;
+            } else {
+                ok = true;
+            }
+        }
+        a.tile_first[r] = ok ? base : 0u;
+        a.tile_cnt[r] = ok ? nt : 0u;
     }
-    const uint32_t len = (uint32_t)len64;
-    uint32_t nt = 0, tl = 0;
-    if (len == 0) {
-        nt = 0;
-    } else if (len <= a.single_max) {
-        nt = 1;
-        tl = len;
-    } else {
-        nt = (len + a.tile_len - 1) / a.tile_len;
-        tl = ((len + nt - 1) / nt + 15u) & ~15u;  // equal-sized windows, 16-byte granular
-        nt = (len + tl - 1) / tl;
+    if (ok && nt <= 4u)
+        for (uint32_t i = 0; i < nt; ++i) hx_emit_tile(a, sh_hist, r, len, tl, base, i);
+    uint32_t longmask = __ballot_sync(0xffffffffu, ok && nt > 4u);
+    while (longmask) {
+        const int src = __ffs((int)longmask) - 1;
+        longmask &= longmask - 1;
+        const uint32_t R = __shfl_sync(0xffffffffu, r, src), NT = __shfl_sync(0xffffffffu, nt, src);
+        const uint32_t TL = __shfl_sync(0xffffffffu, tl, src), LEN = __shfl_sync(0xffffffffu, len, src);
+        const uint32_t BASE = __shfl_sync(0xffffffffu, base, src);
+        for (uint32_t i = lane; i < NT; i += 32u) hx_emit_tile(a, sh_hist, R, LEN, TL, BASE, i);
+        if (lane == 0 && NT > HX_LONG_TILES) a.long_list[atomicAdd(a.n_long, 1u)] = R;
     }
-    const uint32_t base = nt ? atomicAdd(a.ntiles, nt) : 0u;
-    if (base + nt > a.tile_cap) {
-        *a.overflow = 1;
-        a.tile_cnt[r] = 0;
-        a.tile_first[r] = 0;
-        return;
-    }
-    a.tile_first[r] = base;
-    a.tile_cnt[r] = nt;
-    for (uint32_t i = 0; i < nt; ++i) {
-        HxTile t;
-        t.rec = r;
-        t.own_start = i * tl;
-        t.own_len = min(tl, len - t.own_start);
-        t.warm = min(a.warm, t.own_start);
-        a.tiles[base + i] = t;
-        atomicAdd(&a.hist[hx_bucket_of(t.warm + t.own_len, a.bucket_gran)], 1u);
-    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HX_NBUCKETS; i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(&a.hist[i], sh_hist[i]);
 }
 
 // cursor[b] = number of tiles in buckets longer than b (longest bucket is processed first)
@@ -150,17 +175,33 @@ __global__ void __launch_bounds__(HX_NBUCKETS) hx_bucket_scan_kernel(const uint3
 __global__ void __launch_bounds__(256) hx_tile_scatter_kernel(const HxTile *tiles, const uint32_t *ntiles,
                                                               uint32_t tile_cap, uint32_t gran, uint32_t *cursor,
                                                               uint32_t *order) {
+    // counting-sort scatter: per CTA and chunk of 256 tiles, count per bucket in shared memory, reserve one
+    // global range per non-empty bucket, then place every tile at range start + its CTA-local rank
+    __shared__ uint32_t sh_cnt[HX_NBUCKETS];
+    __shared__ uint32_t sh_base[HX_NBUCKETS];
     const uint32_t n = min(*ntiles, tile_cap);
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const HxTile tl = tiles[t];
-        const uint32_t pos = atomicAdd(&cursor[hx_bucket_of(tl.warm + tl.own_len, gran)], 1u);
-        order[pos] = t;
+    for (uint32_t c0 = blockIdx.x * blockDim.x; c0 < n; c0 += gridDim.x * blockDim.x) {
+        for (int i = threadIdx.x; i < HX_NBUCKETS; i += blockDim.x) sh_cnt[i] = 0;
+        __syncthreads();
+        const uint32_t t = c0 + threadIdx.x;
+        uint32_t b = 0, rank = 0;
+        if (t < n) {
+            const HxTile tl = tiles[t];
+            b = hx_bucket_of(tl.warm + tl.own_len, gran);
+            rank = atomicAdd(&sh_cnt[b], 1u);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HX_NBUCKETS; i += blockDim.x)
+            if (sh_cnt[i]) sh_base[i] = atomicAdd(&cursor[i], sh_cnt[i]);
+        __syncthreads();
+        if (t < n) order[sh_base[b] + rank] = t;
+        __syncthreads();
     }
 }
 
 int hx_launch_tile_build(const HxBuildArgs &a, uint32_t *cursor, uint32_t *order, cudaStream_t st) {
     if (a.n_records == 0) return 0;
-    hx_tile_build_kernel<<<(a.n_records + 255) / 256, 256, 0, st>>>(a);
+    hx_tile_build_kernel<<<(a.n_records + 255) / 256, 256, 0, st>>>(a);  // whole warps: no early exit inside
     hx_bucket_scan_kernel<<<1, HX_NBUCKETS, 0, st>>>(a.hist, cursor);
     uint32_t blocks = (a.tile_cap + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -169,8 +210,10 @@ int hx_launch_tile_build(const HxBuildArgs &a, uint32_t *cursor, uint32_t *order
 }
 
 // ------------------------------------------------------------------------------------
-// utils.rs:207-228 sequence_type: per record, does the upper-cased text contain 'U', 'T',
-// or a byte outside "ACGTRYSWKMBDHVN"?  One warp per tile, 16-byte coalesced loads.
+// utils.rs:207-228 sequence_type.  Pass 1 (every record, HBM-bound): does the upper-cased text contain 'U'
+// or 'T'?  One warp per tile, 16-byte coalesced loads, SWAR on 32-bit words: OR 0x20 folds the case
+// (utils.rs:210), XOR with the letter and the zero-byte test (x - 0x01010101) & ~x & 0x80808080 detects it.
+// Pass 2 (only records with neither 'U' nor 'T', utils.rs:218-224): is every byte one of "ACGTRYSWKMBDHVN"?
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hx_classify_kernel(const uint8_t *__restrict__ arena,
                                                           const uint64_t *__restrict__ offsets,
@@ -178,19 +221,6 @@ __global__ void __launch_bounds__(256) hx_classify_kernel(const uint8_t *__restr
                                                           const HxTile *__restrict__ tiles,
                                                           const uint32_t *__restrict__ ntiles_p, uint32_t tile_cap,
                                                           uint32_t *__restrict__ rec_raw) {
-    __shared__ uint8_t cls[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const int u = (i >= 'a' && i <= 'z') ? i - 32 : i;  // to_ascii_uppercase (utils.rs:210)
-        uint32_t f = 0;
-        if (u == 'U') f |= HX_RAW_U;
-        if (u == 'T') f |= HX_RAW_T;
-        const bool iupac = u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'R' || u == 'Y' || u == 'S' ||
-                           u == 'W' || u == 'K' || u == 'M' || u == 'B' || u == 'D' || u == 'H' || u == 'V' ||
-                           u == 'N';
-        if (!iupac) f |= HX_RAW_NONIUPAC;
-        cls[i] = (uint8_t)f;
-    }
-    __syncthreads();
     const uint32_t ntiles = min(*ntiles_p, tile_cap);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -198,22 +228,82 @@ __global__ void __launch_bounds__(256) hx_classify_kernel(const uint8_t *__restr
         const HxTile tl = tiles[t];
         const uint64_t s = offsets[tl.rec] - off_base + tl.own_start;
         const uint64_t e = s + tl.own_len;
+        uint32_t zu = 0, zt = 0;
+        // four 16-byte loads per lane in flight (2 KB per warp and trip) before any of them is consumed
+        for (uint64_t A0 = (s & ~15ull) + lane * 16ull; A0 < e; A0 += 2048ull) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                v[u] = (A0 + 512ull * u < e) ? hx_ldg16(arena + A0 + 512ull * u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t A = A0 + 512ull * u;
+                const bool full = A >= s && A + 16 <= e;
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    uint32_t w = hx_w32(v[u], wi);
+                    if (!full) {  // clear the bytes outside [s, e): 0x00 | 0x20 is neither 'u' nor 't'
+                        uint32_t keep = 0;
+#pragma unroll
+                        for (int bi = 0; bi < 4; ++bi) {
+                            const uint64_t pos = A + wi * 4 + bi;
+                            if (pos >= s && pos < e) keep |= 0xffu << (8 * bi);
+                        }
+                        w &= keep;
+                    }
+                    const uint32_t lw = w | 0x20202020u;
+                    const uint32_t xu = lw ^ 0x75757575u, xt = lw ^ 0x74747474u;
+                    zu |= (xu - 0x01010101u) & ~xu;
+                    zt |= (xt - 0x01010101u) & ~xt;
+                }
+            }
+        }
+        uint32_t f = ((zu & 0x80808080u) ? HX_RAW_U : 0u) | ((zt & 0x80808080u) ? HX_RAW_T : 0u);
+        f = __reduce_or_sync(0xffffffffu, f);
+        if (lane == 0 && f) atomicOr(&rec_raw[tl.rec], f);
+    }
+}
+
+__global__ void __launch_bounds__(256) hx_classify_iupac_kernel(const uint8_t *__restrict__ arena,
+                                                                const uint64_t *__restrict__ offsets,
+                                                                const uint64_t off_base,
+                                                                const HxTile *__restrict__ tiles,
+                                                                const uint32_t *__restrict__ ntiles_p, uint32_t tile_cap,
+                                                                uint32_t *__restrict__ rec_raw) {
+    __shared__ uint8_t bad[256];  // 1: byte is not in "ACGTRYSWKMBDHVN" after to_ascii_uppercase
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int u = (i >= 'a' && i <= 'z') ? i - 32 : i;
+        const bool iupac = u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'R' || u == 'Y' || u == 'S' ||
+                           u == 'W' || u == 'K' || u == 'M' || u == 'B' || u == 'D' || u == 'H' || u == 'V' ||
+                           u == 'N';
+        bad[i] = iupac ? 0 : 1;
+    }
+    __syncthreads();
+    const uint32_t ntiles = min(*ntiles_p, tile_cap);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += warps) {
+        const HxTile tl = tiles[t];
+        // The record's U/T evidence is complete (pass 1 finished).  Bits set by this pass cannot disturb the
+        // test: HX_RAW_NONIUPAC is not part of it.
+        if (rec_raw[tl.rec] & (HX_RAW_U | HX_RAW_T)) continue;
+        const uint64_t s = offsets[tl.rec] - off_base + tl.own_start;
+        const uint64_t e = s + tl.own_len;
         uint32_t f = 0;
         for (uint64_t A = (s & ~15ull) + lane * 16ull; A < e; A += 512ull) {
             const uint4 v = hx_ldg16(arena + A);
-            const bool full = A >= s && A + 16 <= e;
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
                 const uint32_t w = hx_w32(v, wi);
 #pragma unroll
                 for (int bi = 0; bi < 4; ++bi) {
                     const uint64_t pos = A + wi * 4 + bi;
-                    if (full || (pos >= s && pos < e)) f |= cls[(w >> (8 * bi)) & 0xffu];
+                    if (pos >= s && pos < e) f |= bad[(w >> (8 * bi)) & 0xffu];
                 }
             }
         }
         f = __reduce_or_sync(0xffffffffu, f);
-        if (lane == 0 && f) atomicOr(&rec_raw[tl.rec], f);
+        if (lane == 0 && f) atomicOr(&rec_raw[tl.rec], HX_RAW_NONIUPAC);
     }
 }
 
@@ -223,7 +313,8 @@ int hx_launch_classify(const uint8_t *arena, const uint64_t *offsets, uint64_t o
     uint64_t blocks = ((uint64_t)tile_cap * 32 + 255) / 256;
     if (blocks > 148 * 8 * 4) blocks = 148 * 8 * 4;
     hx_classify_kernel<<<(uint32_t)blocks, 256, 0, st>>>(arena, offsets, off_base, tiles, ntiles, tile_cap, rec_raw);
-    return 1;
+    hx_classify_iupac_kernel<<<(uint32_t)blocks, 256, 0, st>>>(arena, offsets, off_base, tiles, ntiles, tile_cap, rec_raw);
+    return 2;
 }
 
 // ------------------------------------------------------------------------------------
@@ -695,7 +786,8 @@ __global__ void __launch_bounds__(256)
     }
     const HxPairRef pr = pairs[q];
     const uint32_t t0 = tile_first[r], nt = tile_cnt[r];
-    if (nt == 1u) return;  // single-tile record: hx_myers_pair_kernel wrote the final result
+    if (nt == 1u) return;             // single-tile record: hx_myers_pair_kernel wrote the final result
+    if (nt > HX_LONG_TILES) return;  // contig: hx_combine_long_kernel
     uint64_t bestF = HX_NONE64;          // (dist<<32 | end) of the best valid forward hit so far
     uint64_t bhi = HX_NONE64;            // combined<<32 | f_end
     uint32_t blo = 0;                    // r_end
@@ -737,16 +829,98 @@ __global__ void __launch_bounds__(256)
     out[(size_t)r * n_pairs + q] = res;
 }
 
+// Records with many windows (contigs): one warp per (long record, pair).  Every lane joins a contiguous run of
+// tiles with the streaming rule, then the 32 ordered partial summaries are merged by a shuffle tree with the
+// (associative, order-sensitive) segment join: best pair = lex-min(left, right, left.bestF + right.bestR).
+struct HxSeg {
+    uint64_t bestF, bestR, phi;
+    uint32_t plo, any;
+};
+
+__device__ __forceinline__ void hx_seg_join(HxSeg &L, const HxSeg &R) {
+    if (L.bestF != HX_NONE64 && R.bestR != HX_NONE64) {
+        const uint64_t chi = (((L.bestF >> 32) + (R.bestR >> 32)) << 32) | (uint32_t)L.bestF;
+        const uint32_t clo = (uint32_t)R.bestR;
+        if (chi < L.phi || (chi == L.phi && clo < L.plo)) {
+            L.phi = chi;
+            L.plo = clo;
+        }
+    }
+    if (R.phi < L.phi || (R.phi == L.phi && R.phi != HX_NONE64 && R.plo < L.plo)) {
+        L.phi = R.phi;
+        L.plo = R.plo;
+    }
+    if (R.bestF < L.bestF) L.bestF = R.bestF;
+    if (R.bestR < L.bestR) L.bestR = R.bestR;
+    L.any |= R.any;
+}
+
+__global__ void __launch_bounds__(256)
+    hx_combine_long_kernel(const uint32_t *__restrict__ long_list, const uint32_t *__restrict__ n_long_p,
+                           const uint32_t *__restrict__ tile_first, const uint32_t *__restrict__ tile_cnt,
+                           const uint32_t *__restrict__ rec_raw, const HxPairRef *__restrict__ pairs, uint32_t n_pairs,
+                           const uint64_t *__restrict__ sum_f, const uint64_t *__restrict__ sum_r,
+                           const uint64_t *__restrict__ pair_hi, const uint32_t *__restrict__ pair_lo, uint32_t ts,
+                           HxResultDev *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t items = (uint64_t)(*n_long_p) * n_pairs;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t it = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < items; it += warps) {
+        const uint32_t r = long_list[it / n_pairs], q = (uint32_t)(it % n_pairs);
+        const int alpha = hx_alpha_of(rec_raw[r]);
+        if (alpha == 2) continue;  // hx_combine_kernel wrote the "alphabet none" result
+        const HxPairRef pr = pairs[q];
+        const uint32_t t0 = tile_first[r], nt = tile_cnt[r];
+        const uint32_t per = (nt + 31u) / 32u;
+        const uint32_t lo = min(nt, lane * per), hi = min(nt, lo + per);
+        HxSeg S = {HX_NONE64, HX_NONE64, HX_NONE64, 0u, 0u};
+        for (uint32_t i = lo; i < hi; ++i) {
+            const size_t t = t0 + i;
+            HxSeg T;
+            T.bestF = sum_f[(size_t)pr.f_slot * ts + t];
+            T.bestR = sum_r[(size_t)pr.r_slot * ts + t];
+            T.phi = pair_hi[(size_t)q * ts + t];
+            T.plo = pair_lo[(size_t)q * ts + t];
+            T.any = (sum_r[(size_t)pr.f_slot * ts + t] != HX_NONE64 ? 1u : 0u) | (T.bestR != HX_NONE64 ? 2u : 0u);
+            hx_seg_join(S, T);
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            HxSeg R;
+            R.bestF = __shfl_down_sync(0xffffffffu, S.bestF, d);
+            R.bestR = __shfl_down_sync(0xffffffffu, S.bestR, d);
+            R.phi = __shfl_down_sync(0xffffffffu, S.phi, d);
+            R.plo = __shfl_down_sync(0xffffffffu, S.plo, d);
+            R.any = __shfl_down_sync(0xffffffffu, S.any, d);
+            if ((lane & (2 * d - 1)) == 0) hx_seg_join(S, R);
+        }
+        if (lane == 0) {
+            HxResultDev res = {0u, 0u, 0u};
+            uint32_t flags = S.any | (alpha == 1 ? 16u : 0u);
+            if (S.phi != HX_NONE64) {
+                flags |= 4u;
+                res.f_start = (uint32_t)S.phi - (pr.len_f - 1u);
+                res.r_end = S.plo;
+                flags |= (uint32_t)((S.phi >> 32) & 0xffu) << 8;
+            }
+            res.meta = flags;
+            out[(size_t)r * n_pairs + q] = res;
+        }
+    }
+}
+
 int hx_launch_combine(const uint32_t *tile_first, const uint32_t *tile_cnt, const uint32_t *rec_raw,
                       const HxPairRef *pairs, uint32_t n_pairs, uint32_t n_records, const uint64_t *sum_f,
                       const uint64_t *sum_r, const uint64_t *pair_hi, const uint32_t *pair_lo, uint32_t tile_stride,
-                      void *out, cudaStream_t st) {
+                      const uint32_t *long_list, const uint32_t *n_long, void *out, cudaStream_t st) {
     const uint64_t total = (uint64_t)n_pairs * n_records;
     if (total == 0) return 0;
+    hx_combine_long_kernel<<<148 * 4, 256, 0, st>>>(long_list, n_long, tile_first, tile_cnt, rec_raw, pairs, n_pairs, sum_f,
+                                                   sum_r, pair_hi, pair_lo, tile_stride, (HxResultDev *)out);
     hx_combine_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, st>>>(tile_first, tile_cnt, rec_raw, pairs, n_pairs,
                                                                       n_records, sum_f, sum_r, pair_hi, pair_lo,
                                                                       tile_stride, (HxResultDev *)out);
-    return 1;
+    return 2;
 }
 
 // ------------------------------------------------------------------------------------

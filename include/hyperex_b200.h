@@ -106,6 +106,10 @@ int64_t hx_find_all_end(hx_ctx *ctx, const char *pattern, uint32_t pattern_len, 
 void *hx_alloc_pinned(size_t bytes);
 void hx_free_pinned(void *p);
 
+/* how hx_set_primers packed the primer set: pattern groups (= scan launches per slab) and the automata stepped
+ * per text byte with 32-bit / 64-bit words (de-duplicated patterns) */
+int hx_group_info(const hx_ctx *ctx, uint32_t *n_groups, uint32_t *steps32_per_base, uint32_t *steps64_per_base);
+
 /* number of kernels the context has launched so far (bench.py's gpu_launches) */
 uint64_t hx_launch_count(const hx_ctx *ctx);
 /* device time (ms) of the dominant kernel (hx_myers_pair_kernel) accumulated by CUDA events
