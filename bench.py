@@ -233,6 +233,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_cpus = hx.bind_to_gpu_numa_node(local) if world > 1 else None  # pinned arenas local to the GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
@@ -385,7 +386,8 @@ def main():
                 "config": {"workload": workload_desc, "records_per_gpu": n,
                            "bases_per_gpu": bases, "pairs": npairs, "k": args.k, "regions_found": found,
                            "l2": f"inputs ({bases / 1e9:.2f} GB/GPU) larger than the 126 MB L2; no flush needed",
-                           "parallelism": f"records sharded over {world} GPU(s), no collective"},
+                           "parallelism": f"records sharded over {world} GPU(s), no collective",
+                           "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
                 "e2e": {"value": e2e, "unit": "Gbases/s", "gcups": e2e * cells, "ms_per_step": e2e_ms_max / args.steps,
                         "h2d_bytes_per_step": int(bases + offsets.nbytes), "d2h_bytes_per_step": int(n * npairs * 12),
                         "timer": "host wall clock around hx_run_batch (synchronous), max over ranks"},

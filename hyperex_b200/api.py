@@ -243,6 +243,33 @@ def int_peak(variant: int, iters: int = 2000, device: int = 0) -> float:
     return g.value
 
 
+def bind_to_gpu_numa_node(device: int = 0):
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist), so that
+    pinned arenas allocated afterwards are local to that GPU's PCIe root.  Host-side plumbing for the
+    one-process-per-GPU layout; returns the cpu set or None when the topology is not exposed."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = torch.cuda.get_device_properties(device).pci_domain_id
+        dev = torch.cuda.get_device_properties(device).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        return None
+    return None
+
+
 def pinned_empty(nbytes: int) -> np.ndarray:
     """uint8 numpy view of cudaHostAlloc'd memory (hx_alloc_pinned); keep the array alive while in use"""
     L = _lib.load()
