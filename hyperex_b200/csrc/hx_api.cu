@@ -77,6 +77,7 @@ struct Device {
     int dev = 0;
     Slot slots[HX_NSLOT];
     uint8_t *d_tables = nullptr;
+    uint8_t *d_tables_wm = nullptr;
     HxGroup *d_groups = nullptr;
     HxPairRef *d_pairs = nullptr;
 };
@@ -101,7 +102,7 @@ struct hx_ctx {
     std::vector<uint8_t> tables;
     bool primers_set = false;
     // options
-    int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0;
+    int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1;
     uint64_t launches = 0;
     std::vector<TimedLaunch> timed;
     double myers_ms = 0;
@@ -241,6 +242,9 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const 
         a.out = d_out;
         a.n_pairs_total = ctx->n_pairs;
         a.tables = D.d_tables + hg.table_off;
+        a.tables_wm = D.d_tables_wm + hg.table_off;
+        // small-k fast path: identical hits, fewer ALU operations; 32-bit groups, vector-load text path
+        a.wm_k = (ctx->opt_fast_small_k && !hg.word64 && ctx->k <= 2 && !ctx->opt_text_tma) ? (int)ctx->k : -1;
         a.group = D.d_groups + gi;
         a.sum_f = S.sum_f.p;
         a.sum_r = S.sum_r.p;
@@ -329,6 +333,7 @@ void hx_destroy(hx_ctx *ctx) {
         cudaDeviceSynchronize();
         for (Slot &S : D.slots) S.release();
         if (D.d_tables) cudaFree(D.d_tables);
+        if (D.d_tables_wm) cudaFree(D.d_tables_wm);
         if (D.d_groups) cudaFree(D.d_groups);
         if (D.d_pairs) cudaFree(D.d_pairs);
     }
@@ -343,6 +348,7 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     else if (n == "slab_bytes") ctx->opt_slab_bytes = std::max<int64_t>(value, 1);
     else if (n == "time_kernels") ctx->opt_time = value;
     else if (n == "text_tma") ctx->opt_text_tma = value ? 1 : 0;
+    else if (n == "fast_small_k") ctx->opt_fast_small_k = value ? 1 : 0;
     else return fail(ctx, HX_ERR_ARG, "unknown option %s", name);
     return HX_OK;
 }
@@ -433,7 +439,7 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
     }
     // tables: [group][alphabet dna|rna][256 rows][row stride]; text bytes are case-folded
     // here (utils.rs:295) so the kernel indexes rows with the raw byte.
-    std::vector<uint8_t> blob;
+    std::vector<uint8_t> blob, blob_wm;
     uint32_t slot_base = 0;
     for (size_t gi = 0; gi < groups.size(); ++gi) {
         HxGroup &g = groups[gi];
@@ -444,6 +450,7 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
         const int stride = hx_row_stride(g.np, wb);
         g.table_off = (uint32_t)blob.size();
         blob.resize(blob.size() + 2 * (size_t)hx_table_bytes(g.np, wb), 0);
+        blob_wm.resize(blob.size(), 0);
         for (int p = 0; p < g.np; ++p) g.m[p] = (uint8_t)gpats[gi][p].dna.size();
         for (int alpha = 0; alpha < 2; ++alpha) {
             uint8_t *tab = blob.data() + g.table_off + (size_t)alpha * hx_table_bytes(g.np, wb);
@@ -453,6 +460,19 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
                     const std::string &pat = alpha ? gpats[gi][p].rna : gpats[gi][p].dna;
                     const uint64_t w = peq_word(pat, u, bits);
                     memcpy(tab + (size_t)b * stride + (size_t)p * wb, &w, wb);  // little endian: low bytes first
+                }
+            }
+            // fast-path table: complemented inside the pattern bits, 0 in the unused low bits; row 0 (the
+            // null byte) matches nothing, i.e. all pattern bits set
+            uint8_t *tabw = blob_wm.data() + g.table_off + (size_t)alpha * hx_table_bytes(g.np, wb);
+            for (int b = 0; b < 256; ++b) {
+                for (int p = 0; p < g.np; ++p) {
+                    const int m = g.m[p];
+                    const uint64_t pmask = m >= bits ? ~0ull : (((1ull << m) - 1) << (bits - m));
+                    uint64_t w = 0;
+                    memcpy(&w, tab + (size_t)b * stride + (size_t)p * wb, wb);
+                    const uint64_t nw = ~w & pmask & (wb == 8 ? ~0ull : 0xffffffffull);
+                    memcpy(tabw + (size_t)b * stride + (size_t)p * wb, &nw, wb);
                 }
             }
         }
@@ -468,10 +488,13 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
         HX_CUDA(ctx, cudaSetDevice(D.dev));
         HX_CUDA(ctx, cudaDeviceSynchronize());
         if (D.d_tables) cudaFree(D.d_tables);
+        if (D.d_tables_wm) cudaFree(D.d_tables_wm);
         if (D.d_groups) cudaFree(D.d_groups);
         if (D.d_pairs) cudaFree(D.d_pairs);
-        D.d_tables = nullptr; D.d_groups = nullptr; D.d_pairs = nullptr;
+        D.d_tables = nullptr; D.d_tables_wm = nullptr; D.d_groups = nullptr; D.d_pairs = nullptr;
         HX_CUDA(ctx, cudaMalloc((void **)&D.d_tables, blob.size()));
+        HX_CUDA(ctx, cudaMalloc((void **)&D.d_tables_wm, blob_wm.size()));
+        HX_CUDA(ctx, cudaMemcpy(D.d_tables_wm, blob_wm.data(), blob_wm.size(), cudaMemcpyHostToDevice));
         HX_CUDA(ctx, cudaMalloc((void **)&D.d_groups, groups.size() * sizeof(HxGroup)));
         HX_CUDA(ctx, cudaMalloc((void **)&D.d_pairs, refs.size() * sizeof(HxPairRef)));
         HX_CUDA(ctx, cudaMemcpy(D.d_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice));

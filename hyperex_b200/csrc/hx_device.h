@@ -71,6 +71,8 @@ struct HxScanArgs {
     void *out;                 // hx_result[n_records][n_pairs_total]
     uint32_t n_pairs_total;
     const uint8_t *tables;     // Peq blob
+    const uint8_t *tables_wm;  // complemented Peq blob of the small-k fast path (Shift-Or convention)
+    int32_t wm_k;              // >= 0: run the Wu-Manber fast path with this many errors (32-bit groups only)
     const HxGroup *group;      // this launch's group (device memory)
     uint64_t *sum_f;           // [slot][tile] best valid forward hit  key = dist<<32 | end
     uint64_t *sum_r;           // [slot][tile] best hit of any position

@@ -382,7 +382,7 @@ struct HxRow {
 };
 
 // ------------------------------------------------------------------------------------
-// hx_myers_pair_kernel<W, NP, TMA>
+// hx_myers_pair_kernel<W, NP, TMA, KWM>
 //   one thread = one tile; per text byte the thread loads one Peq row (all NP patterns of the
 //   group, shared memory, 16-byte LDS) and advances NP independent automata held in registers.
 //
@@ -442,9 +442,11 @@ __device__ __forceinline__ void hx_mbar_wait(uint32_t mbar, uint32_t parity) {
 }
 __device__ __forceinline__ void hx_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <typename W, int NP, bool TMA>
+template <typename W, int NP, bool TMA, int KWM>
 __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((sizeof(W) * NP <= 32) ? 5 : 4))
     hx_myers_pair_kernel(const HxScanArgs a) {
+    constexpr bool WM = KWM >= 0;           // small-k fast path: Wu-Manber / Shift-Or automata instead of Myers
+    constexpr int NR = WM ? KWM + 1 : 1;    // error levels 0..k
     constexpr int WB = sizeof(W);
     constexpr int STRIDE = hx_row_stride(NP, WB);
     constexpr int TBYTES = 256 * STRIDE;
@@ -484,8 +486,9 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
         single = a.tile_cnt[tl.rec] == 1u;
     }
 
-    W pv[NP], mv[NP];
-    int s[NP];
+    W pv[NP], mv[NP];   // Myers state
+    int s[NP];          // Myers biased score; for WM: filled on the rare path only
+    W rv[NR][NP];       // WM state: bit = 0 <=> prefix matches with <= d errors (Shift-Or convention)
     uint64_t bestF[NP], bestR[NP];
     uint64_t phi[HX_MAX_GROUP_PAIRS];
     uint32_t plo[HX_MAX_GROUP_PAIRS];
@@ -496,6 +499,13 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
         pv[p] = ~(W)0;
         mv[p] = 0;
         s[p] = (int)g.m[p] - bias;
+        if constexpr (WM) {
+            // pattern bits are the top m bits; level d starts with its d lowest pattern bits cleared (a
+            // prefix of length <= d always matches with <= d deletions); the unused low bits stay 0
+            const int m = g.m[p];
+#pragma unroll
+            for (int d = 0; d < NR; ++d) rv[d][p] = d < m ? (~(W)0 << (sizeof(W) * 8 - m + d)) : (W)0;
+        }
         bestF[p] = HX_NONE64;
         bestR[p] = HX_NONE64;
     }
@@ -512,13 +522,8 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
     const uint8_t *src = a.arena + ab;
     // UB text bytes are processed per trip of the innermost loop (narrow groups amortise the loop
     // overhead over more bytes; wide groups keep the hot loop small).
-#if HX_EXP == 3
-    constexpr int UB = (NP * WB <= 24) ? 4 : 2;
-#elif HX_EXP == 4
-    constexpr int UB = 4;
-#else
-    constexpr int UB = (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
-#endif
+    constexpr int UB = WM ? ((KWM == 0 || NP * (KWM + 1) <= 16) ? 4 : (NP * (KWM + 1) <= 24 ? 2 : 1))
+                          : (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
     uint32_t cnt = 0;  // records in this lane's queue
     const uint64_t pol = hx_policy_evict_first();
 
@@ -526,7 +531,7 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
         const bool mine = alpha == pass;
         if (!__syncthreads_or(mine ? 1 : 0)) continue;  // no record of this alphabet in the CTA
         {
-            const uint4 *tsrc = reinterpret_cast<const uint4 *>(a.tables) + (size_t)pass * (TBYTES / 16);
+            const uint4 *tsrc = reinterpret_cast<const uint4 *>(WM ? a.tables_wm : a.tables) + (size_t)pass * (TBYTES / 16);
             uint4 *dst = reinterpret_cast<uint4 *>(smem);
             for (int i = threadIdx.x; i < TBYTES / 16; i += HX_THREADS) dst[i] = __ldg(tsrc + i);
         }
@@ -600,15 +605,52 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
                         HxRow<W, NP> row;
                         row.load(tab + byte * STRIDE);
                         int any = 0;
+                        if constexpr (WM) {
+                            // Wu-Manber, Shift-Or form: row.eq(p) is the COMPLEMENTED Peq word
+                            //   R0' = (R0 << 1) | neq
+                            //   Rd' = ((Rd << 1) | neq) & R(d-1) & (R(d-1) << 1) & (R(d-1)' << 1)
+                            // (insertion, substitution, deletion); dist <= k  <=>  top bit of Rk is 0.
+                            W acc = ~(W)0;
 #pragma unroll
-                        for (int p = 0; p < NP; ++p) {
-                            hx_step(row.eq(p), pv[p], mv[p], s[p], a.two);
-                            any |= s[p];
+                            for (int p = 0; p < NP; ++p) {
+                                const W n = row.eq(p);
+                                W prev_old = rv[0][p], prev_old_s = prev_old << 1;
+                                W prev_new = prev_old_s | n;
+                                rv[0][p] = prev_new;
+#pragma unroll
+                                for (int d = 1; d < NR; ++d) {
+                                    const W cur_old = rv[d][p], cur_old_s = cur_old << 1;
+                                    const W cur_new = ((cur_old_s | n) & prev_old_s) & prev_old & (prev_new << 1);
+                                    rv[d][p] = cur_new;
+                                    prev_old = cur_old;
+                                    prev_old_s = cur_old_s;
+                                    prev_new = cur_new;
+                                }
+                                acc &= prev_new;
+                            }
+                            any = (~acc >> (sizeof(W) * 8 - 1)) ? -1 : 0;
+                        } else {
+#pragma unroll
+                            for (int p = 0; p < NP; ++p) {
+                                hx_step(row.eq(p), pv[p], mv[p], s[p], a.two);
+                                any |= s[p];
+                            }
                         }
                         if (any < 0) {
                             // ---- rare: some pattern has dist <= k here; record the event ----
                             const uint32_t pos = pos0 + (c << 4) + (wi << 2) + b0 + bi;
                             if (pos - tl.own_start < own_len) {
+                                if constexpr (WM) {
+                                    // exact distance of a hit = the lowest level whose top bit is 0
+#pragma unroll
+                                    for (int p = 0; p < NP; ++p) {
+                                        int sp = 0;
+#pragma unroll
+                                        for (int d = NR - 1; d >= 0; --d)
+                                            if (!(rv[d][p] >> (sizeof(W) * 8 - 1))) sp = d - bias;
+                                        s[p] = sp;
+                                    }
+                                }
                                 uint32_t *r = queue[cnt];
                                 r[0] = pos;
 #pragma unroll
@@ -722,26 +764,33 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
     }
 }
 
-template <typename W, int NP, bool TMA>
+template <typename W, int NP, bool TMA, int KWM>
 static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
     const int smem = hx_table_bytes(NP, sizeof(W)) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
     static bool attr_done[8] = {false, false, false, false, false, false, false, false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 8 || !attr_done[dev]) {
-        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (dev < 8) attr_done[dev] = true;
     }
     const uint32_t blocks = (tile_cap + HX_THREADS - 1) / HX_THREADS;
-    hx_myers_pair_kernel<W, NP, TMA><<<blocks, HX_THREADS, smem, st>>>(a);
+    hx_myers_pair_kernel<W, NP, TMA, KWM><<<blocks, HX_THREADS, smem, st>>>(a);
     return 1;
 }
 
 template <typename W, int NP>
 struct HxDispatch {
     static int run(int np, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
-        if (np == NP) return a.variant == 1 ? hx_scan_launch_one<W, NP, true>(a, cap, st)
-                                            : hx_scan_launch_one<W, NP, false>(a, cap, st);
+        if (np == NP) {
+            if constexpr (sizeof(W) == 4) {
+                if (a.wm_k == 0) return hx_scan_launch_one<W, NP, false, 0>(a, cap, st);
+                if (a.wm_k == 1) return hx_scan_launch_one<W, NP, false, 1>(a, cap, st);
+                if (a.wm_k == 2) return hx_scan_launch_one<W, NP, false, 2>(a, cap, st);
+            }
+            return a.variant == 1 ? hx_scan_launch_one<W, NP, true, -1>(a, cap, st)
+                                  : hx_scan_launch_one<W, NP, false, -1>(a, cap, st);
+        }
         return HxDispatch<W, NP - 1>::run(np, a, cap, st);
     }
 };

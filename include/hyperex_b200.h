@@ -72,7 +72,9 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
  * window of a long record), "single_max" (records up to this length are one tile),
  * "slab_bytes" (host->device pipeline granule), "time_kernels" (CUDA-event timing of the scan),
  * "text_tma" (1: stage the text through shared memory with TMA bulk copies; 0, default: per-thread
- * 16-byte vector loads, measured 3 % faster). */
+ * 16-byte vector loads, measured 3 % faster), "fast_small_k" (1, default: for -m 0..2 and primers <= 32 nt scan
+ * with Wu-Manber / Shift-Or automata, which accept exactly the same hits with the same distances in fewer ALU
+ * operations; 0: always the Myers automaton). */
 int hx_set_option(hx_ctx *ctx, const char *name, int64_t value);
 
 /* Replaces the record loop body utils.rs:270-351 (sequence_type, to_ascii_uppercase, both

@@ -29,6 +29,7 @@ def _run(ctx, arena, offsets, pairs, k, **opts):
         ctx.set_option(name, opts.get(name, 0))
     ctx.set_option("slab_bytes", opts.get("slab_bytes", 128 << 20))
     ctx.set_option("text_tma", opts.get("text_tma", 0))
+    ctx.set_option("fast_small_k", opts.get("fast", 1))
     ctx.set_primers(pairs, k)
     return ctx.run_batch(arena, offsets)
 
@@ -101,24 +102,37 @@ def test_golden_batches(ctx, golden_dir, name, text_tma):
     z = np.load(os.path.join(golden_dir, name + ".npz"))
     pairs = [list(p) for p in z["pairs"]]
     for tile in ((0, 0), (4096, 4096)):  # windows (auto for a small batch) and whole-record tiles
-        res = _run(ctx, z["arena"], z["offsets"], pairs, int(z["k"]), tile_len=tile[0], single_max=tile[1],
-                   text_tma=text_tma)
-        _cmp(res, z["res"], z["arena"], z["offsets"], pairs, int(z["k"]))
+        for fast in (0, 1):               # Myers everywhere / Wu-Manber fast path where k <= 2
+            res = _run(ctx, z["arena"], z["offsets"], pairs, int(z["k"]), tile_len=tile[0], single_max=tile[1],
+                       text_tma=text_tma, fast=fast)
+            _cmp(res, z["res"], z["arena"], z["offsets"], pairs, int(z["k"]))
 
 
 # ---- seeded batches of the BASELINE.json shapes at oracle-friendly sizes -----------------------------
-def test_c2_reads_all_regions_k0(ctx):
+@pytest.mark.parametrize("fast", [0, 1])
+def test_c2_reads_all_regions_k0(ctx, fast):
     a, o = hx_synth.gen_reads(3000, seed=22)
-    res = _run(ctx, a, o, hx.default_primers(), 0)
+    res = _run(ctx, a, o, hx.default_primers(), 0, fast=fast)
     _cmp(res, O.run_batch(a, o, O.default_pairs(), 0, nthreads=8), a, o, O.default_pairs(), 0)
     assert (res["flags"] & 7 == 7).all()
 
 
-@pytest.mark.parametrize("k", [1, 2, 3])
-def test_c3_degenerate_primers_both_strands(ctx, k):
+@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_c3_degenerate_primers_both_strands(ctx, k, fast):
     a, o = hx_synth.gen_reads_mutated(1500, seed=30 + k, max_edits=3, revcomp_frac=0.5)
     pairs = [hx.region_to_primer("v3v4"), hx.region_to_primer("v4v5")]
-    _cmp(_run(ctx, a, o, pairs, k), O.run_batch(a, o, pairs, k, nthreads=8), a, o, pairs, k)
+    _cmp(_run(ctx, a, o, pairs, k, fast=fast), O.run_batch(a, o, pairs, k, nthreads=8), a, o, pairs, k)
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_all_regions_mutated_small_k_fast_path(ctx, k):
+    """15 automata per thread on the Wu-Manber path (k <= 2), soft-masked + RNA + both strands, with windows"""
+    a, o = hx_synth.gen_reads_mutated(1200, seed=130 + k, max_edits=3, revcomp_frac=0.4, lower_frac=0.3, rna_frac=0.1)
+    pairs = hx.default_primers()
+    ref = O.run_batch(a, o, pairs, k, nthreads=8)
+    for tile in ((4096, 4096), (128, 128)):
+        _cmp(_run(ctx, a, o, pairs, k, tile_len=tile[0], single_max=tile[1], fast=1), ref, a, o, pairs, k)
 
 
 @pytest.mark.parametrize("text_tma", [0, 1])
@@ -165,14 +179,18 @@ def test_edge_records(ctx):
         for tma in (0, 1):
             _cmp(_run(ctx, a, o, pairs, k, text_tma=tma), ref, a, o, pairs, k)
             _cmp(_run(ctx, a, o, pairs, k, tile_len=16, single_max=16, text_tma=tma), ref, a, o, pairs, k)
+        _cmp(_run(ctx, a, o, pairs, k, fast=0), ref, a, o, pairs, k)
+        _cmp(_run(ctx, a, o, pairs, k, tile_len=16, single_max=16, fast=0), ref, a, o, pairs, k)
 
 
 def test_k_at_least_pattern_length_every_position_hits(ctx):
     # README example `-f ATCG -r GGCC -m 1` style: tiny primers, k close to / above m
     a, o = hx_synth.gen_reads_mutated(40, seed=61, lmin=5, lmax=300, sites=[])
     for pairs, k in (([["ATCG", "GGCC"]], 1), ([["ATCG", "GGCC"]], 4), ([["AC", "GTTGCA"]], 3),
-                     ([["A", "C"], ["ACGTN", "T"]], 1)):
-        _cmp(_run(ctx, a, o, pairs, k, tile_len=32, single_max=48), O.run_batch(a, o, pairs, k), a, o, pairs, k)
+                     ([["A", "C"], ["ACGTN", "T"]], 1), ([["A", "C"], ["AC", "T"]], 2), ([["ACG", "CA"]], 0)):
+        ref = O.run_batch(a, o, pairs, k)
+        for fast in (0, 1):
+            _cmp(_run(ctx, a, o, pairs, k, tile_len=32, single_max=48, fast=fast), ref, a, o, pairs, k)
 
 
 def test_rna_records_use_rna_reverse_complement(ctx):
