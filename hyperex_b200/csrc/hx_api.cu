@@ -14,7 +14,6 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -694,5 +693,3 @@ int hx_kernel_time(hx_ctx *ctx, double *myers_ms, uint64_t *myers_launches, int 
 
 }  // extern "C"
 
-// used by hx_host.cpp (the file-level driver) to reach the batch path without the C structs
-int hx_internal_pairs(const hx_ctx *ctx) { return ctx ? (int)ctx->n_pairs : 0; }

@@ -255,7 +255,13 @@ int main(int argc, char **argv) {
 
     // get_hypervar_regions (utils.rs:231-414) on the GPU(s)
     hx_ctx *ctx = nullptr;
+    const bool timing = getenv("HYPEREX_TIMING") != nullptr;
+    auto since_start = [&] {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    };
+    const double t_before_create = since_start();
     int rc = hx_create(&ctx, nullptr, gpus < 1 ? 1 : gpus);
+    const double t_after_create = since_start();
     if (rc != HX_OK) {
         fprintf(stderr, "Error: Failed to extract hypervariable regions\n\nCaused by:\n    %s\n", hx_last_error(nullptr));
         return 1;
@@ -272,7 +278,12 @@ int main(int argc, char **argv) {
         hx_destroy(ctx);
         return 1;
     }
+    const double t_after_run = since_start();
     hx_destroy(ctx);
+    if (timing)
+        fprintf(stderr, "[hyperex timing] startup=%.3fs hx_create=%.3fs get_hypervar_regions=%.3fs hx_destroy=%.3fs\n",
+                t_before_create, t_after_create - t_before_create, t_after_run - t_after_create,
+                since_start() - t_after_run);
     log_msg(INFO, "hyperex", "Done getting hypervariable regions");
     // cleanup_and_log (utils.rs:560-582)
     if (exists("infile.fa") && (!has_file || file == "-")) unlink("infile.fa");

@@ -7,13 +7,18 @@
 #include "../../include/hyperex_b200.h"
 
 #include <dlfcn.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <cerrno>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 
 // ------------------------------------------------------------------------------------
 // IUPAC ambiguity table given to MyersBuilder::ambig (utils.rs:251-263)
@@ -411,7 +416,7 @@ HxhRecordBatch::~HxhRecordBatch() {
 namespace {
 bool grow_arena(HxhRecordBatch &b, size_t need, size_t used) {
     if (need <= b.arena_cap) return true;
-    size_t want = std::max(need + need / 4, (size_t)1 << 20);
+    size_t want = std::max(need + need / 2, (size_t)1 << 20);
     uint8_t *p = (uint8_t *)hx_alloc_pinned(want);
     bool pinned = p != nullptr;
     if (!p) p = (uint8_t *)malloc(want);
@@ -429,7 +434,7 @@ bool grow_arena(HxhRecordBatch &b, size_t need, size_t used) {
 inline bool is_ws(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
 }  // namespace
 
-HxhFastaReader::HxhFastaReader() : buf_(4u << 20) {}
+HxhFastaReader::HxhFastaReader() : buf_(8u << 20) {}
 HxhFastaReader::~HxhFastaReader() { delete src_; }
 
 int HxhFastaReader::open(const char *path, std::string &err) {
@@ -446,6 +451,13 @@ int HxhFastaReader::open(const char *path, std::string &err) {
         return HX_ERR_IO;
     }
     rewind(f);
+    {
+        struct stat st;
+        size_hint_ = (fstat(fileno(f), &st) == 0 && st.st_size > 0) ? (size_t)st.st_size : 0;
+        const bool plain = !((magic[0] == 0x1f && magic[1] == 0x8b) || (magic[0] == 0x42 && magic[1] == 0x5a) ||
+                             (magic[0] == 0xfd && magic[1] == 0x37) || (magic[0] == 0x28 && magic[1] == 0xb5));
+        if (!plain) size_hint_ *= 5;  // typical nucleotide compression ratio; grown on demand beyond that
+    }
     bool ok = true;
     if (magic[0] == 0x1f && magic[1] == 0x8b) {
         fclose(f);
@@ -474,31 +486,35 @@ int HxhFastaReader::open(const char *path, std::string &err) {
     return HX_OK;
 }
 
-bool HxhFastaReader::fill() {
-    if (eof_) return false;
-    long r = src_->read(buf_.data(), buf_.size());
-    if (r <= 0) {
-        eof_ = true;
-        return false;
-    }
-    pos_ = 0;
-    end_ = (size_t)r;
-    return true;
-}
-
-bool HxhFastaReader::read_line(std::string &line) {
-    line.clear();
+// Makes the next complete line available inside buf_ (no copy): [line, line + len) excludes the '\n'.
+// The buffer is compacted / grown / refilled as needed; the last line of the input may lack the '\n'.
+bool HxhFastaReader::next_line(const uint8_t *&line, size_t &len) {
     for (;;) {
-        if (pos_ == end_ && !fill()) return !line.empty();
-        const uint8_t *s = buf_.data() + pos_;
-        const uint8_t *nl = (const uint8_t *)memchr(s, '\n', end_ - pos_);
+        const uint8_t *s0 = buf_.data() + pos_;
+        const uint8_t *nl = pos_ < end_ ? (const uint8_t *)memchr(s0, '\n', end_ - pos_) : nullptr;
         if (nl) {
-            line.append((const char *)s, (size_t)(nl - s) + 1);
-            pos_ += (size_t)(nl - s) + 1;
+            line = s0;
+            len = (size_t)(nl - s0);
+            pos_ += len + 1;
             return true;
         }
-        line.append((const char *)s, end_ - pos_);
-        pos_ = end_;
+        if (eof_) {
+            if (pos_ == end_) return false;
+            line = s0;
+            len = end_ - pos_;
+            pos_ = end_;
+            return true;
+        }
+        // need more bytes: move the partial line to the front, grow if it fills the buffer, refill
+        if (pos_ > 0) {
+            memmove(buf_.data(), buf_.data() + pos_, end_ - pos_);
+            end_ -= pos_;
+            pos_ = 0;
+        }
+        if (end_ == buf_.size()) buf_.resize(buf_.size() * 2);
+        long r = src_->read(buf_.data() + end_, buf_.size() - end_);
+        if (r <= 0) eof_ = true;
+        else end_ += (size_t)r;
     }
 }
 
@@ -506,35 +522,49 @@ size_t HxhFastaReader::next_batch(HxhRecordBatch &b, size_t max_bytes, size_t ma
     b.clear();
     if (finished_ || !src_) return 0;
     size_t used = 0;
+    if (!b.arena) {
+        // one allocation for the common case: a plain file cannot hold more sequence than its size
+        size_t est = size_hint_ ? std::min(max_bytes, size_hint_) : (size_t)1 << 20;
+        if (!grow_arena(b, est + 4096, 0)) { finished_ = true; return 0; }
+    }
+    const uint8_t *line = nullptr;
+    size_t len = 0;
     while (b.ids.size() < max_records && used < max_bytes) {
         if (!have_line_) {
-            if (!read_line(line_)) { finished_ = true; break; }  // clean EOF
+            if (!next_line(line, len)) { finished_ = true; break; }  // clean EOF
+            header_.assign((const char *)line, len);
             have_line_ = true;
         }
-        if (line_.empty() || line_[0] != '>') { finished_ = true; break; }  // "Expected > at record start."
+        if (header_.empty() || header_[0] != '>') { finished_ = true; break; }  // "Expected > at record start."
         // header: line[1..].trim_end(), id = up to the first whitespace
-        size_t he = line_.size();
-        while (he > 1 && is_ws((uint8_t)line_[he - 1])) --he;
+        size_t he = header_.size();
+        while (he > 1 && is_ws((uint8_t)header_[he - 1])) --he;
         size_t ie = 1;
-        while (ie < he && !is_ws((uint8_t)line_[ie])) ++ie;
+        while (ie < he && !is_ws((uint8_t)header_[ie])) ++ie;
         const bool has_desc = ie < he;
-        std::string id = line_.substr(1, ie - 1);
+        std::string id = header_.substr(1, ie - 1);
         const size_t seq_start = used;
         have_line_ = false;
         for (;;) {
-            if (!read_line(line_)) break;  // EOF ends the record
-            if (line_[0] == '>') { have_line_ = true; break; }
-            size_t te = line_.size();
-            while (te > 0 && is_ws((uint8_t)line_[te - 1])) --te;  // trim_end()
-            if (!grow_arena(b, used + te + 64, used)) { finished_ = true; return b.ids.size(); }
-            memcpy(b.arena + used, line_.data(), te);
+            if (!next_line(line, len)) break;  // EOF ends the record
+            if (len && line[0] == '>') {
+                header_.assign((const char *)line, len);
+                have_line_ = true;
+                break;
+            }
+            size_t te = len;
+            while (te > 0 && is_ws(line[te - 1])) --te;  // trim_end()
+            if (used + te + 64 > b.arena_cap && !grow_arena(b, used + te + 64, used)) {
+                finished_ = true;
+                return b.ids.size();
+            }
+            memcpy(b.arena + used, line, te);
             used += te;
         }
         if (id.empty() && !has_desc && used == seq_start) { finished_ = true; break; }  // record.is_empty()
-        b.ids.push_back(id);
+        b.ids.push_back(std::move(id));
         b.offsets.push_back(used);
     }
-    if (!b.arena) grow_arena(b, 64, 0);
     return b.ids.size();
 }
 
@@ -575,7 +605,55 @@ extern "C" void hx_fasta_close(hx_fasta *r) { delete r; }
 
 // ------------------------------------------------------------------------------------
 // utils.rs:231-414 get_hypervar_regions
+//   parser thread: FASTA -> pinned arenas (batches of ~64 MB of sequence, three in flight)
+//   caller thread: hx_run_batch on the GPU(s), then FASTA / GFF3 formatting into large write buffers
 // ------------------------------------------------------------------------------------
+namespace {
+
+struct OutBuf {  // append-only write buffer in front of a FILE*
+    std::vector<char> v;
+    size_t n = 0;
+    FILE *f = nullptr;
+    bool ok = true;
+    explicit OutBuf(FILE *file) : v((size_t)16 << 20), f(file) {}
+    void flush() {
+        if (n && fwrite(v.data(), 1, n, f) != n) ok = false;
+        n = 0;
+    }
+    char *reserve(size_t k) {
+        if (n + k > v.size()) {
+            flush();
+            if (k > v.size()) v.resize(k + (k >> 1));
+        }
+        return v.data() + n;
+    }
+    void put(const void *p, size_t k) {
+        memcpy(reserve(k), p, k);
+        n += k;
+    }
+    void put(const std::string &x) { put(x.data(), x.size()); }
+};
+
+inline size_t put_u32(char *dst, uint32_t v) {  // decimal, no terminator
+    char tmp[12];
+    int i = 0;
+    do {
+        tmp[i++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    for (int j = 0; j < i; ++j) dst[j] = tmp[i - 1 - j];
+    return (size_t)i;
+}
+
+struct BatchQueue {  // parser -> consumer hand-off with recycling
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<HxhRecordBatch *> ready, free_list;
+    bool done = false;
+};
+
+}  // namespace
+
 extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n_pairs, const char *const *fwd,
                                        const char *const *rev, const char *prefix, uint8_t mismatch, hx_log_fn log_fn,
                                        void *user) {
@@ -597,94 +675,159 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
         if (gff) fclose(gff);
         return HX_ERR_IO;
     }
-    fputs("##gff-version 3\n", gff);  // utils.rs:247
-    std::vector<std::string> labels(n_pairs);
+    OutBuf fo(fa), go(gff);
+    go.put("##gff-version 3\n", 16);  // utils.rs:247
+    // per pair: everything of the FASTA header / GFF line that does not depend on the record
+    std::vector<std::string> labels(n_pairs), fa_tail(n_pairs), gff_note(n_pairs);
     for (uint32_t p = 0; p < n_pairs; ++p) {
         char lab[16];
         hx_primers_to_region(fwd[p], rev[p], lab);
         labels[p] = lab;
+        const std::string fr = std::string("forward=") + fwd[p] + " reverse=" + rev[p];
+        fa_tail[p] = labels[p].empty() ? " " + fr + "\n" : " region=" + labels[p] + " " + fr + "\n";      // utils.rs:356-363
+        gff_note[p] = "\t.\t.\t.\tNote=" + (labels[p].empty() ? fr : "Hypervariable region " + labels[p]) + "\n";  // 372-385
     }
-    HxhRecordBatch batch;
+    // HYPEREX_TIMING=1 prints where the wall time of the file-level path goes
+    const bool timing = getenv("HYPEREX_TIMING") != nullptr;
+    double t_parse = 0, t_gpu = 0, t_write = 0, t_wait = 0;
+    uint64_t n_bases = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+
+    HxhRecordBatch pool[3];
+    BatchQueue q;
+    for (HxhRecordBatch &b : pool) q.free_list.push_back(&b);
+    const size_t batch_bytes = (size_t)64 << 20;
+    std::thread parser([&] {
+        for (;;) {
+            HxhRecordBatch *b = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(q.mu);
+                q.cv.wait(lk, [&] { return !q.free_list.empty() || q.done; });
+                if (q.done) return;
+                b = q.free_list.back();
+                q.free_list.pop_back();
+            }
+            const double t0 = now();
+            const size_t n = reader.next_batch(*b, batch_bytes, (size_t)8 << 20);
+            t_parse += now() - t0;
+            std::lock_guard<std::mutex> lk(q.mu);
+            if (n == 0) {
+                q.done = true;
+                q.cv.notify_all();
+                return;
+            }
+            q.ready.push_back(b);
+            q.cv.notify_all();
+        }
+    });
+
     std::vector<hx_result> res;
-    std::string fa_buf, gff_buf, msg;
+    std::string msg;
     char num[96];
-    while (reader.next_batch(batch, (size_t)512 << 20, (size_t)8 << 20) > 0) {
+    for (;;) {
+        HxhRecordBatch *bp = nullptr;
+        {
+            const double t0 = now();
+            std::unique_lock<std::mutex> lk(q.mu);
+            q.cv.wait(lk, [&] { return !q.ready.empty() || q.done; });
+            t_wait += now() - t0;
+            if (q.ready.empty()) break;
+            bp = q.ready.front();
+            q.ready.erase(q.ready.begin());
+        }
+        HxhRecordBatch &batch = *bp;
+        const double t1 = now();
         const uint32_t n = (uint32_t)batch.ids.size();
+        n_bases += batch.offsets[n];
         res.resize((size_t)n * n_pairs);
         rc = hx_run_batch(ctx, batch.arena, batch.offsets.data(), n, res.data());
-        if (rc != HX_OK) break;
-        fa_buf.clear();
-        gff_buf.clear();
-        for (uint32_t r = 0; r < n; ++r) {
-            const std::string &id = batch.ids[r];
-            const uint8_t *seq = batch.arena + batch.offsets[r];
-            const size_t len = (size_t)(batch.offsets[r + 1] - batch.offsets[r]);
-            const hx_result *rr = &res[(size_t)r * n_pairs];
-            if (rr[0].flags & HX_ALPHABET_NONE) {  // utils.rs:276-279
-                if (log_fn) {
-                    msg = "Unrecognized sequence type in record: " + id;
-                    log_fn(2, msg.c_str(), user);
+        const double t2 = now();
+        t_gpu += t2 - t1;
+        if (rc == HX_OK) {
+            for (uint32_t r = 0; r < n; ++r) {
+                const std::string &id = batch.ids[r];
+                const uint8_t *seq = batch.arena + batch.offsets[r];
+                const size_t len = (size_t)(batch.offsets[r + 1] - batch.offsets[r]);
+                const hx_result *rr = &res[(size_t)r * n_pairs];
+                if (rr[0].flags & HX_ALPHABET_NONE) {  // utils.rs:276-279
+                    if (log_fn) {
+                        msg = "Unrecognized sequence type in record: " + id;
+                        log_fn(2, msg.c_str(), user);
+                    }
+                    continue;
                 }
-                continue;
-            }
-            if (len <= 1500 && log_fn) {  // utils.rs:282-288
-                snprintf(num, sizeof num, "%zu", len);
-                msg = "Sequence " + id + " is short (" + num + " bp). Some regions may not be found.";
-                log_fn(1, msg.c_str(), user);
-            }
-            for (uint32_t p = 0; p < n_pairs; ++p) {
-                const hx_result &x = rr[p];
-                const bool f_any = x.flags & HX_FWD_ANY, r_any = x.flags & HX_REV_ANY, ok = x.flags & HX_PAIR_VALID;
-                if (f_any && r_any && ok) {  // utils.rs:354-386
-                    fa_buf += '>';
-                    fa_buf += id;
-                    fa_buf += ' ';
-                    if (!labels[p].empty()) {
-                        fa_buf += "region=";
-                        fa_buf += labels[p];
-                        fa_buf += ' ';
-                    }
-                    fa_buf += "forward=";
-                    fa_buf += fwd[p];
-                    fa_buf += " reverse=";
-                    fa_buf += rev[p];
-                    fa_buf += '\n';
-                    fa_buf.append((const char *)seq + x.f_start, (size_t)x.r_end + 1 - x.f_start);
-                    fa_buf += '\n';
-                    gff_buf += id;
-                    snprintf(num, sizeof num, "\thyperex\tregion\t%u\t%u\t.\t.\t.\tNote=", x.f_start + 1, x.r_end + 1);
-                    gff_buf += num;
-                    if (!labels[p].empty()) {
-                        gff_buf += "Hypervariable region ";
-                        gff_buf += labels[p];
-                    } else {
-                        gff_buf += "forward=";
-                        gff_buf += fwd[p];
-                        gff_buf += " reverse=";
-                        gff_buf += rev[p];
-                    }
-                    gff_buf += '\n';
-                } else if (log_fn) {  // utils.rs:387-408
-                    if (f_any && r_any)
-                        msg = "Forward and reverse primers for region " + labels[p] + " were both found in sequence " +
-                              id + ", but not in a valid order/orientation to define a region";
-                    else if (!f_any && r_any)
-                        msg = std::string("Forward primer ") + fwd[p] + " not found for region " + labels[p] +
-                              " in sequence " + id;
-                    else if (f_any && !r_any)
-                        msg = std::string("Reverse primer ") + rev[p] + " not found for region " + labels[p] +
-                              " in sequence " + id;
-                    else
-                        msg = "Both primers not found for region " + labels[p] + " in sequence " + id;
+                if (len <= 1500 && log_fn) {  // utils.rs:282-288
+                    snprintf(num, sizeof num, "%zu", len);
+                    msg = "Sequence " + id + " is short (" + num + " bp). Some regions may not be found.";
                     log_fn(1, msg.c_str(), user);
                 }
+                for (uint32_t p = 0; p < n_pairs; ++p) {
+                    const hx_result &x = rr[p];
+                    const bool f_any = x.flags & HX_FWD_ANY, r_any = x.flags & HX_REV_ANY, ok = x.flags & HX_PAIR_VALID;
+                    if (f_any && r_any && ok) {  // utils.rs:354-386
+                        const size_t slen = (size_t)x.r_end + 1 - x.f_start;
+                        char *o = fo.reserve(1 + id.size() + fa_tail[p].size() + slen + 1);
+                        *o++ = '>';
+                        memcpy(o, id.data(), id.size());
+                        o += id.size();
+                        memcpy(o, fa_tail[p].data(), fa_tail[p].size());
+                        o += fa_tail[p].size();
+                        memcpy(o, seq + x.f_start, slen);  // original case (utils.rs:368)
+                        o += slen;
+                        *o++ = '\n';
+                        fo.n = (size_t)(o - fo.v.data());
+                        char *g = go.reserve(id.size() + 48 + gff_note[p].size());
+                        memcpy(g, id.data(), id.size());
+                        g += id.size();
+                        memcpy(g, "\thyperex\tregion\t", 16);
+                        g += 16;
+                        g += put_u32(g, x.f_start + 1);  // 1-based (utils.rs:382-383)
+                        *g++ = '\t';
+                        g += put_u32(g, x.r_end + 1);
+                        memcpy(g, gff_note[p].data(), gff_note[p].size());
+                        g += gff_note[p].size();
+                        go.n = (size_t)(g - go.v.data());
+                    } else if (log_fn) {  // utils.rs:387-408
+                        if (f_any && r_any)
+                            msg = "Forward and reverse primers for region " + labels[p] + " were both found in sequence " +
+                                  id + ", but not in a valid order/orientation to define a region";
+                        else if (!f_any && r_any)
+                            msg = std::string("Forward primer ") + fwd[p] + " not found for region " + labels[p] +
+                                  " in sequence " + id;
+                        else if (f_any && !r_any)
+                            msg = std::string("Reverse primer ") + rev[p] + " not found for region " + labels[p] +
+                                  " in sequence " + id;
+                        else
+                            msg = "Both primers not found for region " + labels[p] + " in sequence " + id;
+                        log_fn(1, msg.c_str(), user);
+                    }
+                }
             }
+            if (!fo.ok || !go.ok) rc = HX_ERR_IO;
         }
-        if (!fa_buf.empty() && fwrite(fa_buf.data(), 1, fa_buf.size(), fa) != fa_buf.size()) rc = HX_ERR_IO;
-        if (!gff_buf.empty() && fwrite(gff_buf.data(), 1, gff_buf.size(), gff) != gff_buf.size()) rc = HX_ERR_IO;
+        t_write += now() - t2;
+        {
+            std::lock_guard<std::mutex> lk(q.mu);
+            q.free_list.push_back(bp);
+            if (rc != HX_OK) q.done = true;
+            q.cv.notify_all();
+        }
         if (rc != HX_OK) break;
     }
+    {
+        std::lock_guard<std::mutex> lk(q.mu);
+        q.done = true;
+        q.cv.notify_all();
+    }
+    parser.join();
+    fo.flush();
+    go.flush();
+    if ((!fo.ok || !go.ok) && rc == HX_OK) rc = HX_ERR_IO;
     if (fclose(fa) != 0 && rc == HX_OK) rc = HX_ERR_IO;
     if (fclose(gff) != 0 && rc == HX_OK) rc = HX_ERR_IO;
+    if (timing)
+        fprintf(stderr, "[hyperex timing] bases=%llu parse=%.3fs (own thread) wait_for_parser=%.3fs device=%.3fs "
+                        "format+write=%.3fs\n",
+                (unsigned long long)n_bases, t_parse, t_wait, t_gpu, t_write);
     return rc;
 }

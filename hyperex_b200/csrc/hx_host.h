@@ -34,13 +34,13 @@ class HxhFastaReader {
     size_t next_batch(HxhRecordBatch &batch, size_t max_bytes, size_t max_records);
 
   private:
-    bool fill();
-    bool read_line(std::string &line);  // includes the trailing '\n' when present
+    bool next_line(const uint8_t *&line, size_t &len);  // zero-copy view into buf_, '\n' excluded
     HxhByteSource *src_ = nullptr;
     std::vector<uint8_t> buf_;
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false;
-    std::string line_;   // look-ahead line (rust-bio keeps the next header in self.line)
+    std::string header_;  // look-ahead header line (rust-bio keeps the next header in self.line)
     bool have_line_ = false;
+    size_t size_hint_ = 0;
     bool finished_ = false;
 };

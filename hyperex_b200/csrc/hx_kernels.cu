@@ -327,32 +327,19 @@ int hx_launch_classify(const uint8_t *arena, const uint64_t *offsets, uint64_t o
 // (Measured on B200, profiles/int_peak_r01.json: moving the score update to IMAD.HI or to a carry chain is
 // slower than what ptxas emits for the plain C below, so there is a single step variant.)
 // ------------------------------------------------------------------------------------
-#ifndef HX_EXP
-#define HX_EXP 0
-#endif
-__device__ __forceinline__ void hx_step(const uint32_t eq, uint32_t &pv, uint32_t &mv, int &s, const uint32_t hx_two = 2u) {
+__device__ __forceinline__ void hx_step(const uint32_t eq, uint32_t &pv, uint32_t &mv, int &s) {
     const uint32_t xv = eq | mv;
     const uint32_t xh = (((eq & pv) + pv) ^ pv) | eq;
     uint32_t ph = mv | ~(xh | pv);
     uint32_t mh = pv & xh;
-#if HX_EXP == 1
-    // experiment: both score updates as IMAD.HI (FMA pipe, half rate) with a run-time multiplier
-    asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(s) : "r"(ph), "r"(hx_two));
-    asm("mad.hi.s32 %0, %1, %2, %0;" : "+r"(s) : "r"(mh), "r"(hx_two));
-#elif HX_EXP == 2
-    // experiment: only the ph update as IMAD.HI
-    asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(s) : "r"(ph), "r"(hx_two));
-    s -= (int)(mh >> 31);
-#else
     s += (int)(ph >> 31) - (int)(mh >> 31);  // ptxas: LEA.HI + LEA.HI.SX32 (one ALU op per sign bit)
-#endif
     ph <<= 1;                                // ptxas: IMAD.IADD x+x on the FMA pipe
     mh <<= 1;
     pv = mh | ~(xv | ph);
     mv = ph & xv;
 }
 
-__device__ __forceinline__ void hx_step(const uint64_t eq, uint64_t &pv, uint64_t &mv, int &s, const uint32_t = 2u) {
+__device__ __forceinline__ void hx_step(const uint64_t eq, uint64_t &pv, uint64_t &mv, int &s) {
     const uint64_t xv = eq | mv;
     const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
     uint64_t ph = mv | ~(xh | pv);
@@ -632,7 +619,7 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
                         } else {
 #pragma unroll
                             for (int p = 0; p < NP; ++p) {
-                                hx_step(row.eq(p), pv[p], mv[p], s[p], a.two);
+                                hx_step(row.eq(p), pv[p], mv[p], s[p]);
                                 any |= s[p];
                             }
                         }
