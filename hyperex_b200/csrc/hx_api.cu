@@ -243,7 +243,10 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const 
         a.tables = D.d_tables + hg.table_off;
         a.tables_wm = D.d_tables_wm + hg.table_off;
         // small-k fast path: identical hits, fewer ALU operations; 32-bit groups, vector-load text path
-        a.wm_k = (ctx->opt_fast_small_k && !hg.word64 && ctx->k <= 2 && !ctx->opt_text_tma) ? (int)ctx->k : -1;
+        // (measured: at -m 2 the fast path only pays for narrow groups; wide groups run out of registers)
+        a.wm_k = (ctx->opt_fast_small_k && !hg.word64 && !ctx->opt_text_tma && (ctx->k <= 1 || (ctx->k == 2 && hg.np <= 8)))
+                     ? (int)ctx->k
+                     : -1;
         a.group = D.d_groups + gi;
         a.sum_f = S.sum_f.p;
         a.sum_r = S.sum_r.p;

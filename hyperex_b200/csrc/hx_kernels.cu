@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((siz
                 hx_bulk_g2s((st & 1u) ? stage1 : stage0, src + (size_t)st * HX_CH, bytes, mb);
             }
         };
-        uint4 nxt = make_uint4(0, 0, 0, 0);
+        uint4 nxt = make_uint4(0, 0, 0, 0);  // one 16-byte chunk in flight (two measured slower: more registers)
         if constexpr (TMA) {
             issue(0);
             issue(1);
