@@ -55,6 +55,7 @@ def parse_args():
                     help="c2 is the BASELINE.json metric config; c3/c4/c5 are informational")
     ap.add_argument("--cpu-sample", type=int, default=60_000, help="records of the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=0, help="records per step of the reference arm (0: auto)")
+    ap.add_argument("--slab-mb", type=int, default=0, help="host->device pipeline granule of the e2e leg (0: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ab", action="store_true", help="skip the TMA / LDG text-path A/B")
     return ap.parse_args()
@@ -192,6 +193,8 @@ def run_reference(args, rank, world):
         return
     import hx_synth
     pairs, cells = pairs_and_cells()
+    if args.k < 0:
+        args.k = 0  # configs[1]: -m 0
     cores = os.cpu_count() or 1
     n = args.ref_sample or max(2000, 2500 * cores)
     arena, offsets = hx_synth.gen_reads(n, seed=2)
@@ -251,6 +254,8 @@ def main():
     # GCUPS"), so `value`, `e2e` and `roofline` are measured with the small-k fast path OFF; the library default
     # (fast path ON for -m 0..2) is timed separately below and reported as `fast_path`.
     ctx.set_option("fast_small_k", 0)
+    if args.slab_mb > 0:
+        ctx.set_option("slab_bytes", args.slab_mb << 20)
     ctx.set_primers(pairs, args.k)
 
     # ---- device-resident leg ("value") -------------------------------------------------------
