@@ -2,15 +2,19 @@
 //
 //   hx_tile_build_kernel / hx_bucket_scan_kernel / hx_tile_scatter_kernel
 //       records -> tiles (whole short record, or overlapped window of a long one), ordered
-//       longest-first so the lanes of a warp finish together.
-//   hx_classify_kernel, hx_classify_iupac_kernel
-//                             utils.rs:207-228 sequence_type (HBM-bound byte reduction)
-//   hx_myers_pair_kernel      utils.rs:301-351: the Myers Pv/Mv/score recurrence of rust-bio
-//                             Myers<u64>::find_all_lazy for ALL patterns of a group per text
-//                             byte, fused with the reference's hit-selection rule evaluated
-//                             as a streaming arg-min (no hit lists are materialised)
-//   hx_combine_kernel         joins the per-tile summaries of a record into hx_result
-//   hx_find_kernel            known-answer mirror of find_all_lazy (count / scan / write)
+//       longest-first (CTA-private counting sort) so the lanes of a warp finish together.
+//   hx_classify_kernel / hx_classify_iupac_kernel
+//       utils.rs:207-228 sequence_type: SWAR search for U / T over every record (HBM-bound), then the
+//       IUPAC-set check for the few records that contain neither.
+//   hx_myers_pair_kernel<W, NP, TMA, KWM>
+//       utils.rs:301-351: the Myers Pv/Mv/score recurrence of rust-bio Myers<u64>::find_all_lazy for
+//       ALL patterns of a group per text byte, fused with the reference's hit-selection rule evaluated
+//       as a streaming arg-min (no hit lists are materialised).  TMA selects the text path (vector
+//       loads / TMA bulk copies), KWM >= 0 swaps Myers for Wu-Manber automata when -m is 0..2.
+//   hx_combine_kernel / hx_combine_long_kernel
+//       join the per-window summaries of a multi-window record into hx_result.
+//   hx_find_kernel / hx_scan_u64_kernel
+//       known-answer mirror of find_all_lazy (count / scan / ordered write).
 //
 // Integer bit-parallel work: no tensor cores by design (BASELINE.json north_star).
 #include "hx_device.h"
