@@ -8,7 +8,9 @@
 #define HX_MAX_NP32 16     // patterns per thread in the 32-bit kernel (m <= 32)
 #define HX_MAX_NP64 8      // patterns per thread in the 64-bit kernel (33 <= m <= 64)
 #define HX_MAX_GROUP_PAIRS 16
+#ifndef HX_THREADS
 #define HX_THREADS 128     // threads per CTA of the scan kernel
+#endif
 #define HX_NBUCKETS 1024   // length buckets of the tile ordering
 #define HX_NONE64 0xFFFFFFFFFFFFFFFFull
 #define HX_LONG_TILES 64u  // records with more windows than this are joined by a whole warp

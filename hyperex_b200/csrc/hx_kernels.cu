@@ -434,7 +434,7 @@ __device__ __forceinline__ void hx_mbar_wait(uint32_t mbar, uint32_t parity) {
 __device__ __forceinline__ void hx_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <typename W, int NP, bool TMA, int KWM>
-__global__ void __launch_bounds__(HX_THREADS, (sizeof(W) * NP <= 16) ? 8 : ((sizeof(W) * NP <= 32) ? 5 : 4))
+__global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((sizeof(W) * NP <= 32) ? 5 : 4)) * (128 / HX_THREADS))
     hx_myers_pair_kernel(const HxScanArgs a) {
     constexpr bool WM = KWM >= 0;           // small-k fast path: Wu-Manber / Shift-Or automata instead of Myers
     constexpr int NR = WM ? KWM + 1 : 1;    // error levels 0..k

@@ -193,6 +193,48 @@ def test_k_at_least_pattern_length_every_position_hits(ctx):
             _cmp(_run(ctx, a, o, pairs, k, tile_len=32, single_max=48, fast=fast), ref, a, o, pairs, k)
 
 
+@pytest.mark.parametrize("seed", range(40))
+def test_random_primer_sets_fuzz(ctx, seed):
+    """random IUPAC primer sets (1..64 nt, shared primers between pairs), random k, planted + mutated sites,
+    mixed alphabets, windows of random size; both scan algorithms and both text paths"""
+    rng = np.random.default_rng(1000 + seed)
+    letters = "ACGT" * 5 + "MRWSYKVHDBNU"
+    n_pairs = int(rng.integers(1, 24))
+    max_len = int(rng.choice([6, 20, 32, 33, 64]))
+    prim = ["".join(letters[int(i)] for i in rng.integers(0, len(letters), int(rng.integers(1, max_len + 1))))
+            for _ in range(max(2, n_pairs))]
+    pairs = [[prim[int(rng.integers(0, len(prim)))], prim[int(rng.integers(0, len(prim)))]] for _ in range(n_pairs)]
+    k = int(rng.choice([0, 0, 1, 2, 3, 5]))
+    recs = []
+    for _ in range(int(rng.integers(20, 120))):
+        L = int(rng.integers(0, 900))
+        seq = bytearray(hx_synth.random_acgt(rng, L).tobytes())
+        for _s in range(int(rng.integers(0, 6))):  # plant forward / reverse-complemented sites, some mutated
+            f, r = pairs[int(rng.integers(0, n_pairs))]
+            site = f if rng.random() < 0.5 else O.to_reverse_complement(r, O.DNA).decode()
+            site = "".join(c if c in hx_synth.IUPAC else "A" for c in site)
+            sb = bytearray(hx_synth._resolve(rng, site, 1)[0].tobytes())
+            sb = hx_synth._edit(rng, sb, int(rng.integers(0, 3)))
+            if L > len(sb):
+                p = int(rng.integers(0, L - len(sb)))
+                seq[p:p + len(sb)] = sb
+        a1 = np.frombuffer(bytes(seq), dtype=np.uint8).copy()
+        u = rng.random()
+        if u < 0.15:
+            a1[a1 == ord("T")] = ord("U")
+        elif u < 0.3 and len(a1):
+            a1[int(rng.integers(0, len(a1)))] = ord("X")
+        if rng.random() < 0.3 and len(a1):
+            lo, hi = sorted(rng.integers(0, len(a1) + 1, size=2))
+            a1[lo:hi] |= 0x20
+        recs.append(a1)
+    a, o = hx_synth.pack(recs)
+    ref = O.run_batch(a, o, pairs, k, nthreads=8)
+    tile = int(rng.choice([0, 16, 64, 256, 4096]))
+    for fast, tma in ((0, 0), (1, 0), (0, 1)):
+        _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, text_tma=tma), ref, a, o, pairs, k)
+
+
 def test_rna_records_use_rna_reverse_complement(ctx):
     a, o = hx_synth.gen_reads_mutated(200, seed=71, max_edits=1, revcomp_frac=0.0, rna_frac=0.6)
     pairs = hx.default_primers()
