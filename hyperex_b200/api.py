@@ -184,6 +184,25 @@ class Context:
         self._check(self._L.hx_run_batch(self._h, ap, offsets.ctypes.data, n, out.ctypes.data))
         return out
 
+    def run_batch_fasta(self, arena: np.ndarray, offsets: np.ndarray, ids: Sequence[str], tails: Sequence[str]):
+        """hx_run_batch_fasta: (results, fasta_bytes) with the FASTA text of utils.rs:354-369 assembled on the GPU"""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        out = np.zeros((n, self.n_pairs), dtype=RESULT_DTYPE)
+        idb = [_b(i) for i in ids]
+        id_off = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            id_off[1:] = np.cumsum([len(x) for x in idb])
+        tb = [_b(t) for t in tails]
+        tail_off = np.zeros(len(tb) + 1, dtype=np.uint32)
+        tail_off[1:] = np.cumsum([len(x) for x in tb])
+        text, tlen = C.c_void_p(), C.c_uint64()
+        ap = arena.ctypes.data if arena is not None and arena.size else None
+        self._check(self._L.hx_run_batch_fasta(self._h, ap, offsets.ctypes.data, n, out.ctypes.data, b"".join(idb),
+                                               id_off.ctypes.data, b"".join(tb), tail_off.ctypes.data, C.byref(text),
+                                               C.byref(tlen)))
+        return out, (C.string_at(text.value, tlen.value) if tlen.value else b"")
+
     def run_batch_device(self, d_arena: int, d_offsets: int, n_records: int, arena_bytes: int, d_out: int,
                          stream: int = 0, dev_slot: int = 0):
         """hx_run_batch_device on raw device pointers (ints); asynchronous when stream != 0"""

@@ -103,6 +103,12 @@ struct hx_ctx {
     // options
     int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1;
     uint64_t launches = 0;
+    // on-device extraction (device 0)
+    DevBuf<uint8_t> ex_ids, ex_tails, ex_text;
+    DevBuf<uint64_t> ex_id_off, ex_lens, ex_sums;
+    DevBuf<uint32_t> ex_tail_off;
+    uint8_t *ex_host = nullptr;
+    size_t ex_host_cap = 0;
     std::vector<TimedLaunch> timed;
     double myers_ms = 0;
     uint64_t myers_launches = 0;
@@ -330,6 +336,10 @@ int hx_create(hx_ctx **out, const int *dev_ids, int n_dev) {
 void hx_destroy(hx_ctx *ctx) {
     if (!ctx) return;
     sync_timed(ctx);
+    if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].dev);
+    ctx->ex_ids.release(); ctx->ex_tails.release(); ctx->ex_text.release(); ctx->ex_id_off.release();
+    ctx->ex_lens.release(); ctx->ex_sums.release(); ctx->ex_tail_off.release();
+    if (ctx->ex_host) cudaFreeHost(ctx->ex_host);
     for (Device &D : ctx->devs) {
         cudaSetDevice(D.dev);
         cudaDeviceSynchronize();
@@ -538,6 +548,81 @@ int hx_run_batch_device(hx_ctx *ctx, int dev_slot, const uint8_t *d_arena, const
     return HX_OK;
 }
 
+int hx_run_batch_fasta(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out,
+                       const char *ids, const uint64_t *id_off, const char *tails, const uint32_t *tail_off,
+                       const char **text, uint64_t *text_len) {
+    if (!ctx) return HX_ERR_ARG;
+    if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch_fasta: call hx_set_primers first");
+    if (!text || !text_len) return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: NULL text/text_len");
+    *text = nullptr;
+    *text_len = 0;
+    if (n_records == 0) return HX_OK;
+    if (!offsets || !out || !ids || !id_off || !tails || !tail_off)
+        return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: NULL argument");
+    if (offsets[n_records] < offsets[0]) return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: offsets must be non-decreasing");
+    Device &D = ctx->devs[0];
+    Slot &S = D.slots[0];
+    cudaStream_t st = S.stream;
+    HX_CUDA(ctx, cudaSetDevice(D.dev));
+    const uint32_t np = ctx->n_pairs;
+    const uint64_t n_entries = (uint64_t)n_records * np;
+    const uint64_t base = offsets[0] & ~15ull;
+    const uint64_t copy_bytes = offsets[n_records] - base, bytes = offsets[n_records] - offsets[0];
+    const uint64_t id_bytes = id_off[n_records] - id_off[0];
+    if (id_off[0] != 0 || tail_off[0] != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: id_off / tail_off must start at 0");
+    const uint32_t tail_bytes = tail_off[np];
+    const uint32_t nblk = (uint32_t)((n_entries + 4095) / 4096);
+    HX_CUDA(ctx, cudaStreamSynchronize(st));
+    HX_CUDA(ctx, S.arena.reserve(copy_bytes + 64));
+    HX_CUDA(ctx, S.offsets.reserve((size_t)n_records + 1));
+    HX_CUDA(ctx, S.out.reserve((size_t)n_entries));
+    HX_CUDA(ctx, ctx->ex_ids.reserve(id_bytes + 16));
+    HX_CUDA(ctx, ctx->ex_id_off.reserve((size_t)n_records + 1));
+    HX_CUDA(ctx, ctx->ex_tails.reserve(tail_bytes + 16));
+    HX_CUDA(ctx, ctx->ex_tail_off.reserve(np + 1));
+    HX_CUDA(ctx, ctx->ex_lens.reserve(n_entries + 1));
+    HX_CUDA(ctx, ctx->ex_sums.reserve(nblk + 2));
+    if (copy_bytes) HX_CUDA(ctx, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, st));
+    HX_CUDA(ctx, cudaMemcpyAsync(S.offsets.p, offsets, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (id_bytes) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_ids.p, ids, id_bytes, cudaMemcpyHostToDevice, st));
+    HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_id_off.p, id_off, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (tail_bytes) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_tails.p, tails, tail_bytes, cudaMemcpyHostToDevice, st));
+    HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_tail_off.p, tail_off, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, st));
+    int rc = enqueue_slab(ctx, D, S, S.arena.p, S.offsets.p, base, n_records, bytes, S.out.p, st);
+    if (rc != HX_OK) return rc;
+    HX_CUDA(ctx, cudaMemcpyAsync(out, S.out.p, (size_t)n_entries * sizeof(hx_result), cudaMemcpyDeviceToHost, st));
+    ctx->launches += hx_launch_fasta_offsets(S.out.p, ctx->ex_id_off.p, ctx->ex_tail_off.p, np, n_entries, ctx->ex_lens.p,
+                                             ctx->ex_sums.p, st);
+    // total = offset of the last entry + its length = block offset + in-block prefix; read both pieces
+    uint64_t total = 0, last_off = 0;
+    HX_CUDA(ctx, cudaMemcpyAsync(&total, ctx->ex_sums.p + nblk, 8, cudaMemcpyDeviceToHost, st));
+    (void)last_off;
+    HX_CUDA(ctx, cudaStreamSynchronize(st));
+    rc = check_status(ctx, S);
+    if (rc != HX_OK) return rc;
+    if (total) {
+        HX_CUDA(ctx, ctx->ex_text.reserve(total + 16));
+        if (total > ctx->ex_host_cap) {
+            if (ctx->ex_host) cudaFreeHost(ctx->ex_host);
+            ctx->ex_host = nullptr;
+            ctx->ex_host_cap = 0;
+            const size_t want = (size_t)(total + total / 4 + 4096);
+            HX_CUDA(ctx, cudaHostAlloc((void **)&ctx->ex_host, want, cudaHostAllocDefault));
+            ctx->ex_host_cap = want;
+        }
+        ctx->launches += hx_launch_fasta_write(S.arena.p, S.offsets.p, base, S.out.p, ctx->ex_ids.p, ctx->ex_id_off.p,
+                                               ctx->ex_tails.p, ctx->ex_tail_off.p, np, n_entries, ctx->ex_lens.p,
+                                               ctx->ex_text.p, st);
+        HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_host, ctx->ex_text.p, total, cudaMemcpyDeviceToHost, st));
+        HX_CUDA(ctx, cudaStreamSynchronize(st));
+        HX_CUDA(ctx, cudaGetLastError());
+    }
+    sync_timed(ctx);
+    *text = (const char *)ctx->ex_host;
+    *text_len = total;
+    return HX_OK;
+}
+
 int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out) {
     if (!ctx) return HX_ERR_ARG;
     if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch: call hx_set_primers first");
@@ -696,3 +781,5 @@ int hx_kernel_time(hx_ctx *ctx, double *myers_ms, uint64_t *myers_launches, int 
 
 }  // extern "C"
 
+// internal (C++ linkage): used by the file-level driver in hx_host.cpp
+int hxh_device_count(const hx_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }

@@ -116,3 +116,10 @@ int hx_launch_combine(const uint32_t *tile_first, const uint32_t *tile_cnt, cons
 int hx_launch_find(const uint8_t *text, uint64_t n, const uint8_t *table /*256 x u64*/, uint32_t m, uint32_t k,
                    uint32_t tile_len, uint32_t ntiles, uint64_t *counts /*ntiles+1*/, uint64_t *out_end,
                    uint8_t *out_dist, uint64_t cap, int pass, cudaStream_t st);
+
+// on-device FASTA extraction
+int hx_launch_fasta_offsets(const void *res, const uint64_t *id_off, const uint32_t *tail_off, uint32_t n_pairs,
+                            uint64_t n_entries, uint64_t *lens, uint64_t *sums, cudaStream_t st);
+int hx_launch_fasta_write(const uint8_t *arena, const uint64_t *offsets, uint64_t off_base, const void *res,
+                          const uint8_t *ids, const uint64_t *id_off, const uint8_t *tails, const uint32_t *tail_off,
+                          uint32_t n_pairs, uint64_t n_entries, const uint64_t *where, uint8_t *out, cudaStream_t st);

@@ -687,6 +687,16 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
         fa_tail[p] = labels[p].empty() ? " " + fr + "\n" : " region=" + labels[p] + " " + fr + "\n";      // utils.rs:356-363
         gff_note[p] = "\t.\t.\t.\tNote=" + (labels[p].empty() ? fr : "Hypervariable region " + labels[p]) + "\n";  // 372-385
     }
+    // On-device extraction: with one GPU the FASTA text itself is assembled on the device and the
+    // host only write()s it; HYPEREX_HOST_FORMAT=1 (or a multi-GPU context) keeps the host formatter.
+    const bool device_fasta = hxh_device_count(ctx) == 1 && getenv("HYPEREX_HOST_FORMAT") == nullptr;
+    std::string tails_blob, ids_blob;
+    std::vector<uint32_t> tail_off(1, 0);
+    std::vector<uint64_t> id_off;
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+        tails_blob += fa_tail[p];
+        tail_off.push_back((uint32_t)tails_blob.size());
+    }
     // HYPEREX_TIMING=1 prints where the wall time of the file-level path goes
     const bool timing = getenv("HYPEREX_TIMING") != nullptr;
     double t_parse = 0, t_gpu = 0, t_write = 0, t_wait = 0;
@@ -740,7 +750,20 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
         const uint32_t n = (uint32_t)batch.ids.size();
         n_bases += batch.offsets[n];
         res.resize((size_t)n * n_pairs);
-        rc = hx_run_batch(ctx, batch.arena, batch.offsets.data(), n, res.data());
+        const char *dev_text = nullptr;
+        uint64_t dev_text_len = 0;
+        if (device_fasta) {
+            ids_blob.clear();
+            id_off.assign(1, 0);
+            for (const std::string &id : batch.ids) {
+                ids_blob += id;
+                id_off.push_back(ids_blob.size());
+            }
+            rc = hx_run_batch_fasta(ctx, batch.arena, batch.offsets.data(), n, res.data(), ids_blob.data(), id_off.data(),
+                                    tails_blob.data(), tail_off.data(), &dev_text, &dev_text_len);
+        } else {
+            rc = hx_run_batch(ctx, batch.arena, batch.offsets.data(), n, res.data());
+        }
         const double t2 = now();
         t_gpu += t2 - t1;
         if (rc == HX_OK) {
@@ -765,17 +788,19 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
                     const hx_result &x = rr[p];
                     const bool f_any = x.flags & HX_FWD_ANY, r_any = x.flags & HX_REV_ANY, ok = x.flags & HX_PAIR_VALID;
                     if (f_any && r_any && ok) {  // utils.rs:354-386
-                        const size_t slen = (size_t)x.r_end + 1 - x.f_start;
-                        char *o = fo.reserve(1 + id.size() + fa_tail[p].size() + slen + 1);
-                        *o++ = '>';
-                        memcpy(o, id.data(), id.size());
-                        o += id.size();
-                        memcpy(o, fa_tail[p].data(), fa_tail[p].size());
-                        o += fa_tail[p].size();
-                        memcpy(o, seq + x.f_start, slen);  // original case (utils.rs:368)
-                        o += slen;
-                        *o++ = '\n';
-                        fo.n = (size_t)(o - fo.v.data());
+                        if (!device_fasta) {
+                            const size_t slen = (size_t)x.r_end + 1 - x.f_start;
+                            char *o = fo.reserve(1 + id.size() + fa_tail[p].size() + slen + 1);
+                            *o++ = '>';
+                            memcpy(o, id.data(), id.size());
+                            o += id.size();
+                            memcpy(o, fa_tail[p].data(), fa_tail[p].size());
+                            o += fa_tail[p].size();
+                            memcpy(o, seq + x.f_start, slen);  // original case (utils.rs:368)
+                            o += slen;
+                            *o++ = '\n';
+                            fo.n = (size_t)(o - fo.v.data());
+                        }
                         char *g = go.reserve(id.size() + 48 + gff_note[p].size());
                         memcpy(g, id.data(), id.size());
                         g += id.size();
@@ -802,6 +827,10 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
                         log_fn(1, msg.c_str(), user);
                     }
                 }
+            }
+            if (device_fasta && dev_text_len) {  // the GPU produced the FASTA bytes of this batch
+                fo.flush();
+                if (fwrite(dev_text, 1, dev_text_len, fa) != dev_text_len) fo.ok = false;
             }
             if (!fo.ok || !go.ok) rc = HX_ERR_IO;
         }

@@ -7,6 +7,9 @@
 #include <string>
 #include <vector>
 
+struct hx_ctx;
+int hxh_device_count(const hx_ctx *ctx);  // hx_api.cu
+
 // utils.rs:251-263 + rust-bio build_64: does pattern symbol p match text byte b?
 bool hxh_symbol_matches(uint8_t p, uint8_t b);
 

@@ -1050,3 +1050,129 @@ int hx_launch_find(const uint8_t *text, uint64_t n, const uint8_t *table, uint32
     }
     return 1;
 }
+
+// ------------------------------------------------------------------------------------
+// On-device extraction: the FASTA text of utils.rs:354-369 is assembled on the GPU.
+//   hx_fasta_len_kernel     bytes of every (record, pair) entry in output order (0 when no region)
+//   hx_scan_blocks_kernel / hx_scan_u64_kernel / hx_scan_add_kernel   exclusive scan -> write offsets
+//   hx_fasta_write_kernel   one warp per entry copies '>' id tail slice '\n' (original case, utils.rs:368)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    hx_fasta_len_kernel(const HxResultDev *__restrict__ res, const uint64_t *__restrict__ id_off,
+                        const uint32_t *__restrict__ tail_off, uint32_t n_pairs, uint64_t n_entries,
+                        uint64_t *__restrict__ lens) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_entries) return;
+    const HxResultDev x = res[i];
+    uint64_t len = 0;
+    if ((x.meta & 7u) == 7u) {
+        const uint64_t r = i / n_pairs;
+        const uint32_t p = (uint32_t)(i % n_pairs);
+        len = 1 + (id_off[r + 1] - id_off[r]) + (tail_off[p + 1] - tail_off[p]) + ((uint64_t)x.r_end + 1 - x.f_start) + 1;
+    }
+    lens[i] = len;
+}
+
+#define HX_SCAN_ITEMS 4096  // elements per block of the multi-block scan
+
+// per block: exclusive scan of its HX_SCAN_ITEMS elements in place, block total to sums[block]
+__global__ void __launch_bounds__(1024) hx_scan_blocks_kernel(uint64_t *data, uint64_t n, uint64_t *sums) {
+    __shared__ uint64_t warp_sum[32];
+    const uint64_t base = (uint64_t)blockIdx.x * HX_SCAN_ITEMS + (uint64_t)threadIdx.x * 4;
+    uint64_t v[4], t = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        v[j] = base + j < n ? data[base + j] : 0;
+        t += v[j];
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t x = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = warp_sum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += y;
+        }
+        warp_sum[lane] = w;
+    }
+    __syncthreads();
+    uint64_t run = (wid ? warp_sum[wid - 1] : 0) + x - t;  // exclusive prefix of this thread inside the block
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (base + j < n) data[base + j] = run;
+        run += v[j];
+    }
+    if (threadIdx.x == 1023) sums[blockIdx.x] = warp_sum[31];
+}
+
+__global__ void __launch_bounds__(1024) hx_scan_add_kernel(uint64_t *data, uint64_t n, const uint64_t *sums) {
+    const uint64_t add = sums[blockIdx.x];
+    const uint64_t base = (uint64_t)blockIdx.x * HX_SCAN_ITEMS + (uint64_t)threadIdx.x * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (base + j < n) data[base + j] += add;
+}
+
+__global__ void __launch_bounds__(256)
+    hx_fasta_write_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ offsets, uint64_t off_base,
+                          const HxResultDev *__restrict__ res, const uint8_t *__restrict__ ids,
+                          const uint64_t *__restrict__ id_off, const uint8_t *__restrict__ tails,
+                          const uint32_t *__restrict__ tail_off, uint32_t n_pairs, uint64_t n_entries,
+                          const uint64_t *__restrict__ where, uint8_t *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_entries; i += warps) {
+        const HxResultDev x = res[i];
+        if ((x.meta & 7u) != 7u) continue;
+        const uint64_t r = i / n_pairs;
+        const uint32_t p = (uint32_t)(i % n_pairs);
+        uint8_t *o = out + where[i];
+        if (lane == 0) *o = '>';
+        ++o;
+        const uint8_t *src = ids + id_off[r];
+        uint64_t len = id_off[r + 1] - id_off[r];
+        for (uint64_t j = lane; j < len; j += 32) o[j] = src[j];
+        o += len;
+        src = tails + tail_off[p];
+        len = tail_off[p + 1] - tail_off[p];
+        for (uint64_t j = lane; j < len; j += 32) o[j] = src[j];
+        o += len;
+        src = arena + (offsets[r] - off_base) + x.f_start;
+        len = (uint64_t)x.r_end + 1 - x.f_start;
+        for (uint64_t j = lane; j < len; j += 32) o[j] = src[j];
+        if (lane == 0) o[len] = '\n';
+    }
+}
+
+// lens (n_entries + 1 slots) is replaced by exclusive offsets; lens[n_entries] receives the total.
+// sums must hold ceil(n_entries / HX_SCAN_ITEMS) + 1 elements.
+int hx_launch_fasta_offsets(const void *res, const uint64_t *id_off, const uint32_t *tail_off, uint32_t n_pairs,
+                            uint64_t n_entries, uint64_t *lens, uint64_t *sums, cudaStream_t st) {
+    if (n_entries == 0) return 0;
+    const uint32_t nblk = (uint32_t)((n_entries + HX_SCAN_ITEMS - 1) / HX_SCAN_ITEMS);
+    hx_fasta_len_kernel<<<(uint32_t)((n_entries + 255) / 256), 256, 0, st>>>((const HxResultDev *)res, id_off, tail_off,
+                                                                            n_pairs, n_entries, lens);
+    hx_scan_blocks_kernel<<<nblk, 1024, 0, st>>>(lens, n_entries, sums);
+    hx_scan_u64_kernel<<<1, 1024, 0, st>>>(sums, nblk);  // exclusive scan of the block totals, grand total at sums[nblk]
+    hx_scan_add_kernel<<<nblk, 1024, 0, st>>>(lens, n_entries, sums);
+    return 4;
+}
+
+int hx_launch_fasta_write(const uint8_t *arena, const uint64_t *offsets, uint64_t off_base, const void *res,
+                          const uint8_t *ids, const uint64_t *id_off, const uint8_t *tails, const uint32_t *tail_off,
+                          uint32_t n_pairs, uint64_t n_entries, const uint64_t *where, uint8_t *out, cudaStream_t st) {
+    if (n_entries == 0) return 0;
+    uint64_t blocks = (n_entries * 32 + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    hx_fasta_write_kernel<<<(uint32_t)blocks, 256, 0, st>>>(arena, offsets, off_base, (const HxResultDev *)res, ids, id_off,
+                                                           tails, tail_off, n_pairs, n_entries, where, out);
+    return 1;
+}

@@ -86,6 +86,18 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value);
 int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
                  hx_result *out);
 
+/* hx_run_batch plus on-device extraction: besides the result table, the FASTA text that
+ * utils.rs:354-369 writes for the batch is assembled on the GPU and returned in pinned host memory owned by the
+ * context (valid until the next call on ctx), so the host only has to write() it.
+ *   ids / id_off[n_records + 1]   record ids, concatenated (no separators)
+ *   tails / tail_off[n_pairs + 1] per pair the text that follows the id, up to and including the '\n'
+ *                                 (" region=v3v4 forward=... reverse=...\n", utils.rs:356-363)
+ * Entries appear in output order (record-major, pair order); a (record, pair) without a region contributes
+ * nothing.  Runs on the context's first device. */
+int hx_run_batch_fasta(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out,
+                       const char *ids, const uint64_t *id_off, const char *tails, const uint32_t *tail_off,
+                       const char **text, uint64_t *text_len);
+
 /* Same, for an arena already resident in device memory of the context's device `dev_slot`
  * (index into dev_ids).  d_arena must be 16-byte aligned and readable up to the next
  * multiple of 16 bytes past offsets[n_records]; d_out is device memory.  Work is enqueued on

@@ -285,6 +285,35 @@ def test_device_resident_entry_point(ctx):
     _cmp(res, ref, a, o, pairs, 0)
 
 
+def _fa_tails(pairs):
+    tails = []
+    for f, r in pairs:
+        lab = O.primers_to_region(f, r)
+        tails.append((f" region={lab}" if lab else "") + f" forward={f} reverse={r}\n")
+    return tails
+
+
+@pytest.mark.parametrize("k,tile", [(0, 0), (2, 0), (3, 128)])
+def test_on_device_fasta_extraction(ctx, k, tile):
+    """the FASTA text assembled on the GPU equals the oracle's bytes (original case, output order)"""
+    a, o = hx_synth.gen_reads_mutated(900, seed=140 + k, max_edits=2, revcomp_frac=0.3, lower_frac=0.5, rna_frac=0.1,
+                                      lmin=1, lmax=1200)
+    ids = [f"id{i}" if i % 3 else f"a_much_longer_identifier_{i}" for i in range(900)]
+    pairs = hx.default_primers() + [["ACGTACGTAC", "TTGACA"]]
+    for name in ("tile_len", "single_max"):
+        ctx.set_option(name, tile)
+    ctx.set_primers(pairs, k)
+    res, text = ctx.run_batch_fasta(a, o, ids, _fa_tails(pairs))
+    ref = O.run_batch(a, o, pairs, k, nthreads=8)
+    _cmp(res, ref, a, o, pairs, k)
+    fa, _gff = O.format_outputs(a, o, ids, pairs, ref)
+    assert text == fa
+    # a batch without any region gives an empty text
+    a2, o2 = hx_synth.pack([b"", b"T", b"XX"])
+    res2, text2 = ctx.run_batch_fasta(a2, o2, ["x", "y", "z"], _fa_tails(pairs))
+    assert text2 == b"" and not (res2["flags"] & 4).any()
+
+
 # ---- file-level seam: FASTA in, FASTA + GFF3 bytes out ---------------------------------------------------
 @pytest.mark.parametrize("k,codec", [(0, "plain"), (2, "gz"), (3, "xz")])
 def test_get_hypervar_regions_bytes(ctx, tmp_path, k, codec):
