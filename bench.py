@@ -68,12 +68,13 @@ def pairs_and_cells():
 
 
 def make_workload(name, n, rank, k_arg):
-    """(arena, offsets, pairs, k, description) for one rank; shapes follow BASELINE.json configs[1..4]"""
+    """(arena, offsets, pairs, k, description) for one rank; shapes follow BASELINE.json configs[1..4].
+    The primer tables come from the product's own host helpers (the oracle is only used by the CPU legs)."""
     import hx_synth
-    from oracle import oracle as O
+    import hyperex_b200 as O  # default_primers / region_to_primer / to_reverse_complement of the product
     if name == "c2":
         a, o = hx_synth.gen_reads(n, seed=2 + 1000 * rank)
-        return a, o, O.default_pairs(), 0 if k_arg < 0 else k_arg, (
+        return a, o, O.default_primers(), 0 if k_arg < 0 else k_arg, (
             "c2: 1M synthetic full-length 16S reads ~1.5 kb per GPU, 10 built-in regions (20 searches/base, "
             "393 cells/base), -m 0")
     if name == "c3":
@@ -90,10 +91,10 @@ def make_workload(name, n, rank, k_arg):
     if name == "c4":
         nc = max(1, n // 15625)  # n = 1M -> 64 contigs of 5 Mb
         a, o = hx_synth.gen_contigs(nc, seed=4 + 1000 * rank, length=5_000_000)
-        return a, o, O.default_pairs(), 3 if k_arg < 0 else k_arg, (
+        return a, o, O.default_primers(), 3 if k_arg < 0 else k_arg, (
             f"c4: {nc} soft-masked 5 Mb contigs with multi-copy rRNA operons, 10 built-in regions, -m 3, windows")
     a, o = hx_synth.gen_reads(n, seed=5 + 1000 * rank)
-    pairs = hx_synth.gen_primer_pairs(54, seed=5, builtins=O.default_pairs())
+    pairs = hx_synth.gen_primer_pairs(54, seed=5, builtins=O.default_primers())
     return a, o, pairs, 2 if k_arg < 0 else k_arg, (
         f"c5: {n} SILVA-scale 16S records per GPU + 64-pair primer CSV (some primers > 32 nt), -m 2")
 
