@@ -233,33 +233,26 @@ __global__ void __launch_bounds__(256) hx_classify_kernel(const uint8_t *__restr
         const uint64_t s = offsets[tl.rec] - off_base + tl.own_start;
         const uint64_t e = s + tl.own_len;
         uint32_t zu = 0, zt = 0;
-        // four 16-byte loads per lane in flight (2 KB per warp and trip) before any of them is consumed
-        for (uint64_t A0 = (s & ~15ull) + lane * 16ull; A0 < e; A0 += 2048ull) {
-            uint4 v[4];
+        // (issuing four loads per lane before consuming them measured slower: 0.97 vs 0.70 ms per 1.5 GB)
+        for (uint64_t A = (s & ~15ull) + lane * 16ull; A < e; A += 512ull) {
+            const uint4 v = hx_ldg16(arena + A);
+            const bool full = A >= s && A + 16 <= e;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                v[u] = (A0 + 512ull * u < e) ? hx_ldg16(arena + A0 + 512ull * u) : make_uint4(0, 0, 0, 0);
+            for (int wi = 0; wi < 4; ++wi) {
+                uint32_t w = hx_w32(v, wi);
+                if (!full) {  // clear the bytes outside [s, e): 0x00 | 0x20 is neither 'u' nor 't'
+                    uint32_t keep = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint64_t A = A0 + 512ull * u;
-                const bool full = A >= s && A + 16 <= e;
-#pragma unroll
-                for (int wi = 0; wi < 4; ++wi) {
-                    uint32_t w = hx_w32(v[u], wi);
-                    if (!full) {  // clear the bytes outside [s, e): 0x00 | 0x20 is neither 'u' nor 't'
-                        uint32_t keep = 0;
-#pragma unroll
-                        for (int bi = 0; bi < 4; ++bi) {
-                            const uint64_t pos = A + wi * 4 + bi;
-                            if (pos >= s && pos < e) keep |= 0xffu << (8 * bi);
-                        }
-                        w &= keep;
+                    for (int bi = 0; bi < 4; ++bi) {
+                        const uint64_t pos = A + wi * 4 + bi;
+                        if (pos >= s && pos < e) keep |= 0xffu << (8 * bi);
                     }
-                    const uint32_t lw = w | 0x20202020u;
-                    const uint32_t xu = lw ^ 0x75757575u, xt = lw ^ 0x74747474u;
-                    zu |= (xu - 0x01010101u) & ~xu;
-                    zt |= (xt - 0x01010101u) & ~xt;
+                    w &= keep;
                 }
+                const uint32_t lw = w | 0x20202020u;
+                const uint32_t xu = lw ^ 0x75757575u, xt = lw ^ 0x74747474u;
+                zu |= (xu - 0x01010101u) & ~xu;
+                zt |= (xt - 0x01010101u) & ~xt;
             }
         }
         uint32_t f = ((zu & 0x80808080u) ? HX_RAW_U : 0u) | ((zt & 0x80808080u) ? HX_RAW_T : 0u);
