@@ -55,7 +55,7 @@ struct Slot {
     DevBuf<uint8_t> arena;
     DevBuf<uint64_t> offsets;
     DevBuf<uint32_t> rec_u32;  // rec_raw | tile_first | tile_cnt | long_list   (4 x rec_cap)
-    DevBuf<uint32_t> scratch;  // ntiles, overflow, n_long, pad, hist[NB], cursor[NB]
+    DevBuf<uint32_t> scratch;  // ntiles, overflow, n_long, n_plain, hist[NB], cursor[NB]
     DevBuf<HxTile> tiles;
     DevBuf<uint32_t> order;
     DevBuf<uint64_t> sum_f, sum_r, pair_hi;
@@ -231,7 +231,8 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const 
     b.long_list = long_list;
     b.n_long = n_long;
     ctx->launches += hx_launch_tile_build(b, cursor, S.order.p, st);
-    ctx->launches += hx_launch_classify(d_arena, d_offsets, off_base, S.tiles.p, ntiles, pl.tile_cap, rec_raw, st);
+    ctx->launches += hx_launch_classify(d_arena, d_offsets, off_base, S.tiles.p, ntiles, pl.tile_cap, rec_raw, tile_cnt,
+                                        n_records, ntiles + 3, st);  // scratch[3] = n_plain (zeroed with the scratch block)
 
     for (size_t gi = 0; gi < ctx->groups.size(); ++gi) {
         const HxGroup &hg = ctx->groups[gi];

@@ -106,8 +106,9 @@ struct HxBuildArgs {
 
 // launchers (hx_kernels.cu); each returns the number of kernels it launched
 int hx_launch_tile_build(const HxBuildArgs &a, uint32_t *cursor, uint32_t *order, cudaStream_t st);
-int hx_launch_classify(const uint8_t *arena, const uint64_t *offsets, uint64_t off_base, const HxTile *tiles, const uint32_t *ntiles,
-                       uint32_t tile_cap, uint32_t *rec_raw, cudaStream_t st);
+int hx_launch_classify(const uint8_t *arena, const uint64_t *offsets, uint64_t off_base, const HxTile *tiles,
+                       const uint32_t *ntiles, uint32_t tile_cap, uint32_t *rec_raw, const uint32_t *tile_cnt,
+                       uint32_t n_records, uint32_t *n_plain, cudaStream_t st);
 int hx_launch_scan(const HxScanArgs &a, const HxGroup &hostgroup, uint32_t tile_cap, cudaStream_t st);
 int hx_launch_combine(const uint32_t *tile_first, const uint32_t *tile_cnt, const uint32_t *rec_raw,
                       const HxPairRef *pairs, uint32_t n_pairs, uint32_t n_records, const uint64_t *sum_f,

@@ -228,28 +228,45 @@ __global__ void __launch_bounds__(256) hx_classify_kernel(const uint8_t *__restr
     const uint32_t ntiles = min(*ntiles_p, tile_cap);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += warps) {
-        const HxTile tl = tiles[t];
-        const uint64_t s = offsets[tl.rec] - off_base + tl.own_start;
+    // the (tile, record offset) pair of the warp's NEXT tile is fetched while the current tile streams
+    uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    HxTile tl_n = {0u, 0u, 0u, 0u};
+    uint64_t off_n = 0;
+    if (t < ntiles) {
+        tl_n = tiles[t];
+        off_n = offsets[tl_n.rec];
+    }
+    for (; t < ntiles; t += warps) {
+        const HxTile tl = tl_n;
+        const uint64_t s = off_n - off_base + tl.own_start;
         const uint64_t e = s + tl.own_len;
+        if (t + warps < ntiles) {
+            tl_n = tiles[t + warps];
+            off_n = offsets[tl_n.rec];
+        }
         uint32_t zu = 0, zt = 0;
-        // (issuing four loads per lane before consuming them measured slower: 0.97 vs 0.70 ms per 1.5 GB)
+        // (explicit load pipelining — two or four chunks per lane in flight — measured slower: 0.55 / 0.97 ms
+        //  vs 0.50 ms per 1.5 GB; the kernel sits at 3.0 TB/s, 46 % of the measured HBM copy peak)
         for (uint64_t A = (s & ~15ull) + lane * 16ull; A < e; A += 512ull) {
-            const uint4 v = hx_ldg16(arena + A);
-            const bool full = A >= s && A + 16 <= e;
+            uint4 v = hx_ldg16(arena + A);
+            if (!(A >= s && A + 16 <= e)) {
+                // first / last chunk of the tile: clear the bytes outside [s, e) (0x00 | 0x20 is neither 'u'
+                // nor 't').  Kept out of the common path: ncu showed the predicated per-byte version spending
+                // 178 instructions per chunk on a kernel that should be HBM-bound.
+                const int lo = A < s ? (int)(s - A) : 0, hi = e - A < 16 ? (int)(e - A) : 16;
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    const int a = min(max(lo - 4 * wi, 0), 4), b = min(max(hi - 4 * wi, 0), 4);
+                    const uint32_t below_b = b >= 4 ? 0xffffffffu : ((1u << (8 * b)) - 1u);
+                    const uint32_t below_a = a >= 4 ? 0xffffffffu : ((1u << (8 * a)) - 1u);
+                    w[wi] &= below_b & ~below_a;
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
-                uint32_t w = hx_w32(v, wi);
-                if (!full) {  // clear the bytes outside [s, e): 0x00 | 0x20 is neither 'u' nor 't'
-                    uint32_t keep = 0;
-#pragma unroll
-                    for (int bi = 0; bi < 4; ++bi) {
-                        const uint64_t pos = A + wi * 4 + bi;
-                        if (pos >= s && pos < e) keep |= 0xffu << (8 * bi);
-                    }
-                    w &= keep;
-                }
-                const uint32_t lw = w | 0x20202020u;
+                const uint32_t lw = hx_w32(v, wi) | 0x20202020u;
                 const uint32_t xu = lw ^ 0x75757575u, xt = lw ^ 0x74747474u;
                 zu |= (xu - 0x01010101u) & ~xu;
                 zt |= (xt - 0x01010101u) & ~xt;
@@ -261,12 +278,24 @@ __global__ void __launch_bounds__(256) hx_classify_kernel(const uint8_t *__restr
     }
 }
 
+// counts the records that have text but neither 'U' nor 'T' (the only ones pass 2 has to look at)
+__global__ void __launch_bounds__(256) hx_count_plain_kernel(const uint32_t *__restrict__ rec_raw,
+                                                             const uint32_t *__restrict__ tile_cnt, uint32_t n_records,
+                                                             uint32_t *__restrict__ n_plain) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool plain = r < n_records && tile_cnt[r] != 0u && !(rec_raw[r] & (HX_RAW_U | HX_RAW_T));
+    const uint32_t m = __ballot_sync(0xffffffffu, plain);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_plain, (uint32_t)__popc(m));
+}
+
 __global__ void __launch_bounds__(256) hx_classify_iupac_kernel(const uint8_t *__restrict__ arena,
                                                                 const uint64_t *__restrict__ offsets,
                                                                 const uint64_t off_base,
                                                                 const HxTile *__restrict__ tiles,
                                                                 const uint32_t *__restrict__ ntiles_p, uint32_t tile_cap,
+                                                                const uint32_t *__restrict__ n_plain,
                                                                 uint32_t *__restrict__ rec_raw) {
+    if (*n_plain == 0u) return;  // every record has a 'U' or a 'T': nothing to check (the usual case)
     __shared__ uint8_t bad[256];  // 1: byte is not in "ACGTRYSWKMBDHVN" after to_ascii_uppercase
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const int u = (i >= 'a' && i <= 'z') ? i - 32 : i;
@@ -305,13 +334,16 @@ __global__ void __launch_bounds__(256) hx_classify_iupac_kernel(const uint8_t *_
 }
 
 int hx_launch_classify(const uint8_t *arena, const uint64_t *offsets, uint64_t off_base, const HxTile *tiles,
-                       const uint32_t *ntiles, uint32_t tile_cap, uint32_t *rec_raw, cudaStream_t st) {
+                       const uint32_t *ntiles, uint32_t tile_cap, uint32_t *rec_raw, const uint32_t *tile_cnt,
+                       uint32_t n_records, uint32_t *n_plain, cudaStream_t st) {
     if (tile_cap == 0) return 0;
     uint64_t blocks = ((uint64_t)tile_cap * 32 + 255) / 256;
     if (blocks > 148 * 8 * 4) blocks = 148 * 8 * 4;
     hx_classify_kernel<<<(uint32_t)blocks, 256, 0, st>>>(arena, offsets, off_base, tiles, ntiles, tile_cap, rec_raw);
-    hx_classify_iupac_kernel<<<(uint32_t)blocks, 256, 0, st>>>(arena, offsets, off_base, tiles, ntiles, tile_cap, rec_raw);
-    return 2;
+    hx_count_plain_kernel<<<(n_records + 255) / 256, 256, 0, st>>>(rec_raw, tile_cnt, n_records, n_plain);
+    hx_classify_iupac_kernel<<<(uint32_t)blocks, 256, 0, st>>>(arena, offsets, off_base, tiles, ntiles, tile_cap, n_plain,
+                                                               rec_raw);
+    return 3;
 }
 
 // ------------------------------------------------------------------------------------
