@@ -144,6 +144,19 @@ def test_c4_softmasked_contigs_windows(ctx, tile_len, single_max, text_tma):
     _cmp(_run(ctx, a, o, pairs, 3, tile_len=tile_len, single_max=single_max, text_tma=text_tma), ref, a, o, pairs, 3)
 
 
+def test_c4_megabase_contigs(ctx):
+    """BASELINE.json config 4 at a size the oracle still finishes in seconds: 2 Mb contigs, ~1000 windows each,
+    warp-cooperative tile build and the warp-parallel join of hx_combine_long_kernel"""
+    a, o = hx_synth.gen_contigs(3, seed=43, length=2_000_000, copies=(4, 7), n_runs=4)
+    pairs = hx.default_primers()
+    ref = O.run_batch(a, o, pairs, 3, nthreads=8)
+    assert (ref["flags"] & 4).any()
+    for fast, tma in ((0, 0), (0, 1)):
+        _cmp(_run(ctx, a, o, pairs, 3, fast=fast, text_tma=tma), ref, a, o, pairs, 3)
+    ref1 = O.run_batch(a, o, pairs, 1, nthreads=8)
+    _cmp(_run(ctx, a, o, pairs, 1, fast=1), ref1, a, o, pairs, 1)
+
+
 def test_c5_primer_csv_64_pairs(ctx):
     pairs = hx_synth.gen_primer_pairs(54, seed=5, builtins=O.default_pairs())
     assert len(pairs) == 64 and any(len(p[0]) > 32 or len(p[1]) > 32 for p in pairs)
