@@ -244,35 +244,33 @@ __global__ void __launch_bounds__(256) hx_classify_kernel(const uint8_t *__restr
             tl_n = tiles[t + warps];
             off_n = offsets[tl_n.rec];
         }
-        uint32_t zu = 0, zt = 0;
-        // (explicit load pipelining — two or four chunks per lane in flight — measured slower: 0.55 / 0.97 ms
-        //  vs 0.50 ms per 1.5 GB; the kernel sits at 3.0 TB/s, 46 % of the measured HBM copy peak)
-        for (uint64_t A = (s & ~15ull) + lane * 16ull; A < e; A += 512ull) {
-            uint4 v = hx_ldg16(arena + A);
-            if (!(A >= s && A + 16 <= e)) {
-                // first / last chunk of the tile: clear the bytes outside [s, e) (0x00 | 0x20 is neither 'u'
-                // nor 't').  Kept out of the common path: ncu showed the predicated per-byte version spending
-                // 178 instructions per chunk on a kernel that should be HBM-bound.
-                const int lo = A < s ? (int)(s - A) : 0, hi = e - A < 16 ? (int)(e - A) : 16;
-                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t zu = 0, zt = 0, f = 0;
+        // Interior: whole 16-byte chunks, no per-chunk range test (ncu: the masked first/last chunk and the 64-bit
+        // range compares were half of the instructions of a kernel that should be HBM-bound).  Head and tail
+        // bytes (< 16 each) are checked one byte per lane.  (Explicit load pipelining — two or four chunks per
+        // lane in flight — measured slower.)
+        const uint64_t a_lo = (s + 15ull) & ~15ull, a_hi = e & ~15ull;
+        if (a_lo <= a_hi) {
+            for (uint64_t A = a_lo + lane * 16ull; A < a_hi; A += 512ull) {
+                const uint4 v = hx_ldg16(arena + A);
 #pragma unroll
                 for (int wi = 0; wi < 4; ++wi) {
-                    const int a = min(max(lo - 4 * wi, 0), 4), b = min(max(hi - 4 * wi, 0), 4);
-                    const uint32_t below_b = b >= 4 ? 0xffffffffu : ((1u << (8 * b)) - 1u);
-                    const uint32_t below_a = a >= 4 ? 0xffffffffu : ((1u << (8 * a)) - 1u);
-                    w[wi] &= below_b & ~below_a;
+                    const uint32_t lw = hx_w32(v, wi) | 0x20202020u;
+                    const uint32_t xu = lw ^ 0x75757575u, xt = lw ^ 0x74747474u;
+                    zu |= (xu - 0x01010101u) & ~xu;
+                    zt |= (xt - 0x01010101u) & ~xt;
                 }
-                v = make_uint4(w[0], w[1], w[2], w[3]);
             }
-#pragma unroll
-            for (int wi = 0; wi < 4; ++wi) {
-                const uint32_t lw = hx_w32(v, wi) | 0x20202020u;
-                const uint32_t xu = lw ^ 0x75757575u, xt = lw ^ 0x74747474u;
-                zu |= (xu - 0x01010101u) & ~xu;
-                zt |= (xt - 0x01010101u) & ~xt;
+            const uint64_t p = lane < 16u ? s + lane : a_hi + (lane - 16u);
+            if (lane < 16u ? p < a_lo : p < e) {
+                const uint32_t c = arena[p] | 0x20u;
+                f |= (c == 'u' ? HX_RAW_U : 0u) | (c == 't' ? HX_RAW_T : 0u);
             }
+        } else if (s + lane < e) {  // the whole tile lies inside one 16-byte chunk
+            const uint32_t c = arena[s + lane] | 0x20u;
+            f |= (c == 'u' ? HX_RAW_U : 0u) | (c == 't' ? HX_RAW_T : 0u);
         }
-        uint32_t f = ((zu & 0x80808080u) ? HX_RAW_U : 0u) | ((zt & 0x80808080u) ? HX_RAW_T : 0u);
+        f |= ((zu & 0x80808080u) ? HX_RAW_U : 0u) | ((zt & 0x80808080u) ? HX_RAW_T : 0u);
         f = __reduce_or_sync(0xffffffffu, f);
         if (lane == 0 && f) atomicOr(&rec_raw[tl.rec], f);
     }
