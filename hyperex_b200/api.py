@@ -203,6 +203,33 @@ class Context:
                                                C.byref(tlen)))
         return out, (C.string_at(text.value, tlen.value) if tlen.value else b"")
 
+    def run_batch_text(self, arena: np.ndarray, offsets: np.ndarray, ids: Sequence[str], fa_tails: Sequence[str],
+                       gff_tails: Sequence[str]):
+        """hx_run_batch_text: (results, fasta_bytes, gff_bytes) — both output texts assembled on the GPU"""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        out = np.zeros((n, self.n_pairs), dtype=RESULT_DTYPE)
+        idb = [_b(i) for i in ids]
+        id_off = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            id_off[1:] = np.cumsum([len(x) for x in idb])
+
+        def blob(items):
+            bs = [_b(t) for t in items]
+            off = np.zeros(len(bs) + 1, dtype=np.uint32)
+            off[1:] = np.cumsum([len(x) for x in bs])
+            return b"".join(bs), off
+
+        fb, fo = blob(fa_tails)
+        gb, go = blob(gff_tails)
+        ft, fl, gt, gl = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+        ap = arena.ctypes.data if arena is not None and arena.size else None
+        self._check(self._L.hx_run_batch_text(self._h, ap, offsets.ctypes.data, n, out.ctypes.data, b"".join(idb),
+                                              id_off.ctypes.data, fb, fo.ctypes.data, gb, go.ctypes.data, C.byref(ft),
+                                              C.byref(fl), C.byref(gt), C.byref(gl)))
+        return (out, C.string_at(ft.value, fl.value) if fl.value else b"",
+                C.string_at(gt.value, gl.value) if gl.value else b"")
+
     def run_batch_device(self, d_arena: int, d_offsets: int, n_records: int, arena_bytes: int, d_out: int,
                          stream: int = 0, dev_slot: int = 0):
         """hx_run_batch_device on raw device pointers (ints); asynchronous when stream != 0"""

@@ -104,11 +104,11 @@ struct hx_ctx {
     int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1;
     uint64_t launches = 0;
     // on-device extraction (device 0)
-    DevBuf<uint8_t> ex_ids, ex_tails, ex_text;
-    DevBuf<uint64_t> ex_id_off, ex_lens, ex_sums;
-    DevBuf<uint32_t> ex_tail_off;
-    uint8_t *ex_host = nullptr;
-    size_t ex_host_cap = 0;
+    DevBuf<uint8_t> ex_ids, ex_tails, ex_text, ex_gtails, ex_gtext;
+    DevBuf<uint64_t> ex_id_off, ex_lens, ex_sums, ex_glens, ex_gsums;
+    DevBuf<uint32_t> ex_tail_off, ex_gtail_off;
+    uint8_t *ex_host = nullptr, *ex_ghost = nullptr;
+    size_t ex_host_cap = 0, ex_ghost_cap = 0;
     std::vector<TimedLaunch> timed;
     double myers_ms = 0;
     uint64_t myers_launches = 0;
@@ -340,7 +340,10 @@ void hx_destroy(hx_ctx *ctx) {
     if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].dev);
     ctx->ex_ids.release(); ctx->ex_tails.release(); ctx->ex_text.release(); ctx->ex_id_off.release();
     ctx->ex_lens.release(); ctx->ex_sums.release(); ctx->ex_tail_off.release();
+    ctx->ex_gtails.release(); ctx->ex_gtext.release(); ctx->ex_glens.release(); ctx->ex_gsums.release();
+    ctx->ex_gtail_off.release();
     if (ctx->ex_host) cudaFreeHost(ctx->ex_host);
+    if (ctx->ex_ghost) cudaFreeHost(ctx->ex_ghost);
     for (Device &D : ctx->devs) {
         cudaSetDevice(D.dev);
         cudaDeviceSynchronize();
@@ -552,8 +555,19 @@ int hx_run_batch_device(hx_ctx *ctx, int dev_slot, const uint8_t *d_arena, const
 int hx_run_batch_fasta(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out,
                        const char *ids, const uint64_t *id_off, const char *tails, const uint32_t *tail_off,
                        const char **text, uint64_t *text_len) {
+    return hx_run_batch_text(ctx, arena, offsets, n_records, out, ids, id_off, tails, tail_off, nullptr, nullptr, text,
+                             text_len, nullptr, nullptr);
+}
+
+int hx_run_batch_text(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out,
+                      const char *ids, const uint64_t *id_off, const char *tails, const uint32_t *tail_off,
+                      const char *gff_tails, const uint32_t *gff_tail_off, const char **text, uint64_t *text_len,
+                      const char **gff_text, uint64_t *gff_len) {
     if (!ctx) return HX_ERR_ARG;
-    if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch_fasta: call hx_set_primers first");
+    const bool want_gff = gff_tails && gff_tail_off && gff_text && gff_len;
+    if (gff_text) *gff_text = nullptr;
+    if (gff_len) *gff_len = 0;
+    if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch_text: call hx_set_primers first");
     if (!text || !text_len) return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: NULL text/text_len");
     *text = nullptr;
     *text_len = 0;
@@ -583,6 +597,16 @@ int hx_run_batch_fasta(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offset
     HX_CUDA(ctx, ctx->ex_tail_off.reserve(np + 1));
     HX_CUDA(ctx, ctx->ex_lens.reserve(n_entries + 1));
     HX_CUDA(ctx, ctx->ex_sums.reserve(nblk + 2));
+    if (want_gff) {
+        if (gff_tail_off[0] != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: gff_tail_off must start at 0");
+        HX_CUDA(ctx, ctx->ex_gtails.reserve(gff_tail_off[np] + 16));
+        HX_CUDA(ctx, ctx->ex_gtail_off.reserve(np + 1));
+        HX_CUDA(ctx, ctx->ex_glens.reserve(n_entries + 1));
+        HX_CUDA(ctx, ctx->ex_gsums.reserve(nblk + 2));
+        if (gff_tail_off[np])
+            HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_gtails.p, gff_tails, gff_tail_off[np], cudaMemcpyHostToDevice, st));
+        HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_gtail_off.p, gff_tail_off, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, st));
+    }
     if (copy_bytes) HX_CUDA(ctx, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, st));
     HX_CUDA(ctx, cudaMemcpyAsync(S.offsets.p, offsets, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, st));
     if (id_bytes) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_ids.p, ids, id_bytes, cudaMemcpyHostToDevice, st));
@@ -595,9 +619,13 @@ int hx_run_batch_fasta(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offset
     ctx->launches += hx_launch_fasta_offsets(S.out.p, ctx->ex_id_off.p, ctx->ex_tail_off.p, np, n_entries, ctx->ex_lens.p,
                                              ctx->ex_sums.p, st);
     // total = offset of the last entry + its length = block offset + in-block prefix; read both pieces
-    uint64_t total = 0, last_off = 0;
+    uint64_t total = 0, gtotal = 0;
     HX_CUDA(ctx, cudaMemcpyAsync(&total, ctx->ex_sums.p + nblk, 8, cudaMemcpyDeviceToHost, st));
-    (void)last_off;
+    if (want_gff) {
+        ctx->launches += hx_launch_gff_offsets(S.out.p, ctx->ex_id_off.p, ctx->ex_gtail_off.p, np, n_entries,
+                                               ctx->ex_glens.p, ctx->ex_gsums.p, st);
+        HX_CUDA(ctx, cudaMemcpyAsync(&gtotal, ctx->ex_gsums.p + nblk, 8, cudaMemcpyDeviceToHost, st));
+    }
     HX_CUDA(ctx, cudaStreamSynchronize(st));
     rc = check_status(ctx, S);
     if (rc != HX_OK) return rc;
@@ -615,12 +643,32 @@ int hx_run_batch_fasta(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offset
                                                ctx->ex_tails.p, ctx->ex_tail_off.p, np, n_entries, ctx->ex_lens.p,
                                                ctx->ex_text.p, st);
         HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_host, ctx->ex_text.p, total, cudaMemcpyDeviceToHost, st));
+    }
+    if (gtotal) {
+        HX_CUDA(ctx, ctx->ex_gtext.reserve(gtotal + 16));
+        if (gtotal > ctx->ex_ghost_cap) {
+            if (ctx->ex_ghost) cudaFreeHost(ctx->ex_ghost);
+            ctx->ex_ghost = nullptr;
+            ctx->ex_ghost_cap = 0;
+            const size_t want = (size_t)(gtotal + gtotal / 4 + 4096);
+            HX_CUDA(ctx, cudaHostAlloc((void **)&ctx->ex_ghost, want, cudaHostAllocDefault));
+            ctx->ex_ghost_cap = want;
+        }
+        ctx->launches += hx_launch_gff_write(S.out.p, ctx->ex_ids.p, ctx->ex_id_off.p, ctx->ex_gtails.p,
+                                             ctx->ex_gtail_off.p, np, n_entries, ctx->ex_glens.p, ctx->ex_gtext.p, st);
+        HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_ghost, ctx->ex_gtext.p, gtotal, cudaMemcpyDeviceToHost, st));
+    }
+    if (total || gtotal) {
         HX_CUDA(ctx, cudaStreamSynchronize(st));
         HX_CUDA(ctx, cudaGetLastError());
     }
     sync_timed(ctx);
     *text = (const char *)ctx->ex_host;
     *text_len = total;
+    if (want_gff) {
+        *gff_text = (const char *)ctx->ex_ghost;
+        *gff_len = gtotal;
+    }
     return HX_OK;
 }
 

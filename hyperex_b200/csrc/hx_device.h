@@ -124,3 +124,8 @@ int hx_launch_fasta_offsets(const void *res, const uint64_t *id_off, const uint3
 int hx_launch_fasta_write(const uint8_t *arena, const uint64_t *offsets, uint64_t off_base, const void *res,
                           const uint8_t *ids, const uint64_t *id_off, const uint8_t *tails, const uint32_t *tail_off,
                           uint32_t n_pairs, uint64_t n_entries, const uint64_t *where, uint8_t *out, cudaStream_t st);
+int hx_launch_gff_offsets(const void *res, const uint64_t *id_off, const uint32_t *tail_off, uint32_t n_pairs,
+                          uint64_t n_entries, uint64_t *lens, uint64_t *sums, cudaStream_t st);
+int hx_launch_gff_write(const void *res, const uint8_t *ids, const uint64_t *id_off, const uint8_t *tails,
+                        const uint32_t *tail_off, uint32_t n_pairs, uint64_t n_entries, const uint64_t *where, uint8_t *out,
+                        cudaStream_t st);

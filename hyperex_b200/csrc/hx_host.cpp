@@ -690,12 +690,14 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
     // On-device extraction: with one GPU the FASTA text itself is assembled on the device and the
     // host only write()s it; HYPEREX_HOST_FORMAT=1 (or a multi-GPU context) keeps the host formatter.
     const bool device_fasta = hxh_device_count(ctx) == 1 && getenv("HYPEREX_HOST_FORMAT") == nullptr;
-    std::string tails_blob, ids_blob;
-    std::vector<uint32_t> tail_off(1, 0);
+    std::string tails_blob, gtails_blob, ids_blob;
+    std::vector<uint32_t> tail_off(1, 0), gtail_off(1, 0);
     std::vector<uint64_t> id_off;
     for (uint32_t p = 0; p < n_pairs; ++p) {
         tails_blob += fa_tail[p];
         tail_off.push_back((uint32_t)tails_blob.size());
+        gtails_blob += gff_note[p];
+        gtail_off.push_back((uint32_t)gtails_blob.size());
     }
     // HYPEREX_TIMING=1 prints where the wall time of the file-level path goes
     const bool timing = getenv("HYPEREX_TIMING") != nullptr;
@@ -750,8 +752,8 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
         const uint32_t n = (uint32_t)batch.ids.size();
         n_bases += batch.offsets[n];
         res.resize((size_t)n * n_pairs);
-        const char *dev_text = nullptr;
-        uint64_t dev_text_len = 0;
+        const char *dev_text = nullptr, *dev_gff = nullptr;
+        uint64_t dev_text_len = 0, dev_gff_len = 0;
         if (device_fasta) {
             ids_blob.clear();
             id_off.assign(1, 0);
@@ -759,8 +761,9 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
                 ids_blob += id;
                 id_off.push_back(ids_blob.size());
             }
-            rc = hx_run_batch_fasta(ctx, batch.arena, batch.offsets.data(), n, res.data(), ids_blob.data(), id_off.data(),
-                                    tails_blob.data(), tail_off.data(), &dev_text, &dev_text_len);
+            rc = hx_run_batch_text(ctx, batch.arena, batch.offsets.data(), n, res.data(), ids_blob.data(), id_off.data(),
+                                   tails_blob.data(), tail_off.data(), gtails_blob.data(), gtail_off.data(), &dev_text,
+                                   &dev_text_len, &dev_gff, &dev_gff_len);
         } else {
             rc = hx_run_batch(ctx, batch.arena, batch.offsets.data(), n, res.data());
         }
@@ -801,17 +804,19 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
                             *o++ = '\n';
                             fo.n = (size_t)(o - fo.v.data());
                         }
-                        char *g = go.reserve(id.size() + 48 + gff_note[p].size());
-                        memcpy(g, id.data(), id.size());
-                        g += id.size();
-                        memcpy(g, "\thyperex\tregion\t", 16);
-                        g += 16;
-                        g += put_u32(g, x.f_start + 1);  // 1-based (utils.rs:382-383)
-                        *g++ = '\t';
-                        g += put_u32(g, x.r_end + 1);
-                        memcpy(g, gff_note[p].data(), gff_note[p].size());
-                        g += gff_note[p].size();
-                        go.n = (size_t)(g - go.v.data());
+                        if (!device_fasta) {
+                            char *g = go.reserve(id.size() + 48 + gff_note[p].size());
+                            memcpy(g, id.data(), id.size());
+                            g += id.size();
+                            memcpy(g, "\thyperex\tregion\t", 16);
+                            g += 16;
+                            g += put_u32(g, x.f_start + 1);  // 1-based (utils.rs:382-383)
+                            *g++ = '\t';
+                            g += put_u32(g, x.r_end + 1);
+                            memcpy(g, gff_note[p].data(), gff_note[p].size());
+                            g += gff_note[p].size();
+                            go.n = (size_t)(g - go.v.data());
+                        }
                     } else if (log_fn) {  // utils.rs:387-408
                         if (f_any && r_any)
                             msg = "Forward and reverse primers for region " + labels[p] + " were both found in sequence " +
@@ -828,9 +833,13 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
                     }
                 }
             }
-            if (device_fasta && dev_text_len) {  // the GPU produced the FASTA bytes of this batch
+            if (device_fasta && dev_text_len) {  // the GPU produced the FASTA and GFF3 bytes of this batch
                 fo.flush();
                 if (fwrite(dev_text, 1, dev_text_len, fa) != dev_text_len) fo.ok = false;
+            }
+            if (device_fasta && dev_gff_len) {
+                go.flush();
+                if (fwrite(dev_gff, 1, dev_gff_len, gff) != dev_gff_len) go.ok = false;
             }
             if (!fo.ok || !go.ok) rc = HX_ERR_IO;
         }

@@ -1199,3 +1199,94 @@ int hx_launch_fasta_write(const uint8_t *arena, const uint64_t *offsets, uint64_
                                                            tails, tail_off, n_pairs, n_entries, where, out);
     return 1;
 }
+
+// ---- GFF3 lines of utils.rs:378-385 on the device: id \t hyperex \t region \t start \t end <tail>, 1-based ----
+__device__ __forceinline__ uint32_t hx_digits10(uint32_t v) {
+    uint32_t d = 1;
+    while (v >= 10u) {
+        v /= 10u;
+        ++d;
+    }
+    return d;
+}
+
+__global__ void __launch_bounds__(256)
+    hx_gff_len_kernel(const HxResultDev *__restrict__ res, const uint64_t *__restrict__ id_off,
+                      const uint32_t *__restrict__ tail_off, uint32_t n_pairs, uint64_t n_entries,
+                      uint64_t *__restrict__ lens) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_entries) return;
+    const HxResultDev x = res[i];
+    uint64_t len = 0;
+    if ((x.meta & 7u) == 7u) {
+        const uint64_t r = i / n_pairs;
+        const uint32_t p = (uint32_t)(i % n_pairs);
+        len = (id_off[r + 1] - id_off[r]) + 16 /* "\thyperex\tregion\t" */ + hx_digits10(x.f_start + 1u) + 1 +
+              hx_digits10(x.r_end + 1u) + (tail_off[p + 1] - tail_off[p]);
+    }
+    lens[i] = len;
+}
+
+__global__ void __launch_bounds__(256)
+    hx_gff_write_kernel(const HxResultDev *__restrict__ res, const uint8_t *__restrict__ ids,
+                        const uint64_t *__restrict__ id_off, const uint8_t *__restrict__ tails,
+                        const uint32_t *__restrict__ tail_off, uint32_t n_pairs, uint64_t n_entries,
+                        const uint64_t *__restrict__ where, uint8_t *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_entries; i += warps) {
+        const HxResultDev x = res[i];
+        if ((x.meta & 7u) != 7u) continue;
+        const uint64_t r = i / n_pairs;
+        const uint32_t p = (uint32_t)(i % n_pairs);
+        uint8_t *o = out + where[i];
+        const uint8_t *src = ids + id_off[r];
+        uint64_t len = id_off[r + 1] - id_off[r];
+        for (uint64_t j = lane; j < len; j += 32) o[j] = src[j];
+        o += len;
+        const uint32_t a = x.f_start + 1u, b = x.r_end + 1u;
+        const uint32_t da = hx_digits10(a), db = hx_digits10(b);
+        if (lane < 16u) o[lane] = (uint8_t)"\thyperex\tregion\t"[lane];
+        o += 16;
+        if (lane == 0) {
+            uint32_t v = a;
+            for (int j = (int)da - 1; j >= 0; --j) {
+                o[j] = (uint8_t)('0' + v % 10u);
+                v /= 10u;
+            }
+            o[da] = '\t';
+            v = b;
+            for (int j = (int)db - 1; j >= 0; --j) {
+                o[da + 1 + j] = (uint8_t)('0' + v % 10u);
+                v /= 10u;
+            }
+        }
+        o += da + 1 + db;
+        src = tails + tail_off[p];
+        len = tail_off[p + 1] - tail_off[p];
+        for (uint64_t j = lane; j < len; j += 32) o[j] = src[j];
+    }
+}
+
+int hx_launch_gff_offsets(const void *res, const uint64_t *id_off, const uint32_t *tail_off, uint32_t n_pairs,
+                          uint64_t n_entries, uint64_t *lens, uint64_t *sums, cudaStream_t st) {
+    if (n_entries == 0) return 0;
+    const uint32_t nblk = (uint32_t)((n_entries + HX_SCAN_ITEMS - 1) / HX_SCAN_ITEMS);
+    hx_gff_len_kernel<<<(uint32_t)((n_entries + 255) / 256), 256, 0, st>>>((const HxResultDev *)res, id_off, tail_off,
+                                                                          n_pairs, n_entries, lens);
+    hx_scan_blocks_kernel<<<nblk, 1024, 0, st>>>(lens, n_entries, sums);
+    hx_scan_u64_kernel<<<1, 1024, 0, st>>>(sums, nblk);
+    hx_scan_add_kernel<<<nblk, 1024, 0, st>>>(lens, n_entries, sums);
+    return 4;
+}
+
+int hx_launch_gff_write(const void *res, const uint8_t *ids, const uint64_t *id_off, const uint8_t *tails,
+                        const uint32_t *tail_off, uint32_t n_pairs, uint64_t n_entries, const uint64_t *where, uint8_t *out,
+                        cudaStream_t st) {
+    if (n_entries == 0) return 0;
+    uint64_t blocks = (n_entries * 32 + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    hx_gff_write_kernel<<<(uint32_t)blocks, 256, 0, st>>>((const HxResultDev *)res, ids, id_off, tails, tail_off, n_pairs,
+                                                         n_entries, where, out);
+    return 1;
+}

@@ -98,6 +98,14 @@ int hx_run_batch_fasta(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offset
                        const char *ids, const uint64_t *id_off, const char *tails, const uint32_t *tail_off,
                        const char **text, uint64_t *text_len);
 
+/* hx_run_batch_fasta plus the GFF3 lines of utils.rs:378-385 ("{id}\thyperex\tregion\t{f_start+1}\t{r_end+1}" followed
+ * by the per-pair gff_tails entry "\t.\t.\t.\tNote=...\n"), also assembled on the GPU.  The "##gff-version 3" header
+ * (utils.rs:247) is not part of the text. */
+int hx_run_batch_text(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out,
+                      const char *ids, const uint64_t *id_off, const char *fa_tails, const uint32_t *fa_tail_off,
+                      const char *gff_tails, const uint32_t *gff_tail_off, const char **fa_text, uint64_t *fa_len,
+                      const char **gff_text, uint64_t *gff_len);
+
 /* Same, for an arena already resident in device memory of the context's device `dev_slot`
  * (index into dev_ids).  d_arena must be 16-byte aligned and readable up to the next
  * multiple of 16 bytes past offsets[n_records]; d_out is device memory.  Work is enqueued on

@@ -319,8 +319,14 @@ def test_on_device_fasta_extraction(ctx, k, tile):
     res, text = ctx.run_batch_fasta(a, o, ids, _fa_tails(pairs))
     ref = O.run_batch(a, o, pairs, k, nthreads=8)
     _cmp(res, ref, a, o, pairs, k)
-    fa, _gff = O.format_outputs(a, o, ids, pairs, ref)
+    fa, gff = O.format_outputs(a, o, ids, pairs, ref)
     assert text == fa
+    gtails = []
+    for f, r in pairs:
+        lab = O.primers_to_region(f, r)
+        gtails.append("\t.\t.\t.\tNote=" + (f"Hypervariable region {lab}" if lab else f"forward={f} reverse={r}") + "\n")
+    res3, fa3, gff3 = ctx.run_batch_text(a, o, ids, _fa_tails(pairs), gtails)
+    assert res3.tobytes() == ref.tobytes() and fa3 == fa and b"##gff-version 3\n" + gff3 == gff
     # a batch without any region gives an empty text
     a2, o2 = hx_synth.pack([b"", b"T", b"XX"])
     res2, text2 = ctx.run_batch_fasta(a2, o2, ["x", "y", "z"], _fa_tails(pairs))
