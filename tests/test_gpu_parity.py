@@ -210,7 +210,7 @@ def test_k_at_least_pattern_length_every_position_hits(ctx):
 def test_random_primer_sets_fuzz(ctx, seed):
     """random IUPAC primer sets (1..64 nt, shared primers between pairs), random k, planted + mutated sites,
     mixed alphabets, windows of random size; both scan algorithms and both text paths"""
-    rng = np.random.default_rng(1000 + seed)
+    rng = np.random.default_rng(1000 + int(os.environ.get("HX_FUZZ_BASE", "0")) + seed)
     letters = "ACGT" * 5 + "MRWSYKVHDBNU"
     n_pairs = int(rng.integers(1, 24))
     max_len = int(rng.choice([1, 6, 20, 31, 32, 33, 40, 64]))
