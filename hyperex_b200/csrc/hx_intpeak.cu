@@ -32,6 +32,10 @@ __device__ __forceinline__ void op(uint32_t &x, const uint32_t y, const uint32_t
     else if (VAR == 6) {
         if (chain & 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(nb));
         else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(y), "r"(z));
+    } else if (VAR == 9) {
+        uint32_t t;
+        asm volatile("popc.b32 %0, %1;" : "=r"(t) : "r"(x));
+        x = t | y;  // keeps the chain dependent; the OR is a LOP3 (ALU pipe)
     } else if (VAR == 8) {
         uint64_t acc = ((uint64_t)z << 32) | x;
         asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x), "r"(y));
@@ -134,6 +138,39 @@ __global__ void __launch_bounds__(128, 4) hx_steppeak_wide_kernel(uint32_t *out,
     if (acc == 0x12345678u) out[0] = acc;
 }
 
+// Variant 5: no per-step score at all; dist = popc(pv) - popc(mv) (sum of the vertical deltas) is recomputed
+// from the state for the hit test, moving the two score instructions from the ALU pipe to POPC.
+__global__ void __launch_bounds__(128, 4) hx_steppeak_popc_kernel(uint32_t *out, int iters, uint32_t seed) {
+    uint32_t pv[NPAT], mv[NPAT];
+#pragma unroll
+    for (int p = 0; p < NPAT; ++p) {
+        pv[p] = ~0u;
+        mv[p] = 0;
+    }
+    uint32_t e = seed ^ (threadIdx.x * 2654435761u);
+    int any = 0;
+    for (int it = 0; it < iters; ++it) {
+        e = e * 1664525u + 1013904223u;
+#pragma unroll
+        for (int p = 0; p < NPAT; ++p) {
+            const uint32_t eq = e ^ (0x9e3779b9u * (p + 1));
+            const uint32_t xv = eq | mv[p];
+            const uint32_t xh = (((eq & pv[p]) + pv[p]) ^ pv[p]) | eq;
+            uint32_t ph = mv[p] | ~(xh | pv[p]);
+            uint32_t mh = pv[p] & xh;
+            ph <<= 1;
+            mh <<= 1;
+            pv[p] = mh | ~(xv | ph);
+            mv[p] = ph & xv;
+            any |= __popc(pv[p]) - __popc(mv[p]) - (13 + p);
+        }
+    }
+    uint32_t acc = (uint32_t)any;
+#pragma unroll
+    for (int p = 0; p < NPAT; ++p) acc ^= pv[p] ^ mv[p];
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
 template <int V>
 __global__ void __launch_bounds__(128, 4) hx_steppeak_kernel(uint32_t *out, int iters, uint32_t seed, uint32_t two) {
     uint32_t pv[NPAT], mv[NPAT];
@@ -184,9 +221,11 @@ cudaError_t run_step(uint32_t *d, int iters, float *ms) {
     cudaEventCreate(&b);
     const int blocks = 148 * 4 * 4;
     if (V == 4) hx_steppeak_wide_kernel<<<blocks, 128>>>(d, iters / 8, 12345u, 1u);
+    else if (V == 5) hx_steppeak_popc_kernel<<<blocks, 128>>>(d, iters / 8, 12345u);
     else hx_steppeak_kernel<V><<<blocks, 128>>>(d, iters / 8, 12345u, 2u);
     cudaEventRecord(a);
     if (V == 4) hx_steppeak_wide_kernel<<<blocks, 128>>>(d, iters, 12345u, 1u);
+    else if (V == 5) hx_steppeak_popc_kernel<<<blocks, 128>>>(d, iters, 12345u);
     else hx_steppeak_kernel<V><<<blocks, 128>>>(d, iters, 12345u, 2u);
     cudaEventRecord(b);
     cudaError_t e = cudaEventSynchronize(b);
@@ -218,11 +257,13 @@ extern "C" int hx_int_peak(int device, int variant, int iters, double *gops) {
     case 6: e = run_peak<6>(d, iters, &ms); break;
     case 7: e = run_peak<7>(d, iters, &ms); break;
     case 8: e = run_peak<8>(d, iters, &ms); break;
+    case 9: e = run_peak<9>(d, iters, &ms); break;
     case 10: e = run_step<0>(d, iters, &ms); break;
     case 11: e = run_step<1>(d, iters, &ms); break;
     case 12: e = run_step<2>(d, iters, &ms); break;
     case 13: e = run_step<3>(d, iters, &ms); break;
     case 14: e = run_step<4>(d, iters, &ms); break;
+    case 15: e = run_step<5>(d, iters, &ms); break;
     default: cudaFree(d); return HX_ERR_ARG;
     }
     if (variant < 10) ops = (double)148 * 8 * 256 * (double)iters * UNROLL * CHAINS;
