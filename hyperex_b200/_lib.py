@@ -19,9 +19,11 @@ EXPORTS = [
     "hx_kernel_time", "hx_sequence_type", "hx_to_complement", "hx_to_reverse_complement", "hx_primers_to_region",
     "hx_region_to_primer", "hx_supported_regions", "hx_file_to_vec", "hx_free_primer_file",
     "hx_get_hypervar_regions", "hx_fasta_open", "hx_fasta_next", "hx_fasta_close", "hx_int_peak", "hx_group_info", "hx_run_batch_fasta", "hx_run_batch_text",
+    "hx_run_batch_text_stream",
 ]
 
 LOG_FN = C.CFUNCTYPE(None, C.c_int, C.c_char_p, C.c_void_p)
+TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t)
 
 _lib = None
 
@@ -78,6 +80,8 @@ def load():
     L.hx_int_peak.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.hx_group_info.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.hx_run_batch_fasta.argtypes = [vp, vp, vp, C.c_uint32, vp, cp, vp, cp, vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.hx_run_batch_text_stream.argtypes = [vp, vp, vp, C.c_uint32, vp, cp, vp, cp, vp, cp, vp, TEXT_SINK, vp,
+                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.hx_run_batch_text.argtypes = [vp, vp, vp, C.c_uint32, vp, cp, vp, cp, vp, cp, vp, C.POINTER(vp), C.POINTER(C.c_uint64),
                                     C.POINTER(vp), C.POINTER(C.c_uint64)]
     _lib = L

@@ -204,8 +204,9 @@ class Context:
         return out, (C.string_at(text.value, tlen.value) if tlen.value else b"")
 
     def run_batch_text(self, arena: np.ndarray, offsets: np.ndarray, ids: Sequence[str], fa_tails: Sequence[str],
-                       gff_tails: Sequence[str]):
-        """hx_run_batch_text: (results, fasta_bytes, gff_bytes) — both output texts assembled on the GPU"""
+                       gff_tails: Sequence[str], stream=False):
+        """hx_run_batch_text: (results, fasta_bytes, gff_bytes) — both output texts assembled on the GPU.
+        stream=True (or a callable sink(kind, bytes) -> 0/1) goes through hx_run_batch_text_stream."""
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
         out = np.zeros((n, self.n_pairs), dtype=RESULT_DTYPE)
@@ -224,6 +225,20 @@ class Context:
         gb, go = blob(gff_tails)
         ft, fl, gt, gl = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
         ap = arena.ctypes.data if arena is not None and arena.size else None
+        if stream:  # hx_run_batch_text_stream: the text arrives in chunks through a callback
+            parts = ([], [])
+
+            def sink(_user, kind, ptr, nbytes):
+                parts[kind].append(C.string_at(ptr, nbytes))
+                return int(stream(kind, parts[kind][-1])) if callable(stream) else 0
+
+            cb = _lib.TEXT_SINK(sink)
+            self._check(self._L.hx_run_batch_text_stream(self._h, ap, offsets.ctypes.data, n, out.ctypes.data,
+                                                         b"".join(idb), id_off.ctypes.data, fb, fo.ctypes.data, gb,
+                                                         go.ctypes.data, cb, None, C.byref(fl), C.byref(gl)))
+            fa, gf = b"".join(parts[0]), b"".join(parts[1])
+            assert len(fa) == fl.value and len(gf) == gl.value
+            return out, fa, gf
         self._check(self._L.hx_run_batch_text(self._h, ap, offsets.ctypes.data, n, out.ctypes.data, b"".join(idb),
                                               id_off.ctypes.data, fb, fo.ctypes.data, gb, go.ctypes.data, C.byref(ft),
                                               C.byref(fl), C.byref(gt), C.byref(gl)))

@@ -11,6 +11,7 @@
 #include "hx_host.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -25,33 +26,47 @@ constexpr int HX_NSLOT = 3;  // pipeline depth per device (H2D / scan / D2H over
 
 std::string g_create_error;
 
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t cap = 0;  // elements
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) {
-            cudaError_t e = cudaFree(p);  // synchronises the device: safe to regrow
-            p = nullptr;
+// One device allocation per user (a slab slot, the extraction scratch, the output text), carved afresh for every
+// slab: cudaMalloc / cudaFree cost tens of milliseconds each on a virtualised B200, so the number of calls must not
+// scale with the number of buffers or with how often a size changes.
+struct DevPool {
+    uint8_t *base = nullptr;
+    size_t cap = 0, used = 0;
+    void reset() { used = 0; }
+    size_t bump(size_t bytes) {
+        const size_t off = (used + 255) & ~(size_t)255;
+        used = off + bytes;
+        return off;
+    }
+    bool fits() const { return used <= cap; }
+    cudaError_t grow() {  // callers make sure no work that uses the old block is in flight
+        if (base) {
+            cudaError_t e = cudaFree(base);
+            base = nullptr;
             cap = 0;
             if (e != cudaSuccess) return e;
         }
-        size_t want = n + n / 8 + 64;
-        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
-        if (e != cudaSuccess) return e;
-        cap = want;
-        return cudaSuccess;
+        const size_t want = used + used / 4 + ((size_t)1 << 20);
+        cudaError_t e = cudaMalloc((void **)&base, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
     }
     void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = used = 0;
     }
+};
+
+template <typename T>
+struct DevBuf {  // a typed view into a DevPool; p is only meaningful once the pool fits()
+    T *p = nullptr;
+    void carve(DevPool &pool, size_t n) { p = (T *)(pool.base + pool.bump(n * sizeof(T))); }
 };
 
 struct Slot {
     cudaStream_t stream = nullptr;
+    DevPool pool;
     DevBuf<uint8_t> arena;
     DevBuf<uint64_t> offsets;
     DevBuf<uint32_t> rec_u32;  // rec_raw | tile_first | tile_cnt | long_list   (4 x rec_cap)
@@ -63,8 +78,7 @@ struct Slot {
     DevBuf<hx_result> out;
     uint32_t *h_status = nullptr;  // pinned: [0] ntiles, [1] overflow
     void release() {
-        arena.release(); offsets.release(); rec_u32.release(); scratch.release(); tiles.release();
-        order.release(); sum_f.release(); sum_r.release(); pair_hi.release(); pair_lo.release(); out.release();
+        pool.release();
         if (h_status) cudaFreeHost(h_status);
         if (stream) cudaStreamDestroy(stream);
         h_status = nullptr;
@@ -104,11 +118,14 @@ struct hx_ctx {
     int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1;
     uint64_t launches = 0;
     // on-device extraction (device 0)
+    DevPool ex_pool, ex_text_pool;
     DevBuf<uint8_t> ex_ids, ex_tails, ex_text, ex_gtails, ex_gtext;
     DevBuf<uint64_t> ex_id_off, ex_lens, ex_sums, ex_glens, ex_gsums;
     DevBuf<uint32_t> ex_tail_off, ex_gtail_off;
     uint8_t *ex_host = nullptr, *ex_ghost = nullptr;
     size_t ex_host_cap = 0, ex_ghost_cap = 0;
+    uint8_t *ex_stage[2] = {nullptr, nullptr};  // pinned staging of the streamed text path
+    cudaEvent_t ex_stage_ev[2] = {nullptr, nullptr};
     std::vector<TimedLaunch> timed;
     double myers_ms = 0;
     uint64_t myers_launches = 0;
@@ -194,19 +211,35 @@ SlabPlan plan_slab(const hx_ctx *ctx, uint32_t n_records, uint64_t bytes) {
     return p;
 }
 
-// Enqueue the whole device path for one slab on `st`.  d_out receives n_records x n_pairs results.
-int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const uint8_t *d_arena, const uint64_t *d_offsets, uint64_t off_base,
-                 uint32_t n_records, uint64_t bytes, hx_result *d_out, cudaStream_t st) {
+// Carves the slot's device block for one slab (one cudaMalloc at most, and only when the slab needs more than any
+// before it).  io_bytes > 0: the slot also holds the arena copy, the offsets and the result table (host-buffer
+// entry points); 0: those live in caller-owned device memory (hx_run_batch_device).  The slot must be idle.
+int prepare_slab(hx_ctx *ctx, Slot &S, const SlabPlan &pl, uint32_t n_records, uint64_t io_bytes) {
+    for (int pass = 0;; ++pass) {
+        S.pool.reset();
+        if (io_bytes) {
+            S.arena.carve(S.pool, io_bytes);
+            S.offsets.carve(S.pool, (size_t)n_records + 1);
+            S.out.carve(S.pool, (size_t)n_records * ctx->n_pairs);
+        }
+        S.rec_u32.carve(S.pool, (size_t)n_records * 4);
+        S.scratch.carve(S.pool, 4 + 2 * HX_NBUCKETS);
+        S.tiles.carve(S.pool, pl.tile_cap);
+        S.order.carve(S.pool, pl.tile_cap);
+        S.sum_f.carve(S.pool, (size_t)ctx->n_slots * pl.tile_cap);
+        S.sum_r.carve(S.pool, (size_t)ctx->n_slots * pl.tile_cap);
+        S.pair_hi.carve(S.pool, (size_t)ctx->n_pairs * pl.tile_cap);
+        S.pair_lo.carve(S.pool, (size_t)ctx->n_pairs * pl.tile_cap);
+        if (S.pool.fits()) return HX_OK;
+        if (pass) return fail(ctx, HX_ERR_STATE, "prepare_slab: pool did not fit after growing");
+        HX_CUDA(ctx, S.pool.grow());
+    }
+}
+
+// Enqueue the whole device path for one slab on `st` (after prepare_slab).  d_out receives n_records x n_pairs results.
+int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint8_t *d_arena, const uint64_t *d_offsets,
+                 uint64_t off_base, uint32_t n_records, hx_result *d_out, cudaStream_t st) {
     if (n_records == 0) return HX_OK;
-    const SlabPlan pl = plan_slab(ctx, n_records, bytes);
-    HX_CUDA(ctx, S.rec_u32.reserve((size_t)n_records * 4));
-    HX_CUDA(ctx, S.scratch.reserve(4 + 2 * HX_NBUCKETS));
-    HX_CUDA(ctx, S.tiles.reserve(pl.tile_cap));
-    HX_CUDA(ctx, S.order.reserve(pl.tile_cap));
-    HX_CUDA(ctx, S.sum_f.reserve((size_t)ctx->n_slots * pl.tile_cap));
-    HX_CUDA(ctx, S.sum_r.reserve((size_t)ctx->n_slots * pl.tile_cap));
-    HX_CUDA(ctx, S.pair_hi.reserve((size_t)ctx->n_pairs * pl.tile_cap));
-    HX_CUDA(ctx, S.pair_lo.reserve((size_t)ctx->n_pairs * pl.tile_cap));
 
     uint32_t *rec_raw = S.rec_u32.p, *tile_first = rec_raw + n_records, *tile_cnt = tile_first + n_records;
     uint32_t *long_list = tile_cnt + n_records;
@@ -338,12 +371,14 @@ void hx_destroy(hx_ctx *ctx) {
     if (!ctx) return;
     sync_timed(ctx);
     if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].dev);
-    ctx->ex_ids.release(); ctx->ex_tails.release(); ctx->ex_text.release(); ctx->ex_id_off.release();
-    ctx->ex_lens.release(); ctx->ex_sums.release(); ctx->ex_tail_off.release();
-    ctx->ex_gtails.release(); ctx->ex_gtext.release(); ctx->ex_glens.release(); ctx->ex_gsums.release();
-    ctx->ex_gtail_off.release();
+    ctx->ex_pool.release();
+    ctx->ex_text_pool.release();
     if (ctx->ex_host) cudaFreeHost(ctx->ex_host);
     if (ctx->ex_ghost) cudaFreeHost(ctx->ex_ghost);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ex_stage[i]) cudaFreeHost(ctx->ex_stage[i]);
+        if (ctx->ex_stage_ev[i]) cudaEventDestroy(ctx->ex_stage_ev[i]);
+    }
     for (Device &D : ctx->devs) {
         cudaSetDevice(D.dev);
         cudaDeviceSynchronize();
@@ -539,7 +574,9 @@ int hx_run_batch_device(hx_ctx *ctx, int dev_slot, const uint8_t *d_arena, const
     HX_CUDA(ctx, cudaSetDevice(D.dev));
     Slot &S = D.slots[0];
     cudaStream_t st = stream ? (cudaStream_t)stream : S.stream;
-    int rc = enqueue_slab(ctx, D, S, d_arena, d_offsets, 0, n_records, arena_bytes, d_out, st);
+    const SlabPlan pl = plan_slab(ctx, n_records, arena_bytes);
+    int rc = prepare_slab(ctx, S, pl, n_records, 0);
+    if (rc == HX_OK) rc = enqueue_slab(ctx, D, S, pl, d_arena, d_offsets, 0, n_records, d_out, st);
     if (rc != HX_OK) return rc;
     if (!stream) {
         HX_CUDA(ctx, cudaStreamSynchronize(st));
@@ -559,10 +596,78 @@ int hx_run_batch_fasta(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offset
                              text_len, nullptr, nullptr);
 }
 
+// Streams device text to the sink through two pinned staging buffers: the copy of chunk i + 1 is in flight
+// while the sink consumes chunk i.
+static const size_t HX_STAGE_BYTES = (size_t)16 << 20;
+static int stream_text(hx_ctx *ctx, cudaStream_t st, const uint8_t *const d_src[2], const uint64_t len[2],
+                       hx_text_sink sink, void *user) {
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->ex_stage[i]) HX_CUDA(ctx, cudaHostAlloc((void **)&ctx->ex_stage[i], HX_STAGE_BYTES, cudaHostAllocDefault));
+        if (!ctx->ex_stage_ev[i]) HX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ex_stage_ev[i], cudaEventDisableTiming));
+    }
+    struct Chunk { int kind; uint64_t off; size_t n; };
+    auto chunk_at = [&](uint64_t i, Chunk &c) {
+        const uint64_t n0 = (len[0] + HX_STAGE_BYTES - 1) / HX_STAGE_BYTES;
+        c.kind = i < n0 ? 0 : 1;
+        c.off = (c.kind ? i - n0 : i) * HX_STAGE_BYTES;
+        c.n = (size_t)std::min<uint64_t>(HX_STAGE_BYTES, len[c.kind] - c.off);
+    };
+    const uint64_t n_chunks = (len[0] + HX_STAGE_BYTES - 1) / HX_STAGE_BYTES + (len[1] + HX_STAGE_BYTES - 1) / HX_STAGE_BYTES;
+    auto issue = [&](uint64_t i) -> cudaError_t {
+        Chunk c;
+        chunk_at(i, c);
+        cudaError_t e = cudaMemcpyAsync(ctx->ex_stage[i & 1], d_src[c.kind] + c.off, c.n, cudaMemcpyDeviceToHost, st);
+        return e == cudaSuccess ? cudaEventRecord(ctx->ex_stage_ev[i & 1], st) : e;
+    };
+    if (n_chunks) HX_CUDA(ctx, issue(0));
+    for (uint64_t i = 0; i < n_chunks; ++i) {
+        if (i + 1 < n_chunks) HX_CUDA(ctx, issue(i + 1));
+        HX_CUDA(ctx, cudaEventSynchronize(ctx->ex_stage_ev[i & 1]));
+        Chunk c;
+        chunk_at(i, c);
+        if (sink(user, c.kind, (const char *)ctx->ex_stage[i & 1], c.n) != 0) {
+            cudaStreamSynchronize(st);
+            return fail(ctx, HX_ERR_IO, "hx_run_batch_text_stream: the sink reported an error");
+        }
+    }
+    return HX_OK;
+}
+
+static int run_batch_text_impl(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                               hx_result *out, const char *ids, const uint64_t *id_off, const char *tails,
+                               const uint32_t *tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
+                               const char **text, uint64_t *text_len, const char **gff_text, uint64_t *gff_len,
+                               hx_text_sink sink, void *user);
+
 int hx_run_batch_text(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out,
                       const char *ids, const uint64_t *id_off, const char *tails, const uint32_t *tail_off,
                       const char *gff_tails, const uint32_t *gff_tail_off, const char **text, uint64_t *text_len,
                       const char **gff_text, uint64_t *gff_len) {
+    return run_batch_text_impl(ctx, arena, offsets, n_records, out, ids, id_off, tails, tail_off, gff_tails, gff_tail_off,
+                               text, text_len, gff_text, gff_len, nullptr, nullptr);
+}
+
+int hx_run_batch_text_stream(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                             hx_result *out, const char *ids, const uint64_t *id_off, const char *tails,
+                             const uint32_t *tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
+                             hx_text_sink sink, void *user, uint64_t *text_len, uint64_t *gff_len) {
+    if (!ctx) return HX_ERR_ARG;
+    if (!sink) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text_stream: NULL sink");
+    const char *t = nullptr, *g = nullptr;
+    uint64_t tl = 0, gl = 0;
+    const bool want_gff = gff_tails && gff_tail_off;
+    int rc = run_batch_text_impl(ctx, arena, offsets, n_records, out, ids, id_off, tails, tail_off, gff_tails, gff_tail_off,
+                                 &t, &tl, want_gff ? &g : nullptr, want_gff ? &gl : nullptr, sink, user);
+    if (text_len) *text_len = tl;
+    if (gff_len) *gff_len = gl;
+    return rc;
+}
+
+static int run_batch_text_impl(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                               hx_result *out, const char *ids, const uint64_t *id_off, const char *tails,
+                               const uint32_t *tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
+                               const char **text, uint64_t *text_len, const char **gff_text, uint64_t *gff_len,
+                               hx_text_sink sink, void *user) {
     if (!ctx) return HX_ERR_ARG;
     const bool want_gff = gff_tails && gff_tail_off && gff_text && gff_len;
     if (gff_text) *gff_text = nullptr;
@@ -587,35 +692,56 @@ int hx_run_batch_text(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets
     if (id_off[0] != 0 || tail_off[0] != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: id_off / tail_off must start at 0");
     const uint32_t tail_bytes = tail_off[np];
     const uint32_t nblk = (uint32_t)((n_entries + 4095) / 4096);
+    static const bool trace = getenv("HYPEREX_TIMING") && atoi(getenv("HYPEREX_TIMING")) >= 2;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tt0 = now();
     HX_CUDA(ctx, cudaStreamSynchronize(st));
-    HX_CUDA(ctx, S.arena.reserve(copy_bytes + 64));
-    HX_CUDA(ctx, S.offsets.reserve((size_t)n_records + 1));
-    HX_CUDA(ctx, S.out.reserve((size_t)n_entries));
-    HX_CUDA(ctx, ctx->ex_ids.reserve(id_bytes + 16));
-    HX_CUDA(ctx, ctx->ex_id_off.reserve((size_t)n_records + 1));
-    HX_CUDA(ctx, ctx->ex_tails.reserve(tail_bytes + 16));
-    HX_CUDA(ctx, ctx->ex_tail_off.reserve(np + 1));
-    HX_CUDA(ctx, ctx->ex_lens.reserve(n_entries + 1));
-    HX_CUDA(ctx, ctx->ex_sums.reserve(nblk + 2));
+    if (want_gff && gff_tail_off[0] != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: gff_tail_off must start at 0");
+    const SlabPlan pl = plan_slab(ctx, n_records, bytes);
+    int rc = prepare_slab(ctx, S, pl, n_records, copy_bytes + 64);
+    if (rc != HX_OK) return rc;
+    for (int pass = 0;; ++pass) {  // the extraction scratch: one block, carved per call
+        DevPool &P = ctx->ex_pool;
+        P.reset();
+        ctx->ex_ids.carve(P, id_bytes + 16);
+        ctx->ex_id_off.carve(P, (size_t)n_records + 1);
+        ctx->ex_tails.carve(P, tail_bytes + 16);
+        ctx->ex_tail_off.carve(P, np + 1);
+        ctx->ex_lens.carve(P, n_entries + 1);
+        ctx->ex_sums.carve(P, nblk + 2);
+        if (want_gff) {
+            ctx->ex_gtails.carve(P, gff_tail_off[np] + 16);
+            ctx->ex_gtail_off.carve(P, np + 1);
+            ctx->ex_glens.carve(P, n_entries + 1);
+            ctx->ex_gsums.carve(P, nblk + 2);
+        }
+        if (P.fits()) break;
+        if (pass) return fail(ctx, HX_ERR_STATE, "hx_run_batch_text: pool did not fit after growing");
+        HX_CUDA(ctx, P.grow());
+    }
     if (want_gff) {
-        if (gff_tail_off[0] != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: gff_tail_off must start at 0");
-        HX_CUDA(ctx, ctx->ex_gtails.reserve(gff_tail_off[np] + 16));
-        HX_CUDA(ctx, ctx->ex_gtail_off.reserve(np + 1));
-        HX_CUDA(ctx, ctx->ex_glens.reserve(n_entries + 1));
-        HX_CUDA(ctx, ctx->ex_gsums.reserve(nblk + 2));
         if (gff_tail_off[np])
             HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_gtails.p, gff_tails, gff_tail_off[np], cudaMemcpyHostToDevice, st));
         HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_gtail_off.p, gff_tail_off, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, st));
     }
+    const double ta = now();
     if (copy_bytes) HX_CUDA(ctx, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, st));
+    const double tb = now();
     HX_CUDA(ctx, cudaMemcpyAsync(S.offsets.p, offsets, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, st));
     if (id_bytes) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_ids.p, ids, id_bytes, cudaMemcpyHostToDevice, st));
     HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_id_off.p, id_off, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, st));
     if (tail_bytes) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_tails.p, tails, tail_bytes, cudaMemcpyHostToDevice, st));
     HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_tail_off.p, tail_off, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, st));
-    int rc = enqueue_slab(ctx, D, S, S.arena.p, S.offsets.p, base, n_records, bytes, S.out.p, st);
+    const double tc = now();
+    rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, base, n_records, S.out.p, st);
     if (rc != HX_OK) return rc;
+    const double td = now();
     HX_CUDA(ctx, cudaMemcpyAsync(out, S.out.p, (size_t)n_entries * sizeof(hx_result), cudaMemcpyDeviceToHost, st));
+    const double te = now();
+    if (trace)
+        fprintf(stderr, "[hx_run_batch_text]   reserve %.1f, arena memcpy call %.1f, small memcpys %.1f, enqueue_slab %.1f, "
+                        "result memcpy call %.1f ms\n",
+                (ta - tt0) * 1e3, (tb - ta) * 1e3, (tc - tb) * 1e3, (td - tc) * 1e3, (te - td) * 1e3);
     ctx->launches += hx_launch_fasta_offsets(S.out.p, ctx->ex_id_off.p, ctx->ex_tail_off.p, np, n_entries, ctx->ex_lens.p,
                                              ctx->ex_sums.p, st);
     // total = offset of the last entry + its length = block offset + in-block prefix; read both pieces
@@ -626,12 +752,22 @@ int hx_run_batch_text(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets
                                                ctx->ex_glens.p, ctx->ex_gsums.p, st);
         HX_CUDA(ctx, cudaMemcpyAsync(&gtotal, ctx->ex_gsums.p + nblk, 8, cudaMemcpyDeviceToHost, st));
     }
+    const double tt1 = now();
     HX_CUDA(ctx, cudaStreamSynchronize(st));
+    const double tt2 = now();
     rc = check_status(ctx, S);
     if (rc != HX_OK) return rc;
+    for (int pass = 0; total || gtotal; ++pass) {  // both output texts share one device block
+        DevPool &P = ctx->ex_text_pool;
+        P.reset();
+        ctx->ex_text.carve(P, total + 16);
+        ctx->ex_gtext.carve(P, gtotal + 16);
+        if (P.fits()) break;
+        if (pass) return fail(ctx, HX_ERR_STATE, "hx_run_batch_text: text pool did not fit after growing");
+        HX_CUDA(ctx, P.grow());
+    }
     if (total) {
-        HX_CUDA(ctx, ctx->ex_text.reserve(total + 16));
-        if (total > ctx->ex_host_cap) {
+        if (!sink && total > ctx->ex_host_cap) {
             if (ctx->ex_host) cudaFreeHost(ctx->ex_host);
             ctx->ex_host = nullptr;
             ctx->ex_host_cap = 0;
@@ -642,11 +778,10 @@ int hx_run_batch_text(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets
         ctx->launches += hx_launch_fasta_write(S.arena.p, S.offsets.p, base, S.out.p, ctx->ex_ids.p, ctx->ex_id_off.p,
                                                ctx->ex_tails.p, ctx->ex_tail_off.p, np, n_entries, ctx->ex_lens.p,
                                                ctx->ex_text.p, st);
-        HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_host, ctx->ex_text.p, total, cudaMemcpyDeviceToHost, st));
+        if (!sink) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_host, ctx->ex_text.p, total, cudaMemcpyDeviceToHost, st));
     }
     if (gtotal) {
-        HX_CUDA(ctx, ctx->ex_gtext.reserve(gtotal + 16));
-        if (gtotal > ctx->ex_ghost_cap) {
+        if (!sink && gtotal > ctx->ex_ghost_cap) {
             if (ctx->ex_ghost) cudaFreeHost(ctx->ex_ghost);
             ctx->ex_ghost = nullptr;
             ctx->ex_ghost_cap = 0;
@@ -656,17 +791,29 @@ int hx_run_batch_text(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets
         }
         ctx->launches += hx_launch_gff_write(S.out.p, ctx->ex_ids.p, ctx->ex_id_off.p, ctx->ex_gtails.p,
                                              ctx->ex_gtail_off.p, np, n_entries, ctx->ex_glens.p, ctx->ex_gtext.p, st);
-        HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_ghost, ctx->ex_gtext.p, gtotal, cudaMemcpyDeviceToHost, st));
+        if (!sink) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_ghost, ctx->ex_gtext.p, gtotal, cudaMemcpyDeviceToHost, st));
+    }
+    const double tt3 = now();
+    if (sink && (total || gtotal)) {
+        const uint8_t *const src[2] = {ctx->ex_text.p, ctx->ex_gtext.p};
+        const uint64_t lens[2] = {total, gtotal};
+        rc = stream_text(ctx, st, src, lens, sink, user);
+        if (rc != HX_OK) return rc;
     }
     if (total || gtotal) {
         HX_CUDA(ctx, cudaStreamSynchronize(st));
         HX_CUDA(ctx, cudaGetLastError());
     }
+    if (trace)
+        fprintf(stderr, "[hx_run_batch_text] records=%u bases=%llu text=%llu: enqueue %.1f ms, scan sync %.1f ms, "
+                        "alloc+enqueue text %.1f ms, text sync %.1f ms\n",
+                n_records, (unsigned long long)bytes, (unsigned long long)(total + gtotal), (tt1 - tt0) * 1e3,
+                (tt2 - tt1) * 1e3, (tt3 - tt2) * 1e3, (now() - tt3) * 1e3);
     sync_timed(ctx);
-    *text = (const char *)ctx->ex_host;
+    *text = sink ? nullptr : (const char *)ctx->ex_host;
     *text_len = total;
     if (want_gff) {
-        *gff_text = (const char *)ctx->ex_ghost;
+        *gff_text = sink ? nullptr : (const char *)ctx->ex_ghost;
         *gff_len = gtotal;
     }
     return HX_OK;
@@ -711,14 +858,14 @@ int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uin
         // addresses keep the alignment of the arena offsets
         const uint64_t base = offsets[r0] & ~15ull;
         const uint64_t copy_bytes = offsets[r1] - base;
-        HX_CUDA(ctx, S.arena.reserve(copy_bytes + 64));
-        HX_CUDA(ctx, S.offsets.reserve((size_t)n + 1));
-        HX_CUDA(ctx, S.out.reserve((size_t)n * np));
+        const SlabPlan pl = plan_slab(ctx, n, bytes);
+        rc = prepare_slab(ctx, S, pl, n, copy_bytes + 64);
+        if (rc != HX_OK) break;
         if (copy_bytes)
             HX_CUDA(ctx, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, S.stream));
         HX_CUDA(ctx, cudaMemcpyAsync(S.offsets.p, offsets + r0, ((size_t)n + 1) * sizeof(uint64_t),
                                      cudaMemcpyHostToDevice, S.stream));
-        rc = enqueue_slab(ctx, D, S, S.arena.p, S.offsets.p, base, n, bytes, S.out.p, S.stream);
+        rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, base, n, S.out.p, S.stream);
         if (rc != HX_OK) break;
         HX_CUDA(ctx, cudaMemcpyAsync(out + (size_t)r0 * np, S.out.p, (size_t)n * np * sizeof(hx_result),
                                      cudaMemcpyDeviceToHost, S.stream));

@@ -645,6 +645,18 @@ inline size_t put_u32(char *dst, uint32_t v) {  // decimal, no terminator
     return (size_t)i;
 }
 
+struct TextSink {  // hx_text_sink of the file-level path: kind 0 -> FASTA file, kind 1 -> GFF3 file
+    FILE *fa, *gff;
+    double seconds;
+    static int write(void *user, int kind, const char *bytes, size_t n) {
+        TextSink *t = (TextSink *)user;
+        const auto t0 = std::chrono::steady_clock::now();
+        const bool ok = fwrite(bytes, 1, n, kind ? t->gff : t->fa) == n;
+        t->seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return ok ? 0 : 1;
+    }
+};
+
 struct BatchQueue {  // parser -> consumer hand-off with recycling
     std::mutex mu;
     std::condition_variable cv;
@@ -752,8 +764,6 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
         const uint32_t n = (uint32_t)batch.ids.size();
         n_bases += batch.offsets[n];
         res.resize((size_t)n * n_pairs);
-        const char *dev_text = nullptr, *dev_gff = nullptr;
-        uint64_t dev_text_len = 0, dev_gff_len = 0;
         if (device_fasta) {
             ids_blob.clear();
             id_off.assign(1, 0);
@@ -761,9 +771,15 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
                 ids_blob += id;
                 id_off.push_back(ids_blob.size());
             }
-            rc = hx_run_batch_text(ctx, batch.arena, batch.offsets.data(), n, res.data(), ids_blob.data(), id_off.data(),
-                                   tails_blob.data(), tail_off.data(), gtails_blob.data(), gtail_off.data(), &dev_text,
-                                   &dev_text_len, &dev_gff, &dev_gff_len);
+            // the GPU produces the FASTA and GFF3 bytes of this batch; they are written as they arrive
+            fo.flush();
+            go.flush();
+            TextSink sink{fa, gff, 0.0};
+            rc = hx_run_batch_text_stream(ctx, batch.arena, batch.offsets.data(), n, res.data(), ids_blob.data(),
+                                          id_off.data(), tails_blob.data(), tail_off.data(), gtails_blob.data(),
+                                          gtail_off.data(), &TextSink::write, &sink, nullptr, nullptr);
+            t_write += sink.seconds;
+            t_gpu -= sink.seconds;
         } else {
             rc = hx_run_batch(ctx, batch.arena, batch.offsets.data(), n, res.data());
         }
@@ -832,14 +848,6 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
                         log_fn(1, msg.c_str(), user);
                     }
                 }
-            }
-            if (device_fasta && dev_text_len) {  // the GPU produced the FASTA and GFF3 bytes of this batch
-                fo.flush();
-                if (fwrite(dev_text, 1, dev_text_len, fa) != dev_text_len) fo.ok = false;
-            }
-            if (device_fasta && dev_gff_len) {
-                go.flush();
-                if (fwrite(dev_gff, 1, dev_gff_len, gff) != dev_gff_len) go.ok = false;
             }
             if (!fo.ok || !go.ok) rc = HX_ERR_IO;
         }

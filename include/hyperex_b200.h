@@ -106,6 +106,17 @@ int hx_run_batch_text(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets
                       const char *gff_tails, const uint32_t *gff_tail_off, const char **fa_text, uint64_t *fa_len,
                       const char **gff_text, uint64_t *gff_len);
 
+/* hx_run_batch_text with the text delivered in order through a callback instead of one pinned buffer: first the
+ * FASTA bytes (kind 0), then the GFF3 bytes (kind 1), in chunks of at most 16 MiB that are valid only during the
+ * call.  The device->host copy of the next chunk runs while the sink consumes the current one, so a sink that
+ * write()s (what fasta::Writer / the GFF File do at utils.rs:365-369, 378-385) overlaps with the transfer.  A
+ * non-zero return from the sink aborts with HX_ERR_IO.  text_len / gff_len receive the totals (may be NULL). */
+typedef int (*hx_text_sink)(void *user, int kind, const char *bytes, size_t n);
+int hx_run_batch_text_stream(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                             hx_result *out, const char *ids, const uint64_t *id_off, const char *fa_tails,
+                             const uint32_t *fa_tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
+                             hx_text_sink sink, void *user, uint64_t *text_len, uint64_t *gff_len);
+
 /* Same, for an arena already resident in device memory of the context's device `dev_slot`
  * (index into dev_ids).  d_arena must be 16-byte aligned and readable up to the next
  * multiple of 16 bytes past offsets[n_records]; d_out is device memory.  Work is enqueued on

@@ -333,6 +333,31 @@ def test_on_device_fasta_extraction(ctx, k, tile):
     assert text2 == b"" and not (res2["flags"] & 4).any()
 
 
+def test_text_stream_chunks(ctx):
+    """hx_run_batch_text_stream: > 16 MiB of text arrives in order through the sink and equals the buffered call"""
+    a, o = hx_synth.gen_reads(9000, seed=77)
+    ids = [f"read_{i}" for i in range(9000)]
+    pairs = hx.default_primers()
+    for name in ("tile_len", "single_max"):
+        ctx.set_option(name, 0)
+    ctx.set_primers(pairs, 0)
+    gtails = ["\t.\t.\t.\tNote=Hypervariable region " + O.primers_to_region(f, r) + "\n" for f, r in pairs]
+    res, fa, gff = ctx.run_batch_text(a, o, ids, _fa_tails(pairs), gtails)
+    chunks = []
+    res2, fa2, gff2 = ctx.run_batch_text(a, o, ids, _fa_tails(pairs), gtails,
+                                         stream=lambda kind, b: chunks.append((kind, len(b))) or 0)
+    assert len(fa) > (32 << 20) and fa2 == fa and gff2 == gff and res2.tobytes() == res.tobytes()
+    assert len(chunks) >= 4 and all(n <= (16 << 20) for _, n in chunks)
+    assert [k for k, _ in chunks] == sorted(k for k, _ in chunks)          # FASTA chunks first, then GFF3
+    ref = O.run_batch(a, o, pairs, 0, nthreads=8)
+    rfa, rgff = O.format_outputs(a, o, ids, pairs, ref)
+    assert fa2 == rfa and b"##gff-version 3\n" + gff2 == rgff
+    with pytest.raises(hx.HyperexError):                                   # a failing sink is an error, not a truncation
+        ctx.run_batch_text(a, o, ids, _fa_tails(pairs), gtails, stream=lambda kind, b: 1)
+    res3, fa3, _ = ctx.run_batch_text(a, o, ids, _fa_tails(pairs), gtails, stream=True)   # context still usable
+    assert fa3 == fa and res3.tobytes() == res.tobytes()
+
+
 # ---- file-level seam: FASTA in, FASTA + GFF3 bytes out ---------------------------------------------------
 @pytest.mark.parametrize("k,codec", [(0, "plain"), (2, "gz"), (3, "xz")])
 def test_get_hypervar_regions_bytes(ctx, tmp_path, k, codec):

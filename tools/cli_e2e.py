@@ -25,10 +25,10 @@ with open(path, "wb") as f:
     f.write(b"".join(chunk))
 t0 = time.perf_counter()
 r = subprocess.run([os.path.join(ROOT, "bin", "hyperex"), path, "-p", os.path.join(work, "out"), "--force", "-q",
-                    "--gpus", gpus], cwd=work, capture_output=True, env=dict(os.environ, HYPEREX_TIMING="1"))
+                    "--gpus", gpus], cwd=work, capture_output=True, env=dict(os.environ, HYPEREX_TIMING=os.environ.get("HYPEREX_TIMING", "1")))
 dt = time.perf_counter() - t0
 out = {"records": n, "bases": int(o[-1]), "gpus": gpus, "wall_s": dt, "gbases_per_s": int(o[-1]) / dt / 1e9,
-       "rc": r.returncode, "timing": r.stderr.decode()[-400:].strip(),
+       "rc": r.returncode, "timing": r.stderr.decode()[-3000:].strip(),
        "fa_bytes": os.path.getsize(os.path.join(work, "out.fa")), "gff_bytes": os.path.getsize(os.path.join(work, "out.gff"))}
 import shutil  # noqa: E402
 shutil.rmtree(work, ignore_errors=True)  # gpurun_out/ must stay small
