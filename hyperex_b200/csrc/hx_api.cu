@@ -118,7 +118,7 @@ struct hx_ctx {
     int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1;
     uint64_t launches = 0;
     // on-device extraction (device 0)
-    DevPool ex_pool, ex_text_pool;
+    DevPool ex_pool, ex_text_pool, find_pool;
     DevBuf<uint8_t> ex_ids, ex_tails, ex_text, ex_gtails, ex_gtext;
     DevBuf<uint64_t> ex_id_off, ex_lens, ex_sums, ex_glens, ex_gsums;
     DevBuf<uint32_t> ex_tail_off, ex_gtail_off;
@@ -373,6 +373,7 @@ void hx_destroy(hx_ctx *ctx) {
     if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].dev);
     ctx->ex_pool.release();
     ctx->ex_text_pool.release();
+    ctx->find_pool.release();
     if (ctx->ex_host) cudaFreeHost(ctx->ex_host);
     if (ctx->ex_ghost) cudaFreeHost(ctx->ex_ghost);
     for (int i = 0; i < 2; ++i) {
@@ -826,9 +827,14 @@ int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uin
     if (!offsets || !out) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL offsets/out");
     if (offsets[n_records] < offsets[0]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
     if (offsets[n_records] > offsets[0] && !arena) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL arena");
-    const uint64_t slab_bytes = (uint64_t)ctx->opt_slab_bytes;
     const size_t np = ctx->n_pairs;
     const int ndev = (int)ctx->devs.size();
+    // a batch smaller than ndev slabs is still spread over every device of the context
+    uint64_t slab_bytes = (uint64_t)ctx->opt_slab_bytes;
+    if (ndev > 1) {
+        const uint64_t share = (offsets[n_records] - offsets[0] + ndev - 1) / ndev;
+        slab_bytes = std::min(slab_bytes, std::max<uint64_t>(share, (uint64_t)4 << 20));
+    }
     // per (device, slot): the slab it last ran, so its status word can be checked before reuse
     std::vector<int> used(ndev * HX_NSLOT, 0);
     uint32_t r0 = 0;
@@ -907,17 +913,26 @@ int64_t hx_find_all_end(hx_ctx *ctx, const char *pattern, uint32_t pattern_len, 
     const uint64_t ntiles64 = (text_len + tile_len - 1) / tile_len;
     if (ntiles64 > 0x7fffffffull) return fail(ctx, HX_ERR_ARG, "hx_find_all_end: text too long");
     const uint32_t ntiles = (uint32_t)ntiles64;
-    uint8_t *d_text = nullptr, *d_dist = nullptr;
-    uint64_t *d_table = nullptr, *d_counts = nullptr, *d_end = nullptr;
     int64_t result = HX_ERR_CUDA;
     uint64_t total = 0;
     const uint64_t ocap = std::min<uint64_t>(cap, text_len);
-    cudaError_t e = cudaMalloc((void **)&d_text, text_len);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_table, 256 * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_counts, ((size_t)ntiles + 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_end, std::max<uint64_t>(ocap, 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_dist, std::max<uint64_t>(ocap, 1));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_text, text, text_len, cudaMemcpyHostToDevice, st);
+    DevBuf<uint8_t> b_text, b_dist;
+    DevBuf<uint64_t> b_table, b_counts, b_end;
+    for (int pass = 0;; ++pass) {  // one context-owned block, carved per call
+        DevPool &P = ctx->find_pool;
+        P.reset();
+        b_text.carve(P, text_len);
+        b_table.carve(P, 256);
+        b_counts.carve(P, (size_t)ntiles + 1);
+        b_end.carve(P, std::max<uint64_t>(ocap, 1));
+        b_dist.carve(P, std::max<uint64_t>(ocap, 1));
+        if (P.fits()) break;
+        if (pass) return fail(ctx, HX_ERR_STATE, "hx_find_all_end: pool did not fit after growing");
+        HX_CUDA(ctx, P.grow());
+    }
+    uint8_t *d_text = b_text.p, *d_dist = b_dist.p;
+    uint64_t *d_table = b_table.p, *d_counts = b_counts.p, *d_end = b_end.p;
+    cudaError_t e = cudaMemcpyAsync(d_text, text, text_len, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_table, table.data(), 256 * 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         ctx->launches += hx_launch_find(d_text, text_len, (const uint8_t *)d_table, pattern_len, k, tile_len, ntiles,
@@ -937,7 +952,6 @@ int64_t hx_find_all_end(hx_ctx *ctx, const char *pattern, uint32_t pattern_len, 
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) result = (int64_t)total;
     else fail(ctx, HX_ERR_CUDA, "hx_find_all_end: %s", cudaGetErrorString(e));
-    cudaFree(d_text); cudaFree(d_table); cudaFree(d_counts); cudaFree(d_end); cudaFree(d_dist);
     return result;
 }
 
