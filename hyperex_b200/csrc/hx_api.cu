@@ -829,11 +829,13 @@ int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uin
     if (offsets[n_records] > offsets[0] && !arena) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL arena");
     const size_t np = ctx->n_pairs;
     const int ndev = (int)ctx->devs.size();
-    // a batch smaller than ndev slabs is still spread over every device of the context
+    // Slab size: opt_slab_bytes for large batches; a batch of only a few slabs is cut finer (>= 8 slabs per device,
+    // >= 8 MB each) so that the first copy and the last kernel, which nothing overlaps, stay short and every
+    // device of the context gets work.
     uint64_t slab_bytes = (uint64_t)ctx->opt_slab_bytes;
-    if (ndev > 1) {
-        const uint64_t share = (offsets[n_records] - offsets[0] + ndev - 1) / ndev;
-        slab_bytes = std::min(slab_bytes, std::max<uint64_t>(share, (uint64_t)4 << 20));
+    {
+        const uint64_t share = (offsets[n_records] - offsets[0]) / (8ull * ndev) + 1;
+        slab_bytes = std::min(slab_bytes, std::max<uint64_t>(share, (uint64_t)8 << 20));
     }
     // per (device, slot): the slab it last ran, so its status word can be checked before reuse
     std::vector<int> used(ndev * HX_NSLOT, 0);
