@@ -346,6 +346,17 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
+    # context for e2e: the same arena as one plain pinned -> device copy (what PCIe alone costs), outside the timed region
+    t_arena = torch.from_numpy(h_arena[:bases])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_arena[:bases].copy_(t_arena, non_blocking=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(3):
+        d_arena[:bases].copy_(t_arena, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_only_ms = ev0.elapsed_time(ev1) / 3
 
     # results sanity: device-resident and host legs agree, every planted region found (k = 0)
     dev_res = d_out.cpu().numpy().view(hx.RESULT_DTYPE).reshape(n, npairs)
@@ -420,7 +431,10 @@ def main():
                            "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
                 "e2e": {"value": e2e, "unit": "Gbases/s", "gcups": e2e * cells, "ms_per_step": e2e_ms_max / args.steps,
                         "h2d_bytes_per_step": int(bases + offsets.nbytes), "d2h_bytes_per_step": int(n * npairs * 12),
-                        "timer": "host wall clock around hx_run_batch (synchronous), max over ranks"},
+                        "timer": "host wall clock around hx_run_batch (synchronous), max over ranks",
+                        "h2d_copy_alone_ms": h2d_only_ms,
+                        "h2d_copy_alone_gbs": bases / (h2d_only_ms * 1e-3) / 1e9,
+                        "frac_of_copy_alone": h2d_only_ms / (e2e_ms_max / args.steps)},
                 "gpu_launches": int(total_launches), "roofline": roofline, "clocks": clocks}
         if fast_ms_max > 0:
             fv = total_bases / (fast_ms_max * 1e-3) / 1e9

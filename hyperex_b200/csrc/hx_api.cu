@@ -843,8 +843,11 @@ int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uin
     uint64_t slab_idx = 0;
     int rc = HX_OK;
     while (r0 < n_records && rc == HX_OK) {
-        // largest r1 with offsets[r1] - offsets[r0] <= slab_bytes (at least one record)
-        const uint64_t limit = offsets[r0] + slab_bytes;
+        // largest r1 with offsets[r1] - offsets[r0] <= this slab's size (at least one record).  The last slabs of
+        // a batch taper (half of what is left per device, >= 8 MB): only the kernels and the result copy of the very
+        // last slab are not hidden under a host->device copy, so that slab should be small.
+        const uint64_t left = (offsets[n_records] - offsets[r0]) / ndev;
+        const uint64_t limit = offsets[r0] + std::min(slab_bytes, std::max<uint64_t>(left / 2, (uint64_t)8 << 20));
         uint32_t r1 = (uint32_t)(std::upper_bound(offsets + r0 + 1, offsets + n_records + 1, limit) - offsets) - 1;
         if (r1 <= r0) r1 = r0 + 1;
         for (uint32_t i = r0; i < r1; ++i)  // cheap sanity: monotone offsets inside the slab edges
