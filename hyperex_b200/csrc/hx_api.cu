@@ -693,7 +693,7 @@ static int run_batch_text_impl(hx_ctx *ctx, const uint8_t *arena, const uint64_t
     if (id_off[0] != 0 || tail_off[0] != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: id_off / tail_off must start at 0");
     const uint32_t tail_bytes = tail_off[np];
     const uint32_t nblk = (uint32_t)((n_entries + 4095) / 4096);
-    static const bool trace = getenv("HYPEREX_TIMING") && atoi(getenv("HYPEREX_TIMING")) >= 2;
+    static const bool trace = getenv("HYPEREX_TIMING") && atoi(getenv("HYPEREX_TIMING")) >= 2;  // per-call phase times
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tt0 = now();
     HX_CUDA(ctx, cudaStreamSynchronize(st));
@@ -725,24 +725,15 @@ static int run_batch_text_impl(hx_ctx *ctx, const uint8_t *arena, const uint64_t
             HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_gtails.p, gff_tails, gff_tail_off[np], cudaMemcpyHostToDevice, st));
         HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_gtail_off.p, gff_tail_off, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, st));
     }
-    const double ta = now();
     if (copy_bytes) HX_CUDA(ctx, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, st));
-    const double tb = now();
     HX_CUDA(ctx, cudaMemcpyAsync(S.offsets.p, offsets, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, st));
     if (id_bytes) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_ids.p, ids, id_bytes, cudaMemcpyHostToDevice, st));
     HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_id_off.p, id_off, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, st));
     if (tail_bytes) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_tails.p, tails, tail_bytes, cudaMemcpyHostToDevice, st));
     HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_tail_off.p, tail_off, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, st));
-    const double tc = now();
     rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, base, n_records, S.out.p, st);
     if (rc != HX_OK) return rc;
-    const double td = now();
     HX_CUDA(ctx, cudaMemcpyAsync(out, S.out.p, (size_t)n_entries * sizeof(hx_result), cudaMemcpyDeviceToHost, st));
-    const double te = now();
-    if (trace)
-        fprintf(stderr, "[hx_run_batch_text]   reserve %.1f, arena memcpy call %.1f, small memcpys %.1f, enqueue_slab %.1f, "
-                        "result memcpy call %.1f ms\n",
-                (ta - tt0) * 1e3, (tb - ta) * 1e3, (tc - tb) * 1e3, (td - tc) * 1e3, (te - td) * 1e3);
     ctx->launches += hx_launch_fasta_offsets(S.out.p, ctx->ex_id_off.p, ctx->ex_tail_off.p, np, n_entries, ctx->ex_lens.p,
                                              ctx->ex_sums.p, st);
     // total = offset of the last entry + its length = block offset + in-block prefix; read both pieces
@@ -806,8 +797,8 @@ static int run_batch_text_impl(hx_ctx *ctx, const uint8_t *arena, const uint64_t
         HX_CUDA(ctx, cudaGetLastError());
     }
     if (trace)
-        fprintf(stderr, "[hx_run_batch_text] records=%u bases=%llu text=%llu: enqueue %.1f ms, scan sync %.1f ms, "
-                        "alloc+enqueue text %.1f ms, text sync %.1f ms\n",
+        fprintf(stderr, "[hx_run_batch_text] records=%u bases=%llu text=%llu: carve+enqueue %.1f ms, scan sync %.1f ms, "
+                        "enqueue text %.1f ms, text copy/sink %.1f ms\n",
                 n_records, (unsigned long long)bytes, (unsigned long long)(total + gtotal), (tt1 - tt0) * 1e3,
                 (tt2 - tt1) * 1e3, (tt3 - tt2) * 1e3, (now() - tt3) * 1e3);
     sync_timed(ctx);
