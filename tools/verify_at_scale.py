@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--records", type=int, default=1_000_000)
     ap.add_argument("--sample", type=int, default=1000)
     ap.add_argument("--k", type=int, default=-1)
+    ap.add_argument("--fast", type=int, default=1, help="library option fast_small_k (1 = default)")
     args = ap.parse_args()
     rank, world, local = bench.env_int("RANK", 0), bench.env_int("WORLD_SIZE", 1), bench.env_int("LOCAL_RANK", 0)
     import torch
@@ -42,6 +43,7 @@ def main():
     n = len(offsets) - 1
     t0 = time.perf_counter()
     with hx.Context((local,)) as ctx:
+        ctx.set_option("fast_small_k", args.fast)
         ctx.set_primers(pairs, k)
         res = ctx.run_batch(arena, offsets)
         groups = ctx.group_info()
@@ -67,7 +69,7 @@ def main():
         allr = [None] * world
         dist.all_gather_object(allr, mine)
     if rank == 0:
-        print(json.dumps({"workload": desc, "k": k, "pairs": len(pairs), "groups": groups, "world": world,
+        print(json.dumps({"workload": desc, "k": k, "fast_small_k": args.fast, "pairs": len(pairs), "groups": groups, "world": world,
                           "all_samples_equal": all(r["sample_equal_oracle"] for r in allr), "ranks": allr}))
     if world > 1:
         dist.destroy_process_group()
