@@ -4,8 +4,8 @@
  * Every function cites the reference lines it restates (Ebedthan/hyperex v0.2.0,
  * /root/reference/src/utils.rs) or the rust-bio 1.6.0 item whose published algorithm
  * it restates (the crate is not vendored in the reference tree).
- * PARITY STATUS: "parity unpinned" by reference tests; pinned by rust-bio doc vectors
- * + the independent DP below (tests/test_oracle.py).
+ * PARITY STATUS: "parity unpinned" by reference tests; pinned by rust-bio doc vectors,
+ * the independent DP below and a third-party fuzzy-regex engine (tests/test_oracle.py).
  */
 #include "hx_oracle.h"
 

@@ -52,6 +52,30 @@ def test_bitparallel_equals_dp(seed):
         assert O.find_all_end(pat, txt, k) == O.dp_find_all_end(pat, txt, k), (pat, txt, k)
 
 
+def test_bitparallel_equals_third_party_fuzzy_regex():
+    """(end, dist) of the oracle against an implementation nobody here wrote: the `regex` module's fuzzy matching
+    ((?:P){e<=d}, unit-cost insert / delete / substitute).  A hit (i, d) means: d is the smallest error count with which
+    the pattern matches some substring of the text ENDING at i — checked as an anchored match of the reversed pattern on
+    the reversed prefix; pattern symbols become character classes with the asymmetric table of utils.rs:251-263."""
+    regex = pytest.importorskip("regex")
+    amb = {"M": "AC", "R": "AG", "W": "AT", "S": "CG", "Y": "CT", "K": "GT", "V": "ACGMRS", "H": "ACTMWY",
+           "D": "AGTRWK", "B": "CGTSYK", "N": "ACGTMRWSYKVHDB"}
+    rng = np.random.default_rng(5)
+    for _ in range(250):
+        m, n, k = int(rng.integers(2, 12)), int(rng.integers(5, 60)), int(rng.integers(0, 3))
+        pat = "".join(rng.choice(list("ACGTRYNMWVB"), m))
+        text = "".join(rng.choice(list("ACGTNRY"), n, p=[.22, .22, .22, .22, .04, .04, .04]))
+        rp = "".join("[" + c + amb.get(c, "") + "]" for c in reversed(pat))
+        res = [regex.compile("(?:%s){e<=%d}" % (rp, d)) for d in range(k + 1)]
+        want = []
+        for i in range(n):
+            suffix = text[:i + 1][::-1]
+            d = next((d for d in range(k + 1) if res[d].match(suffix)), None)
+            if d is not None:
+                want.append((i, d))
+        assert O.find_all_end(pat, text, k) == want, (pat, text, k)
+
+
 def test_window_restart_is_exact():
     """an automaton restarted m+k-1 bytes before j reports the same dist <= k hits"""
     rng = np.random.default_rng(7)
