@@ -51,6 +51,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--records", type=int, default=1_000_000, help="records per GPU")
     ap.add_argument("--k", type=int, default=-1, help="-m value (default: the workload's own)")
+    ap.add_argument("--long-filter", type=int, default=1, choices=[0, 1],
+                    help="1 (library default): primers > 32 nt are scanned as 32-bit suffix automata + verification; "
+                         "0: 64-bit automata (only matters for c5)")
+    ap.add_argument("--group-max", type=int, default=0, help="experiment: cap on patterns per group (0 = automatic)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 is the BASELINE.json metric config; c3/c4/c5 are informational")
     ap.add_argument("--cpu-sample", type=int, default=60_000, help="records of the cpu_baseline sample")
@@ -255,6 +259,8 @@ def main():
     # GCUPS"), so `value`, `e2e` and `roofline` are measured with the small-k fast path OFF; the library default
     # (fast path ON for -m 0..2) is timed separately below and reported as `fast_path`.
     ctx.set_option("fast_small_k", 0)
+    ctx.set_option("long_filter", args.long_filter)
+    ctx.set_option("group_np_max", args.group_max)
     if args.slab_mb > 0:
         ctx.set_option("slab_bytes", args.slab_mb << 20)
     ctx.set_primers(pairs, args.k)
@@ -313,9 +319,11 @@ def main():
         ctx.set_option("text_tma", 0)
 
     # ---- the library default for small k: Wu-Manber / Shift-Or fast path (not part of the timed region) ----
-    fast_ms = None
+    fast_ms, fast_groups = None, (0, 0, 0)
     if args.k <= 2 and not args.no_ab:
         ctx.set_option("fast_small_k", 1)
+        ctx.set_primers(pairs, args.k)  # the grouping depends on it (-m 2: groups of <= 8 automata)
+        fast_groups = ctx.group_info()
         for _ in range(2):
             dev_step()
         barrier()
@@ -328,6 +336,7 @@ def main():
         fast_ms = e0.elapsed_time(e1) / args.steps
         fast_res = d_out.cpu().numpy().tobytes()
         ctx.set_option("fast_small_k", 0)
+        ctx.set_primers(pairs, args.k)
         dev_step()
         torch.cuda.synchronize()
         assert fast_res == d_out.cpu().numpy().tobytes(), "fast path and Myers path disagree"
@@ -414,10 +423,12 @@ def main():
                                     "frac": (steps_per_s * (alu_ops + fma_ops) / 1e12 / peak["lop3_imad"])
                                     if peak.get("lop3_imad") else None},
                     "bare_step_peak_gsteps": (peak.get("myers_step") or 0) * 1e3,
-                    "traffic": load_traffic(bases) if args.workload == "c2" else None,
+                    "traffic": None, "traffic_detail": load_traffic(bases) if args.workload == "c2" else None,
                     "hbm": {"achieved": bases * n_groups / (scan_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": bases * n_groups / (scan_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                             "algorithmic_bytes_per_launch": bases}}
+        if roofline["traffic_detail"]:  # contract: `traffic` = dram bytes read + written per launch (ncu), a number
+            roofline["traffic"] = roofline["traffic_detail"]["bytes"]
         if ab_ms is not None:
             roofline["text_path_ab"] = {"ldg_ms_per_step": dev_ms_max / args.steps, "tma_ms_per_step": ab_ms}
         line = {"metric": "Gbases/s", "value": value, "unit": "Gbases/s", "gcups": value * cells,
@@ -425,6 +436,8 @@ def main():
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": workload_desc, "records_per_gpu": n,
+                           "automata_per_base": {"u32": steps32, "u64": steps64, "groups": n_groups,
+                                                 "long_filter": args.long_filter},
                            "bases_per_gpu": bases, "pairs": npairs, "k": args.k, "regions_found": found,
                            "l2": f"inputs ({bases / 1e9:.2f} GB/GPU) larger than the 126 MB L2; no flush needed",
                            "parallelism": f"records sharded over {world} GPU(s), no collective",
@@ -440,7 +453,8 @@ def main():
             fv = total_bases / (fast_ms_max * 1e-3) / 1e9
             line["fast_path"] = {"what": "library default for -m 0..2: Wu-Manber / Shift-Or automata, identical results "
                                          "(asserted), not counted as Myers GCUPS", "value": fv, "unit": "Gbases/s",
-                                 "ms_per_step": fast_ms_max, "speedup_vs_myers": dev_ms_max / args.steps / fast_ms_max}
+                                 "ms_per_step": fast_ms_max, "speedup_vs_myers": dev_ms_max / args.steps / fast_ms_max,
+                                 "groups": fast_groups[0], "automata_per_base": fast_groups[1] + fast_groups[2]}
         if not args.no_cpu_baseline:
             ns = min(args.cpu_sample, n)
             cb, cdt = cpu_port_run(arena, offsets, ns, pairs, args.k, 1)

@@ -295,6 +295,24 @@ def get_hypervar_regions(file: str, primers, prefix: str, mismatch: int, devices
         ctx.get_hypervar_regions(file, primers, prefix, mismatch, log=log)
 
 
+def plan_groups(primers: Sequence[Sequence[str]], mismatch: int, fast_small_k: bool = True, long_filter: bool = True,
+                group_np_max: int = 0):
+    """hx_plan_groups (host only, no GPU): (n_groups, 32-bit automata per base, 64-bit automata per base, group of
+    every pair) for what hx_set_primers would build from this primer set and these options"""
+    L = _lib.load()
+    fw = [_b(p[0]) for p in primers]
+    rv = [_b(p[1]) for p in primers]
+    fl = (C.c_uint32 * max(1, len(fw)))(*[len(x) for x in fw])
+    rl = (C.c_uint32 * max(1, len(rv)))(*[len(x) for x in rv])
+    g, a, b = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    pg = np.zeros(max(1, len(primers)), np.uint32)
+    rc = L.hx_plan_groups(len(primers), _cstrs(fw), fl, _cstrs(rv), rl, mismatch, int(fast_small_k), int(long_filter),
+                          group_np_max, C.byref(g), C.byref(a), C.byref(b), pg.ctypes.data)
+    if rc != 0:
+        raise HyperexError(rc, (L.hx_last_error(None) or b"").decode())
+    return g.value, a.value, b.value, pg[:len(primers)].tolist()
+
+
 def int_peak(variant: int, iters: int = 2000, device: int = 0) -> float:
     """measured integer throughput (1e9 lane-ops/s) of one instruction class; see hx_int_peak"""
     g = C.c_double()

@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,7 @@ struct Device {
     Slot slots[HX_NSLOT];
     uint8_t *d_tables = nullptr;
     uint8_t *d_tables_wm = nullptr;
+    uint64_t *d_vtables = nullptr;  // 64-bit verification tables of the suffix-filtered primers
     HxGroup *d_groups = nullptr;
     HxPairRef *d_pairs = nullptr;
 };
@@ -115,7 +117,8 @@ struct hx_ctx {
     std::vector<uint8_t> tables;
     bool primers_set = false;
     // options
-    int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1;
+    int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1,
+            opt_long_filter = 1, opt_group_np_max = 0;
     uint64_t launches = 0;
     // on-device extraction (device 0)
     DevPool ex_pool, ex_text_pool, find_pool;
@@ -282,6 +285,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
         a.n_pairs_total = ctx->n_pairs;
         a.tables = D.d_tables + hg.table_off;
         a.tables_wm = D.d_tables_wm + hg.table_off;
+        a.vtables = D.d_vtables;
         // small-k fast path: identical hits, fewer ALU operations; 32-bit groups, vector-load text path
         // (measured: at -m 2 the fast path only pays for narrow groups; wide groups run out of registers)
         a.wm_k = (ctx->opt_fast_small_k && !hg.word64 && !ctx->opt_text_tma && (ctx->k <= 1 || (ctx->k == 2 && hg.np <= 8)))
@@ -294,7 +298,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
         a.pair_lo = S.pair_lo.p;
         a.tile_stride = pl.tile_cap;
         a.k = ctx->k;
-        a.variant = (int)ctx->opt_text_tma;
+        a.variant = hg.longmask ? 0 : (int)ctx->opt_text_tma;  // suffix-filtered groups: vector-load text path only
         a.two = 2;
         TimedLaunch tl;
         if (ctx->opt_time) {
@@ -321,6 +325,241 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
 int check_status(hx_ctx *ctx, const Slot &S) {
     if (S.h_status[1] == 2) return fail(ctx, HX_ERR_ARG, "a record is longer than 2^32-257 bytes");
     if (S.h_status[1]) return fail(ctx, HX_ERR_CAPACITY, "internal tile capacity exceeded");
+    return HX_OK;
+}
+
+// Host half of hx_set_primers (no CUDA): primer strings -> pattern groups, Peq tables, verification tables.
+struct PlanOpts {
+    int64_t fast_small_k, long_filter, group_np_max;
+};
+struct PrimerPlan {
+    std::vector<HxGroup> groups;
+    std::vector<HxPairRef> refs;
+    std::vector<uint8_t> blob, blob_wm;
+    std::vector<uint64_t> vblob;  // [vslot][alphabet][256]
+    uint32_t m_max = 0, n_slots = 0;
+};
+
+int pfail(std::string &err, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+}
+
+int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len,
+                 const char *const *rev, const uint32_t *rev_len, uint8_t k, PrimerPlan &P, std::string &err) {
+    if (n_pairs == 0 || n_pairs > 65535 || !fwd || !rev)
+        return pfail(err, HX_ERR_ARG, "hx_set_primers: need 1..65535 primer pairs");
+    std::vector<std::string> F(n_pairs), R(n_pairs);
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        if (!fwd[i] || !rev[i]) return pfail(err, HX_ERR_ARG, "hx_set_primers: NULL primer in pair %u", i);
+        const size_t lf = fwd_len ? fwd_len[i] : strlen(fwd[i]);
+        const size_t lr = rev_len ? rev_len[i] : strlen(rev[i]);
+        // rust-bio build_64 asserts 0 < m <= 64 (call sites utils.rs:301-302)
+        if (lf == 0 || lf > 64 || lr == 0 || lr > 64)
+            return pfail(err, HX_ERR_ARG, "hx_set_primers: pair %u: primer length must be 1..64 (got %zu, %zu)", i, lf,
+                        lr);
+        F[i].assign(fwd[i], lf);
+        R[i].assign(rev[i], lr);
+        if (memchr(F[i].data(), 0, lf) || memchr(R[i].data(), 0, lr))
+            return pfail(err, HX_ERR_ARG, "hx_set_primers: pair %u: NUL byte inside a primer", i);
+    }
+    // unique patterns per pair: forward as given; reverse = reverse complement per alphabet (utils.rs:299)
+    struct PairPat { PatternKey f, r; bool is_long; };
+    std::vector<PairPat> pp(n_pairs);
+    uint32_t m_max = 0;
+    // Suffix filter (hx_kernels.cu: hx_verify_long): primers of 33..64 symbols are scanned as the 32-bit automaton of
+    // their last 32 symbols and every candidate is verified against the whole primer, so no 64-bit group is needed.
+    // Only for small k: with k close to 32 every position becomes a candidate.
+    const bool filter = o.long_filter && k <= 8;
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        pp[i].f = PatternKey{F[i], F[i]};
+        std::string rd(R[i].size(), '\0'), rr(R[i].size(), '\0');
+        hx_to_reverse_complement(R[i].data(), R[i].size(), 0, &rd[0]);
+        hx_to_reverse_complement(R[i].data(), R[i].size(), 1, &rr[0]);
+        pp[i].r = PatternKey{rd, rr};
+        pp[i].is_long = !filter && (F[i].size() > 32 || R[i].size() > 32);
+        m_max = std::max<uint32_t>(m_max, (uint32_t)std::max(F[i].size(), R[i].size()));
+    }
+    // Grouping, short (32-bit words) and long (64-bit words) pairs separately.  Pairs that share a pattern (27F and
+    // 1492Rmod serve three built-in regions each) should land in the same group, or the shared automaton is stepped
+    // once per group: pairs are first joined into the connected components of the "shares a pattern" relation, whole
+    // components are packed first-fit-decreasing into groups of <= np_max patterns and <= HX_MAX_GROUP_PAIRS pairs,
+    // and only a component that does not fit a group by itself is cut (in pair order, duplicating what it must).
+    std::vector<HxGroup> &groups = P.groups;
+    std::vector<std::vector<PatternKey>> gpats;
+    std::vector<HxPairRef> &refs = P.refs;
+    groups.clear();
+    refs.assign(n_pairs, HxPairRef{0, 0, 0, 0});
+    std::map<std::pair<std::string, std::string>, int> pat_id;
+    std::vector<int> fid(n_pairs), rid(n_pairs);
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        fid[i] = pat_id.emplace(std::make_pair(pp[i].f.dna, pp[i].f.rna), (int)pat_id.size()).first->second;
+        rid[i] = pat_id.emplace(std::make_pair(pp[i].r.dna, pp[i].r.rna), (int)pat_id.size()).first->second;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool want_long = pass == 1;
+        int np_max = want_long ? HX_MAX_NP64 : HX_MAX_NP32;
+        // -m 2 on the Wu-Manber path: three bit-vectors per automaton, so only groups of <= 8 patterns stay in
+        // registers (measured: c5 108.7 -> 86.4 ms, built-in regions 14.3 -> 13.3 ms even with two automata duplicated)
+        if (!want_long && k == 2 && o.fast_small_k) np_max = 8;
+        if (o.group_np_max >= 2) np_max = std::min<int>(np_max, (int)o.group_np_max);
+        // connected components over the pairs of this class (union-find on pattern ids)
+        std::vector<int> parent(pat_id.size());
+        for (size_t j = 0; j < parent.size(); ++j) parent[j] = (int)j;
+        auto root = [&](int x) {
+            while (parent[x] != x) x = parent[x] = parent[parent[x]];
+            return x;
+        };
+        for (uint32_t i = 0; i < n_pairs; ++i)
+            if (pp[i].is_long == want_long) parent[root(fid[i])] = root(rid[i]);
+        std::map<int, std::vector<uint32_t>> comps;  // root -> pairs, ascending
+        for (uint32_t i = 0; i < n_pairs; ++i)
+            if (pp[i].is_long == want_long) comps[root(fid[i])].push_back(i);
+        // items = whole components, or the pair-order pieces of one that is too large for a group
+        struct Item { std::vector<uint32_t> pairs; std::vector<int> pats; uint32_t first; };
+        std::vector<Item> items;
+        for (auto &c : comps) {
+            Item it;
+            it.first = c.second[0];
+            for (uint32_t i : c.second) {
+                const int need = (std::find(it.pats.begin(), it.pats.end(), fid[i]) == it.pats.end() ? 1 : 0) +
+                                 ((rid[i] != fid[i] && std::find(it.pats.begin(), it.pats.end(), rid[i]) == it.pats.end()) ? 1 : 0);
+                if (!it.pairs.empty() && ((int)it.pats.size() + need > np_max || it.pairs.size() >= HX_MAX_GROUP_PAIRS)) {
+                    items.push_back(it);
+                    it = Item();
+                    it.first = i;
+                }
+                if (std::find(it.pats.begin(), it.pats.end(), fid[i]) == it.pats.end()) it.pats.push_back(fid[i]);
+                if (std::find(it.pats.begin(), it.pats.end(), rid[i]) == it.pats.end()) it.pats.push_back(rid[i]);
+                it.pairs.push_back(i);
+            }
+            items.push_back(it);
+        }
+        std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) {
+            return x.pats.size() != y.pats.size() ? x.pats.size() > y.pats.size() : x.first < y.first;
+        });
+        struct Bin { std::vector<uint32_t> pairs; size_t npat; uint32_t first; };
+        std::vector<Bin> bins;
+        size_t first_open = 0;
+        for (const Item &it : items) {
+            size_t b = first_open;
+            for (; b < bins.size(); ++b)
+                if (bins[b].npat + it.pats.size() <= (size_t)np_max && bins[b].pairs.size() + it.pairs.size() <= HX_MAX_GROUP_PAIRS)
+                    break;
+            if (b == bins.size()) bins.push_back(Bin{{}, 0, it.first});
+            bins[b].pairs.insert(bins[b].pairs.end(), it.pairs.begin(), it.pairs.end());
+            bins[b].npat += it.pats.size();
+            bins[b].first = std::min(bins[b].first, it.first);
+            while (first_open < bins.size() && (bins[first_open].npat >= (size_t)np_max || bins[first_open].pairs.size() >= HX_MAX_GROUP_PAIRS ||
+                                                bins.size() - first_open > 64))
+                ++first_open;  // full, or too far back to be worth searching
+        }
+        std::sort(bins.begin(), bins.end(), [](const Bin &x, const Bin &y) { return x.first < y.first; });
+        for (Bin &bin : bins) {
+            std::sort(bin.pairs.begin(), bin.pairs.end());
+            HxGroup g;
+            memset(&g, 0, sizeof g);
+            g.word64 = want_long ? 1 : 0;
+            groups.push_back(g);
+            gpats.emplace_back();
+            const int cur = (int)groups.size() - 1;
+            auto slot_of = [&](const PatternKey &key) -> int {
+                for (size_t j = 0; j < gpats[cur].size(); ++j)
+                    if (gpats[cur][j] == key) return (int)j;
+                gpats[cur].push_back(key);
+                return (int)gpats[cur].size() - 1;
+            };
+            for (uint32_t i : bin.pairs) {
+                const int fi = slot_of(pp[i].f), ri = slot_of(pp[i].r);
+                HxGroup &gg = groups[cur];
+                gg.pair_f[gg.npairs] = (uint8_t)fi;
+                gg.pair_r[gg.npairs] = (uint8_t)ri;
+                gg.pair_global[gg.npairs] = (uint16_t)i;
+                gg.rmask[ri] |= (uint16_t)(1u << gg.npairs);
+                gg.npairs++;
+                refs[i].len_f = (uint32_t)F[i].size();  // utils.rs:327 forward_len
+                refs[i].pad = (uint32_t)cur;            // group index for now, slots resolved below
+                refs[i].f_slot = (uint32_t)fi;
+                refs[i].r_slot = (uint32_t)ri;
+            }
+            if ((int)gpats[cur].size() > np_max || groups[cur].npairs > HX_MAX_GROUP_PAIRS)
+                return pfail(err, HX_ERR_STATE, "hx_set_primers: internal grouping error");
+        }
+    }
+    // tables: [group][alphabet dna|rna][256 rows][row stride]; text bytes are case-folded
+    // here (utils.rs:295) so the kernel indexes rows with the raw byte.
+    std::vector<uint8_t> &blob = P.blob, &blob_wm = P.blob_wm;
+    std::vector<uint64_t> &vblob = P.vblob;
+    blob.clear();
+    blob_wm.clear();
+    vblob.clear();
+    uint32_t slot_base = 0;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        HxGroup &g = groups[gi];
+        g.np = (int)gpats[gi].size();
+        g.slot_base = slot_base;
+        slot_base += (uint32_t)g.np;
+        const int wb = g.word64 ? 8 : 4, bits = wb * 8;
+        const int stride = hx_row_stride(g.np, wb);
+        g.table_off = (uint32_t)blob.size();
+        blob.resize(blob.size() + 2 * (size_t)hx_table_bytes(g.np, wb), 0);
+        blob_wm.resize(blob.size(), 0);
+        // what the group's automata scan: the primer, or its last `bits` symbols when it is longer than the word
+        std::vector<PatternKey> scan(gpats[gi]);
+        for (int p = 0; p < g.np; ++p) {
+            const size_t full = gpats[gi][p].dna.size();
+            g.mfull[p] = (uint8_t)full;
+            if (full > (size_t)bits) {
+                scan[p].dna = scan[p].dna.substr(full - bits);
+                scan[p].rna = scan[p].rna.substr(full - bits);
+                g.longmask |= 1u << p;
+                g.vslot[p] = (uint32_t)(vblob.size() / 512);
+                for (int alpha = 0; alpha < 2; ++alpha)
+                    for (int b = 0; b < 256; ++b) {
+                        const uint8_t u = (b >= 'a' && b <= 'z') ? (uint8_t)(b - 32) : (uint8_t)b;
+                        vblob.push_back(b ? peq_word(alpha ? gpats[gi][p].rna : gpats[gi][p].dna, u, 64) : 0ull);
+                    }
+            }
+            g.m[p] = (uint8_t)scan[p].dna.size();
+        }
+        for (int alpha = 0; alpha < 2; ++alpha) {
+            uint8_t *tab = blob.data() + g.table_off + (size_t)alpha * hx_table_bytes(g.np, wb);
+            for (int b = 1; b < 256; ++b) {  // row 0 stays all-zero: the "null" byte
+                const uint8_t u = (b >= 'a' && b <= 'z') ? (uint8_t)(b - 32) : (uint8_t)b;
+                for (int p = 0; p < g.np; ++p) {
+                    const std::string &pat = alpha ? scan[p].rna : scan[p].dna;
+                    const uint64_t w = peq_word(pat, u, bits);
+                    memcpy(tab + (size_t)b * stride + (size_t)p * wb, &w, wb);  // little endian: low bytes first
+                }
+            }
+            // fast-path table: complemented inside the pattern bits, 0 in the unused low bits; row 0 (the
+            // null byte) matches nothing, i.e. all pattern bits set
+            uint8_t *tabw = blob_wm.data() + g.table_off + (size_t)alpha * hx_table_bytes(g.np, wb);
+            for (int b = 0; b < 256; ++b) {
+                for (int p = 0; p < g.np; ++p) {
+                    const int m = g.m[p];
+                    const uint64_t pmask = m >= bits ? ~0ull : (((1ull << m) - 1) << (bits - m));
+                    uint64_t w = 0;
+                    memcpy(&w, tab + (size_t)b * stride + (size_t)p * wb, wb);
+                    const uint64_t nw = ~w & pmask & (wb == 8 ? ~0ull : 0xffffffffull);
+                    memcpy(tabw + (size_t)b * stride + (size_t)p * wb, &nw, wb);
+                }
+            }
+        }
+    }
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        const HxGroup &g = groups[refs[i].pad];
+        refs[i].f_slot += g.slot_base;
+        refs[i].r_slot += g.slot_base;
+        refs[i].pad = 0;
+    }
+    P.m_max = m_max;
+    P.n_slots = slot_base;
     return HX_OK;
 }
 
@@ -386,6 +625,7 @@ void hx_destroy(hx_ctx *ctx) {
         for (Slot &S : D.slots) S.release();
         if (D.d_tables) cudaFree(D.d_tables);
         if (D.d_tables_wm) cudaFree(D.d_tables_wm);
+        if (D.d_vtables) cudaFree(D.d_vtables);
         if (D.d_groups) cudaFree(D.d_groups);
         if (D.d_pairs) cudaFree(D.d_pairs);
     }
@@ -401,6 +641,8 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     else if (n == "time_kernels") ctx->opt_time = value;
     else if (n == "text_tma") ctx->opt_text_tma = value ? 1 : 0;
     else if (n == "fast_small_k") ctx->opt_fast_small_k = value ? 1 : 0;
+    else if (n == "long_filter") ctx->opt_long_filter = value ? 1 : 0;  // read by hx_set_primers
+    else if (n == "group_np_max") ctx->opt_group_np_max = value;         // read by hx_set_primers; 0 = automatic
     else return fail(ctx, HX_ERR_ARG, "unknown option %s", name);
     return HX_OK;
 }
@@ -408,142 +650,33 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
 int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len,
                    const char *const *rev, const uint32_t *rev_len, uint8_t k) {
     if (!ctx) return HX_ERR_ARG;
-    if (n_pairs == 0 || n_pairs > 65535 || !fwd || !rev)
-        return fail(ctx, HX_ERR_ARG, "hx_set_primers: need 1..65535 primer pairs");
     ctx->primers_set = false;
-    std::vector<std::string> F(n_pairs), R(n_pairs);
-    for (uint32_t i = 0; i < n_pairs; ++i) {
-        if (!fwd[i] || !rev[i]) return fail(ctx, HX_ERR_ARG, "hx_set_primers: NULL primer in pair %u", i);
-        const size_t lf = fwd_len ? fwd_len[i] : strlen(fwd[i]);
-        const size_t lr = rev_len ? rev_len[i] : strlen(rev[i]);
-        // rust-bio build_64 asserts 0 < m <= 64 (call sites utils.rs:301-302)
-        if (lf == 0 || lf > 64 || lr == 0 || lr > 64)
-            return fail(ctx, HX_ERR_ARG, "hx_set_primers: pair %u: primer length must be 1..64 (got %zu, %zu)", i, lf,
-                        lr);
-        F[i].assign(fwd[i], lf);
-        R[i].assign(rev[i], lr);
-        if (memchr(F[i].data(), 0, lf) || memchr(R[i].data(), 0, lr))
-            return fail(ctx, HX_ERR_ARG, "hx_set_primers: pair %u: NUL byte inside a primer", i);
+    PrimerPlan P;
+    {
+        const PlanOpts o = {ctx->opt_fast_small_k, ctx->opt_long_filter, ctx->opt_group_np_max};
+        std::string err;
+        const int rc = plan_primers(o, n_pairs, fwd, fwd_len, rev, rev_len, k, P, err);
+        if (rc != HX_OK) return fail(ctx, rc, "%s", err.c_str());
     }
-    // unique patterns per pair: forward as given; reverse = reverse complement per alphabet (utils.rs:299)
-    struct PairPat { PatternKey f, r; bool is_long; };
-    std::vector<PairPat> pp(n_pairs);
-    uint32_t m_max = 0;
-    for (uint32_t i = 0; i < n_pairs; ++i) {
-        pp[i].f = PatternKey{F[i], F[i]};
-        std::string rd(R[i].size(), '\0'), rr(R[i].size(), '\0');
-        hx_to_reverse_complement(R[i].data(), R[i].size(), 0, &rd[0]);
-        hx_to_reverse_complement(R[i].data(), R[i].size(), 1, &rr[0]);
-        pp[i].r = PatternKey{rd, rr};
-        pp[i].is_long = F[i].size() > 32 || R[i].size() > 32;
-        m_max = std::max<uint32_t>(m_max, (uint32_t)std::max(F[i].size(), R[i].size()));
-    }
-    // greedy grouping, short (32-bit words) and long (64-bit words) pairs separately
-    std::vector<HxGroup> groups;
-    std::vector<std::vector<PatternKey>> gpats;
-    std::vector<HxPairRef> refs(n_pairs);
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool want_long = pass == 1;
-        const int np_max = want_long ? HX_MAX_NP64 : HX_MAX_NP32;
-        int cur = -1;
-        for (uint32_t i = 0; i < n_pairs; ++i) {
-            if (pp[i].is_long != want_long) continue;
-            auto find_in = [&](int gidx, const PatternKey &key) -> int {
-                for (size_t j = 0; j < gpats[gidx].size(); ++j)
-                    if (gpats[gidx][j] == key) return (int)j;
-                return -1;
-            };
-            int fi = -1, ri = -1, need = 0;
-            if (cur >= 0) {
-                fi = find_in(cur, pp[i].f);
-                ri = find_in(cur, pp[i].r);
-                need = (fi < 0 ? 1 : 0) + ((ri < 0 && !(pp[i].r == pp[i].f)) ? 1 : 0);
-            }
-            if (cur < 0 || (int)gpats[cur].size() + need > np_max || groups[cur].npairs >= HX_MAX_GROUP_PAIRS) {
-                HxGroup g;
-                memset(&g, 0, sizeof g);
-                g.word64 = want_long ? 1 : 0;
-                groups.push_back(g);
-                gpats.emplace_back();
-                cur = (int)groups.size() - 1;
-                fi = ri = -1;
-            }
-            if (fi < 0) {
-                gpats[cur].push_back(pp[i].f);
-                fi = (int)gpats[cur].size() - 1;
-            }
-            ri = find_in(cur, pp[i].r);
-            if (ri < 0) {
-                gpats[cur].push_back(pp[i].r);
-                ri = (int)gpats[cur].size() - 1;
-            }
-            HxGroup &g = groups[cur];
-            g.pair_f[g.npairs] = (uint8_t)fi;
-            g.pair_r[g.npairs] = (uint8_t)ri;
-            g.pair_global[g.npairs] = (uint16_t)i;
-            g.rmask[ri] |= (uint16_t)(1u << g.npairs);
-            g.npairs++;
-            refs[i].len_f = (uint32_t)F[i].size();  // utils.rs:327 forward_len
-            refs[i].pad = (uint32_t)cur;            // group index for now, slots resolved below
-            refs[i].f_slot = (uint32_t)fi;
-            refs[i].r_slot = (uint32_t)ri;
-        }
-    }
-    // tables: [group][alphabet dna|rna][256 rows][row stride]; text bytes are case-folded
-    // here (utils.rs:295) so the kernel indexes rows with the raw byte.
-    std::vector<uint8_t> blob, blob_wm;
-    uint32_t slot_base = 0;
-    for (size_t gi = 0; gi < groups.size(); ++gi) {
-        HxGroup &g = groups[gi];
-        g.np = (int)gpats[gi].size();
-        g.slot_base = slot_base;
-        slot_base += (uint32_t)g.np;
-        const int wb = g.word64 ? 8 : 4, bits = wb * 8;
-        const int stride = hx_row_stride(g.np, wb);
-        g.table_off = (uint32_t)blob.size();
-        blob.resize(blob.size() + 2 * (size_t)hx_table_bytes(g.np, wb), 0);
-        blob_wm.resize(blob.size(), 0);
-        for (int p = 0; p < g.np; ++p) g.m[p] = (uint8_t)gpats[gi][p].dna.size();
-        for (int alpha = 0; alpha < 2; ++alpha) {
-            uint8_t *tab = blob.data() + g.table_off + (size_t)alpha * hx_table_bytes(g.np, wb);
-            for (int b = 1; b < 256; ++b) {  // row 0 stays all-zero: the "null" byte
-                const uint8_t u = (b >= 'a' && b <= 'z') ? (uint8_t)(b - 32) : (uint8_t)b;
-                for (int p = 0; p < g.np; ++p) {
-                    const std::string &pat = alpha ? gpats[gi][p].rna : gpats[gi][p].dna;
-                    const uint64_t w = peq_word(pat, u, bits);
-                    memcpy(tab + (size_t)b * stride + (size_t)p * wb, &w, wb);  // little endian: low bytes first
-                }
-            }
-            // fast-path table: complemented inside the pattern bits, 0 in the unused low bits; row 0 (the
-            // null byte) matches nothing, i.e. all pattern bits set
-            uint8_t *tabw = blob_wm.data() + g.table_off + (size_t)alpha * hx_table_bytes(g.np, wb);
-            for (int b = 0; b < 256; ++b) {
-                for (int p = 0; p < g.np; ++p) {
-                    const int m = g.m[p];
-                    const uint64_t pmask = m >= bits ? ~0ull : (((1ull << m) - 1) << (bits - m));
-                    uint64_t w = 0;
-                    memcpy(&w, tab + (size_t)b * stride + (size_t)p * wb, wb);
-                    const uint64_t nw = ~w & pmask & (wb == 8 ? ~0ull : 0xffffffffull);
-                    memcpy(tabw + (size_t)b * stride + (size_t)p * wb, &nw, wb);
-                }
-            }
-        }
-    }
-    for (uint32_t i = 0; i < n_pairs; ++i) {
-        const HxGroup &g = groups[refs[i].pad];
-        refs[i].f_slot += g.slot_base;
-        refs[i].r_slot += g.slot_base;
-        refs[i].pad = 0;
-    }
+    std::vector<HxGroup> &groups = P.groups;
+    std::vector<HxPairRef> &refs = P.refs;
+    std::vector<uint8_t> &blob = P.blob, &blob_wm = P.blob_wm;
+    std::vector<uint64_t> &vblob = P.vblob;
+    const uint32_t m_max = P.m_max, slot_base = P.n_slots;
     // upload to every device
     for (Device &D : ctx->devs) {
         HX_CUDA(ctx, cudaSetDevice(D.dev));
         HX_CUDA(ctx, cudaDeviceSynchronize());
         if (D.d_tables) cudaFree(D.d_tables);
         if (D.d_tables_wm) cudaFree(D.d_tables_wm);
+        if (D.d_vtables) cudaFree(D.d_vtables);
         if (D.d_groups) cudaFree(D.d_groups);
         if (D.d_pairs) cudaFree(D.d_pairs);
-        D.d_tables = nullptr; D.d_tables_wm = nullptr; D.d_groups = nullptr; D.d_pairs = nullptr;
+        D.d_tables = nullptr; D.d_tables_wm = nullptr; D.d_vtables = nullptr; D.d_groups = nullptr; D.d_pairs = nullptr;
+        if (!vblob.empty()) {
+            HX_CUDA(ctx, cudaMalloc((void **)&D.d_vtables, vblob.size() * sizeof(uint64_t)));
+            HX_CUDA(ctx, cudaMemcpy(D.d_vtables, vblob.data(), vblob.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        }
         HX_CUDA(ctx, cudaMalloc((void **)&D.d_tables, blob.size()));
         HX_CUDA(ctx, cudaMalloc((void **)&D.d_tables_wm, blob_wm.size()));
         HX_CUDA(ctx, cudaMemcpy(D.d_tables_wm, blob_wm.data(), blob_wm.size(), cudaMemcpyHostToDevice));
@@ -968,6 +1101,27 @@ int hx_group_info(const hx_ctx *ctx, uint32_t *n_groups, uint32_t *steps32_per_b
     uint32_t s32 = 0, s64 = 0;
     for (const HxGroup &g : ctx->groups) (g.word64 ? s64 : s32) += (uint32_t)g.np;
     if (n_groups) *n_groups = (uint32_t)ctx->groups.size();
+    if (steps32_per_base) *steps32_per_base = s32;
+    if (steps64_per_base) *steps64_per_base = s64;
+    return HX_OK;
+}
+
+int hx_plan_groups(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len, const char *const *rev,
+                   const uint32_t *rev_len, uint8_t k, int fast_small_k, int long_filter, int group_np_max,
+                   uint32_t *n_groups, uint32_t *steps32_per_base, uint32_t *steps64_per_base, uint32_t *pair_group) {
+    PrimerPlan P;
+    const PlanOpts o = {fast_small_k, long_filter, group_np_max};
+    std::string err;
+    const int rc = plan_primers(o, n_pairs, fwd, fwd_len, rev, rev_len, k, P, err);
+    if (rc != HX_OK) return fail(nullptr, rc, "%s", err.c_str());
+    uint32_t s32 = 0, s64 = 0;
+    for (size_t gi = 0; gi < P.groups.size(); ++gi) {
+        const HxGroup &g = P.groups[gi];
+        (g.word64 ? s64 : s32) += (uint32_t)g.np;
+        if (pair_group)
+            for (int q = 0; q < g.npairs; ++q) pair_group[g.pair_global[q]] = (uint32_t)gi;
+    }
+    if (n_groups) *n_groups = (uint32_t)P.groups.size();
     if (steps32_per_base) *steps32_per_base = s32;
     if (steps64_per_base) *steps64_per_base = s64;
     return HX_OK;

@@ -39,11 +39,16 @@ struct HxGroup {
     int32_t word64;                           // 1 => 64-bit automaton words
     uint32_t table_off;                       // byte offset of the group's Peq table in the blob
     uint32_t slot_base;                       // first per-pattern summary slot of the group
-    uint8_t m[HX_MAX_NP32];                   // pattern lengths
+    uint8_t m[HX_MAX_NP32];                   // SCANNED pattern lengths (<= 32 in a 32-bit group: a primer longer
+                                              // than the word is scanned as its 32-symbol suffix, see longmask)
+    uint8_t mfull[HX_MAX_NP32];               // primer lengths as given (utils.rs:327, 334-337 use these)
     uint8_t pair_f[HX_MAX_GROUP_PAIRS];       // group-local forward pattern of each pair
     uint8_t pair_r[HX_MAX_GROUP_PAIRS];       // group-local reverse pattern of each pair
     uint16_t pair_global[HX_MAX_GROUP_PAIRS]; // index of the pair in hx_set_primers order
     uint16_t rmask[HX_MAX_NP32];              // bit q set: pair q of the group has this pattern as reverse
+    uint32_t vslot[HX_MAX_NP32];              // suffix-filtered pattern: index of its 64-bit verification table
+    uint32_t longmask;                        // bit p set: pattern p is the 32-symbol suffix of a longer primer; its
+                                              // events are candidates, verified against the whole primer in the drain
 };
 
 // global pair -> where its summaries live (used by the pairing/combine kernel)
@@ -74,6 +79,7 @@ struct HxScanArgs {
     uint32_t n_pairs_total;
     const uint8_t *tables;     // Peq blob
     const uint8_t *tables_wm;  // complemented Peq blob of the small-k fast path (Shift-Or convention)
+    const uint64_t *vtables;   // [vslot][alphabet dna|rna][256] top-aligned 64-bit Peq words of the suffix-filtered primers
     int32_t wm_k;              // >= 0: run the Wu-Manber fast path with this many errors (32-bit groups only)
     const HxGroup *group;      // this launch's group (device memory)
     uint64_t *sum_f;           // [slot][tile] best valid forward hit  key = dist<<32 | end

@@ -456,7 +456,23 @@ __device__ __forceinline__ void hx_mbar_wait(uint32_t mbar, uint32_t parity) {
 }
 __device__ __forceinline__ void hx_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <typename W, int NP, bool TMA, int KWM>
+// Suffix filter (LF = true): a primer longer than 32 symbols is scanned as the 32-bit automaton of its LAST 32
+// symbols.  An alignment of the whole primer ending at text position j with <= k edits contains an alignment of
+// that suffix ending at j with <= k edits, so {j : dist_suffix(j) <= k} is a superset of the primer's hits and a
+// 64-bit automaton never has to be stepped over the whole text.  Each candidate is verified here, in the
+// warp-synchronous drain: a fresh 64-bit automaton of the whole primer over the m + k text bytes that end at j
+// reports the exact distance whenever it is <= k, and never <= k otherwise (the window-restart property of
+// DESIGN.md §3.1; at the record start the scan is the full scan).  Returns the unbiased distance at `pos`.
+__device__ __forceinline__ uint32_t hx_verify_long(const uint8_t *__restrict__ rec_text, uint32_t pos,
+                                                   const uint64_t *__restrict__ vt, uint32_t m, uint32_t k) {
+    const uint32_t span = m + k - 1u;
+    uint64_t pv = ~0ull, mv = 0ull;
+    int s = (int)m;
+    for (uint32_t i = pos >= span ? pos - span : 0u; i <= pos; ++i) hx_step(__ldg(vt + rec_text[i]), pv, mv, s);
+    return (uint32_t)s;
+}
+
+template <typename W, int NP, bool TMA, int KWM, bool LF>
 __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((sizeof(W) * NP <= 32) ? 5 : 4)) * (128 / HX_THREADS))
     hx_myers_pair_kernel(const HxScanArgs a) {
     constexpr bool WM = KWM >= 0;           // small-k fast path: Wu-Manber / Shift-Or automata instead of Myers
@@ -695,6 +711,22 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
                             const uint32_t neg = sw[j] & 0x80808080u;
                             hm |= (((neg >> 7) & 1u) | ((neg >> 14) & 2u) | ((neg >> 21) & 4u) | ((neg >> 28) & 8u)) << (4 * j);
                         }
+                        if constexpr (LF) {
+                            // events of suffix-filtered patterns are candidates: exact distance of the whole primer
+                            uint32_t lm = hm & g.longmask;
+                            const uint8_t *rec_text = a.arena + (a.offsets[tl.rec] - a.off_base);  // only lanes with a tile hold events
+                            while (lm) {
+                                const int p = __ffs((int)lm) - 1;
+                                lm &= lm - 1;
+                                const uint32_t d = hx_verify_long(rec_text, pos, a.vtables + ((size_t)g.vslot[p] * 2 + pass) * 256,
+                                                                  g.mfull[p], a.k);
+                                const uint32_t sh = 8u * (p & 3);
+                                if (d > a.k) hm &= ~(1u << p);
+#pragma unroll
+                                for (int j = 0; j < SW; ++j)
+                                    if ((p >> 2) == j) sw[j] = (sw[j] & ~(0xffu << sh)) | (((d - (uint32_t)bias) & 0xffu) << sh);
+                            }
+                        }
                         // reverse roles first: forward candidates must end strictly before pos
                         uint32_t m1 = hm;
                         while (m1) {
@@ -728,7 +760,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
                             const uint32_t d = (uint32_t)((int)(int8_t)(word >> (8 * (p & 3))) + bias);
                             const uint64_t key = ((uint64_t)d << 32) | pos;
                             if (key < bestR[p + dz]) bestR[p + dz] = key;
-                            if (pos + 1 >= g.m[p] && key < bestF[p + dz]) bestF[p + dz] = key;
+                            if (pos + 1 >= g.mfull[p] && key < bestF[p + dz]) bestF[p + dz] = key;
                         }
                     }
                     cnt = 0;
@@ -756,7 +788,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
             const uint64_t hi = phi[q + dz];
             if (hi != HX_NONE64) {
                 flags |= 4u;
-                f_start = (uint32_t)hi - ((uint32_t)g.m[f] - 1u);
+                f_start = (uint32_t)hi - ((uint32_t)g.mfull[f] - 1u);
                 r_end = plo[q + dz];
                 comb = (uint32_t)(hi >> 32) & 0xffu;
             }
@@ -778,26 +810,32 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
     }
 }
 
-template <typename W, int NP, bool TMA, int KWM>
+template <typename W, int NP, bool TMA, int KWM, bool LF = false>
 static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
     const int smem = hx_table_bytes(NP, sizeof(W)) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
     static bool attr_done[8] = {false, false, false, false, false, false, false, false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 8 || !attr_done[dev]) {
-        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM, LF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (dev < 8) attr_done[dev] = true;
     }
     const uint32_t blocks = (tile_cap + HX_THREADS - 1) / HX_THREADS;
-    hx_myers_pair_kernel<W, NP, TMA, KWM><<<blocks, HX_THREADS, smem, st>>>(a);
+    hx_myers_pair_kernel<W, NP, TMA, KWM, LF><<<blocks, HX_THREADS, smem, st>>>(a);
     return 1;
 }
 
 template <typename W, int NP>
 struct HxDispatch {
-    static int run(int np, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
+    static int run(int np, bool lf, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
         if (np == NP) {
             if constexpr (sizeof(W) == 4) {
+                if (lf) {  // group with suffix-filtered primers: vector-load text path only
+                    if (a.wm_k == 0) return hx_scan_launch_one<W, NP, false, 0, true>(a, cap, st);
+                    if (a.wm_k == 1) return hx_scan_launch_one<W, NP, false, 1, true>(a, cap, st);
+                    if (a.wm_k == 2) return hx_scan_launch_one<W, NP, false, 2, true>(a, cap, st);
+                    return hx_scan_launch_one<W, NP, false, -1, true>(a, cap, st);
+                }
                 if (a.wm_k == 0) return hx_scan_launch_one<W, NP, false, 0>(a, cap, st);
                 if (a.wm_k == 1) return hx_scan_launch_one<W, NP, false, 1>(a, cap, st);
                 if (a.wm_k == 2) return hx_scan_launch_one<W, NP, false, 2>(a, cap, st);
@@ -805,18 +843,18 @@ struct HxDispatch {
             return a.variant == 1 ? hx_scan_launch_one<W, NP, true, -1>(a, cap, st)
                                   : hx_scan_launch_one<W, NP, false, -1>(a, cap, st);
         }
-        return HxDispatch<W, NP - 1>::run(np, a, cap, st);
+        return HxDispatch<W, NP - 1>::run(np, lf, a, cap, st);
     }
 };
 template <typename W>
 struct HxDispatch<W, 0> {
-    static int run(int, const HxScanArgs &, uint32_t, cudaStream_t) { return -1; }
+    static int run(int, bool, const HxScanArgs &, uint32_t, cudaStream_t) { return -1; }
 };
 
 int hx_launch_scan(const HxScanArgs &a, const HxGroup &hg, uint32_t tile_cap, cudaStream_t st) {
     if (tile_cap == 0) return 0;
-    if (hg.word64) return HxDispatch<uint64_t, HX_MAX_NP64>::run(hg.np, a, tile_cap, st);
-    return HxDispatch<uint32_t, HX_MAX_NP32>::run(hg.np, a, tile_cap, st);
+    if (hg.word64) return HxDispatch<uint64_t, HX_MAX_NP64>::run(hg.np, false, a, tile_cap, st);
+    return HxDispatch<uint32_t, HX_MAX_NP32>::run(hg.np, hg.longmask != 0u, a, tile_cap, st);
 }
 
 // ------------------------------------------------------------------------------------

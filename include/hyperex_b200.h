@@ -74,7 +74,12 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
  * "text_tma" (1: stage the text through shared memory with TMA bulk copies; 0, default: per-thread
  * 16-byte vector loads, measured 3 % faster), "fast_small_k" (1, default: for -m 0..2 and primers <= 32 nt scan
  * with Wu-Manber / Shift-Or automata, which accept exactly the same hits with the same distances in fewer ALU
- * operations; 0: always the Myers automaton). */
+ * operations; 0: always the Myers automaton), "long_filter" (read by hx_set_primers; 1, default: for -m <= 8 a
+ * primer of 33..64 nt is scanned as the 32-bit automaton of its last 32 symbols and every candidate end is verified
+ * against the whole primer on the device, which accepts exactly the same hits with the same distances; 0: such
+ * primers are stepped as 64-bit automata over the whole text), "group_np_max" (read by hx_set_primers; cap on the
+ * automata one scan thread steps per text byte, 0 = automatic: 16 with 32-bit words, 8 with 64-bit words and on the
+ * Wu-Manber path at -m 2). */
 int hx_set_option(hx_ctx *ctx, const char *name, int64_t value);
 
 /* Replaces the record loop body utils.rs:270-351 (sequence_type, to_ascii_uppercase, both
@@ -142,6 +147,13 @@ void hx_free_pinned(void *p);
 /* how hx_set_primers packed the primer set: pattern groups (= scan launches per slab) and the automata stepped
  * per text byte with 32-bit / 64-bit words (de-duplicated patterns) */
 int hx_group_info(const hx_ctx *ctx, uint32_t *n_groups, uint32_t *steps32_per_base, uint32_t *steps64_per_base);
+
+/* The same packing computed on the host alone (no CUDA, no context): what hx_set_primers would do with this primer set,
+ * -m value and these options ("fast_small_k", "long_filter", "group_np_max" of hx_set_option).  pair_group (n_pairs
+ * entries, may be NULL) receives the group of every pair.  Used by the CPU test-suite and for capacity planning. */
+int hx_plan_groups(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len, const char *const *rev,
+                   const uint32_t *rev_len, uint8_t k, int fast_small_k, int long_filter, int group_np_max,
+                   uint32_t *n_groups, uint32_t *steps32_per_base, uint32_t *steps64_per_base, uint32_t *pair_group);
 
 /* number of kernels the context has launched so far (bench.py's gpu_launches) */
 uint64_t hx_launch_count(const hx_ctx *ctx);

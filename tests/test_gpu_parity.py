@@ -30,6 +30,7 @@ def _run(ctx, arena, offsets, pairs, k, **opts):
     ctx.set_option("slab_bytes", opts.get("slab_bytes", 128 << 20))
     ctx.set_option("text_tma", opts.get("text_tma", 0))
     ctx.set_option("fast_small_k", opts.get("fast", 1))
+    ctx.set_option("long_filter", opts.get("lf", 1))
     ctx.set_primers(pairs, k)
     return ctx.run_batch(arena, offsets)
 
@@ -173,8 +174,55 @@ def test_c5_primer_csv_64_pairs(ctx):
         a[s + 700:s + 700 + len(rs)] = rs
     ref = O.run_batch(a, o, pairs, 2, nthreads=8)
     assert (ref[:, 10:]["flags"] & 4).any()
-    for tma in (0, 1):
-        _cmp(_run(ctx, a, o, pairs, 2, text_tma=tma), ref, a, o, pairs, 2)
+    for tma, lf in ((0, 1), (1, 1), (0, 0), (1, 0)):  # lf: suffix filter for primers > 32 nt / 64-bit groups
+        _cmp(_run(ctx, a, o, pairs, 2, text_tma=tma, lf=lf), ref, a, o, pairs, 2)
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 6, 8, 9])
+def test_long_primers_suffix_filter(ctx, k):
+    """primers of 33..64 nt are scanned as the 32-bit automaton of their last 32 symbols and every candidate is
+    verified against the whole primer (hx_verify_long): same table as the oracle and as the 64-bit groups, with
+    sites planted at record starts / ends, mutated inside and outside the suffix, degenerate primers whose suffix
+    matches almost anywhere, RNA records and windows"""
+    rng = np.random.default_rng(700 + k)
+    letters = "ACGT" * 6 + "MRWSYKVHDBN"
+    def prim(n, alphabet=letters):
+        return "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), n))
+    pairs = [[prim(40), prim(33)], [prim(64), prim(20)], [prim(18), prim(64)], [prim(33), prim(33)],
+             [prim(45, "ACGT") + "N" * 19, prim(36)],                       # suffix of N: every position is a candidate
+             ["N" * 30 + prim(10, "ACGT"), prim(50, "ACGTN")],
+             hx.region_to_primer("v4")]
+    pairs.append([pairs[0][0], pairs[1][1]])                                 # patterns shared between pairs
+    recs = []
+    for i in range(150):
+        L = int(rng.integers(0, 700))
+        seq = bytearray(hx_synth.random_acgt(rng, L).tobytes())
+        for _s in range(int(rng.integers(0, 5))):
+            f, r = pairs[int(rng.integers(0, len(pairs)))]
+            site = f if rng.random() < 0.5 else O.to_reverse_complement(r, O.DNA).decode()
+            sb = bytearray(hx_synth._resolve(rng, site, 1)[0].tobytes())
+            sb = hx_synth._edit(rng, sb, int(rng.integers(0, min(k, 4) + 2)))
+            if L >= len(sb):
+                p = int(rng.choice([0, L - len(sb), int(rng.integers(0, L - len(sb) + 1))]))
+                seq[p:p + len(sb)] = sb
+        a1 = np.frombuffer(bytes(seq), dtype=np.uint8).copy()
+        if i % 7 == 0:
+            a1[a1 == ord("T")] = ord("U")
+        if i % 5 == 0 and len(a1):
+            lo, hi = sorted(rng.integers(0, len(a1) + 1, size=2))
+            a1[lo:hi] |= 0x20
+        recs.append(a1)
+    a, o = hx_synth.pack(recs)
+    ref = O.run_batch(a, o, pairs, k, nthreads=8)
+    assert (ref["flags"] & 4).any()
+    for tile in (0, 64, 4096):
+        for fast, lf in ((1, 1), (0, 1), (0, 0)):
+            _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, lf=lf), ref, a, o, pairs, k)
+    if k <= 8:
+        n32, n64 = ctx.group_info()[1:]
+        ctx.set_option("long_filter", 1)
+        ctx.set_primers(pairs, k)
+        assert ctx.group_info()[2] == 0 and n64 > 0   # the filter leaves no 64-bit automaton to step
 
 
 # ---- edge cases the domain has -------------------------------------------------------------------------
@@ -244,8 +292,9 @@ def test_random_primer_sets_fuzz(ctx, seed):
     a, o = hx_synth.pack(recs)
     ref = O.run_batch(a, o, pairs, k, nthreads=8)
     tile = int(rng.choice([0, 16, 64, 256, 4096]))
-    for fast, tma in ((0, 0), (1, 0), (0, 1)):
-        _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, text_tma=tma), ref, a, o, pairs, k)
+    for fast, tma, lf in ((0, 0, 1), (1, 0, 1), (0, 1, 1), (0, 0, 0)):
+        _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, text_tma=tma, lf=lf), ref, a, o, pairs,
+             k)
 
 
 def test_rna_records_use_rna_reverse_complement(ctx):

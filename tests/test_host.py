@@ -191,3 +191,57 @@ def test_read_fasta_errors(tmp_path):
     notfa = tmp_path / "not.fa"
     notfa.write_bytes(b"ACGTACGT\n>x\nAC\n")
     assert list(hx.read_fasta(str(notfa))) == []
+
+
+# ---- pattern grouping (host half of hx_set_primers; hx_plan_groups needs no GPU) -------------------------
+def test_builtin_regions_are_one_group_of_15_automata():
+    pairs = hx.default_primers()
+    for k in (0, 1, 3):
+        assert hx.plan_groups(pairs, k)[:3] == (1, 15, 0)       # 20 searches -> 15 unique patterns, one launch
+    # -m 2 on the Wu-Manber path: groups of <= 8; the shared primers (27F x3, 341F x2, 1492Rmod x3) stay together,
+    # so the split costs no duplicated automaton
+    g, s32, s64, pg = hx.plan_groups(pairs, 2)
+    assert (g, s32, s64) == (2, 15, 0)
+    regions = hx.supported_regions()
+    grp = dict(zip(regions, pg))
+    assert grp["v1v2"] == grp["v1v3"] == grp["v1v9"] == grp["v6v9"] == grp["v7v9"] and grp["v3v4"] == grp["v3v5"]
+    assert hx.plan_groups(pairs, 2, fast_small_k=False)[:3] == (1, 15, 0)
+
+
+def test_grouping_invariants_on_random_primer_sets():
+    import hx_synth
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        n = int(rng.integers(1, 90))
+        prim = ["".join("ACGTRYN"[int(i)] for i in rng.integers(0, 7, int(rng.integers(1, 65)))) for _ in range(n + 2)]
+        disjoint = trial % 2 == 0
+        if disjoint:   # no primer shared between pairs: nothing ever has to be stepped twice
+            pairs = [["A" + "ACGT"[i % 4] * (i // 4 + 1) + prim[i], "C" + "ACGT"[i % 4] * (i // 4 + 1) + prim[i + 1]][:2]
+                     for i in range(min(n, 60))]
+            pairs = [[f[:64], r[:64]] for f, r in pairs]
+            n = len(pairs)
+        else:          # primers drawn with replacement: large connected components that must be cut
+            pairs = [[prim[int(rng.integers(0, len(prim)))], prim[int(rng.integers(0, len(prim)))]] for _ in range(n)]
+        k = int(rng.choice([0, 2, 3, 9]))
+        uniq = len({"f:" + p[0] for p in pairs} | {"r:" + p[1] for p in pairs})
+        for fast, lf, cap in ((1, 1, 0), (0, 0, 0), (1, 1, 3), (0, 1, 2)):
+            g, s32, s64, pg = hx.plan_groups(pairs, k, fast_small_k=bool(fast), long_filter=bool(lf), group_np_max=cap)
+            assert len(pg) == n and max(pg) == g - 1 and set(pg) == set(range(g))
+            assert 1 <= s32 + s64 <= 2 * n and g <= n
+            if lf and k <= 8:
+                assert s64 == 0                                   # suffix filter: nothing is stepped with 64-bit words
+            if disjoint and len({p[0] for p in pairs} & {hx.to_reverse_complement(p[1], "dna") for p in pairs}) == 0:
+                assert s32 + s64 == uniq
+    # 64-pair CSV of config 5: every pair placed, 123 automata with the filter, fewer launches than pairs
+    pairs = hx_synth.gen_primer_pairs(54, seed=5, builtins=hx.default_primers())
+    g, s32, s64, pg = hx.plan_groups(pairs, 2, fast_small_k=False)
+    assert (s32, s64) == (123, 0) and g == 8
+    g0, a0, b0, _ = hx.plan_groups(pairs, 2, fast_small_k=False, long_filter=False)
+    assert b0 > 0 and a0 + b0 == 123
+
+
+def test_plan_groups_rejects_what_set_primers_rejects():
+    for bad in ([["", "ACGT"]], [["A" * 65, "ACGT"]], []):
+        with pytest.raises(hx.HyperexError) as e:
+            hx.plan_groups(bad, 0)
+        assert e.value.code == -1

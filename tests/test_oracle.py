@@ -91,6 +91,35 @@ def test_window_restart_is_exact():
         assert win == [h for h in full if h[0] >= cut]
 
 
+def test_suffix_filter_is_lossless_and_its_verification_exact():
+    """hx_verify_long: the hits of a primer longer than 32 nt are a subset of the hits of its 32-symbol suffix
+    (same k), and re-scanning the m + k bytes that end at a candidate gives the exact distance when it is <= k"""
+    rng = np.random.default_rng(11)
+    letters = "ACGT" * 5 + "MRWSYKVHDBN"
+    for _ in range(150):
+        m = int(rng.integers(33, 65))
+        k = int(rng.integers(0, 9))
+        pat = "".join(letters[i] for i in rng.integers(0, len(letters), m))
+        txt = bytearray("".join("ACGT"[i] for i in rng.integers(0, 4, 400)).encode())
+        for _s in range(3):  # planted, mutated sites (one at the very start)
+            site = bytearray("".join(c if c in "ACGT" else "A" for c in pat).encode())
+            for _e in range(int(rng.integers(0, k + 2))):
+                site[int(rng.integers(0, len(site)))] = ord("ACGT"[int(rng.integers(0, 4))])
+            p = 0 if _s == 0 else int(rng.integers(0, 400 - m))
+            txt[p:p + m] = site
+        txt = txt.decode()
+        full = dict(O.find_all_end(pat, txt, k))
+        cand = [e for e, _ in O.find_all_end(pat[-32:], txt, k)]
+        assert set(full) <= set(cand)
+        got = {}
+        for e in cand:
+            start = max(0, e - (m + k - 1))
+            win = dict(O.find_all_end(pat, txt[start:e + 1], k))
+            if e - start in win:
+                got[e] = win[e - start]
+        assert got == full, (pat, k)
+
+
 def test_null_bytes_keep_a_fresh_automaton_fresh():
     """DESIGN: a fresh state stepped over never-matching bytes is unchanged (used to mask lead bytes)"""
     pat, txt = "GTGCCAGCMGCCGCGGTAA", "ACGTGTGCCAGCAGCCGCGGTAATTT"
