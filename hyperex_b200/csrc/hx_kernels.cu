@@ -671,13 +671,17 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
                             const uint32_t pos = pos0 + (c << 4) + (wi << 2) + b0 + bi;
                             if (pos - tl.own_start < own_len) {
                                 if constexpr (WM) {
-                                    // exact distance of a hit = the lowest level whose top bit is 0
+                                    // Exact distance of a hit = the lowest level whose top bit is 0.  "<= d errors"
+                                    // implies "<= d + 1 errors", so the top bits are monotone over the levels and that
+                                    // level is simply the NUMBER of levels whose top bit is set (k + 1, i.e. a biased
+                                    // score of 0 = no hit, when all are).  One add per level instead of a compare +
+                                    // select: this path runs once per hit position and lane with 31 lanes idle, and at
+                                    // -m 2 a read has ~65 hit positions (ncu/SASS: it was as long as 1.5 text bytes).
 #pragma unroll
                                     for (int p = 0; p < NP; ++p) {
-                                        int sp = 0;
+                                        int sp = -bias;
 #pragma unroll
-                                        for (int d = NR - 1; d >= 0; --d)
-                                            if (!(rv[d][p] >> (sizeof(W) * 8 - 1))) sp = d - bias;
+                                        for (int d = 0; d < NR; ++d) sp += (int)(rv[d][p] >> (sizeof(W) * 8 - 1));
                                         s[p] = sp;
                                     }
                                 }
