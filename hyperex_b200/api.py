@@ -295,7 +295,7 @@ def get_hypervar_regions(file: str, primers, prefix: str, mismatch: int, devices
         ctx.get_hypervar_regions(file, primers, prefix, mismatch, log=log)
 
 
-def plan_groups(primers: Sequence[Sequence[str]], mismatch: int, fast_small_k: bool = True, long_filter: bool = True,
+def plan_groups(primers: Sequence[Sequence[str]], mismatch: int, fast_small_k: bool = True, long_filter: int = 1,
                 group_np_max: int = 0):
     """hx_plan_groups (host only, no GPU): (n_groups, 32-bit automata per base, 64-bit automata per base, group of
     every pair) for what hx_set_primers would build from this primer set and these options"""

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -376,13 +377,29 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
     // their last 32 symbols and every candidate is verified against the whole primer, so no 64-bit group is needed.
     // Only for small k: with k close to 32 every position becomes a candidate.
     const bool filter = o.long_filter && k <= 8;
+    // ... and only for a suffix that is specific enough: the expected candidate rate on random ACGT text,
+    // 2^-bits(suffix) x (number of k-edit neighbourhoods of a 32-mer), must stay below 1e-3 per position, or the
+    // verification (m + k 64-bit steps per candidate) would cost more than stepping the 64-bit automaton.  A primer
+    // whose last 32 symbols are mostly N keeps its 64-bit group.  long_filter = 2 skips this test (test-suite).
+    auto suffix_ok = [&](const std::string &pat) {
+        if (pat.size() <= 32 || o.long_filter >= 2) return true;
+        double bits = 0;
+        for (size_t i = pat.size() - 32; i < pat.size(); ++i) {
+            const char c = pat[i];
+            const int deg = strchr("RYSWKM", c) ? 2 : strchr("BDHV", c) ? 3 : c == 'N' ? 4 : 1;
+            bits += std::log2(4.0 / deg);
+        }
+        double nb = 20.0;  // indels on top of substitutions
+        for (int i = 0; i < (int)k; ++i) nb *= (32.0 - i) / (i + 1) * 3.0;
+        return bits >= std::log2(nb / 1e-3);
+    };
     for (uint32_t i = 0; i < n_pairs; ++i) {
         pp[i].f = PatternKey{F[i], F[i]};
         std::string rd(R[i].size(), '\0'), rr(R[i].size(), '\0');
         hx_to_reverse_complement(R[i].data(), R[i].size(), 0, &rd[0]);
         hx_to_reverse_complement(R[i].data(), R[i].size(), 1, &rr[0]);
         pp[i].r = PatternKey{rd, rr};
-        pp[i].is_long = !filter && (F[i].size() > 32 || R[i].size() > 32);
+        pp[i].is_long = (F[i].size() > 32 || R[i].size() > 32) && !(filter && suffix_ok(F[i]) && suffix_ok(rd));
         m_max = std::max<uint32_t>(m_max, (uint32_t)std::max(F[i].size(), R[i].size()));
     }
     // Grouping, short (32-bit words) and long (64-bit words) pairs separately.  Pairs that share a pattern (27F and
@@ -641,7 +658,7 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     else if (n == "time_kernels") ctx->opt_time = value;
     else if (n == "text_tma") ctx->opt_text_tma = value ? 1 : 0;
     else if (n == "fast_small_k") ctx->opt_fast_small_k = value ? 1 : 0;
-    else if (n == "long_filter") ctx->opt_long_filter = value ? 1 : 0;  // read by hx_set_primers
+    else if (n == "long_filter") ctx->opt_long_filter = value < 0 ? 0 : (value > 2 ? 2 : value);  // read by hx_set_primers
     else if (n == "group_np_max") ctx->opt_group_np_max = value;         // read by hx_set_primers; 0 = automatic
     else return fail(ctx, HX_ERR_ARG, "unknown option %s", name);
     return HX_OK;

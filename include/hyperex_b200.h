@@ -76,7 +76,8 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
  * with Wu-Manber / Shift-Or automata, which accept exactly the same hits with the same distances in fewer ALU
  * operations; 0: always the Myers automaton), "long_filter" (read by hx_set_primers; 1, default: for -m <= 8 a
  * primer of 33..64 nt is scanned as the 32-bit automaton of its last 32 symbols and every candidate end is verified
- * against the whole primer on the device, which accepts exactly the same hits with the same distances; 0: such
+ * against the whole primer on the device, which accepts exactly the same hits with the same distances — unless those
+ * 32 symbols are so degenerate (mostly N) that too many positions would be candidates; 2: filter those too; 0: such
  * primers are stepped as 64-bit automata over the whole text), "group_np_max" (read by hx_set_primers; cap on the
  * automata one scan thread steps per text byte, 0 = automatic: 16 with 32-bit words, 8 with 64-bit words and on the
  * Wu-Manber path at -m 2). */

@@ -216,11 +216,11 @@ def test_long_primers_suffix_filter(ctx, k):
     ref = O.run_batch(a, o, pairs, k, nthreads=8)
     assert (ref["flags"] & 4).any()
     for tile in (0, 64, 4096):
-        for fast, lf in ((1, 1), (0, 1), (0, 0)):
+        for fast, lf in ((1, 2), (0, 2), (1, 1), (0, 0)):  # lf 2: filter even the degenerate suffixes, 1: default, 0: off
             _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, lf=lf), ref, a, o, pairs, k)
     if k <= 8:
         n32, n64 = ctx.group_info()[1:]
-        ctx.set_option("long_filter", 1)
+        ctx.set_option("long_filter", 2)
         ctx.set_primers(pairs, k)
         assert ctx.group_info()[2] == 0 and n64 > 0   # the filter leaves no 64-bit automaton to step
 
@@ -292,7 +292,7 @@ def test_random_primer_sets_fuzz(ctx, seed):
     a, o = hx_synth.pack(recs)
     ref = O.run_batch(a, o, pairs, k, nthreads=8)
     tile = int(rng.choice([0, 16, 64, 256, 4096]))
-    for fast, tma, lf in ((0, 0, 1), (1, 0, 1), (0, 1, 1), (0, 0, 0)):
+    for fast, tma, lf in ((0, 0, 1), (1, 0, 2), (0, 1, 1), (0, 0, 0)):
         _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, text_tma=tma, lf=lf), ref, a, o, pairs,
              k)
 

@@ -224,20 +224,28 @@ def test_grouping_invariants_on_random_primer_sets():
             pairs = [[prim[int(rng.integers(0, len(prim)))], prim[int(rng.integers(0, len(prim)))]] for _ in range(n)]
         k = int(rng.choice([0, 2, 3, 9]))
         uniq = len({"f:" + p[0] for p in pairs} | {"r:" + p[1] for p in pairs})
-        for fast, lf, cap in ((1, 1, 0), (0, 0, 0), (1, 1, 3), (0, 1, 2)):
-            g, s32, s64, pg = hx.plan_groups(pairs, k, fast_small_k=bool(fast), long_filter=bool(lf), group_np_max=cap)
+        for fast, lf, cap in ((1, 2, 0), (0, 0, 0), (1, 2, 3), (0, 2, 2), (1, 1, 0)):
+            g, s32, s64, pg = hx.plan_groups(pairs, k, fast_small_k=bool(fast), long_filter=lf, group_np_max=cap)
             assert len(pg) == n and max(pg) == g - 1 and set(pg) == set(range(g))
             assert 1 <= s32 + s64 <= 2 * n and g <= n
-            if lf and k <= 8:
-                assert s64 == 0                                   # suffix filter: nothing is stepped with 64-bit words
+            if lf == 2 and k <= 8:
+                assert s64 == 0                                   # forced suffix filter: no 64-bit automaton is stepped
             if disjoint and len({p[0] for p in pairs} & {hx.to_reverse_complement(p[1], "dna") for p in pairs}) == 0:
                 assert s32 + s64 == uniq
     # 64-pair CSV of config 5: every pair placed, 123 automata with the filter, fewer launches than pairs
     pairs = hx_synth.gen_primer_pairs(54, seed=5, builtins=hx.default_primers())
     g, s32, s64, pg = hx.plan_groups(pairs, 2, fast_small_k=False)
     assert (s32, s64) == (123, 0) and g == 8
-    g0, a0, b0, _ = hx.plan_groups(pairs, 2, fast_small_k=False, long_filter=False)
+    g0, a0, b0, _ = hx.plan_groups(pairs, 2, fast_small_k=False, long_filter=0)
     assert b0 > 0 and a0 + b0 == 123
+    # a primer whose last 32 symbols are too degenerate keeps its 64-bit automaton (every position would be a
+    # candidate); a specific one is filtered; beyond -m 8 nothing is
+    spec, vague = "ACGTTGCAAGCTTGCATGCAAGCTAGCTAGGATCCATGCA", "ACGTTGCA" + "N" * 32
+    assert hx.plan_groups([[spec, "ACGTACGTACGTACGT"]], 2)[1:3] == (2, 0)
+    assert hx.plan_groups([[vague, "ACGTACGTACGTACGT"]], 2)[1:3] == (0, 2)
+    assert hx.plan_groups([[vague, "ACGTACGTACGTACGT"]], 2, long_filter=2)[1:3] == (2, 0)
+    assert hx.plan_groups([[spec, "ACGTACGTACGTACGT"]], 9)[1:3] == (0, 2)
+    assert hx.plan_groups([["ACGTTGCAAGCTTGCATGCAAGCTRGCYAGGATCCATGSW", "ACGTACGTACGTACGT"]], 8)[1:3] == (2, 0)
 
 
 def test_plan_groups_rejects_what_set_primers_rejects():
