@@ -118,7 +118,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("HX_BENCH_SMI_MS", "100")], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -366,6 +366,16 @@ def main():
     ev1.record()
     torch.cuda.synchronize()
     h2d_only_ms = ev0.elapsed_time(ev1) / 3
+    # ... and with every rank copying AT THE SAME TIME (N > 1): what the host can feed to N GPUs at once, i.e. the
+    # ceiling of `e2e` on this box
+    h2d_conc_ms = h2d_only_ms
+    if world > 1:
+        barrier()
+        t0c = time.perf_counter()
+        for _ in range(3):
+            d_arena[:bases].copy_(t_arena, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_conc_ms = (time.perf_counter() - t0c) * 1e3 / 3
 
     # results sanity: device-resident and host legs agree, every planted region found (k = 0)
     dev_res = d_out.cpu().numpy().view(hx.RESULT_DTYPE).reshape(n, npairs)
@@ -373,12 +383,12 @@ def main():
     found = int((h_out["flags"] & 4).astype(bool).sum())
 
     # ---- max over ranks ---------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s * 1e3, myers_ms, fast_ms or 0.0], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, myers_ms, fast_ms or 0.0, h2d_conc_ms], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(bases), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max, myers_ms_max, fast_ms_max = (float(x) for x in t.cpu())
+    dev_ms_max, e2e_ms_max, myers_ms_max, fast_ms_max, h2d_conc_ms_max = (float(x) for x in t.cpu())
     total_bases, total_launches = (float(x) for x in tot.cpu())
 
     if rank == 0:
@@ -447,7 +457,10 @@ def main():
                         "timer": "host wall clock around hx_run_batch (synchronous), max over ranks",
                         "h2d_copy_alone_ms": h2d_only_ms,
                         "h2d_copy_alone_gbs": bases / (h2d_only_ms * 1e-3) / 1e9,
-                        "frac_of_copy_alone": h2d_only_ms / (e2e_ms_max / args.steps)},
+                        "frac_of_copy_alone": h2d_only_ms / (e2e_ms_max / args.steps),
+                        "h2d_copy_all_ranks_at_once_ms": h2d_conc_ms_max,
+                        "h2d_copy_all_ranks_at_once_gbs_total": total_bases / (h2d_conc_ms_max * 1e-3) / 1e9,
+                        "frac_of_copy_all_ranks_at_once": h2d_conc_ms_max / (e2e_ms_max / args.steps)},
                 "gpu_launches": int(total_launches), "roofline": roofline, "clocks": clocks}
         if fast_ms_max > 0:
             fv = total_bases / (fast_ms_max * 1e-3) / 1e9
