@@ -556,9 +556,9 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
 // text bytes per trip of the Wu-Manber loop when 16 < automata x levels <= 24; measured: 4 is 7 % faster than 2 for
 // 8 automata at -m 2 (5.93 -> 5.54 ms per 0.75 Gbases): the level shifts of a byte are reused by the next one
 #define HX_WM_UB24 4
+#endif
 #ifndef HX_WM_UBWIDE
 #define HX_WM_UBWIDE 2  // ... and beyond 24 (15 automata at -m 1): 2 is 7 % faster than 1 (2.62 -> 2.44 ms per 0.45 Gbases)
-#endif
 #endif
     constexpr int UB = WM ? ((KWM == 0 || NP * (KWM + 1) <= 16) ? 4 : (NP * (KWM + 1) <= 24 ? HX_WM_UB24 : HX_WM_UBWIDE))
                           : (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
