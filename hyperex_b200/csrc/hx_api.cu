@@ -422,7 +422,7 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
         const bool want_long = pass == 1;
         int np_max = want_long ? HX_MAX_NP64 : HX_MAX_NP32;
         // -m 2 on the Wu-Manber path: three bit-vectors per automaton, so only groups of <= 8 patterns stay in
-        // registers (measured: c5 108.7 -> 86.4 ms, built-in regions 14.3 -> 13.3 ms even with two automata duplicated)
+        // registers (measured per 1.5 Gbases: config 5 108.7 -> 84.8 ms, built-in regions as 8 + 7 automata 14.3 -> 11.4 ms)
         if (!want_long && k == 2 && o.fast_small_k) np_max = 8;
         if (o.group_np_max >= 2) np_max = std::min<int>(np_max, (int)o.group_np_max);
         // connected components over the pairs of this class (union-find on pattern ids)
