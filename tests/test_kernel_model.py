@@ -1,0 +1,147 @@
+"""CPU statement of the device arithmetic of hx_myers_pair_kernel (hyperex_b200/csrc/hx_kernels.cu), checked against the
+oracle: the claims DESIGN.md §3.1, §3.5 and §3.7 rest on are restated here in plain Python integers so that they are
+pinned without a GPU —
+  * top alignment: the pattern in the HIGH bits of a 32-bit word, unused low bits pv = 1 / mv = 0 / eq = 0, the score
+    kept biased (dist - (k + 1)) so that "hit" is its sign (hx_step, utils.rs:305-309 through rust-bio's step);
+  * case folding baked into the Peq rows (utils.rs:295) and the all-zero row of the null byte;
+  * the Wu-Manber / Shift-Or automata of the small-k fast path, their initial state, and the distance of a hit taken as
+    the NUMBER of levels whose top bit is set (the levels are monotone);
+  * the suffix filter: candidates of the last 32 symbols, verified by a fresh 64-bit automaton over m + k bytes.
+This is a model of the product's arithmetic, not the product: nothing here is imported by hyperex_b200/."""
+import functools
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+M32 = 0xFFFFFFFF
+M64 = 0xFFFFFFFFFFFFFFFF
+
+
+@functools.lru_cache(maxsize=None)
+def _matches(sym: str, byte: int) -> bool:
+    """utils.rs:251-268 through the oracle: does pattern symbol `sym` accept text byte `byte`?"""
+    return bool(O.find_all_end(sym, bytes([byte]), 0)) if byte else False
+
+
+def _peq_top(pat: str, byte: int, bits: int) -> int:
+    """hx_api.cu peq_word + the row indexing of the kernel: the row of a raw text byte is that of its upper case"""
+    u = byte - 32 if 97 <= byte <= 122 else byte
+    m = len(pat)
+    w = 0
+    for i, c in enumerate(pat):
+        if _matches(c, u):
+            w |= 1 << (i + bits - m)
+    return w
+
+
+def _step(eq, pv, mv, s, mask):
+    """hx_step of hx_kernels.cu on a `mask`-wide word"""
+    top = (mask + 1) >> 1
+    xv = eq | mv
+    xh = ((((eq & pv) + pv) & mask) ^ pv) | eq
+    ph = (mv | ~(xh | pv)) & mask
+    mh = pv & xh
+    s += (1 if ph & top else 0) - (1 if mh & top else 0)
+    ph = (ph << 1) & mask
+    mh = (mh << 1) & mask
+    pv = (mh | ~(xv | ph)) & mask
+    mv = ph & xv
+    return pv, mv, s
+
+
+def myers_top_aligned(pat: str, text: bytes, k: int, bits: int = 32):
+    mask = M32 if bits == 32 else M64
+    pv, mv, s = mask, 0, len(pat) - (k + 1)
+    out = []
+    for i, b in enumerate(text):
+        pv, mv, s = _step(_peq_top(pat, b, bits), pv, mv, s, mask)
+        if s < 0:
+            out.append((i, s + k + 1))
+    return out
+
+
+def wu_manber_top_aligned(pat: str, text: bytes, k: int):
+    """the KWM >= 0 branch of the scan kernel: Shift-Or levels R0..Rk, bit = 0 <=> prefix matches with <= d errors"""
+    m = len(pat)
+    pmask = (M32 << (32 - m)) & M32
+    rv = [((M32 << (32 - m + d)) & M32) if d < m else 0 for d in range(k + 1)]  # level d: d lowest pattern bits clear
+    out = []
+    for i, b in enumerate(text):
+        n = ~_peq_top(pat, b, 32) & pmask                                        # the complemented table (tables_wm)
+        prev_old = rv[0]
+        prev_old_s = (prev_old << 1) & M32
+        prev_new = prev_old_s | n
+        rv[0] = prev_new
+        for d in range(1, k + 1):
+            cur_old = rv[d]
+            cur_old_s = (cur_old << 1) & M32
+            cur_new = ((cur_old_s | n) & prev_old_s) & prev_old & ((prev_new << 1) & M32)
+            rv[d] = cur_new
+            prev_old, prev_old_s, prev_new = cur_old, cur_old_s, cur_new
+        tops = [r >> 31 for r in rv]
+        assert tops == sorted(tops, reverse=True), "levels must be monotone: <= d errors implies <= d + 1 errors"
+        if not tops[k]:
+            out.append((i, sum(tops)))                                           # hit path: one add per level
+    return out
+
+
+def _cases(seed, n, mmax):
+    rng = np.random.default_rng(seed)
+    letters = "ACGT" * 4 + "MRWSYKVHDBNU"
+    for _ in range(n):
+        m = int(rng.integers(1, mmax + 1))
+        pat = "".join(letters[int(i)] for i in rng.integers(0, len(letters), m))
+        txt = bytearray("".join("ACGTACGTNRUacgtn"[int(i)] for i in rng.integers(0, 16, int(rng.integers(0, 160)))).encode())
+        if m <= len(txt) and rng.random() < 0.7:                                 # plant a (possibly mutated) site
+            site = bytearray("".join(c if c in "ACGTU" else "A" for c in pat).encode())
+            for _e in range(int(rng.integers(0, 3))):
+                site[int(rng.integers(0, m))] = ord("ACGT"[int(rng.integers(0, 4))])
+            p = int(rng.integers(0, len(txt) - m + 1))
+            txt[p:p + m] = site
+        yield pat, bytes(txt)
+
+
+def test_top_aligned_biased_myers_equals_the_oracle():
+    for pat, txt in _cases(1, 150, 32):
+        for k in (0, 1, 3, len(pat)):
+            assert myers_top_aligned(pat, txt, k) == O.find_all_end(pat, txt.upper(), k), (pat, txt, k)
+    for pat, txt in _cases(2, 60, 64):                                           # 64-bit words (long_filter off, -m > 8)
+        assert myers_top_aligned(pat, txt, 2, bits=64) == O.find_all_end(pat, txt.upper(), 2), (pat, txt)
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_wu_manber_levels_equal_the_oracle(k):
+    for pat, txt in _cases(10 + k, 150, 32):
+        assert wu_manber_top_aligned(pat, txt, k) == O.find_all_end(pat, txt.upper(), k), (pat, txt, k)
+
+
+def test_null_byte_row_leaves_both_automata_fresh():
+    """the <= 15 bytes before a record start are cleared to 0: row 0 matches nothing and must not disturb a fresh state"""
+    pat, txt = "GTGCCAGCMGCCGCGGTAA", b"ACGTGTGCCAGCAGCCGCGGTAATTT"
+    pad = bytes(13)
+    for k in (0, 2):
+        ref = O.find_all_end(pat, txt, k)
+        assert [(e - 13, d) for e, d in myers_top_aligned(pat, pad + txt, k)] == ref
+        assert [(e - 13, d) for e, d in wu_manber_top_aligned(pat, pad + txt, k)] == ref
+
+
+def test_suffix_filter_with_64_bit_verification_equals_the_oracle():
+    """hx_verify_long as the kernel runs it: 32-bit scan of the last 32 symbols (either automaton), then a fresh
+    top-aligned 64-bit automaton over the m + k bytes that end at the candidate"""
+    rng = np.random.default_rng(21)
+    for pat, txt in _cases(20, 80, 64):
+        if len(pat) <= 32:
+            continue
+        m = len(pat)
+        k = int(rng.integers(0, 3))
+        got = []
+        scan = wu_manber_top_aligned if rng.random() < 0.5 else myers_top_aligned
+        for e, _d in scan(pat[-32:], txt, k):
+            start = max(0, e - (m + k - 1))
+            win = myers_top_aligned(pat, txt[start:e + 1], 64, bits=64)          # k = 64: report every position
+            d = dict(win)[e - start]
+            if d <= k:
+                got.append((e, d))
+        assert got == O.find_all_end(pat, txt.upper(), k), (pat, txt, k)
