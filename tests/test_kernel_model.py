@@ -145,3 +145,61 @@ def test_suffix_filter_with_64_bit_verification_equals_the_oracle():
             if d <= k:
                 got.append((e, d))
         assert got == O.find_all_end(pat, txt.upper(), k), (pat, txt, k)
+
+
+# ---- joining the windows of a long record: hx_combine_kernel / hx_seg_join -------------------
+NONE = None
+
+
+def _lexmin(a, b):
+    return b if a is NONE or (b is not NONE and b < a) else a
+
+
+def _segment(fh, rh, len_f, lo, hi):
+    """what one scan thread leaves for its tile [lo, hi): bestF / bestR as (dist, end), pair best as (comb, f_end, r_end)"""
+    bf = br = pair = NONE
+    ev = sorted([(e, 1, d) for e, d in fh if lo <= e < hi] + [(e, 0, d) for e, d in rh if lo <= e < hi])
+    for e, role, d in ev:                                  # reverse role first at equal positions (r_end > f_end)
+        if role == 0:
+            if bf is not NONE:
+                cand = (bf[0] + d, bf[1], e)
+                if pair is NONE or cand[0] < pair[0]:      # streaming rule: replace iff strictly smaller combined
+                    pair = cand
+            br = _lexmin(br, (d, e))
+        elif e >= len_f - 1:                               # utils.rs:334-337
+            bf = _lexmin(bf, (d, e))
+    return {"bf": bf, "br": br, "pair": pair}
+
+
+def _seg_join(L, R):
+    """hx_seg_join: associative, order-sensitive"""
+    pair = L["pair"]
+    if L["bf"] is not NONE and R["br"] is not NONE:
+        pair = _lexmin(pair, (L["bf"][0] + R["br"][0], L["bf"][1], R["br"][1]))
+    pair = _lexmin(pair, R["pair"])
+    return {"bf": _lexmin(L["bf"], R["bf"]), "br": _lexmin(L["br"], R["br"]), "pair": pair}
+
+
+def _tree(segs):
+    while len(segs) > 1:                                   # the shuffle tree of hx_combine_long_kernel: neighbours first
+        segs = [_seg_join(segs[i], segs[i + 1]) if i + 1 < len(segs) else segs[i] for i in range(0, len(segs), 2)]
+    return segs[0]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_window_join_equals_the_literal_pairing_loop(seed):
+    rng = np.random.default_rng(300 + seed)
+    for _ in range(600):
+        span = int(rng.integers(8, 200))
+        f = sorted(set(int(x) for x in rng.integers(0, span, int(rng.integers(0, 12)))))
+        r = sorted(set(int(x) for x in rng.integers(0, span, int(rng.integers(0, 12)))))
+        fh = [(e, int(rng.integers(0, 4))) for e in f]
+        rh = [(e, int(rng.integers(0, 4))) for e in r]
+        len_f = int(rng.integers(1, 12))
+        cuts = sorted(set([0, span] + [int(x) for x in rng.integers(1, span, int(rng.integers(0, 9)))]))
+        segs = [_segment(fh, rh, len_f, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+        want = O.pair_literal(fh, rh, len_f)               # (f_start, r_end, combined) or None
+        for joined in (functools.reduce(_seg_join, segs), _tree(list(segs))):
+            got = joined["pair"]
+            got = None if got is NONE else (got[1] - (len_f - 1), got[2], got[0])
+            assert got == want, (fh, rh, len_f, cuts)
