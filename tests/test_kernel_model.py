@@ -203,3 +203,56 @@ def test_window_join_equals_the_literal_pairing_loop(seed):
             got = joined["pair"]
             got = None if got is NONE else (got[1] - (len_f - 1), got[2], got[0])
             assert got == want, (fh, rh, len_f, cuts)
+
+
+# ---- hx_classify_kernel: SWAR search for 'U' / 'T' on 32-bit words (utils.rs:207-217) ---------------------------
+def _swar_has(word: int, letter_lc: int) -> bool:
+    lw = word | 0x20202020                                  # folds the case (utils.rs:210)
+    x = lw ^ (letter_lc * 0x01010101)
+    return bool(((x - 0x01010101) & M32) & ~x & 0x80808080)  # zero-byte test
+
+
+def test_swar_letter_search_equals_bytewise():
+    rng = np.random.default_rng(5)
+    pool = np.frombuffer(b"ACGTUNacgtun\x00\xff\x55\x54\x75\x74\x35\x34\x15\x14uUtT", dtype=np.uint8)
+    for _ in range(20000):
+        bs = bytes(pool[rng.integers(0, len(pool), 4)]) if rng.random() < 0.8 else bytes(rng.integers(0, 256, 4, dtype=np.uint8))
+        w = int.from_bytes(bs, "little")
+        assert _swar_has(w, 0x75) == (b"U" in bs.upper() or b"u" in bs), bs
+        assert _swar_has(w, 0x74) == (b"T" in bs.upper() or b"t" in bs), bs
+
+
+# ---- hx_tile_build_kernel: a record as one tile or as equal 16-byte-granular windows with warm-up ----------------
+def _tiles(length, single_max, tile_len, warm):
+    if length == 0:
+        return []
+    if length <= single_max:
+        return [(0, length, 0)]
+    nt = (length + tile_len - 1) // tile_len
+    tl = ((length + nt - 1) // nt + 15) & ~15
+    nt = (length + tl - 1) // tl
+    return [(i * tl, min(tl, length - i * tl), min(warm, i * tl)) for i in range(nt)]
+
+
+def test_tiles_partition_the_record_and_windows_are_exact():
+    rng = np.random.default_rng(9)
+    for _ in range(3000):
+        tile_len = int(rng.choice([16, 64, 256, 2048]))
+        single_max = max(tile_len, int(rng.choice([16, 300, 4096])))
+        warm = int(rng.integers(1, 80))
+        length = int(rng.integers(0, 40000))
+        ts = _tiles(length, single_max, tile_len, warm)
+        assert sum(t[1] for t in ts) == length
+        pos = 0
+        for start, own, w in ts:
+            assert start == pos and own > 0 and start % 16 == 0 and w == min(warm, start) and own <= max(single_max, tile_len + 15)
+            pos += own
+    # scanning every window from its warm-up start reproduces the whole-record hits (warm = m + k - 1)
+    pat, k = "GTGCCAGCMGCCGCGGTAA", 2
+    txt = ("ACGT" * 40 + "GTGCCAGCAGCCGCGGTAA" + "TTGA" * 33 + "GTGCCAGCCGCCGCGTAA" + "ACCA" * 21).encode()
+    ref = O.find_all_end(pat, txt, k)
+    for tile_len in (16, 48, 64):
+        got = []
+        for start, own, w in _tiles(len(txt), tile_len, tile_len, len(pat) + k - 1):
+            got += [(e + start - w, d) for e, d in myers_top_aligned(pat, txt[start - w:start + own], k) if e - w >= 0]
+        assert got == ref
