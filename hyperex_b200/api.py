@@ -313,6 +313,24 @@ def plan_groups(primers: Sequence[Sequence[str]], mismatch: int, fast_small_k: b
     return g.value, a.value, b.value, pg[:len(primers)].tolist()
 
 
+def plan_peq_word(primers: Sequence[Sequence[str]], mismatch: int, pair: int, role: int, alphabet: int, byte: int,
+                  fast_small_k: bool = True, long_filter: int = 1, group_np_max: int = 0):
+    """hx_plan_peq_word (host only): dict(scan, wm, verify, bits, m_scan, m_full) for one table entry of the plan"""
+    L = _lib.load()
+    fw = [_b(p[0]) for p in primers]
+    rv = [_b(p[1]) for p in primers]
+    fl = (C.c_uint32 * max(1, len(fw)))(*[len(x) for x in fw])
+    rl = (C.c_uint32 * max(1, len(rv)))(*[len(x) for x in rv])
+    w, ww, vw = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    bits, ms, mf = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = L.hx_plan_peq_word(len(primers), _cstrs(fw), fl, _cstrs(rv), rl, mismatch, int(fast_small_k), int(long_filter),
+                            group_np_max, pair, role, alphabet, byte, C.byref(w), C.byref(ww), C.byref(vw), C.byref(bits),
+                            C.byref(ms), C.byref(mf))
+    if rc != 0:
+        raise HyperexError(rc, (L.hx_last_error(None) or b"").decode())
+    return {"scan": w.value, "wm": ww.value, "verify": vw.value, "bits": bits.value, "m_scan": ms.value, "m_full": mf.value}
+
+
 def int_peak(variant: int, iters: int = 2000, device: int = 0) -> float:
     """measured integer throughput (1e9 lane-ops/s) of one instruction class; see hx_int_peak"""
     g = C.c_double()

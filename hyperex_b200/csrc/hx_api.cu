@@ -1144,6 +1144,36 @@ int hx_plan_groups(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd
     return HX_OK;
 }
 
+int hx_plan_peq_word(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len, const char *const *rev,
+                     const uint32_t *rev_len, uint8_t k, int fast_small_k, int long_filter, int group_np_max, uint32_t pair,
+                     int role, int alphabet, uint8_t byte, uint64_t *scan_word, uint64_t *wm_word, uint64_t *verify_word,
+                     uint32_t *word_bits, uint32_t *m_scan, uint32_t *m_full) {
+    PrimerPlan P;
+    const PlanOpts o = {fast_small_k, long_filter, group_np_max};
+    std::string err;
+    const int rc = plan_primers(o, n_pairs, fwd, fwd_len, rev, rev_len, k, P, err);
+    if (rc != HX_OK) return fail(nullptr, rc, "%s", err.c_str());
+    if (pair >= n_pairs || alphabet < 0 || alphabet > 1) return fail(nullptr, HX_ERR_ARG, "hx_plan_peq_word: bad arguments");
+    for (const HxGroup &g : P.groups)
+        for (int q = 0; q < g.npairs; ++q) {
+            if (g.pair_global[q] != pair) continue;
+            const int p = role ? g.pair_r[q] : g.pair_f[q];
+            const int wb = g.word64 ? 8 : 4, stride = hx_row_stride(g.np, wb);
+            const size_t off = g.table_off + (size_t)alphabet * hx_table_bytes(g.np, wb) + (size_t)byte * stride + (size_t)p * wb;
+            uint64_t w = 0, ww = 0;
+            memcpy(&w, P.blob.data() + off, wb);
+            memcpy(&ww, P.blob_wm.data() + off, wb);
+            if (scan_word) *scan_word = w;
+            if (wm_word) *wm_word = ww;
+            if (verify_word) *verify_word = (g.longmask >> p & 1u) ? P.vblob[((size_t)g.vslot[p] * 2 + alphabet) * 256 + byte] : 0;
+            if (word_bits) *word_bits = (uint32_t)wb * 8;
+            if (m_scan) *m_scan = g.m[p];
+            if (m_full) *m_full = g.mfull[p];
+            return HX_OK;
+        }
+    return fail(nullptr, HX_ERR_STATE, "hx_plan_peq_word: pair not placed");
+}
+
 int hx_kernel_time(hx_ctx *ctx, double *myers_ms, uint64_t *myers_launches, int reset) {
     if (!ctx) return HX_ERR_ARG;
     sync_timed(ctx);

@@ -156,6 +156,15 @@ int hx_plan_groups(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd
                    const uint32_t *rev_len, uint8_t k, int fast_small_k, int long_filter, int group_np_max,
                    uint32_t *n_groups, uint32_t *steps32_per_base, uint32_t *steps64_per_base, uint32_t *pair_group);
 
+/* One entry of the tables that plan would upload (host only; test-suite): for primer `role` (0 forward, 1 reverse) of
+ * `pair`, alphabet (0 dna, 1 rna) and raw text byte — the Peq word of the scanned automaton (top-aligned in word_bits
+ * bits; a primer longer than the word is scanned as its last word_bits symbols: m_scan < m_full), its complemented
+ * Wu-Manber form, and the 64-bit word of the whole primer used by the verification (0 when the primer is not filtered). */
+int hx_plan_peq_word(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len, const char *const *rev,
+                     const uint32_t *rev_len, uint8_t k, int fast_small_k, int long_filter, int group_np_max, uint32_t pair,
+                     int role, int alphabet, uint8_t byte, uint64_t *scan_word, uint64_t *wm_word, uint64_t *verify_word,
+                     uint32_t *word_bits, uint32_t *m_scan, uint32_t *m_full);
+
 /* number of kernels the context has launched so far (bench.py's gpu_launches) */
 uint64_t hx_launch_count(const hx_ctx *ctx);
 /* device time (ms) of the dominant kernel (hx_myers_pair_kernel) accumulated by CUDA events

@@ -256,3 +256,34 @@ def test_tiles_partition_the_record_and_windows_are_exact():
         for start, own, w in _tiles(len(txt), tile_len, tile_len, len(pat) + k - 1):
             got += [(e + start - w, d) for e, d in myers_top_aligned(pat, txt[start - w:start + own], k) if e - w >= 0]
         assert got == ref
+
+
+# ---- the tables hx_set_primers uploads (host half, hx_plan_peq_word) against the model above ---------------------
+def test_planned_tables_equal_the_model():
+    import hyperex_b200 as hx
+    rng = np.random.default_rng(31)
+    letters = "ACGT" * 4 + "MRWSYKVHDBNU"
+    text_bytes = [ord(c) for c in "ACGTUNRYKMSWBDHVacgtunx"] + [0, 1, 0x40, 0xFF]
+    for trial in range(12):
+        n = int(rng.integers(1, 20))
+        prim = ["".join(letters[int(i)] for i in rng.integers(0, len(letters), int(rng.integers(1, 65)))) for _ in range(n + 1)]
+        pairs = [[prim[int(rng.integers(0, len(prim)))], prim[int(rng.integers(0, len(prim)))]] for _ in range(n)]
+        k = int(rng.choice([0, 2, 9]))
+        lf = int(rng.choice([0, 2]))
+        for _ in range(25):
+            q, role, alpha = int(rng.integers(0, n)), int(rng.integers(0, 2)), int(rng.integers(0, 2))
+            byte = int(text_bytes[int(rng.integers(0, len(text_bytes)))])
+            e = hx.plan_peq_word(pairs, k, q, role, alpha, byte, long_filter=lf)
+            full = pairs[q][0] if role == 0 else O.to_reverse_complement(pairs[q][1], O.RNA if alpha else O.DNA).decode()
+            bits = e["bits"]
+            assert e["m_full"] == len(full) and e["m_scan"] == min(len(full), bits)
+            if lf == 0 or k > 8:
+                assert bits == (64 if max(len(pairs[q][0]), len(pairs[q][1])) > 32 else 32)
+            else:
+                assert bits == 32
+            scan = full[-bits:]
+            want = _peq_top(scan, byte, bits)
+            assert e["scan"] == want, (full, byte, bits)
+            pmask = ((1 << len(scan)) - 1) << (bits - len(scan))
+            assert e["wm"] == (~want & pmask)
+            assert e["verify"] == (_peq_top(full, byte, 64) if len(full) > bits else 0)
