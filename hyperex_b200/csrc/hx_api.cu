@@ -166,6 +166,29 @@ uint64_t peq_word(const std::string &pat, uint8_t b, int bits) {
     return w;
 }
 
+// All 256 rows of one pattern at once: rows[b] = Peq word of the text byte b AFTER case folding (utils.rs:295), row 0
+// (the null byte) all-zero.  Walks the pattern once and sets the bit in the rows of the few bytes each symbol accepts
+// (itself + its IUPAC expansion) instead of testing 256 bytes against every symbol: 65 535 pairs plan in seconds.
+void peq_rows(const std::string &pat, int bits, uint64_t rows[256]) {
+    struct Accepts {  // text bytes a pattern symbol accepts; built once (thread-safe function-local static)
+        std::vector<uint8_t> v[256];
+        Accepts() {
+            for (int c = 0; c < 256; ++c)
+                for (int b = 1; b < 256; ++b)
+                    if (hxh_symbol_matches((uint8_t)c, (uint8_t)b)) v[c].push_back((uint8_t)b);
+        }
+    };
+    static const Accepts acc;
+    const std::vector<uint8_t> *accepts = acc.v;
+    uint64_t up[256];
+    memset(up, 0, sizeof up);
+    const int m = (int)pat.size();
+    for (int i = 0; i < m; ++i)
+        for (uint8_t b : accepts[(uint8_t)pat[i]]) up[b] |= 1ull << (i + bits - m);
+    rows[0] = 0;
+    for (int b = 1; b < 256; ++b) rows[b] = up[(b >= 'a' && b <= 'z') ? b - 32 : b];
+}
+
 struct PatternKey {
     std::string dna, rna;
     bool operator==(const PatternKey &o) const { return dna == o.dna && rna == o.rna; }
@@ -536,23 +559,21 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
                 scan[p].rna = scan[p].rna.substr(full - bits);
                 g.longmask |= 1u << p;
                 g.vslot[p] = (uint32_t)(vblob.size() / 512);
-                for (int alpha = 0; alpha < 2; ++alpha)
-                    for (int b = 0; b < 256; ++b) {
-                        const uint8_t u = (b >= 'a' && b <= 'z') ? (uint8_t)(b - 32) : (uint8_t)b;
-                        vblob.push_back(b ? peq_word(alpha ? gpats[gi][p].rna : gpats[gi][p].dna, u, 64) : 0ull);
-                    }
+                for (int alpha = 0; alpha < 2; ++alpha) {
+                    uint64_t rows[256];
+                    peq_rows(alpha ? gpats[gi][p].rna : gpats[gi][p].dna, 64, rows);
+                    vblob.insert(vblob.end(), rows, rows + 256);
+                }
             }
             g.m[p] = (uint8_t)scan[p].dna.size();
         }
         for (int alpha = 0; alpha < 2; ++alpha) {
             uint8_t *tab = blob.data() + g.table_off + (size_t)alpha * hx_table_bytes(g.np, wb);
-            for (int b = 1; b < 256; ++b) {  // row 0 stays all-zero: the "null" byte
-                const uint8_t u = (b >= 'a' && b <= 'z') ? (uint8_t)(b - 32) : (uint8_t)b;
-                for (int p = 0; p < g.np; ++p) {
-                    const std::string &pat = alpha ? scan[p].rna : scan[p].dna;
-                    const uint64_t w = peq_word(pat, u, bits);
-                    memcpy(tab + (size_t)b * stride + (size_t)p * wb, &w, wb);  // little endian: low bytes first
-                }
+            for (int p = 0; p < g.np; ++p) {
+                uint64_t rows[256];
+                peq_rows(alpha ? scan[p].rna : scan[p].dna, bits, rows);
+                for (int b = 1; b < 256; ++b)  // row 0 stays all-zero: the "null" byte
+                    memcpy(tab + (size_t)b * stride + (size_t)p * wb, &rows[b], wb);  // little endian: low bytes first
             }
             // fast-path table: complemented inside the pattern bits, 0 in the unused low bits; row 0 (the
             // null byte) matches nothing, i.e. all pattern bits set

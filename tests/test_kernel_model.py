@@ -262,7 +262,7 @@ def test_tiles_partition_the_record_and_windows_are_exact():
 def test_planned_tables_equal_the_model():
     import hyperex_b200 as hx
     rng = np.random.default_rng(31)
-    letters = "ACGT" * 4 + "MRWSYKVHDBNU"
+    letters = "ACGT" * 4 + "MRWSYKVHDBNU" + "anX"       # lower-case primer symbols never match (the text is folded, primers are not)
     text_bytes = [ord(c) for c in "ACGTUNRYKMSWBDHVacgtunx"] + [0, 1, 0x40, 0xFF]
     for trial in range(12):
         n = int(rng.integers(1, 20))
@@ -287,3 +287,12 @@ def test_planned_tables_equal_the_model():
             pmask = ((1 << len(scan)) - 1) << (bits - len(scan))
             assert e["wm"] == (~want & pmask)
             assert e["verify"] == (_peq_top(full, byte, 64) if len(full) > bits else 0)
+    # every text byte of one long degenerate primer pair, both roles and alphabets
+    pairs = [["ACGTUNRYKMSWBDHVanXACGTTGCAAGCTTGCATGCAAGCT", "TTGACANNRYACGU"]]
+    for role in (0, 1):
+        for alpha in (0, 1):
+            full = pairs[0][0] if role == 0 else O.to_reverse_complement(pairs[0][1], O.RNA if alpha else O.DNA).decode()
+            for byte in range(256):
+                e = hx.plan_peq_word(pairs, 2, 0, role, alpha, byte, long_filter=2)
+                assert e["scan"] == _peq_top(full[-32:], byte, 32) and e["m_full"] == len(full)
+                assert e["verify"] == (_peq_top(full, byte, 64) if len(full) > 32 else 0)
