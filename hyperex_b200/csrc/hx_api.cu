@@ -11,13 +11,16 @@
 #include "hx_host.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 static_assert(sizeof(hx_result) == 12, "hx_result must be 12 bytes");
@@ -25,6 +28,7 @@ static_assert(sizeof(hx_result) == 12, "hx_result must be 12 bytes");
 namespace {
 
 constexpr int HX_NSLOT = 3;  // pipeline depth per device (H2D / scan / D2H overlap)
+constexpr int HX_NLANE = 2;  // text lanes per device (see TextLane)
 
 std::string g_create_error;
 
@@ -88,9 +92,44 @@ struct Slot {
     }
 };
 
+// A text lane = everything ONE in-flight batch of the text path (scan + on-device FASTA/GFF3 assembly) owns on a device:
+// a slot, the extraction scratch, the output text block and the pinned staging of the streamed copy.  Two lanes per
+// device let the kernels of one batch run under the device->host text copy of the previous one; a lane is driven by
+// one host thread at a time (hx_get_hypervar_regions runs one thread per lane).
+struct TextLane {
+    Slot slot;
+    DevPool ex_pool, ex_text_pool;
+    DevBuf<uint8_t> ex_ids, ex_tails, ex_text, ex_gtails, ex_gtext;
+    DevBuf<uint64_t> ex_id_off, ex_lens, ex_sums, ex_glens, ex_gsums;
+    DevBuf<uint32_t> ex_tail_off, ex_gtail_off;
+    uint8_t *ex_host = nullptr, *ex_ghost = nullptr;  // whole-text pinned buffers of hx_run_batch_text
+    size_t ex_host_cap = 0, ex_ghost_cap = 0;
+    uint8_t *ex_stage[2] = {nullptr, nullptr};  // pinned staging of the streamed text path
+    cudaEvent_t ex_stage_ev[2] = {nullptr, nullptr};
+    uint64_t *h_totals = nullptr;  // pinned: [0] FASTA bytes, [1] GFF3 bytes of the batch
+    void release() {
+        slot.release();
+        ex_pool.release();
+        ex_text_pool.release();
+        if (ex_host) cudaFreeHost(ex_host);
+        if (ex_ghost) cudaFreeHost(ex_ghost);
+        if (h_totals) cudaFreeHost(h_totals);
+        for (int i = 0; i < 2; ++i) {
+            if (ex_stage[i]) cudaFreeHost(ex_stage[i]);
+            if (ex_stage_ev[i]) cudaEventDestroy(ex_stage_ev[i]);
+            ex_stage[i] = nullptr;
+            ex_stage_ev[i] = nullptr;
+        }
+        ex_host = ex_ghost = nullptr;
+        h_totals = nullptr;
+        ex_host_cap = ex_ghost_cap = 0;
+    }
+};
+
 struct Device {
     int dev = 0;
     Slot slots[HX_NSLOT];
+    TextLane lanes[HX_NLANE];
     uint8_t *d_tables = nullptr;
     uint8_t *d_tables_wm = nullptr;
     uint64_t *d_vtables = nullptr;  // 64-bit verification tables of the suffix-filtered primers
@@ -120,16 +159,12 @@ struct hx_ctx {
     // options
     int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1,
             opt_long_filter = 1, opt_group_np_max = 0;
-    uint64_t launches = 0;
-    // on-device extraction (device 0)
-    DevPool ex_pool, ex_text_pool, find_pool;
-    DevBuf<uint8_t> ex_ids, ex_tails, ex_text, ex_gtails, ex_gtext;
-    DevBuf<uint64_t> ex_id_off, ex_lens, ex_sums, ex_glens, ex_gsums;
-    DevBuf<uint32_t> ex_tail_off, ex_gtail_off;
-    uint8_t *ex_host = nullptr, *ex_ghost = nullptr;
-    size_t ex_host_cap = 0, ex_ghost_cap = 0;
-    uint8_t *ex_stage[2] = {nullptr, nullptr};  // pinned staging of the streamed text path
-    cudaEvent_t ex_stage_ev[2] = {nullptr, nullptr};
+    std::atomic<uint64_t> launches{0};
+    std::mutex mu;  // guards err and timed: text lanes of one context run on several host threads
+    DevPool find_pool;
+    // host-side state the file-level driver (hx_host.cpp) keeps across calls: pinned record batches etc.
+    void *host_cache = nullptr;
+    void (*host_cache_free)(void *) = nullptr;
     std::vector<TimedLaunch> timed;
     double myers_ms = 0;
     uint64_t myers_launches = 0;
@@ -143,8 +178,12 @@ int fail(hx_ctx *ctx, int code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (ctx) ctx->err = buf;
-    else g_create_error = buf;
+    if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->err = buf;
+    } else {
+        g_create_error = buf;
+    }
     return code;
 }
 
@@ -189,24 +228,45 @@ void peq_rows(const std::string &pat, int bits, uint64_t rows[256]) {
     for (int b = 1; b < 256; ++b) rows[b] = up[(b >= 'a' && b <= 'z') ? b - 32 : b];
 }
 
+// Like HX_CUDA, for loops that must not return while earlier asynchronous copies still use caller memory: records the
+// error in `rc` and leaves the loop; the caller's epilogue then drains every stream it touched.
+#define HX_CUDA_BREAK(ctx, rc, call)                                                                          \
+    {                                                                                                         \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            rc = fail(ctx, e__ == cudaErrorMemoryAllocation ? HX_ERR_NOMEM : HX_ERR_CUDA, "%s: %s", #call,    \
+                      cudaGetErrorString(e__));                                                               \
+            break;                                                                                            \
+        }                                                                                                     \
+    }
+
 struct PatternKey {
     std::string dna, rna;
     bool operator==(const PatternKey &o) const { return dna == o.dna && rna == o.rna; }
 };
 
 void sync_timed(hx_ctx *ctx) {
-    for (auto &t : ctx->timed) {
+    std::vector<TimedLaunch> timed;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        timed.swap(ctx->timed);
+    }
+    double ms_sum = 0;
+    uint64_t n_sum = 0;
+    for (auto &t : timed) {
         cudaSetDevice(t.dev);
         cudaEventSynchronize(t.b);
         float ms = 0;
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
-            ctx->myers_ms += ms;
-            ctx->myers_launches += 1;
+            ms_sum += ms;
+            n_sum += 1;
         }
         cudaEventDestroy(t.a);
         cudaEventDestroy(t.b);
     }
-    ctx->timed.clear();
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->myers_ms += ms_sum;
+    ctx->myers_launches += n_sum;
 }
 
 struct SlabPlan {
@@ -336,6 +396,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
         ctx->launches += nl;
         if (ctx->opt_time) {
             cudaEventRecord(tl.b, st);
+            std::lock_guard<std::mutex> lk(ctx->mu);
             ctx->timed.push_back(tl);
         }
     }
@@ -628,18 +689,38 @@ int hx_create(hx_ctx **out, const int *dev_ids, int n_dev) {
             hx_destroy(ctx);
             return HX_ERR_ARG;
         }
+    }
+    // Per-device state on parallel host threads: the first call on a device creates its CUDA primary context, which
+    // takes 0.4 s and more per device on a virtualised box and used to run device after device (8 GPUs: seconds).
+    std::vector<cudaError_t> dev_err(n_dev, cudaSuccess);
+    auto init_dev = [&](int i) {
+        Device &D = ctx->devs[i];
         cudaError_t ce = cudaSetDevice(D.dev);
-        for (int s = 0; s < HX_NSLOT && ce == cudaSuccess; ++s) {
-            ce = cudaStreamCreateWithFlags(&D.slots[s].stream, cudaStreamNonBlocking);
-            if (ce == cudaSuccess) ce = cudaHostAlloc((void **)&D.slots[s].h_status, 16, cudaHostAllocDefault);
-            if (ce == cudaSuccess) memset(D.slots[s].h_status, 0, 16);
+        auto init_slot = [&](Slot &S) {
+            if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking);
+            if (ce == cudaSuccess) ce = cudaHostAlloc((void **)&S.h_status, 16, cudaHostAllocDefault);
+            if (ce == cudaSuccess) memset(S.h_status, 0, 16);
+        };
+        for (int s = 0; s < HX_NSLOT; ++s) init_slot(D.slots[s]);
+        for (int l = 0; l < HX_NLANE; ++l) {
+            init_slot(D.lanes[l].slot);
+            if (ce == cudaSuccess) ce = cudaHostAlloc((void **)&D.lanes[l].h_totals, 16, cudaHostAllocDefault);
         }
-        if (ce != cudaSuccess) {
-            fail(nullptr, HX_ERR_CUDA, "hx_create: device %d: %s", D.dev, cudaGetErrorString(ce));
+        dev_err[i] = ce;
+    };
+    if (n_dev == 1) {
+        init_dev(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_dev; ++i) th.emplace_back(init_dev, i);
+        for (std::thread &t : th) t.join();
+    }
+    for (int i = 0; i < n_dev; ++i)
+        if (dev_err[i] != cudaSuccess) {
+            fail(nullptr, HX_ERR_CUDA, "hx_create: device %d: %s", ctx->devs[i].dev, cudaGetErrorString(dev_err[i]));
             hx_destroy(ctx);
             return HX_ERR_CUDA;
         }
-    }
     *out = ctx;
     return HX_OK;
 }
@@ -647,20 +728,15 @@ int hx_create(hx_ctx **out, const int *dev_ids, int n_dev) {
 void hx_destroy(hx_ctx *ctx) {
     if (!ctx) return;
     sync_timed(ctx);
+    if (ctx->host_cache && ctx->host_cache_free) ctx->host_cache_free(ctx->host_cache);  // pinned memory: before the devices go
+    ctx->host_cache = nullptr;
     if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].dev);
-    ctx->ex_pool.release();
-    ctx->ex_text_pool.release();
     ctx->find_pool.release();
-    if (ctx->ex_host) cudaFreeHost(ctx->ex_host);
-    if (ctx->ex_ghost) cudaFreeHost(ctx->ex_ghost);
-    for (int i = 0; i < 2; ++i) {
-        if (ctx->ex_stage[i]) cudaFreeHost(ctx->ex_stage[i]);
-        if (ctx->ex_stage_ev[i]) cudaEventDestroy(ctx->ex_stage_ev[i]);
-    }
     for (Device &D : ctx->devs) {
         cudaSetDevice(D.dev);
         cudaDeviceSynchronize();
         for (Slot &S : D.slots) S.release();
+        for (TextLane &L : D.lanes) L.release();
         if (D.d_tables) cudaFree(D.d_tables);
         if (D.d_tables_wm) cudaFree(D.d_tables_wm);
         if (D.d_vtables) cudaFree(D.d_vtables);
@@ -761,21 +837,16 @@ int hx_run_batch_device(hx_ctx *ctx, int dev_slot, const uint8_t *d_arena, const
     return HX_OK;
 }
 
-int hx_run_batch_fasta(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out,
-                       const char *ids, const uint64_t *id_off, const char *tails, const uint32_t *tail_off,
-                       const char **text, uint64_t *text_len) {
-    return hx_run_batch_text(ctx, arena, offsets, n_records, out, ids, id_off, tails, tail_off, nullptr, nullptr, text,
-                             text_len, nullptr, nullptr);
-}
-
-// Streams device text to the sink through two pinned staging buffers: the copy of chunk i + 1 is in flight
-// while the sink consumes chunk i.
+// ---- the text path: scan + on-device FASTA / GFF3 assembly on one text lane ------------------------------------------
+// Streams device text to the sink through the lane's two pinned staging buffers: the copy of chunk i + 1 is in
+// flight while the sink consumes chunk i.
 static const size_t HX_STAGE_BYTES = (size_t)16 << 20;
-static int stream_text(hx_ctx *ctx, cudaStream_t st, const uint8_t *const d_src[2], const uint64_t len[2],
-                       hx_text_sink sink, void *user) {
+static int stream_text(hx_ctx *ctx, TextLane &L, const uint8_t *const d_src[2], const uint64_t len[2],
+                       const HxhTextSink &sink) {
+    cudaStream_t st = L.slot.stream;
     for (int i = 0; i < 2; ++i) {
-        if (!ctx->ex_stage[i]) HX_CUDA(ctx, cudaHostAlloc((void **)&ctx->ex_stage[i], HX_STAGE_BYTES, cudaHostAllocDefault));
-        if (!ctx->ex_stage_ev[i]) HX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ex_stage_ev[i], cudaEventDisableTiming));
+        if (!L.ex_stage[i]) HX_CUDA(ctx, cudaHostAlloc((void **)&L.ex_stage[i], HX_STAGE_BYTES, cudaHostAllocDefault));
+        if (!L.ex_stage_ev[i]) HX_CUDA(ctx, cudaEventCreateWithFlags(&L.ex_stage_ev[i], cudaEventDisableTiming));
     }
     struct Chunk { int kind; uint64_t off; size_t n; };
     auto chunk_at = [&](uint64_t i, Chunk &c) {
@@ -788,16 +859,16 @@ static int stream_text(hx_ctx *ctx, cudaStream_t st, const uint8_t *const d_src[
     auto issue = [&](uint64_t i) -> cudaError_t {
         Chunk c;
         chunk_at(i, c);
-        cudaError_t e = cudaMemcpyAsync(ctx->ex_stage[i & 1], d_src[c.kind] + c.off, c.n, cudaMemcpyDeviceToHost, st);
-        return e == cudaSuccess ? cudaEventRecord(ctx->ex_stage_ev[i & 1], st) : e;
+        cudaError_t e = cudaMemcpyAsync(L.ex_stage[i & 1], d_src[c.kind] + c.off, c.n, cudaMemcpyDeviceToHost, st);
+        return e == cudaSuccess ? cudaEventRecord(L.ex_stage_ev[i & 1], st) : e;
     };
     if (n_chunks) HX_CUDA(ctx, issue(0));
     for (uint64_t i = 0; i < n_chunks; ++i) {
         if (i + 1 < n_chunks) HX_CUDA(ctx, issue(i + 1));
-        HX_CUDA(ctx, cudaEventSynchronize(ctx->ex_stage_ev[i & 1]));
+        HX_CUDA(ctx, cudaEventSynchronize(L.ex_stage_ev[i & 1]));
         Chunk c;
         chunk_at(i, c);
-        if (sink(user, c.kind, (const char *)ctx->ex_stage[i & 1], c.n) != 0) {
+        if (sink.chunk(sink.user, c.kind, c.off, (const char *)L.ex_stage[i & 1], c.n) != 0) {
             cudaStreamSynchronize(st);
             return fail(ctx, HX_ERR_IO, "hx_run_batch_text_stream: the sink reported an error");
         }
@@ -805,55 +876,29 @@ static int stream_text(hx_ctx *ctx, cudaStream_t st, const uint8_t *const d_src[
     return HX_OK;
 }
 
-static int run_batch_text_impl(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
-                               hx_result *out, const char *ids, const uint64_t *id_off, const char *tails,
-                               const uint32_t *tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
-                               const char **text, uint64_t *text_len, const char **gff_text, uint64_t *gff_len,
-                               hx_text_sink sink, void *user);
-
-int hx_run_batch_text(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out,
-                      const char *ids, const uint64_t *id_off, const char *tails, const uint32_t *tail_off,
-                      const char *gff_tails, const uint32_t *gff_tail_off, const char **text, uint64_t *text_len,
-                      const char **gff_text, uint64_t *gff_len) {
-    return run_batch_text_impl(ctx, arena, offsets, n_records, out, ids, id_off, tails, tail_off, gff_tails, gff_tail_off,
-                               text, text_len, gff_text, gff_len, nullptr, nullptr);
-}
-
-int hx_run_batch_text_stream(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
-                             hx_result *out, const char *ids, const uint64_t *id_off, const char *tails,
-                             const uint32_t *tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
-                             hx_text_sink sink, void *user, uint64_t *text_len, uint64_t *gff_len) {
+// One batch through scan + extraction on text lane `lane_id` (= device index * HX_NLANE + lane).  With a sink the text is
+// streamed (sink->begin receives both totals before the first chunk); without, it is returned whole in the lane's pinned
+// buffers.  Lanes are independent: different host threads may drive different lanes of one context at the same time.
+static int run_text_lane(hx_ctx *ctx, int lane_id, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                         hx_result *out, const char *ids, const uint64_t *id_off, const char *tails,
+                         const uint32_t *tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
+                         const char **text, uint64_t *text_len, const char **gff_text, uint64_t *gff_len,
+                         const HxhTextSink *sink) {
     if (!ctx) return HX_ERR_ARG;
-    if (!sink) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text_stream: NULL sink");
-    const char *t = nullptr, *g = nullptr;
-    uint64_t tl = 0, gl = 0;
     const bool want_gff = gff_tails && gff_tail_off;
-    int rc = run_batch_text_impl(ctx, arena, offsets, n_records, out, ids, id_off, tails, tail_off, gff_tails, gff_tail_off,
-                                 &t, &tl, want_gff ? &g : nullptr, want_gff ? &gl : nullptr, sink, user);
-    if (text_len) *text_len = tl;
-    if (gff_len) *gff_len = gl;
-    return rc;
-}
-
-static int run_batch_text_impl(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
-                               hx_result *out, const char *ids, const uint64_t *id_off, const char *tails,
-                               const uint32_t *tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
-                               const char **text, uint64_t *text_len, const char **gff_text, uint64_t *gff_len,
-                               hx_text_sink sink, void *user) {
-    if (!ctx) return HX_ERR_ARG;
-    const bool want_gff = gff_tails && gff_tail_off && gff_text && gff_len;
+    if (text) *text = nullptr;
+    if (text_len) *text_len = 0;
     if (gff_text) *gff_text = nullptr;
     if (gff_len) *gff_len = 0;
     if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch_text: call hx_set_primers first");
-    if (!text || !text_len) return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: NULL text/text_len");
-    *text = nullptr;
-    *text_len = 0;
+    if (lane_id < 0 || lane_id >= (int)ctx->devs.size() * HX_NLANE) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: bad lane");
     if (n_records == 0) return HX_OK;
-    if (!offsets || !out || !ids || !id_off || !tails || !tail_off)
-        return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: NULL argument");
-    if (offsets[n_records] < offsets[0]) return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: offsets must be non-decreasing");
-    Device &D = ctx->devs[0];
-    Slot &S = D.slots[0];
+    if (!offsets || !ids || !id_off || !tails || !tail_off) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: NULL argument");
+    if (offsets[n_records] < offsets[0]) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: offsets must be non-decreasing");
+    if (offsets[n_records] > offsets[0] && !arena) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: NULL arena");
+    Device &D = ctx->devs[lane_id / HX_NLANE];
+    TextLane &L = D.lanes[lane_id % HX_NLANE];
+    Slot &S = L.slot;
     cudaStream_t st = S.stream;
     HX_CUDA(ctx, cudaSetDevice(D.dev));
     const uint32_t np = ctx->n_pairs;
@@ -861,31 +906,31 @@ static int run_batch_text_impl(hx_ctx *ctx, const uint8_t *arena, const uint64_t
     const uint64_t base = offsets[0] & ~15ull;
     const uint64_t copy_bytes = offsets[n_records] - base, bytes = offsets[n_records] - offsets[0];
     const uint64_t id_bytes = id_off[n_records] - id_off[0];
-    if (id_off[0] != 0 || tail_off[0] != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: id_off / tail_off must start at 0");
+    if (id_off[0] != 0 || tail_off[0] != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: id_off / tail_off must start at 0");
+    if (want_gff && gff_tail_off[0] != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: gff_tail_off must start at 0");
     const uint32_t tail_bytes = tail_off[np];
     const uint32_t nblk = (uint32_t)((n_entries + 4095) / 4096);
     static const bool trace = getenv("HYPEREX_TIMING") && atoi(getenv("HYPEREX_TIMING")) >= 2;  // per-call phase times
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tt0 = now();
     HX_CUDA(ctx, cudaStreamSynchronize(st));
-    if (want_gff && gff_tail_off[0] != 0) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: gff_tail_off must start at 0");
     const SlabPlan pl = plan_slab(ctx, n_records, bytes);
     int rc = prepare_slab(ctx, S, pl, n_records, copy_bytes + 64);
     if (rc != HX_OK) return rc;
     for (int pass = 0;; ++pass) {  // the extraction scratch: one block, carved per call
-        DevPool &P = ctx->ex_pool;
+        DevPool &P = L.ex_pool;
         P.reset();
-        ctx->ex_ids.carve(P, id_bytes + 16);
-        ctx->ex_id_off.carve(P, (size_t)n_records + 1);
-        ctx->ex_tails.carve(P, tail_bytes + 16);
-        ctx->ex_tail_off.carve(P, np + 1);
-        ctx->ex_lens.carve(P, n_entries + 1);
-        ctx->ex_sums.carve(P, nblk + 2);
+        L.ex_ids.carve(P, id_bytes + 16);
+        L.ex_id_off.carve(P, (size_t)n_records + 1);
+        L.ex_tails.carve(P, tail_bytes + 16);
+        L.ex_tail_off.carve(P, np + 1);
+        L.ex_lens.carve(P, n_entries + 1);
+        L.ex_sums.carve(P, nblk + 2);
         if (want_gff) {
-            ctx->ex_gtails.carve(P, gff_tail_off[np] + 16);
-            ctx->ex_gtail_off.carve(P, np + 1);
-            ctx->ex_glens.carve(P, n_entries + 1);
-            ctx->ex_gsums.carve(P, nblk + 2);
+            L.ex_gtails.carve(P, gff_tail_off[np] + 16);
+            L.ex_gtail_off.carve(P, np + 1);
+            L.ex_glens.carve(P, n_entries + 1);
+            L.ex_gsums.carve(P, nblk + 2);
         }
         if (P.fits()) break;
         if (pass) return fail(ctx, HX_ERR_STATE, "hx_run_batch_text: pool did not fit after growing");
@@ -893,93 +938,135 @@ static int run_batch_text_impl(hx_ctx *ctx, const uint8_t *arena, const uint64_t
     }
     if (want_gff) {
         if (gff_tail_off[np])
-            HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_gtails.p, gff_tails, gff_tail_off[np], cudaMemcpyHostToDevice, st));
-        HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_gtail_off.p, gff_tail_off, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, st));
+            HX_CUDA(ctx, cudaMemcpyAsync(L.ex_gtails.p, gff_tails, gff_tail_off[np], cudaMemcpyHostToDevice, st));
+        HX_CUDA(ctx, cudaMemcpyAsync(L.ex_gtail_off.p, gff_tail_off, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, st));
     }
     if (copy_bytes) HX_CUDA(ctx, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, st));
     HX_CUDA(ctx, cudaMemcpyAsync(S.offsets.p, offsets, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (id_bytes) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_ids.p, ids, id_bytes, cudaMemcpyHostToDevice, st));
-    HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_id_off.p, id_off, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (tail_bytes) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_tails.p, tails, tail_bytes, cudaMemcpyHostToDevice, st));
-    HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_tail_off.p, tail_off, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (id_bytes) HX_CUDA(ctx, cudaMemcpyAsync(L.ex_ids.p, ids, id_bytes, cudaMemcpyHostToDevice, st));
+    HX_CUDA(ctx, cudaMemcpyAsync(L.ex_id_off.p, id_off, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (tail_bytes) HX_CUDA(ctx, cudaMemcpyAsync(L.ex_tails.p, tails, tail_bytes, cudaMemcpyHostToDevice, st));
+    HX_CUDA(ctx, cudaMemcpyAsync(L.ex_tail_off.p, tail_off, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, st));
     rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, base, n_records, S.out.p, st);
     if (rc != HX_OK) return rc;
-    HX_CUDA(ctx, cudaMemcpyAsync(out, S.out.p, (size_t)n_entries * sizeof(hx_result), cudaMemcpyDeviceToHost, st));
-    ctx->launches += hx_launch_fasta_offsets(S.out.p, ctx->ex_id_off.p, ctx->ex_tail_off.p, np, n_entries, ctx->ex_lens.p,
-                                             ctx->ex_sums.p, st);
+    if (out) HX_CUDA(ctx, cudaMemcpyAsync(out, S.out.p, (size_t)n_entries * sizeof(hx_result), cudaMemcpyDeviceToHost, st));
+    ctx->launches += hx_launch_fasta_offsets(S.out.p, L.ex_id_off.p, L.ex_tail_off.p, np, n_entries, L.ex_lens.p,
+                                             L.ex_sums.p, st);
     // total = offset of the last entry + its length = block offset + in-block prefix; read both pieces
-    uint64_t total = 0, gtotal = 0;
-    HX_CUDA(ctx, cudaMemcpyAsync(&total, ctx->ex_sums.p + nblk, 8, cudaMemcpyDeviceToHost, st));
+    L.h_totals[0] = L.h_totals[1] = 0;
+    HX_CUDA(ctx, cudaMemcpyAsync(&L.h_totals[0], L.ex_sums.p + nblk, 8, cudaMemcpyDeviceToHost, st));
     if (want_gff) {
-        ctx->launches += hx_launch_gff_offsets(S.out.p, ctx->ex_id_off.p, ctx->ex_gtail_off.p, np, n_entries,
-                                               ctx->ex_glens.p, ctx->ex_gsums.p, st);
-        HX_CUDA(ctx, cudaMemcpyAsync(&gtotal, ctx->ex_gsums.p + nblk, 8, cudaMemcpyDeviceToHost, st));
+        ctx->launches += hx_launch_gff_offsets(S.out.p, L.ex_id_off.p, L.ex_gtail_off.p, np, n_entries, L.ex_glens.p,
+                                               L.ex_gsums.p, st);
+        HX_CUDA(ctx, cudaMemcpyAsync(&L.h_totals[1], L.ex_gsums.p + nblk, 8, cudaMemcpyDeviceToHost, st));
     }
     const double tt1 = now();
     HX_CUDA(ctx, cudaStreamSynchronize(st));
     const double tt2 = now();
     rc = check_status(ctx, S);
     if (rc != HX_OK) return rc;
+    const uint64_t total = L.h_totals[0], gtotal = L.h_totals[1];
+    if (sink && sink->begin && sink->begin(sink->user, total, gtotal) != 0)
+        return fail(ctx, HX_ERR_IO, "hx_run_batch_text_stream: the sink reported an error");
     for (int pass = 0; total || gtotal; ++pass) {  // both output texts share one device block
-        DevPool &P = ctx->ex_text_pool;
+        DevPool &P = L.ex_text_pool;
         P.reset();
-        ctx->ex_text.carve(P, total + 16);
-        ctx->ex_gtext.carve(P, gtotal + 16);
+        L.ex_text.carve(P, total + 16);
+        L.ex_gtext.carve(P, gtotal + 16);
         if (P.fits()) break;
         if (pass) return fail(ctx, HX_ERR_STATE, "hx_run_batch_text: text pool did not fit after growing");
         HX_CUDA(ctx, P.grow());
     }
     if (total) {
-        if (!sink && total > ctx->ex_host_cap) {
-            if (ctx->ex_host) cudaFreeHost(ctx->ex_host);
-            ctx->ex_host = nullptr;
-            ctx->ex_host_cap = 0;
+        if (!sink && total > L.ex_host_cap) {
+            if (L.ex_host) cudaFreeHost(L.ex_host);
+            L.ex_host = nullptr;
+            L.ex_host_cap = 0;
             const size_t want = (size_t)(total + total / 4 + 4096);
-            HX_CUDA(ctx, cudaHostAlloc((void **)&ctx->ex_host, want, cudaHostAllocDefault));
-            ctx->ex_host_cap = want;
+            HX_CUDA(ctx, cudaHostAlloc((void **)&L.ex_host, want, cudaHostAllocDefault));
+            L.ex_host_cap = want;
         }
-        ctx->launches += hx_launch_fasta_write(S.arena.p, S.offsets.p, base, S.out.p, ctx->ex_ids.p, ctx->ex_id_off.p,
-                                               ctx->ex_tails.p, ctx->ex_tail_off.p, np, n_entries, ctx->ex_lens.p,
-                                               ctx->ex_text.p, st);
-        if (!sink) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_host, ctx->ex_text.p, total, cudaMemcpyDeviceToHost, st));
+        ctx->launches += hx_launch_fasta_write(S.arena.p, S.offsets.p, base, S.out.p, L.ex_ids.p, L.ex_id_off.p,
+                                               L.ex_tails.p, L.ex_tail_off.p, np, n_entries, L.ex_lens.p, L.ex_text.p, st);
+        if (!sink) HX_CUDA(ctx, cudaMemcpyAsync(L.ex_host, L.ex_text.p, total, cudaMemcpyDeviceToHost, st));
     }
     if (gtotal) {
-        if (!sink && gtotal > ctx->ex_ghost_cap) {
-            if (ctx->ex_ghost) cudaFreeHost(ctx->ex_ghost);
-            ctx->ex_ghost = nullptr;
-            ctx->ex_ghost_cap = 0;
+        if (!sink && gtotal > L.ex_ghost_cap) {
+            if (L.ex_ghost) cudaFreeHost(L.ex_ghost);
+            L.ex_ghost = nullptr;
+            L.ex_ghost_cap = 0;
             const size_t want = (size_t)(gtotal + gtotal / 4 + 4096);
-            HX_CUDA(ctx, cudaHostAlloc((void **)&ctx->ex_ghost, want, cudaHostAllocDefault));
-            ctx->ex_ghost_cap = want;
+            HX_CUDA(ctx, cudaHostAlloc((void **)&L.ex_ghost, want, cudaHostAllocDefault));
+            L.ex_ghost_cap = want;
         }
-        ctx->launches += hx_launch_gff_write(S.out.p, ctx->ex_ids.p, ctx->ex_id_off.p, ctx->ex_gtails.p,
-                                             ctx->ex_gtail_off.p, np, n_entries, ctx->ex_glens.p, ctx->ex_gtext.p, st);
-        if (!sink) HX_CUDA(ctx, cudaMemcpyAsync(ctx->ex_ghost, ctx->ex_gtext.p, gtotal, cudaMemcpyDeviceToHost, st));
+        ctx->launches += hx_launch_gff_write(S.out.p, L.ex_ids.p, L.ex_id_off.p, L.ex_gtails.p, L.ex_gtail_off.p, np,
+                                             n_entries, L.ex_glens.p, L.ex_gtext.p, st);
+        if (!sink) HX_CUDA(ctx, cudaMemcpyAsync(L.ex_ghost, L.ex_gtext.p, gtotal, cudaMemcpyDeviceToHost, st));
     }
     const double tt3 = now();
     if (sink && (total || gtotal)) {
-        const uint8_t *const src[2] = {ctx->ex_text.p, ctx->ex_gtext.p};
+        const uint8_t *const src[2] = {L.ex_text.p, L.ex_gtext.p};
         const uint64_t lens[2] = {total, gtotal};
-        rc = stream_text(ctx, st, src, lens, sink, user);
+        rc = stream_text(ctx, L, src, lens, *sink);
         if (rc != HX_OK) return rc;
     }
-    if (total || gtotal) {
-        HX_CUDA(ctx, cudaStreamSynchronize(st));
-        HX_CUDA(ctx, cudaGetLastError());
-    }
+    HX_CUDA(ctx, cudaStreamSynchronize(st));  // also covers the result-table copy into `out`
+    HX_CUDA(ctx, cudaGetLastError());
     if (trace)
-        fprintf(stderr, "[hx_run_batch_text] records=%u bases=%llu text=%llu: carve+enqueue %.1f ms, scan sync %.1f ms, "
+        fprintf(stderr, "[hx_run_batch_text lane %d] records=%u bases=%llu text=%llu: carve+enqueue %.1f ms, scan sync %.1f ms, "
                         "enqueue text %.1f ms, text copy/sink %.1f ms\n",
-                n_records, (unsigned long long)bytes, (unsigned long long)(total + gtotal), (tt1 - tt0) * 1e3,
+                lane_id, n_records, (unsigned long long)bytes, (unsigned long long)(total + gtotal), (tt1 - tt0) * 1e3,
                 (tt2 - tt1) * 1e3, (tt3 - tt2) * 1e3, (now() - tt3) * 1e3);
-    sync_timed(ctx);
-    *text = sink ? nullptr : (const char *)ctx->ex_host;
-    *text_len = total;
+    if (ctx->opt_time) sync_timed(ctx);
+    if (text) *text = sink ? nullptr : (const char *)L.ex_host;
+    if (text_len) *text_len = total;
     if (want_gff) {
-        *gff_text = sink ? nullptr : (const char *)ctx->ex_ghost;
-        *gff_len = gtotal;
+        if (gff_text) *gff_text = sink ? nullptr : (const char *)L.ex_ghost;
+        if (gff_len) *gff_len = gtotal;
     }
     return HX_OK;
+}
+
+int hx_run_batch_fasta(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out,
+                       const char *ids, const uint64_t *id_off, const char *tails, const uint32_t *tail_off,
+                       const char **text, uint64_t *text_len) {
+    if (ctx && (!text || !text_len || (n_records && !out))) return fail(ctx, HX_ERR_ARG, "hx_run_batch_fasta: NULL out/text/text_len");
+    return run_text_lane(ctx, 0, arena, offsets, n_records, out, ids, id_off, tails, tail_off, nullptr, nullptr, text,
+                         text_len, nullptr, nullptr, nullptr);
+}
+
+int hx_run_batch_text(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out,
+                      const char *ids, const uint64_t *id_off, const char *tails, const uint32_t *tail_off,
+                      const char *gff_tails, const uint32_t *gff_tail_off, const char **text, uint64_t *text_len,
+                      const char **gff_text, uint64_t *gff_len) {
+    if (ctx && (!text || !text_len || (n_records && !out))) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text: NULL out/text/text_len");
+    const bool want_gff = gff_tails && gff_tail_off && gff_text && gff_len;
+    return run_text_lane(ctx, 0, arena, offsets, n_records, out, ids, id_off, tails, tail_off, want_gff ? gff_tails : nullptr,
+                         want_gff ? gff_tail_off : nullptr, text, text_len, gff_text, gff_len, nullptr);
+}
+
+namespace {
+struct PublicSink {  // hx_text_sink (kind, bytes, n) behind the internal sink (which also carries totals and offsets)
+    hx_text_sink fn;
+    void *user;
+    static int chunk(void *u, int kind, uint64_t, const char *bytes, size_t n) {
+        PublicSink *p = (PublicSink *)u;
+        return p->fn(p->user, kind, bytes, n);
+    }
+};
+}  // namespace
+
+int hx_run_batch_text_stream(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                             hx_result *out, const char *ids, const uint64_t *id_off, const char *tails,
+                             const uint32_t *tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
+                             hx_text_sink sink, void *user, uint64_t *text_len, uint64_t *gff_len) {
+    if (!ctx) return HX_ERR_ARG;
+    if (!sink || (n_records && !out)) return fail(ctx, HX_ERR_ARG, "hx_run_batch_text_stream: NULL sink/out");
+    PublicSink ps{sink, user};
+    const HxhTextSink s{nullptr, &PublicSink::chunk, &ps};
+    const bool want_gff = gff_tails && gff_tail_off;
+    return run_text_lane(ctx, 0, arena, offsets, n_records, out, ids, id_off, tails, tail_off, want_gff ? gff_tails : nullptr,
+                         want_gff ? gff_tail_off : nullptr, nullptr, text_len, nullptr, gff_len, &s);
 }
 
 int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out) {
@@ -1012,18 +1099,22 @@ int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uin
         const uint64_t limit = offsets[r0] + std::min(slab_bytes, std::max<uint64_t>(left / 2, (uint64_t)8 << 20));
         uint32_t r1 = (uint32_t)(std::upper_bound(offsets + r0 + 1, offsets + n_records + 1, limit) - offsets) - 1;
         if (r1 <= r0) r1 = r0 + 1;
-        for (uint32_t i = r0; i < r1; ++i)  // cheap sanity: monotone offsets inside the slab edges
-            if (offsets[i + 1] < offsets[i]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
+        bool monotone = true;  // cheap sanity: monotone offsets inside the slab edges
+        for (uint32_t i = r0; i < r1 && monotone; ++i) monotone = offsets[i + 1] >= offsets[i];
+        if (!monotone) {
+            rc = fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
+            break;  // never return from inside the loop: earlier slabs' copies still use the caller's arena and out
+        }
         const uint32_t n = r1 - r0;
         const uint64_t bytes = offsets[r1] - offsets[r0];
         const int di = (int)(slab_idx % ndev);
         const int si = (int)((slab_idx / ndev) % HX_NSLOT);
         Device &D = ctx->devs[di];
         Slot &S = D.slots[si];
-        HX_CUDA(ctx, cudaSetDevice(D.dev));
+        HX_CUDA_BREAK(ctx, rc, cudaSetDevice(D.dev));
         if (used[di * HX_NSLOT + si]) {
             // buffers of this slot may be regrown below: wait for its previous slab and check it
-            HX_CUDA(ctx, cudaStreamSynchronize(S.stream));
+            HX_CUDA_BREAK(ctx, rc, cudaStreamSynchronize(S.stream));
             rc = check_status(ctx, S);
             if (rc != HX_OK) break;
         }
@@ -1034,25 +1125,27 @@ int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uin
         const SlabPlan pl = plan_slab(ctx, n, bytes);
         rc = prepare_slab(ctx, S, pl, n, copy_bytes + 64);
         if (rc != HX_OK) break;
+        used[di * HX_NSLOT + si] = 1;  // from here on the slot's stream may hold work on caller memory
         if (copy_bytes)
-            HX_CUDA(ctx, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, S.stream));
-        HX_CUDA(ctx, cudaMemcpyAsync(S.offsets.p, offsets + r0, ((size_t)n + 1) * sizeof(uint64_t),
-                                     cudaMemcpyHostToDevice, S.stream));
+            HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, S.stream));
+        HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.offsets.p, offsets + r0, ((size_t)n + 1) * sizeof(uint64_t),
+                                               cudaMemcpyHostToDevice, S.stream));
         rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, base, n, S.out.p, S.stream);
         if (rc != HX_OK) break;
-        HX_CUDA(ctx, cudaMemcpyAsync(out + (size_t)r0 * np, S.out.p, (size_t)n * np * sizeof(hx_result),
-                                     cudaMemcpyDeviceToHost, S.stream));
-        used[di * HX_NSLOT + si] = 1;
+        HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(out + (size_t)r0 * np, S.out.p, (size_t)n * np * sizeof(hx_result),
+                                               cudaMemcpyDeviceToHost, S.stream));
         r0 = r1;
         ++slab_idx;
     }
+    // epilogue on every path: drain each (device, slot) stream that was used, so that no copy from the caller's arena
+    // or into the caller's table is in flight when this function returns, and the slots are idle for the next call
     for (int di = 0; di < ndev; ++di) {
         cudaSetDevice(ctx->devs[di].dev);
         for (int si = 0; si < HX_NSLOT; ++si) {
             if (!used[di * HX_NSLOT + si]) continue;
             cudaError_t e = cudaStreamSynchronize(ctx->devs[di].slots[si].stream);
             if (e != cudaSuccess && rc == HX_OK) rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: %s", cudaGetErrorString(e));
-            if (rc == HX_OK) rc = check_status(ctx, ctx->devs[di].slots[si]);
+            if (rc == HX_OK && e == cudaSuccess) rc = check_status(ctx, ctx->devs[di].slots[si]);
         }
     }
     sync_timed(ctx);
@@ -1132,7 +1225,7 @@ void hx_free_pinned(void *p) {
     if (p) cudaFreeHost(p);
 }
 
-uint64_t hx_launch_count(const hx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t hx_launch_count(const hx_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int hx_group_info(const hx_ctx *ctx, uint32_t *n_groups, uint32_t *steps32_per_base, uint32_t *steps64_per_base) {
     if (!ctx || !ctx->primers_set) return HX_ERR_STATE;
@@ -1209,5 +1302,53 @@ int hx_kernel_time(hx_ctx *ctx, double *myers_ms, uint64_t *myers_launches, int 
 
 }  // extern "C"
 
-// internal (C++ linkage): used by the file-level driver in hx_host.cpp
+// ---- internal (C++ linkage, hx_host.h): used by the file-level driver in hx_host.cpp ----------------------------------
 int hxh_device_count(const hx_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+int hxh_lane_count(const hx_ctx *ctx) { return ctx ? (int)ctx->devs.size() * HX_NLANE : 0; }
+
+int hxh_run_text_lane(hx_ctx *ctx, int lane, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                      hx_result *out, const char *ids, const uint64_t *id_off, const char *fa_tails,
+                      const uint32_t *fa_tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
+                      const HxhTextSink *sink) {
+    return run_text_lane(ctx, lane, arena, offsets, n_records, out, ids, id_off, fa_tails, fa_tail_off, gff_tails,
+                         gff_tail_off, nullptr, nullptr, nullptr, nullptr, sink);
+}
+
+// result table only, on the lane's own device and stream (the host-formatter path of the file-level driver)
+int hxh_run_batch_lane(hx_ctx *ctx, int lane, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                       hx_result *out) {
+    if (!ctx) return HX_ERR_ARG;
+    if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch: call hx_set_primers first");
+    if (lane < 0 || lane >= (int)ctx->devs.size() * HX_NLANE) return fail(ctx, HX_ERR_ARG, "hx_run_batch: bad lane");
+    if (n_records == 0) return HX_OK;
+    if (!offsets || !out || offsets[n_records] < offsets[0] || (offsets[n_records] > offsets[0] && !arena))
+        return fail(ctx, HX_ERR_ARG, "hx_run_batch: bad arguments");
+    Device &D = ctx->devs[lane / HX_NLANE];
+    Slot &S = D.lanes[lane % HX_NLANE].slot;
+    HX_CUDA(ctx, cudaSetDevice(D.dev));
+    HX_CUDA(ctx, cudaStreamSynchronize(S.stream));
+    const uint64_t base = offsets[0] & ~15ull, copy_bytes = offsets[n_records] - base;
+    const SlabPlan pl = plan_slab(ctx, n_records, offsets[n_records] - offsets[0]);
+    int rc = prepare_slab(ctx, S, pl, n_records, copy_bytes + 64);
+    if (rc != HX_OK) return rc;
+    if (copy_bytes) HX_CUDA(ctx, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, S.stream));
+    HX_CUDA(ctx, cudaMemcpyAsync(S.offsets.p, offsets, ((size_t)n_records + 1) * 8, cudaMemcpyHostToDevice, S.stream));
+    rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, base, n_records, S.out.p, S.stream);
+    if (rc != HX_OK) return rc;
+    HX_CUDA(ctx, cudaMemcpyAsync(out, S.out.p, (size_t)n_records * ctx->n_pairs * sizeof(hx_result), cudaMemcpyDeviceToHost,
+                                 S.stream));
+    HX_CUDA(ctx, cudaStreamSynchronize(S.stream));
+    return check_status(ctx, S);
+}
+
+void **hxh_host_cache(hx_ctx *ctx, void (*free_fn)(void *)) {
+    if (!ctx) return nullptr;
+    ctx->host_cache_free = free_fn;
+    return &ctx->host_cache;
+}
+
+void hxh_set_error(hx_ctx *ctx, const char *msg) {
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err = msg ? msg : "";
+}

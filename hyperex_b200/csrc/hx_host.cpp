@@ -7,7 +7,10 @@
 #include "../../include/hyperex_b200.h"
 
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <cerrno>
@@ -16,8 +19,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
+#include <deque>
+#include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <thread>
 
 // ------------------------------------------------------------------------------------
@@ -398,12 +404,35 @@ class ZstdSource : public HxhByteSource {
 
 }  // namespace
 
+
 // ------------------------------------------------------------------------------------
-// FASTA reader: rust-bio 1.6.0 fasta::Reader::read + Records
+// FASTA ingest: rust-bio 1.6.0 fasta::Reader::read + Records, restated over whole
+// chunks of text so that chunks parse independently on parallel threads.
 // ------------------------------------------------------------------------------------
 void HxhRecordBatch::clear() {
     offsets.assign(1, 0);
     ids.clear();
+    id_off.assign(1, 0);
+    descs.clear();
+    stop = false;
+}
+
+bool HxhRecordBatch::reserve(size_t bytes) {  // contents are not preserved: callers reserve before they fill
+    if (bytes <= arena_cap) return true;
+    if (arena) {
+        if (pinned) hx_free_pinned(arena);
+        else free(arena);
+        arena = nullptr;
+        arena_cap = 0;
+    }
+    const size_t want = std::max(bytes + bytes / 4, (size_t)1 << 20);
+    uint8_t *p = (uint8_t *)hx_alloc_pinned(want);
+    pinned = p != nullptr;
+    if (!p) p = (uint8_t *)malloc(want);  // no CUDA device (CPU-only reader tests): plain memory
+    if (!p) return false;
+    arena = p;
+    arena_cap = want;
+    return true;
 }
 
 HxhRecordBatch::~HxhRecordBatch() {
@@ -414,50 +443,82 @@ HxhRecordBatch::~HxhRecordBatch() {
 }
 
 namespace {
-bool grow_arena(HxhRecordBatch &b, size_t need, size_t used) {
-    if (need <= b.arena_cap) return true;
-    size_t want = std::max(need + need / 2, (size_t)1 << 20);
-    uint8_t *p = (uint8_t *)hx_alloc_pinned(want);
-    bool pinned = p != nullptr;
-    if (!p) p = (uint8_t *)malloc(want);
-    if (!p) return false;
-    if (b.arena) {
-        memcpy(p, b.arena, used);
-        if (b.pinned) hx_free_pinned(b.arena);
-        else free(b.arena);
-    }
-    b.arena = p;
-    b.arena_cap = want;
-    b.pinned = pinned;
-    return true;
-}
 inline bool is_ws(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
 }  // namespace
 
-HxhFastaReader::HxhFastaReader() : buf_(8u << 20) {}
-HxhFastaReader::~HxhFastaReader() { delete src_; }
+int hxh_parse_fasta_text(const uint8_t *p, size_t n, bool drop_last, bool keep_desc, HxhRecordBatch &b) {
+    b.clear();
+    if (!b.reserve(n + 64)) return HX_ERR_NOMEM;  // the sequence bytes of a text are fewer than the text
+    uint8_t *const dst = b.arena;
+    size_t used = 0;
+    const uint8_t *cur = p, *const end = p + n;
+    while (cur < end) {
+        // header line: "Expected > at record start." ends the iteration
+        if (*cur != '>') {
+            b.stop = true;
+            break;
+        }
+        const uint8_t *nl = (const uint8_t *)memchr(cur, '\n', (size_t)(end - cur));
+        const uint8_t *le = nl ? nl : end;
+        // line[1..].trim_end().splitn(2, char::is_whitespace): id = up to the first whitespace, desc = the rest
+        const uint8_t *he = le;
+        while (he > cur + 1 && is_ws(he[-1])) --he;
+        const uint8_t *ie = cur + 1;
+        while (ie < he && !is_ws(*ie)) ++ie;
+        const bool has_desc = ie < he;
+        const uint8_t *const id_s = cur + 1;
+        cur = nl ? nl + 1 : end;
+        const size_t seq_start = used;
+        while (cur < end && *cur != '>') {  // a line that starts with '>' starts the next record
+            nl = (const uint8_t *)memchr(cur, '\n', (size_t)(end - cur));
+            le = nl ? nl : end;
+            const uint8_t *te = le;
+            while (te > cur && is_ws(te[-1])) --te;  // trim_end(): "\r", trailing blanks; interior bytes are kept
+            memcpy(dst + used, cur, (size_t)(te - cur));
+            used += (size_t)(te - cur);
+            cur = nl ? nl + 1 : end;
+        }
+        if (ie == id_s && !has_desc && used == seq_start) {  // record.is_empty() ends the iteration
+            b.stop = true;
+            break;
+        }
+        b.ids.insert(b.ids.end(), (const char *)id_s, (const char *)ie);
+        b.id_off.push_back(b.ids.size());
+        b.offsets.push_back(used);
+        if (keep_desc) b.descs.emplace_back(has_desc ? std::string((const char *)ie + 1, (const char *)he) : std::string());
+    }
+    if (drop_last && !b.stop) {  // the read that failed takes the record in progress with it and ends the iteration
+        if (b.offsets.size() > 1) {
+            b.offsets.pop_back();
+            b.id_off.pop_back();
+            b.ids.resize(b.id_off.back());
+            if (keep_desc) b.descs.pop_back();
+        }
+        b.stop = true;
+    }
+    return HX_OK;
+}
 
-int HxhFastaReader::open(const char *path, std::string &err) {
+HxhChunker::HxhChunker() {}
+HxhChunker::~HxhChunker() {
+    delete src_;
+    if (map_) munmap((void *)map_, map_len_);
+}
+
+int HxhChunker::open(const char *path, std::string &err) {
     FILE *f = fopen(path, "rb");
     if (!f) {
         err = std::string("Failed to open file: ") + path;
         return HX_ERR_IO;
     }
     uint8_t magic[6] = {0, 0, 0, 0, 0, 0};
-    size_t n = fread(magic, 1, 5, f);
+    const size_t n = fread(magic, 1, 5, f);
     if (n < 5) {  // niffler: FileTooShort
         fclose(f);
         err = std::string("Failed to determine compression for: ") + path;
         return HX_ERR_IO;
     }
     rewind(f);
-    {
-        struct stat st;
-        size_hint_ = (fstat(fileno(f), &st) == 0 && st.st_size > 0) ? (size_t)st.st_size : 0;
-        const bool plain = !((magic[0] == 0x1f && magic[1] == 0x8b) || (magic[0] == 0x42 && magic[1] == 0x5a) ||
-                             (magic[0] == 0xfd && magic[1] == 0x37) || (magic[0] == 0x28 && magic[1] == 0xb5));
-        if (!plain) size_hint_ *= 5;  // typical nucleotide compression ratio; grown on demand beyond that
-    }
     bool ok = true;
     if (magic[0] == 0x1f && magic[1] == 0x8b) {
         fclose(f);
@@ -477,6 +538,19 @@ int HxhFastaReader::open(const char *path, std::string &err) {
         ok = z->ok();
         src_ = z;
     } else {
+        // plain text: map the file, chunks are views into the mapping (no read() copy at all)
+        struct stat st;
+        if (fstat(fileno(f), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fileno(f), 0);
+            if (m != MAP_FAILED) {
+                map_ = (const uint8_t *)m;
+                map_len_ = (size_t)st.st_size;
+                madvise(m, map_len_, MADV_SEQUENTIAL);
+                madvise(m, map_len_, MADV_WILLNEED);
+                fclose(f);
+                return HX_OK;
+            }
+        }
         src_ = new PlainSource(f);
     }
     if (!ok) {
@@ -486,91 +560,96 @@ int HxhFastaReader::open(const char *path, std::string &err) {
     return HX_OK;
 }
 
-// Makes the next complete line available inside buf_ (no copy): [line, line + len) excludes the '\n'.
-// The buffer is compacted / grown / refilled as needed; the last line of the input may lack the '\n'.
-bool HxhFastaReader::next_line(const uint8_t *&line, size_t &len) {
+bool HxhChunker::next(size_t target, std::vector<uint8_t> &buf, const uint8_t *&p, size_t &n, bool &ended_by_error) {
+    ended_by_error = false;
+    if (target < 1) target = 1;
+    if (map_) {
+        if (map_pos_ >= map_len_) return false;
+        const size_t s = map_pos_;
+        size_t e = map_len_ - s > target ? s + target : map_len_;
+        if (e < map_len_) {  // first line start at or after e that begins with '>'
+            const uint8_t *q = map_ + e, *const end = map_ + map_len_;
+            for (;;) {
+                q = (const uint8_t *)memchr(q, '>', (size_t)(end - q));
+                if (!q) {
+                    e = map_len_;
+                    break;
+                }
+                if (q[-1] == '\n') {
+                    e = (size_t)(q - map_);
+                    break;
+                }
+                ++q;
+            }
+        }
+        p = map_ + s;
+        n = e - s;
+        map_pos_ = e;
+        return true;
+    }
+    if (!src_) return false;
+    buf.clear();
+    buf.swap(carry_);  // starts with what followed the previous chunk's last record boundary
     for (;;) {
-        const uint8_t *s0 = buf_.data() + pos_;
-        const uint8_t *nl = pos_ < end_ ? (const uint8_t *)memchr(s0, '\n', end_ - pos_) : nullptr;
-        if (nl) {
-            line = s0;
-            len = (size_t)(nl - s0);
-            pos_ += len + 1;
-            return true;
+        while (buf.size() < target && !eof_) {
+            const size_t have = buf.size(), want = std::max<size_t>(target - have, (size_t)1 << 16);
+            buf.resize(have + want);
+            const long r = src_->read(buf.data() + have, want);
+            buf.resize(have + (r > 0 ? (size_t)r : 0));
+            if (r < 0) error_ = true;
+            if (r <= 0) eof_ = true;
         }
-        if (eof_) {
-            if (pos_ == end_) return false;
-            line = s0;
-            len = end_ - pos_;
-            pos_ = end_;
-            return true;
-        }
-        // need more bytes: move the partial line to the front, grow if it fills the buffer, refill
-        if (pos_ > 0) {
-            memmove(buf_.data(), buf_.data() + pos_, end_ - pos_);
-            end_ -= pos_;
-            pos_ = 0;
-        }
-        if (end_ == buf_.size()) buf_.resize(buf_.size() * 2);
-        long r = src_->read(buf_.data() + end_, buf_.size() - end_);
-        if (r <= 0) eof_ = true;
-        else end_ += (size_t)r;
-    }
-}
-
-size_t HxhFastaReader::next_batch(HxhRecordBatch &b, size_t max_bytes, size_t max_records) {
-    b.clear();
-    if (finished_ || !src_) return 0;
-    size_t used = 0;
-    if (!b.arena) {
-        // one allocation for the common case: a plain file cannot hold more sequence than its size
-        size_t est = size_hint_ ? std::min(max_bytes, size_hint_) : (size_t)1 << 20;
-        if (!grow_arena(b, est + 4096, 0)) { finished_ = true; return 0; }
-    }
-    const uint8_t *line = nullptr;
-    size_t len = 0;
-    while (b.ids.size() < max_records && used < max_bytes) {
-        if (!have_line_) {
-            if (!next_line(line, len)) { finished_ = true; break; }  // clean EOF
-            header_.assign((const char *)line, len);
-            have_line_ = true;
-        }
-        if (header_.empty() || header_[0] != '>') { finished_ = true; break; }  // "Expected > at record start."
-        // header: line[1..].trim_end(), id = up to the first whitespace
-        size_t he = header_.size();
-        while (he > 1 && is_ws((uint8_t)header_[he - 1])) --he;
-        size_t ie = 1;
-        while (ie < he && !is_ws((uint8_t)header_[ie])) ++ie;
-        const bool has_desc = ie < he;
-        std::string id = header_.substr(1, ie - 1);
-        const size_t seq_start = used;
-        have_line_ = false;
-        for (;;) {
-            if (!next_line(line, len)) break;  // EOF ends the record
-            if (len && line[0] == '>') {
-                header_.assign((const char *)line, len);
-                have_line_ = true;
+        if (eof_) break;
+        // cut at the last line that starts with '>' (not the chunk's own first line)
+        size_t cut = 0;
+        for (size_t len = buf.size(); len > 1;) {
+            const uint8_t *q = (const uint8_t *)memrchr(buf.data() + 1, '>', len - 1);
+            if (!q) break;
+            if (q[-1] == '\n') {
+                cut = (size_t)(q - buf.data());
                 break;
             }
-            size_t te = len;
-            while (te > 0 && is_ws(line[te - 1])) --te;  // trim_end()
-            if (used + te + 64 > b.arena_cap && !grow_arena(b, used + te + 64, used)) {
-                finished_ = true;
-                return b.ids.size();
-            }
-            memcpy(b.arena + used, line, te);
-            used += te;
+            len = (size_t)(q - buf.data());
         }
-        if (id.empty() && !has_desc && used == seq_start) { finished_ = true; break; }  // record.is_empty()
-        b.ids.push_back(std::move(id));
-        b.offsets.push_back(used);
+        if (cut) {
+            carry_.assign(buf.begin() + (ptrdiff_t)cut, buf.end());
+            buf.resize(cut);
+            break;
+        }
+        target = buf.size() * 2;  // one record larger than the target: keep reading
     }
-    return b.ids.size();
+    if (buf.empty()) return false;
+    ended_by_error = eof_ && error_ && carry_.empty();
+    p = buf.data();
+    n = buf.size();
+    return true;
+}
+
+int64_t HxhFastaReader::next_batch(HxhRecordBatch &b, size_t max_bytes, bool keep_desc) {
+    b.clear();
+    while (!finished_) {
+        const uint8_t *p = nullptr;
+        size_t n = 0;
+        bool err = false;
+        if (!chunker_.next(max_bytes, buf_, p, n, err)) {
+            finished_ = true;
+            break;
+        }
+        const int rc = hxh_parse_fasta_text(p, n, err, keep_desc, b);
+        if (rc != HX_OK) {
+            finished_ = true;
+            return rc;
+        }
+        if (b.stop) finished_ = true;
+        if (b.n_records()) return (int64_t)b.n_records();
+    }
+    return 0;
 }
 
 struct hx_fasta {
     HxhFastaReader reader;
     HxhRecordBatch batch;
+    std::vector<char> id_cstr;  // ids with terminators, for the C strings handed out
     std::vector<const char *> id_ptrs;
 };
 
@@ -592,47 +671,42 @@ extern "C" int hx_fasta_open(const char *path, hx_fasta **out) {
 extern "C" int64_t hx_fasta_next(hx_fasta *r, size_t max_bytes, const uint8_t **arena, const uint64_t **offsets,
                                  const char *const **ids) {
     if (!r) return HX_ERR_ARG;
-    size_t n = r->reader.next_batch(r->batch, max_bytes ? max_bytes : ((size_t)256 << 20), (size_t)0xFFFFFF00u);
+    const int64_t n = r->reader.next_batch(r->batch, max_bytes ? max_bytes : ((size_t)256 << 20), false);
+    if (n < 0) return n;
+    const HxhRecordBatch &b = r->batch;
+    r->id_cstr.clear();
     r->id_ptrs.clear();
-    for (const std::string &s : r->batch.ids) r->id_ptrs.push_back(s.c_str());
-    if (arena) *arena = r->batch.arena;
-    if (offsets) *offsets = r->batch.offsets.data();
+    std::vector<size_t> starts;
+    for (int64_t i = 0; i < n; ++i) {
+        starts.push_back(r->id_cstr.size());
+        r->id_cstr.insert(r->id_cstr.end(), b.ids.begin() + (ptrdiff_t)b.id_off[i], b.ids.begin() + (ptrdiff_t)b.id_off[i + 1]);
+        r->id_cstr.push_back('\0');
+    }
+    for (size_t s : starts) r->id_ptrs.push_back(r->id_cstr.data() + s);
+    if (arena) *arena = b.arena;
+    if (offsets) *offsets = b.offsets.data();
     if (ids) *ids = r->id_ptrs.data();
-    return (int64_t)n;
+    return n;
 }
 
 extern "C" void hx_fasta_close(hx_fasta *r) { delete r; }
 
 // ------------------------------------------------------------------------------------
-// utils.rs:231-414 get_hypervar_regions
-//   parser thread: FASTA -> pinned arenas (batches of ~64 MB of sequence, three in flight)
-//   caller thread: hx_run_batch on the GPU(s), then FASTA / GFF3 formatting into large write buffers
+// utils.rs:231-414 get_hypervar_regions, as a pipeline of host threads around the device path:
+//
+//   chunker  (calling thread)   cuts the input at record boundaries (mapped file: no copy; compressed: the decoder)
+//   parsers  (P threads)        chunk -> record batch in a pinned arena            [fasta::Reader, utils.rs:238,270]
+//   lanes    (2 per device)     batch -> H2D, scan, on-device FASTA / GFF3 text, D2H through pinned staging
+//   writers  (W threads)        pwrite() the staged text at its final file offset  [utils.rs:365-369, 378-385]
+//
+// Batches finish out of order on different lanes and devices, the files do not: every batch learns the byte totals
+// of its two texts on the device before any text is copied, takes its turn (batch index order) to reserve its byte
+// range in both files, and then writes into that range from any thread.  The reference's warn!/error! lines are
+// emitted by the lane threads, again in batch index order.
 // ------------------------------------------------------------------------------------
 namespace {
 
-struct OutBuf {  // append-only write buffer in front of a FILE*
-    std::vector<char> v;
-    size_t n = 0;
-    FILE *f = nullptr;
-    bool ok = true;
-    explicit OutBuf(FILE *file) : v((size_t)16 << 20), f(file) {}
-    void flush() {
-        if (n && fwrite(v.data(), 1, n, f) != n) ok = false;
-        n = 0;
-    }
-    char *reserve(size_t k) {
-        if (n + k > v.size()) {
-            flush();
-            if (k > v.size()) v.resize(k + (k >> 1));
-        }
-        return v.data() + n;
-    }
-    void put(const void *p, size_t k) {
-        memcpy(reserve(k), p, k);
-        n += k;
-    }
-    void put(const std::string &x) { put(x.data(), x.size()); }
-};
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 inline size_t put_u32(char *dst, uint32_t v) {  // decimal, no terminator
     char tmp[12];
@@ -645,24 +719,438 @@ inline size_t put_u32(char *dst, uint32_t v) {  // decimal, no terminator
     return (size_t)i;
 }
 
-struct TextSink {  // hx_text_sink of the file-level path: kind 0 -> FASTA file, kind 1 -> GFF3 file
-    FILE *fa, *gff;
-    double seconds;
-    static int write(void *user, int kind, const char *bytes, size_t n) {
-        TextSink *t = (TextSink *)user;
-        const auto t0 = std::chrono::steady_clock::now();
-        const bool ok = fwrite(bytes, 1, n, kind ? t->gff : t->fa) == n;
-        t->seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        return ok ? 0 : 1;
+bool pwrite_all(int fd, const char *p, size_t n, uint64_t off) {
+    while (n) {
+        const ssize_t w = pwrite(fd, p, n, (off_t)off);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        p += w;
+        n -= (size_t)w;
+        off += (uint64_t)w;
+    }
+    return true;
+}
+
+// Writes one block of bytes at a file offset on several threads at once (page-cache copies scale with threads;
+// one thread moves 2-4 GB/s).  The caller writes the first slice itself and returns when all slices are written.
+class WritePool {
+  public:
+    explicit WritePool(int n_threads) {
+        for (int i = 0; i < n_threads; ++i) th_.emplace_back([this] { run(); });
+    }
+    ~WritePool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread &t : th_) t.join();
+    }
+    bool write(int fd, const char *p, size_t n, uint64_t off) {
+        const size_t min_slice = (size_t)1 << 20;
+        size_t parts = std::min<size_t>(th_.size() + 1, (n + min_slice - 1) / min_slice);
+        if (parts <= 1) return pwrite_all(fd, p, n, off);
+        const size_t slice = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
+        Call call;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t s = slice; s < n; s += slice) {
+                q_.push_back(Task{fd, p + s, std::min(slice, n - s), off + s, &call});
+                ++call.pending;
+            }
+        }
+        cv_.notify_all();
+        bool ok = pwrite_all(fd, p, std::min(slice, n), off);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return call.pending == 0; });
+        return ok && call.ok;
+    }
+
+  private:
+    struct Call {
+        int pending = 0;
+        bool ok = true;
+    };
+    struct Task {
+        int fd;
+        const char *p;
+        size_t n;
+        uint64_t off;
+        Call *call;
+    };
+    void run() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                t = q_.front();
+                q_.pop_front();
+            }
+            const bool ok = pwrite_all(t.fd, t.p, t.n, t.off);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (!ok) t.call->ok = false;
+            if (--t.call->pending == 0) done_cv_.notify_all();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::deque<Task> q_;
+    bool stop_ = false;
+};
+
+// Host-side state kept in the context across calls (hxh_host_cache): pinned memory is expensive to allocate
+// (tens of milliseconds per 100 MB), so record batches and the lanes' result tables are reused.
+struct PinnedTable {
+    hx_result *p = nullptr;
+    size_t cap = 0;  // entries
+    bool pinned = false;
+    hx_result *get(size_t n) {
+        if (n <= cap) return p;
+        release();
+        const size_t want = n + n / 4 + 1024;
+        p = (hx_result *)hx_alloc_pinned(want * sizeof(hx_result));
+        pinned = p != nullptr;
+        if (!p) p = (hx_result *)malloc(want * sizeof(hx_result));
+        cap = p ? want : 0;
+        return p;
+    }
+    void release() {
+        if (p) {
+            if (pinned) hx_free_pinned(p);
+            else free(p);
+        }
+        p = nullptr;
+        cap = 0;
     }
 };
 
-struct BatchQueue {  // parser -> consumer hand-off with recycling
+struct HostCache {
+    std::mutex mu;
+    std::vector<HxhRecordBatch *> batches;
+    std::vector<PinnedTable> tables;  // per lane
+    double stats[HX_FILE_STATS_N] = {0};
+    ~HostCache() {
+        for (HxhRecordBatch *b : batches) delete b;
+        for (PinnedTable &t : tables) t.release();
+    }
+};
+void free_host_cache(void *p) { delete (HostCache *)p; }
+
+HostCache *host_cache_of(hx_ctx *ctx) {
+    void **slot = hxh_host_cache(ctx, free_host_cache);
+    if (!*slot) *slot = new HostCache();
+    return (HostCache *)*slot;
+}
+
+struct Chunk {
+    uint64_t index;
+    const uint8_t *p;
+    size_t n;
+    bool drop_last;
+    std::vector<uint8_t> *buf;  // decoded bytes of a compressed input (NULL: view into the mapped file)
+};
+
+struct FileJob {
+    hx_ctx *ctx = nullptr;
+    uint32_t n_pairs = 0;
+    const char *const *fwd = nullptr, *const *rev = nullptr;
+    hx_log_fn log_fn = nullptr;
+    void *user = nullptr;
+    bool device_text = true;
+    int fd[2] = {-1, -1};  // FASTA, GFF3
+    std::vector<std::string> labels, fa_tail, gff_note;
+    std::string tails_blob, gtails_blob;
+    std::vector<uint32_t> tail_off, gtail_off;
+    WritePool *writers = nullptr;
+    HostCache *cache = nullptr;
+
     std::mutex mu;
     std::condition_variable cv;
-    std::vector<HxhRecordBatch *> ready, free_list;
-    bool done = false;
+    std::deque<Chunk> chunks;
+    std::vector<std::vector<uint8_t> *> free_bufs;
+    std::vector<HxhRecordBatch *> free_batches;
+    std::map<uint64_t, HxhRecordBatch *> ready;
+    uint64_t parsed_prefix = 0;        // every chunk with a smaller index has been parsed (its `stop` is known)
+    std::set<uint64_t> parsed_ahead;   // parsed indices beyond the prefix
+    uint64_t n_chunks = 0;             // chunks cut so far (final once chunker_done)
+    bool chunker_done = false;
+    uint64_t last_index = UINT64_MAX;  // the batch on which the reader's iteration ended (none after it counts)
+    uint64_t next_claim = 0;           // next batch index a lane takes
+    uint64_t out_turn = 0, log_turn = 0;
+    uint64_t file_pos[2] = {0, 0};     // next free byte of each output file
+    int rc = HX_OK;
+    bool abort = false;
+    std::string err;
+    // statistics (seconds are summed over the threads of a stage)
+    double t_parse = 0, t_device = 0, t_write = 0, t_log = 0;
+    uint64_t n_bases = 0, n_records = 0, n_batches = 0;
+
+    void fail(int code, const std::string &msg) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (rc == HX_OK) {
+            rc = code;
+            err = msg;
+        }
+        abort = true;
+        cv.notify_all();
+    }
 };
+
+void parser_thread(FileJob *J) {
+    for (;;) {
+        Chunk c;
+        HxhRecordBatch *b = nullptr;
+        {
+            // a chunk and a free batch are taken together, so batches go to chunks in index order and the lowest
+            // unparsed index can never starve behind later ones
+            std::unique_lock<std::mutex> lk(J->mu);
+            for (;;) {
+                J->cv.wait(lk, [&] {
+                    return J->abort || (J->chunker_done && J->chunks.empty()) ||
+                           (!J->chunks.empty() && (J->chunks.front().index > J->last_index || !J->free_batches.empty()));
+                });
+                if (J->abort || J->chunks.empty()) return;
+                c = J->chunks.front();
+                if (c.index <= J->last_index) break;
+                J->chunks.pop_front();  // cut before the reader's iteration was known to have ended: dropped unparsed
+                if (c.buf) J->free_bufs.push_back(c.buf);
+                J->cv.notify_all();
+            }
+            J->chunks.pop_front();
+            b = J->free_batches.back();
+            J->free_batches.pop_back();
+        }
+        const double t0 = now_s();
+        const int rc = hxh_parse_fasta_text(c.p, c.n, c.drop_last, false, *b);
+        const double dt = now_s() - t0;
+        if (rc != HX_OK) {
+            J->fail(rc, "out of memory while reading the input");
+            return;
+        }
+        std::lock_guard<std::mutex> lk(J->mu);
+        J->t_parse += dt;
+        if (c.buf) J->free_bufs.push_back(c.buf);
+        if (b->stop && c.index < J->last_index) J->last_index = c.index;
+        J->ready[c.index] = b;
+        J->parsed_ahead.insert(c.index);
+        while (J->parsed_ahead.erase(J->parsed_prefix)) ++J->parsed_prefix;
+        J->cv.notify_all();
+    }
+}
+
+struct LaneSink {  // HxhTextSink of one batch
+    FileJob *J;
+    uint64_t index;
+    uint64_t base[2];
+    bool begun;
+    double t_write;
+};
+
+// takes the batch's turn to reserve its byte range in both files; false when the job was aborted
+bool reserve_output(FileJob *J, uint64_t index, uint64_t fa_total, uint64_t gff_total, uint64_t base[2]) {
+    std::unique_lock<std::mutex> lk(J->mu);
+    J->cv.wait(lk, [&] { return J->abort || J->out_turn == index; });
+    if (J->abort) return false;
+    base[0] = J->file_pos[0];
+    base[1] = J->file_pos[1];
+    J->file_pos[0] += fa_total;
+    J->file_pos[1] += gff_total;
+    J->out_turn = index + 1;
+    J->cv.notify_all();
+    return true;
+}
+
+int sink_begin(void *user, uint64_t fa_total, uint64_t gff_total) {
+    LaneSink *s = (LaneSink *)user;
+    s->begun = true;
+    return reserve_output(s->J, s->index, fa_total, gff_total, s->base) ? 0 : 1;
+}
+
+int sink_chunk(void *user, int kind, uint64_t off, const char *bytes, size_t n) {
+    LaneSink *s = (LaneSink *)user;
+    const double t0 = now_s();
+    const bool ok = s->J->writers->write(s->J->fd[kind], bytes, n, s->base[kind] + off);
+    s->t_write += now_s() - t0;
+    return ok ? 0 : 1;
+}
+
+// the reference's per-record / per-pair log lines of one batch (utils.rs:276-288, 387-408), in record x pair order
+void emit_logs(FileJob *J, const HxhRecordBatch &b, const hx_result *res) {
+    std::string msg, id;
+    char num[32];
+    const uint32_t n = (uint32_t)b.n_records(), np = J->n_pairs;
+    for (uint32_t r = 0; r < n; ++r) {
+        const hx_result *rr = res + (size_t)r * np;
+        const size_t len = (size_t)(b.offsets[r + 1] - b.offsets[r]);
+        bool need = (rr[0].flags & HX_ALPHABET_NONE) || len <= 1500;
+        for (uint32_t p = 0; p < np && !need; ++p) need = (rr[p].flags & 7u) != 7u;
+        if (!need) continue;
+        id.assign(b.ids.data() + b.id_off[r], b.ids.data() + b.id_off[r + 1]);
+        if (rr[0].flags & HX_ALPHABET_NONE) {  // utils.rs:276-279
+            msg = "Unrecognized sequence type in record: " + id;
+            J->log_fn(2, msg.c_str(), J->user);
+            continue;
+        }
+        if (len <= 1500) {  // utils.rs:282-288
+            snprintf(num, sizeof num, "%zu", len);
+            msg = "Sequence " + id + " is short (" + num + " bp). Some regions may not be found.";
+            J->log_fn(1, msg.c_str(), J->user);
+        }
+        for (uint32_t p = 0; p < np; ++p) {
+            const hx_result &x = rr[p];
+            const bool f_any = x.flags & HX_FWD_ANY, r_any = x.flags & HX_REV_ANY, ok = x.flags & HX_PAIR_VALID;
+            if (f_any && r_any && ok) continue;
+            if (f_any && r_any)  // utils.rs:387-408
+                msg = "Forward and reverse primers for region " + J->labels[p] + " were both found in sequence " + id +
+                      ", but not in a valid order/orientation to define a region";
+            else if (!f_any && r_any)
+                msg = std::string("Forward primer ") + J->fwd[p] + " not found for region " + J->labels[p] + " in sequence " + id;
+            else if (f_any && !r_any)
+                msg = std::string("Reverse primer ") + J->rev[p] + " not found for region " + J->labels[p] + " in sequence " + id;
+            else
+                msg = "Both primers not found for region " + J->labels[p] + " in sequence " + id;
+            J->log_fn(1, msg.c_str(), J->user);
+        }
+    }
+}
+
+// host formatter (HYPEREX_HOST_FORMAT=1): the bytes of utils.rs:354-385 for one batch from its result table
+void format_on_host(const FileJob *J, const HxhRecordBatch &b, const hx_result *res, std::vector<char> &fa, std::vector<char> &gff) {
+    fa.clear();
+    gff.clear();
+    const uint32_t n = (uint32_t)b.n_records(), np = J->n_pairs;
+    for (uint32_t r = 0; r < n; ++r) {
+        const hx_result *rr = res + (size_t)r * np;
+        if (rr[0].flags & HX_ALPHABET_NONE) continue;
+        const char *id = b.ids.data() + b.id_off[r];
+        const size_t idn = (size_t)(b.id_off[r + 1] - b.id_off[r]);
+        const uint8_t *seq = b.arena + b.offsets[r];
+        for (uint32_t p = 0; p < np; ++p) {
+            const hx_result &x = rr[p];
+            if ((x.flags & 7u) != 7u) continue;
+            const size_t slen = (size_t)x.r_end + 1 - x.f_start;
+            const std::string &ft = J->fa_tail[p], &gt = J->gff_note[p];
+            size_t o = fa.size();
+            fa.resize(o + 1 + idn + ft.size() + slen + 1);
+            fa[o++] = '>';
+            memcpy(&fa[o], id, idn);
+            o += idn;
+            memcpy(&fa[o], ft.data(), ft.size());
+            o += ft.size();
+            memcpy(&fa[o], seq + x.f_start, slen);  // original case (utils.rs:368)
+            fa[o + slen] = '\n';
+            size_t g = gff.size();
+            gff.resize(g + idn + 16 + 24 + gt.size());
+            memcpy(&gff[g], id, idn);
+            g += idn;
+            memcpy(&gff[g], "\thyperex\tregion\t", 16);
+            g += 16;
+            g += put_u32(&gff[g], x.f_start + 1);  // 1-based (utils.rs:382-383)
+            gff[g++] = '\t';
+            g += put_u32(&gff[g], x.r_end + 1);
+            memcpy(&gff[g], gt.data(), gt.size());
+            gff.resize(g + gt.size());
+        }
+    }
+}
+
+void lane_thread(FileJob *J, int lane) {
+    std::vector<char> fa_host, gff_host;
+    for (;;) {
+        uint64_t index;
+        HxhRecordBatch *b = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(J->mu);
+            index = J->next_claim++;
+            // a batch may only start once every earlier chunk is parsed: one of them may end the reader's iteration
+            J->cv.wait(lk, [&] {
+                return J->abort || (J->ready.count(index) && J->parsed_prefix >= index) || index > J->last_index ||
+                       (J->chunker_done && index >= J->n_chunks);
+            });
+            if (J->abort || index > J->last_index || !J->ready.count(index)) return;
+            b = J->ready[index];
+            J->ready.erase(index);
+        }
+        const uint32_t n = (uint32_t)b->n_records();
+        const size_t n_entries = (size_t)n * J->n_pairs;
+        const bool want_table = J->log_fn != nullptr || !J->device_text;
+        hx_result *res = nullptr;
+        if (want_table && n) {
+            res = J->cache->tables[lane].get(n_entries);
+            if (!res) {
+                J->fail(HX_ERR_NOMEM, "out of memory for the result table");
+                return;
+            }
+        }
+        const double t0 = now_s();
+        double t_write = 0;
+        int rc = HX_OK;
+        if (n == 0) {
+            uint64_t base[2];
+            if (!reserve_output(J, index, 0, 0, base)) return;
+        } else if (J->device_text) {
+            LaneSink sink{J, index, {0, 0}, false, 0.0};
+            const HxhTextSink hs{sink_begin, sink_chunk, &sink};
+            rc = hxh_run_text_lane(J->ctx, lane, b->arena, b->offsets.data(), n, res, b->ids.data(), b->id_off.data(),
+                                   J->tails_blob.data(), J->tail_off.data(), J->gtails_blob.data(), J->gtail_off.data(), &hs);
+            t_write = sink.t_write;
+            if (rc != HX_OK) {
+                J->fail(rc, hx_last_error(J->ctx));
+                return;
+            }
+        } else {
+            rc = hxh_run_batch_lane(J->ctx, lane, b->arena, b->offsets.data(), n, res);
+            if (rc != HX_OK) {
+                J->fail(rc, hx_last_error(J->ctx));
+                return;
+            }
+            const double tw = now_s();
+            format_on_host(J, *b, res, fa_host, gff_host);
+            uint64_t base[2];
+            if (!reserve_output(J, index, fa_host.size(), gff_host.size(), base)) return;
+            const bool ok = J->writers->write(J->fd[0], fa_host.data(), fa_host.size(), base[0]) &&
+                            J->writers->write(J->fd[1], gff_host.data(), gff_host.size(), base[1]);
+            t_write = now_s() - tw;
+            if (!ok) {
+                J->fail(HX_ERR_IO, "write error on the output files");
+                return;
+            }
+        }
+        const double t1 = now_s();
+        double t_log = 0;
+        if (J->log_fn) {  // in batch order, like the single loop of the reference
+            std::unique_lock<std::mutex> lk(J->mu);
+            J->cv.wait(lk, [&] { return J->abort || J->log_turn == index; });
+            if (J->abort) return;
+            lk.unlock();
+            const double tl = now_s();
+            if (n) emit_logs(J, *b, res);
+            t_log = now_s() - tl;
+            lk.lock();
+            J->log_turn = index + 1;
+            J->cv.notify_all();
+        }
+        std::lock_guard<std::mutex> lk(J->mu);
+        J->t_device += (t1 - t0) - t_write;
+        J->t_write += t_write;
+        J->t_log += t_log;
+        J->n_bases += b->offsets[n];
+        J->n_records += n;
+        J->n_batches += 1;
+        J->free_batches.push_back(b);
+        J->cv.notify_all();
+    }
+}
+
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
 
 }  // namespace
 
@@ -670,210 +1158,159 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
                                        const char *const *rev, const char *prefix, uint8_t mismatch, hx_log_fn log_fn,
                                        void *user) {
     if (!ctx || !file || !fwd || !rev || !prefix || n_pairs == 0) return HX_ERR_ARG;
+    const double t_start = now_s();
     int rc = hx_set_primers(ctx, n_pairs, fwd, nullptr, rev, nullptr, mismatch);
     if (rc != HX_OK) return rc;
-    HxhFastaReader reader;
+    HxhChunker chunker;
     std::string err;
-    rc = reader.open(file, err);
+    rc = chunker.open(file, err);
     if (rc != HX_OK) {
         if (log_fn) log_fn(2, err.c_str(), user);
+        hxh_set_error(ctx, err.c_str());
         return rc;
     }
+    FileJob J;
+    J.ctx = ctx;
+    J.n_pairs = n_pairs;
+    J.fwd = fwd;
+    J.rev = rev;
+    J.log_fn = log_fn;
+    J.user = user;
+    // On-device extraction is the default on every device of the context: the FASTA / GFF3 text itself
+    // is assembled on the GPU and the host only writes it; HYPEREX_HOST_FORMAT=1 keeps the host formatter.
+    J.device_text = env_int("HYPEREX_HOST_FORMAT", 0) == 0;
     const std::string fa_path = std::string(prefix) + ".fa", gff_path = std::string(prefix) + ".gff";
-    FILE *fa = fopen(fa_path.c_str(), "wb");   // fasta::Writer::to_file truncates (utils.rs:241)
-    FILE *gff = fopen(gff_path.c_str(), "ab"); // OpenOptions create+append (utils.rs:242-245)
-    if (!fa || !gff) {
-        if (fa) fclose(fa);
-        if (gff) fclose(gff);
+    J.fd[0] = open(fa_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);  // fasta::Writer::to_file truncates (utils.rs:241)
+    J.fd[1] = open(gff_path.c_str(), O_WRONLY | O_CREAT, 0644);           // OpenOptions create+append (utils.rs:242-245)
+    if (J.fd[0] < 0 || J.fd[1] < 0) {
+        if (J.fd[0] >= 0) close(J.fd[0]);
+        if (J.fd[1] >= 0) close(J.fd[1]);
+        hxh_set_error(ctx, "cannot create the output files");
         return HX_ERR_IO;
     }
-    OutBuf fo(fa), go(gff);
-    go.put("##gff-version 3\n", 16);  // utils.rs:247
+    {
+        struct stat st;  // append: the GFF3 text starts at the current end of the file
+        J.file_pos[1] = fstat(J.fd[1], &st) == 0 ? (uint64_t)st.st_size : 0;
+        if (!pwrite_all(J.fd[1], "##gff-version 3\n", 16, J.file_pos[1])) rc = HX_ERR_IO;  // utils.rs:247
+        J.file_pos[1] += 16;
+    }
     // per pair: everything of the FASTA header / GFF line that does not depend on the record
-    std::vector<std::string> labels(n_pairs), fa_tail(n_pairs), gff_note(n_pairs);
+    J.labels.resize(n_pairs);
+    J.fa_tail.resize(n_pairs);
+    J.gff_note.resize(n_pairs);
+    J.tail_off.assign(1, 0);
+    J.gtail_off.assign(1, 0);
     for (uint32_t p = 0; p < n_pairs; ++p) {
         char lab[16];
         hx_primers_to_region(fwd[p], rev[p], lab);
-        labels[p] = lab;
+        J.labels[p] = lab;
         const std::string fr = std::string("forward=") + fwd[p] + " reverse=" + rev[p];
-        fa_tail[p] = labels[p].empty() ? " " + fr + "\n" : " region=" + labels[p] + " " + fr + "\n";      // utils.rs:356-363
-        gff_note[p] = "\t.\t.\t.\tNote=" + (labels[p].empty() ? fr : "Hypervariable region " + labels[p]) + "\n";  // 372-385
+        J.fa_tail[p] = J.labels[p].empty() ? " " + fr + "\n" : " region=" + J.labels[p] + " " + fr + "\n";  // utils.rs:356-363
+        J.gff_note[p] = "\t.\t.\t.\tNote=" + (J.labels[p].empty() ? fr : "Hypervariable region " + J.labels[p]) + "\n";  // 372-385
+        J.tails_blob += J.fa_tail[p];
+        J.tail_off.push_back((uint32_t)J.tails_blob.size());
+        J.gtails_blob += J.gff_note[p];
+        J.gtail_off.push_back((uint32_t)J.gtails_blob.size());
     }
-    // On-device extraction: with one GPU the FASTA text itself is assembled on the device and the
-    // host only write()s it; HYPEREX_HOST_FORMAT=1 (or a multi-GPU context) keeps the host formatter.
-    const bool device_fasta = hxh_device_count(ctx) == 1 && getenv("HYPEREX_HOST_FORMAT") == nullptr;
-    std::string tails_blob, gtails_blob, ids_blob;
-    std::vector<uint32_t> tail_off(1, 0), gtail_off(1, 0);
-    std::vector<uint64_t> id_off;
-    for (uint32_t p = 0; p < n_pairs; ++p) {
-        tails_blob += fa_tail[p];
-        tail_off.push_back((uint32_t)tails_blob.size());
-        gtails_blob += gff_note[p];
-        gtail_off.push_back((uint32_t)gtails_blob.size());
+    // threads: HYPEREX_THREADS caps the parser and the writer pools (default: the machine's hardware threads)
+    const int n_lanes = hxh_lane_count(ctx);
+    const int hw = std::max(1, env_int("HYPEREX_THREADS", (int)std::thread::hardware_concurrency()));
+    const int n_parsers = std::max(1, std::min(16, hw - 1));
+    const int n_writers = std::max(1, std::min(16, hw - 1));
+    // chunk size: large enough to amortise the per-batch device round trip, small enough that every lane gets
+    // several batches and the first / last batch (which nothing overlaps) stay short
+    size_t chunk_bytes = (size_t)32 << 20;
+    if (chunker.mapped()) {
+        const size_t share = chunker.mapped_bytes() / ((size_t)n_lanes * 4) + 1;
+        chunk_bytes = std::min(chunk_bytes, std::max<size_t>(share, (size_t)4 << 20));
     }
-    // HYPEREX_TIMING=1 prints where the wall time of the file-level path goes
-    const bool timing = getenv("HYPEREX_TIMING") != nullptr;
-    double t_parse = 0, t_gpu = 0, t_write = 0, t_wait = 0;
-    uint64_t n_bases = 0;
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-
-    HxhRecordBatch pool[3];
-    BatchQueue q;
-    for (HxhRecordBatch &b : pool) q.free_list.push_back(&b);
-    const size_t batch_bytes = (size_t)64 << 20;
-    std::thread parser([&] {
-        for (;;) {
-            HxhRecordBatch *b = nullptr;
-            {
-                std::unique_lock<std::mutex> lk(q.mu);
-                q.cv.wait(lk, [&] { return !q.free_list.empty() || q.done; });
-                if (q.done) return;
-                b = q.free_list.back();
-                q.free_list.pop_back();
-            }
-            const double t0 = now();
-            const size_t n = reader.next_batch(*b, batch_bytes, (size_t)8 << 20);
-            t_parse += now() - t0;
-            std::lock_guard<std::mutex> lk(q.mu);
-            if (n == 0) {
-                q.done = true;
-                q.cv.notify_all();
-                return;
-            }
-            q.ready.push_back(b);
-            q.cv.notify_all();
-        }
-    });
-
-    std::vector<hx_result> res;
-    std::string msg;
-    char num[96];
-    for (;;) {
-        HxhRecordBatch *bp = nullptr;
-        {
-            const double t0 = now();
-            std::unique_lock<std::mutex> lk(q.mu);
-            q.cv.wait(lk, [&] { return !q.ready.empty() || q.done; });
-            t_wait += now() - t0;
-            if (q.ready.empty()) break;
-            bp = q.ready.front();
-            q.ready.erase(q.ready.begin());
-        }
-        HxhRecordBatch &batch = *bp;
-        const double t1 = now();
-        const uint32_t n = (uint32_t)batch.ids.size();
-        n_bases += batch.offsets[n];
-        res.resize((size_t)n * n_pairs);
-        if (device_fasta) {
-            ids_blob.clear();
-            id_off.assign(1, 0);
-            for (const std::string &id : batch.ids) {
-                ids_blob += id;
-                id_off.push_back(ids_blob.size());
-            }
-            // the GPU produces the FASTA and GFF3 bytes of this batch; they are written as they arrive
-            fo.flush();
-            go.flush();
-            TextSink sink{fa, gff, 0.0};
-            rc = hx_run_batch_text_stream(ctx, batch.arena, batch.offsets.data(), n, res.data(), ids_blob.data(),
-                                          id_off.data(), tails_blob.data(), tail_off.data(), gtails_blob.data(),
-                                          gtail_off.data(), &TextSink::write, &sink, nullptr, nullptr);
-            t_write += sink.seconds;
-            t_gpu -= sink.seconds;
-        } else {
-            rc = hx_run_batch(ctx, batch.arena, batch.offsets.data(), n, res.data());
-        }
-        const double t2 = now();
-        t_gpu += t2 - t1;
-        if (rc == HX_OK) {
-            for (uint32_t r = 0; r < n; ++r) {
-                const std::string &id = batch.ids[r];
-                const uint8_t *seq = batch.arena + batch.offsets[r];
-                const size_t len = (size_t)(batch.offsets[r + 1] - batch.offsets[r]);
-                const hx_result *rr = &res[(size_t)r * n_pairs];
-                if (rr[0].flags & HX_ALPHABET_NONE) {  // utils.rs:276-279
-                    if (log_fn) {
-                        msg = "Unrecognized sequence type in record: " + id;
-                        log_fn(2, msg.c_str(), user);
-                    }
-                    continue;
-                }
-                if (len <= 1500 && log_fn) {  // utils.rs:282-288
-                    snprintf(num, sizeof num, "%zu", len);
-                    msg = "Sequence " + id + " is short (" + num + " bp). Some regions may not be found.";
-                    log_fn(1, msg.c_str(), user);
-                }
-                for (uint32_t p = 0; p < n_pairs; ++p) {
-                    const hx_result &x = rr[p];
-                    const bool f_any = x.flags & HX_FWD_ANY, r_any = x.flags & HX_REV_ANY, ok = x.flags & HX_PAIR_VALID;
-                    if (f_any && r_any && ok) {  // utils.rs:354-386
-                        if (!device_fasta) {
-                            const size_t slen = (size_t)x.r_end + 1 - x.f_start;
-                            char *o = fo.reserve(1 + id.size() + fa_tail[p].size() + slen + 1);
-                            *o++ = '>';
-                            memcpy(o, id.data(), id.size());
-                            o += id.size();
-                            memcpy(o, fa_tail[p].data(), fa_tail[p].size());
-                            o += fa_tail[p].size();
-                            memcpy(o, seq + x.f_start, slen);  // original case (utils.rs:368)
-                            o += slen;
-                            *o++ = '\n';
-                            fo.n = (size_t)(o - fo.v.data());
-                        }
-                        if (!device_fasta) {
-                            char *g = go.reserve(id.size() + 48 + gff_note[p].size());
-                            memcpy(g, id.data(), id.size());
-                            g += id.size();
-                            memcpy(g, "\thyperex\tregion\t", 16);
-                            g += 16;
-                            g += put_u32(g, x.f_start + 1);  // 1-based (utils.rs:382-383)
-                            *g++ = '\t';
-                            g += put_u32(g, x.r_end + 1);
-                            memcpy(g, gff_note[p].data(), gff_note[p].size());
-                            g += gff_note[p].size();
-                            go.n = (size_t)(g - go.v.data());
-                        }
-                    } else if (log_fn) {  // utils.rs:387-408
-                        if (f_any && r_any)
-                            msg = "Forward and reverse primers for region " + labels[p] + " were both found in sequence " +
-                                  id + ", but not in a valid order/orientation to define a region";
-                        else if (!f_any && r_any)
-                            msg = std::string("Forward primer ") + fwd[p] + " not found for region " + labels[p] +
-                                  " in sequence " + id;
-                        else if (f_any && !r_any)
-                            msg = std::string("Reverse primer ") + rev[p] + " not found for region " + labels[p] +
-                                  " in sequence " + id;
-                        else
-                            msg = "Both primers not found for region " + labels[p] + " in sequence " + id;
-                        log_fn(1, msg.c_str(), user);
-                    }
-                }
-            }
-            if (!fo.ok || !go.ok) rc = HX_ERR_IO;
-        }
-        t_write += now() - t2;
-        {
-            std::lock_guard<std::mutex> lk(q.mu);
-            q.free_list.push_back(bp);
-            if (rc != HX_OK) q.done = true;
-            q.cv.notify_all();
-        }
-        if (rc != HX_OK) break;
-    }
+    if (env_int("HYPEREX_CHUNK_BYTES", 0) > 0) chunk_bytes = (size_t)env_int("HYPEREX_CHUNK_BYTES", 0);  // tests: many tiny batches
+    HostCache *cache = host_cache_of(ctx);
+    J.cache = cache;
+    WritePool writers(n_writers);
+    J.writers = &writers;
+    const int n_batches = n_parsers + n_lanes + 1;
     {
-        std::lock_guard<std::mutex> lk(q.mu);
-        q.done = true;
-        q.cv.notify_all();
+        std::lock_guard<std::mutex> lk(cache->mu);
+        if ((int)cache->tables.size() < n_lanes) cache->tables.resize(n_lanes);
+        while ((int)cache->batches.size() < n_batches) cache->batches.push_back(new HxhRecordBatch());
+        J.free_batches.assign(cache->batches.begin(), cache->batches.begin() + n_batches);
     }
-    parser.join();
-    fo.flush();
-    go.flush();
-    if ((!fo.ok || !go.ok) && rc == HX_OK) rc = HX_ERR_IO;
-    if (fclose(fa) != 0 && rc == HX_OK) rc = HX_ERR_IO;
-    if (fclose(gff) != 0 && rc == HX_OK) rc = HX_ERR_IO;
-    if (timing)
-        fprintf(stderr, "[hyperex timing] bases=%llu parse=%.3fs (own thread) wait_for_parser=%.3fs device=%.3fs "
-                        "format+write=%.3fs\n",
-                (unsigned long long)n_bases, t_parse, t_wait, t_gpu, t_write);
+    std::vector<std::vector<uint8_t>> bufs(chunker.mapped() ? 0 : n_parsers + 2);
+    for (auto &b : bufs) J.free_bufs.push_back(&b);
+
+    std::vector<std::thread> threads;
+    if (rc == HX_OK) {
+        for (int i = 0; i < n_parsers; ++i) threads.emplace_back(parser_thread, &J);
+        for (int l = 0; l < n_lanes; ++l) threads.emplace_back(lane_thread, &J, l);
+        // the chunker runs here, on the calling thread
+        double t_chunk = 0;
+        for (;;) {
+            std::vector<uint8_t> *buf = nullptr;
+            std::vector<uint8_t> none;
+            {
+                // bound the look-ahead: a decode buffer must be free (compressed input), and at most the batch pool's
+                // worth of chunks wait in the queue
+                std::unique_lock<std::mutex> lk(J.mu);
+                J.cv.wait(lk, [&] {
+                    return J.abort || J.last_index != UINT64_MAX ||
+                           (chunker.mapped() ? (int)J.chunks.size() < n_batches : !J.free_bufs.empty());
+                });
+                if (J.abort || J.last_index != UINT64_MAX) break;
+                if (!chunker.mapped()) {
+                    buf = J.free_bufs.back();
+                    J.free_bufs.pop_back();
+                }
+            }
+            Chunk c{0, nullptr, 0, false, buf};
+            const double t0 = now_s();
+            const bool more = chunker.next(chunk_bytes, buf ? *buf : none, c.p, c.n, c.drop_last);
+            t_chunk += now_s() - t0;
+            if (!more) break;
+            std::lock_guard<std::mutex> lk(J.mu);
+            c.index = J.n_chunks++;
+            J.chunks.push_back(c);
+            J.cv.notify_all();
+        }
+        {
+            std::lock_guard<std::mutex> lk(J.mu);
+            J.chunker_done = true;
+            J.cv.notify_all();
+        }
+        for (std::thread &t : threads) t.join();
+        cache->stats[HX_FS_CHUNK_S] = t_chunk;
+    }
+    if (rc == HX_OK) rc = J.rc;
+    if (rc != HX_OK && !J.err.empty()) hxh_set_error(ctx, J.err.c_str());
+    if (close(J.fd[0]) != 0 && rc == HX_OK) rc = HX_ERR_IO;
+    if (close(J.fd[1]) != 0 && rc == HX_OK) rc = HX_ERR_IO;
+    const double wall = now_s() - t_start;
+    double *s = cache->stats;
+    s[HX_FS_WALL_S] = wall;
+    s[HX_FS_BASES] = (double)J.n_bases;
+    s[HX_FS_RECORDS] = (double)J.n_records;
+    s[HX_FS_BATCHES] = (double)J.n_batches;
+    s[HX_FS_PARSE_S] = J.t_parse;
+    s[HX_FS_DEVICE_S] = J.t_device;
+    s[HX_FS_WRITE_S] = J.t_write;
+    s[HX_FS_LOG_S] = J.t_log;
+    s[HX_FS_FASTA_BYTES] = (double)J.file_pos[0];
+    s[HX_FS_GFF_BYTES] = (double)J.file_pos[1];
+    s[HX_FS_PARSERS] = n_parsers;
+    s[HX_FS_LANES] = n_lanes;
+    s[HX_FS_WRITERS] = n_writers;
+    if (getenv("HYPEREX_TIMING"))  // where the wall time of the file-level path goes (stage seconds are summed over threads)
+        fprintf(stderr, "[hyperex timing] wall=%.3fs bases=%llu records=%llu batches=%llu | chunk=%.3fs parse=%.3fs/%d thr "
+                        "device=%.3fs/%d lanes write=%.3fs/%d thr log=%.3fs | fasta=%llu B gff=%llu B\n",
+                wall, (unsigned long long)J.n_bases, (unsigned long long)J.n_records, (unsigned long long)J.n_batches,
+                s[HX_FS_CHUNK_S], J.t_parse, n_parsers, J.t_device, n_lanes, J.t_write, n_writers, J.t_log,
+                (unsigned long long)J.file_pos[0], (unsigned long long)J.file_pos[1]);
     return rc;
+}
+
+extern "C" int hx_file_stats(hx_ctx *ctx, double *out, int n) {
+    if (!ctx || !out || n < 0) return HX_ERR_ARG;
+    HostCache *cache = host_cache_of(ctx);
+    for (int i = 0; i < n; ++i) out[i] = i < HX_FILE_STATS_N ? cache->stats[i] : 0.0;
+    return HX_OK;
 }

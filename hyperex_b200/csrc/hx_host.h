@@ -8,42 +8,93 @@
 #include <vector>
 
 struct hx_ctx;
-int hxh_device_count(const hx_ctx *ctx);  // hx_api.cu
+struct hx_result;
 
 // utils.rs:251-263 + rust-bio build_64: does pattern symbol p match text byte b?
 bool hxh_symbol_matches(uint8_t p, uint8_t b);
 
-// rust-bio fasta::Reader rules (call sites utils.rs:238,270) over a decompressed stream.
+// ---- internal interface between the file-level driver (hx_host.cpp) and the device runtime (hx_api.cu) ----------
+// Sink of the streamed text path.  begin (may be NULL) receives the FASTA / GFF3 byte totals of the batch before the
+// first chunk; chunk receives `n` bytes of text `kind` (0 FASTA, 1 GFF3) that belong at byte `off` of that kind's text
+// for this batch, valid only during the call.  Non-zero return aborts the batch with HX_ERR_IO.
+struct HxhTextSink {
+    int (*begin)(void *user, uint64_t fa_total, uint64_t gff_total);
+    int (*chunk)(void *user, int kind, uint64_t off, const char *bytes, size_t n);
+    void *user;
+};
+int hxh_device_count(const hx_ctx *ctx);
+int hxh_lane_count(const hx_ctx *ctx);  // text lanes of the context: devices x lanes per device
+// hx_run_batch_text_stream on text lane `lane` (its own device, stream, buffers); lanes may run concurrently.  `out`
+// may be NULL when the caller does not need the result table on the host.
+int hxh_run_text_lane(hx_ctx *ctx, int lane, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                      hx_result *out, const char *ids, const uint64_t *id_off, const char *fa_tails,
+                      const uint32_t *fa_tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
+                      const HxhTextSink *sink);
+// hx_run_batch (result table only) on the lane's device
+int hxh_run_batch_lane(hx_ctx *ctx, int lane, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
+                       hx_result *out);
+// slot for host-side state the driver keeps in the context across calls (freed with free_fn by hx_destroy)
+void **hxh_host_cache(hx_ctx *ctx, void (*free_fn)(void *));
+void hxh_set_error(hx_ctx *ctx, const char *msg);
+
+// ---- FASTA ingest: rust-bio fasta::Reader rules (call sites utils.rs:238,270) over a decompressed stream ----------
 struct HxhRecordBatch {
-    uint8_t *arena = nullptr;      // pinned when possible (hx_alloc_pinned), else malloc
+    uint8_t *arena = nullptr;      // sequence bytes back to back; pinned when possible (hx_alloc_pinned), else malloc
     size_t arena_cap = 0;
     bool pinned = false;
     std::vector<uint64_t> offsets; // n + 1
-    std::vector<std::string> ids;
+    std::vector<char> ids;         // record ids back to back, no separators
+    std::vector<uint64_t> id_off;  // n + 1
+    std::vector<std::string> descs; // only filled when the parser is asked to keep descriptions ("" = none)
+    bool stop = false;             // the reader's iteration ends after this batch (malformed / empty record)
+    size_t n_records() const { return offsets.size() - 1; }
     void clear();
+    bool reserve(size_t bytes);    // arena capacity; false when the allocation fails
     ~HxhRecordBatch();
 };
 
+// Parses FASTA text [p, p + n) that starts at a record start (or at the start of the input) into `b`.
+// drop_last: the byte stream ended with a read error right after these bytes — the record in progress is lost, like in
+// rust-bio where the failing read_line fails the whole record.  Returns 0, or HX_ERR_NOMEM; b.stop is set when the
+// reader's iteration ends inside this text ("Expected > at record start." / an empty record).
+int hxh_parse_fasta_text(const uint8_t *p, size_t n, bool drop_last, bool keep_desc, HxhRecordBatch &b);
+
 class HxhByteSource;  // plain / gzip / bzip2 / xz / zstd byte stream (utils.rs:148-154)
 
-class HxhFastaReader {
+// Cuts the (decompressed) input into chunks that end at record boundaries — a line that starts with '>' always starts
+// a new record in rust-bio's reader — so that chunks can be parsed independently, on parallel threads, and their
+// batches simply follow each other in input order.  A plain file is memory-mapped and chunks are views into the
+// mapping; compressed input is decoded into the caller's buffer.
+class HxhChunker {
   public:
-    HxhFastaReader();
-    ~HxhFastaReader();
-    // returns 0 or a negative hx_status; err receives the message
-    int open(const char *path, std::string &err);
-    // appends records until the arena holds >= max_bytes or max_records; returns the number of
-    // records appended, 0 at the end of the input.
-    size_t next_batch(HxhRecordBatch &batch, size_t max_bytes, size_t max_records);
+    HxhChunker();
+    ~HxhChunker();
+    int open(const char *path, std::string &err);  // 0 or a negative hx_status (niffler: file too short to sniff, ...)
+    // Next chunk of about `target` bytes (at least one whole record).  Returns false at the end of the input.  `buf` is
+    // scratch owned by the caller (used for compressed input); [p, p + n) stays valid until the next call with the
+    // same `buf` (forever for a mapped file).  ended_by_error: see hxh_parse_fasta_text(drop_last).
+    bool next(size_t target, std::vector<uint8_t> &buf, const uint8_t *&p, size_t &n, bool &ended_by_error);
+    bool mapped() const { return map_ != nullptr; }
+    size_t mapped_bytes() const { return map_len_; }
 
   private:
-    bool next_line(const uint8_t *&line, size_t &len);  // zero-copy view into buf_, '\n' excluded
     HxhByteSource *src_ = nullptr;
+    const uint8_t *map_ = nullptr;
+    size_t map_len_ = 0, map_pos_ = 0;
+    std::vector<uint8_t> carry_;  // bytes after the last record boundary of the previous chunk
+    bool eof_ = false, error_ = false;
+};
+
+// Sequential reader behind the C ABI's hx_fasta_open / hx_fasta_next: chunker + parser on the calling thread.
+class HxhFastaReader {
+  public:
+    int open(const char *path, std::string &err) { return chunker_.open(path, err); }
+    // parses the next chunk of about max_bytes of FASTA text; returns the number of records, 0 at the end of the
+    // input, or a negative hx_status
+    int64_t next_batch(HxhRecordBatch &batch, size_t max_bytes, bool keep_desc);
+
+  private:
+    HxhChunker chunker_;
     std::vector<uint8_t> buf_;
-    size_t pos_ = 0, end_ = 0;
-    bool eof_ = false;
-    std::string header_;  // look-ahead header line (rust-bio keeps the next header in self.line)
-    bool have_line_ = false;
-    size_t size_hint_ = 0;
     bool finished_ = false;
 };

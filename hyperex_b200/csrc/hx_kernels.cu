@@ -21,6 +21,9 @@
 
 #include <stdio.h>
 
+#include <algorithm>
+#include <atomic>
+
 // ------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------
@@ -825,12 +828,14 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
 template <typename W, int NP, bool TMA, int KWM, bool LF = false>
 static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
     const int smem = hx_table_bytes(NP, sizeof(W)) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
-    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
+    // per (instantiation, device) once; contexts on different host threads may race here, so the flags are atomic
+    // (setting the attribute twice is harmless, skipping it is not)
+    static std::atomic<bool> attr_done[64];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 8 || !attr_done[dev]) {
+    if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
         cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM, LF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (dev < 8) attr_done[dev] = true;
+        if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
     }
     const uint32_t blocks = (tile_cap + HX_THREADS - 1) / HX_THREADS;
     hx_myers_pair_kernel<W, NP, TMA, KWM, LF><<<blocks, HX_THREADS, smem, st>>>(a);
@@ -886,60 +891,63 @@ __global__ void __launch_bounds__(256)
                       uint32_t n_records, const uint64_t *__restrict__ sum_f, const uint64_t *__restrict__ sum_r,
                       const uint64_t *__restrict__ pair_hi, const uint32_t *__restrict__ pair_lo, uint32_t ts,
                       HxResultDev *__restrict__ out) {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)n_pairs * n_records) return;
-    const uint32_t q = (uint32_t)(idx / n_records);
-    const uint32_t r = (uint32_t)(idx % n_records);
-    const int alpha = hx_alpha_of(rec_raw[r]);
-    HxResultDev res = {0u, 0u, 0u};
-    if (alpha == 2) {
-        res.meta = 8u;
+    // grid-stride over (record, pair) with the pair as the fast index: neighbouring threads store neighbouring
+    // hx_result entries, and the grid stays far below gridDim.x's limit for any n_pairs x n_records
+    const uint64_t total = (uint64_t)n_pairs * n_records;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(idx / n_pairs);
+        const uint32_t q = (uint32_t)(idx % n_pairs);
+        const int alpha = hx_alpha_of(rec_raw[r]);
+        HxResultDev res = {0u, 0u, 0u};
+        if (alpha == 2) {
+            res.meta = 8u;
+            out[(size_t)r * n_pairs + q] = res;
+            continue;
+        }
+        const HxPairRef pr = pairs[q];
+        const uint32_t t0 = tile_first[r], nt = tile_cnt[r];
+        if (nt == 1u) continue;             // single-tile record: hx_myers_pair_kernel wrote the final result
+        if (nt > HX_LONG_TILES) continue;  // contig: hx_combine_long_kernel
+        uint64_t bestF = HX_NONE64;          // (dist<<32 | end) of the best valid forward hit so far
+        uint64_t bhi = HX_NONE64;            // combined<<32 | f_end
+        uint32_t blo = 0;                    // r_end
+        bool fany = false, rany = false;
+        for (uint32_t i = 0; i < nt; ++i) {
+            const size_t t = t0 + i;
+            const uint64_t tf = sum_f[(size_t)pr.f_slot * ts + t];
+            const uint64_t tfr = sum_r[(size_t)pr.f_slot * ts + t];
+            const uint64_t tr = sum_r[(size_t)pr.r_slot * ts + t];
+            fany |= tfr != HX_NONE64;
+            rany |= tr != HX_NONE64;
+            if (bestF != HX_NONE64 && tr != HX_NONE64) {
+                const uint64_t chi = (((bestF >> 32) + (tr >> 32)) << 32) | (uint32_t)bestF;
+                const uint32_t clo = (uint32_t)tr;
+                if (chi < bhi || (chi == bhi && clo < blo)) {
+                    bhi = chi;
+                    blo = clo;
+                }
+            }
+            const uint64_t whi = pair_hi[(size_t)q * ts + t];
+            if (whi != HX_NONE64) {
+                const uint32_t wlo = pair_lo[(size_t)q * ts + t];
+                if (whi < bhi || (whi == bhi && wlo < blo)) {
+                    bhi = whi;
+                    blo = wlo;
+                }
+            }
+            if (tf < bestF) bestF = tf;
+        }
+        uint32_t flags = (fany ? 1u : 0u) | (rany ? 2u : 0u) | (alpha == 1 ? 16u : 0u);
+        if (bhi != HX_NONE64) {
+            flags |= 4u;
+            res.f_start = (uint32_t)bhi - (pr.len_f - 1u);
+            res.r_end = blo;
+            res.meta = flags | (uint32_t)((bhi >> 32) & 0xffu) << 8;
+        } else {
+            res.meta = flags;
+        }
         out[(size_t)r * n_pairs + q] = res;
-        return;
     }
-    const HxPairRef pr = pairs[q];
-    const uint32_t t0 = tile_first[r], nt = tile_cnt[r];
-    if (nt == 1u) return;             // single-tile record: hx_myers_pair_kernel wrote the final result
-    if (nt > HX_LONG_TILES) return;  // contig: hx_combine_long_kernel
-    uint64_t bestF = HX_NONE64;          // (dist<<32 | end) of the best valid forward hit so far
-    uint64_t bhi = HX_NONE64;            // combined<<32 | f_end
-    uint32_t blo = 0;                    // r_end
-    bool fany = false, rany = false;
-    for (uint32_t i = 0; i < nt; ++i) {
-        const size_t t = t0 + i;
-        const uint64_t tf = sum_f[(size_t)pr.f_slot * ts + t];
-        const uint64_t tfr = sum_r[(size_t)pr.f_slot * ts + t];
-        const uint64_t tr = sum_r[(size_t)pr.r_slot * ts + t];
-        fany |= tfr != HX_NONE64;
-        rany |= tr != HX_NONE64;
-        if (bestF != HX_NONE64 && tr != HX_NONE64) {
-            const uint64_t chi = (((bestF >> 32) + (tr >> 32)) << 32) | (uint32_t)bestF;
-            const uint32_t clo = (uint32_t)tr;
-            if (chi < bhi || (chi == bhi && clo < blo)) {
-                bhi = chi;
-                blo = clo;
-            }
-        }
-        const uint64_t whi = pair_hi[(size_t)q * ts + t];
-        if (whi != HX_NONE64) {
-            const uint32_t wlo = pair_lo[(size_t)q * ts + t];
-            if (whi < bhi || (whi == bhi && wlo < blo)) {
-                bhi = whi;
-                blo = wlo;
-            }
-        }
-        if (tf < bestF) bestF = tf;
-    }
-    uint32_t flags = (fany ? 1u : 0u) | (rany ? 2u : 0u) | (alpha == 1 ? 16u : 0u);
-    if (bhi != HX_NONE64) {
-        flags |= 4u;
-        res.f_start = (uint32_t)bhi - (pr.len_f - 1u);
-        res.r_end = blo;
-        res.meta = flags | (uint32_t)((bhi >> 32) & 0xffu) << 8;
-    } else {
-        res.meta = flags;
-    }
-    out[(size_t)r * n_pairs + q] = res;
 }
 
 // Records with many windows (contigs): one warp per (long record, pair).  Every lane joins a contiguous run of
@@ -1030,7 +1038,8 @@ int hx_launch_combine(const uint32_t *tile_first, const uint32_t *tile_cnt, cons
     if (total == 0) return 0;
     hx_combine_long_kernel<<<148 * 4, 256, 0, st>>>(long_list, n_long, tile_first, tile_cnt, rec_raw, pairs, n_pairs, sum_f,
                                                    sum_r, pair_hi, pair_lo, tile_stride, (HxResultDev *)out);
-    hx_combine_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, st>>>(tile_first, tile_cnt, rec_raw, pairs, n_pairs,
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((total + 255) / 256, 148ull * 64);
+    hx_combine_kernel<<<blocks, 256, 0, st>>>(tile_first, tile_cnt, rec_raw, pairs, n_pairs,
                                                                       n_records, sum_f, sum_r, pair_hi, pair_lo,
                                                                       tile_stride, (HxResultDev *)out);
     return 2;

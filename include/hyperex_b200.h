@@ -199,9 +199,10 @@ void hx_free_primer_file(char **fwd, char **rev, int n);
 /* ---- FASTA ingest -> arena packer (replaces fasta::Reader::new(reader).records(), utils.rs:237-238,270)
  * rust-bio reader rules: id = header up to the first whitespace, sequence lines joined with
  * trim_end(), iteration stops at the first malformed or empty record; input may be plain, gzip,
- * bzip2, xz or zstd (niffler sniffing, utils.rs:148-154).  hx_fasta_next packs up to max_bytes of
- * sequence into a pinned arena owned by the reader (valid until the next call / close) and returns
- * the number of records (0 at the end of the input, negative hx_status on error). */
+ * bzip2, xz or zstd (niffler sniffing, utils.rs:148-154).  hx_fasta_next packs the records of the next
+ * ~max_bytes of FASTA text (always whole records, at least one; 0 = 256 MiB) into a pinned arena owned by the
+ * reader (valid until the next call / close) and returns the number of records (0 at the end of the
+ * input, negative hx_status on error, e.g. HX_ERR_NOMEM). */
 typedef struct hx_fasta hx_fasta;
 int hx_fasta_open(const char *path, hx_fasta **out);
 int64_t hx_fasta_next(hx_fasta *r, size_t max_bytes, const uint8_t **arena, const uint64_t **offsets,
@@ -217,6 +218,29 @@ typedef void (*hx_log_fn)(int level, const char *msg, void *user);
 int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n_pairs, const char *const *fwd,
                             const char *const *rev, const char *prefix, uint8_t mismatch, hx_log_fn log_fn,
                             void *user);
+
+/* Where the time of the last hx_get_hypervar_regions call on ctx went (bench.py's file_e2e block; HYPEREX_TIMING=1
+ * prints the same).  The call is a pipeline of host threads — chunker, parsers, two text lanes per device, writers —
+ * so the per-stage seconds are SUMS over the threads of a stage and may exceed the wall time.  Fills
+ * out[0 .. min(n, HX_FILE_STATS_N)) in the order of the enum. */
+enum {
+    HX_FS_WALL_S = 0,    /* wall time of the call */
+    HX_FS_BASES,         /* sequence bytes read */
+    HX_FS_RECORDS,
+    HX_FS_BATCHES,
+    HX_FS_CHUNK_S,       /* cutting the input at record boundaries (compressed input: the decoder) */
+    HX_FS_PARSE_S,       /* FASTA text -> pinned record arenas, summed over parser threads */
+    HX_FS_DEVICE_S,      /* H2D + kernels + D2H, summed over lanes, waiting for writes excluded */
+    HX_FS_WRITE_S,       /* lanes waiting for pwrite() of the output text */
+    HX_FS_LOG_S,         /* log_fn calls */
+    HX_FS_FASTA_BYTES,   /* size of <prefix>.fa */
+    HX_FS_GFF_BYTES,     /* size of <prefix>.gff */
+    HX_FS_PARSERS,       /* threads per stage */
+    HX_FS_LANES,
+    HX_FS_WRITERS,
+    HX_FILE_STATS_N
+};
+int hx_file_stats(hx_ctx *ctx, double *out, int n);
 
 #ifdef __cplusplus
 }
