@@ -10,7 +10,9 @@ max over ranks.
 
   value        Gbases/s with the arena resident in HBM (CUDA events on the launching stream)
   e2e          Gbases/s through hx_run_batch with HOST buffers: pinned arena -> H2D -> kernels -> D2H
-               result table, every step
+               result table, every step (library defaults: the small-k fast path is on, as shipped)
+  file_e2e     Gbases/s of the drop-in seam itself, hx_get_hypervar_regions: FASTA file in, <prefix>.fa and
+               <prefix>.gff out (utils.rs:231-414 / main.rs:38), with the parse / device / write phases
   roofline     the Myers kernel against the measured integer-ALU peak (hx_int_peak) and HBM peak
   cpu_baseline the CPU oracle (C port of the reference path) on a bounded sample, one thread like the
                single-threaded reference
@@ -62,6 +64,9 @@ def parse_args():
     ap.add_argument("--slab-mb", type=int, default=0, help="host->device pipeline granule of the e2e leg (0: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ab", action="store_true", help="skip the TMA / LDG text-path A/B")
+    ap.add_argument("--no-file-e2e", action="store_true", help="skip the file-level leg (FASTA file in, two files out)")
+    ap.add_argument("--file-steps", type=int, default=3, help="timed calls of the file-level leg")
+    ap.add_argument("--file-dir", default="", help="where the file-level leg keeps its files (default: /dev/shm if it has room)")
     return ap.parse_args()
 
 
@@ -192,6 +197,75 @@ def cpu_port_run(arena, offsets, n, pairs, k, nthreads, rebuild=True):
     return int(sub_o[-1] - sub_o[0]), dt
 
 
+def scratch_dir(need_bytes, override=""):
+    """directory for the file-level leg: /dev/shm when it has room (the leg measures the pipeline, not a disk)"""
+    import shutil
+    import tempfile
+    for d in ([override] if override else []) + ["/dev/shm", tempfile.gettempdir(), os.path.join(ROOT, "gpurun_out")]:
+        try:
+            os.makedirs(d, exist_ok=True)
+            if shutil.disk_usage(d).free > need_bytes:
+                return tempfile.mkdtemp(prefix="hx_file_e2e_", dir=d)
+        except OSError:
+            continue
+    return None
+
+
+def sha256_file(path):
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        while True:
+            b = f.read(16 << 20)
+            if not b:
+                break
+            h.update(b)
+    return h.hexdigest()
+
+
+def file_e2e_leg(hx, devices, arena, offsets, pairs, k, steps, work_override=""):
+    """FASTA file in -> <prefix>.fa + <prefix>.gff out through hx_get_hypervar_regions on a context over `devices`
+    (what `bin/hyperex --gpus N` runs).  No log callback (the reference's per-record warn! lines are a side channel,
+    SURVEY.md §2 row 3).  One untimed call first: it allocates the pinned batches the context then reuses."""
+    import shutil
+    import hx_synth
+    n, bases = len(offsets) - 1, int(offsets[-1])
+    work = scratch_dir(int(bases * 7.5) + (2 << 30), work_override)
+    if work is None:
+        return {"unavailable": "no scratch directory with room for the input and output files"}
+    try:
+        path = os.path.join(work, "in.fa")
+        in_bytes = hx_synth.write_fasta_file(path, arena, offsets)
+        prefix = os.path.join(work, "out")
+        times, stats = [], None
+        with hx.Context(tuple(devices)) as fctx:
+            for it in range(steps + 1):
+                for ext in (".fa", ".gff"):
+                    if os.path.exists(prefix + ext):
+                        os.remove(prefix + ext)
+                t0 = time.perf_counter()
+                fctx.get_hypervar_regions(path, pairs, prefix, k)
+                dt = time.perf_counter() - t0
+                if it:
+                    times.append(dt)
+                    if stats is None or dt <= min(times):
+                        stats = fctx.file_stats()
+        fa_bytes, gff_bytes = os.path.getsize(prefix + ".fa"), os.path.getsize(prefix + ".gff")
+        mean = sum(times) / len(times)
+        out = {"what": "hx_get_hypervar_regions: plain FASTA file -> .fa + .gff files, no log callback, host threads + "
+                       f"{len(devices)} GPU(s) in one context", "value": bases / mean / 1e9, "unit": "Gbases/s",
+               "best": bases / min(times) / 1e9, "seconds": times, "records": n, "bases": bases,
+               "input_bytes": in_bytes, "fasta_bytes": fa_bytes, "gff_bytes": gff_bytes, "dir": os.path.dirname(work),
+               "sha256": {"fa": sha256_file(prefix + ".fa"), "gff": sha256_file(prefix + ".gff")},
+               "phases_of_best_call": {kk: stats[kk] for kk in ("wall_s", "chunk_s", "parse_s", "device_s", "write_s", "parsers",
+                                                              "lanes", "writers", "batches")},
+               "phases_note": "stage seconds are summed over the threads of the stage (pipeline: they overlap)",
+               "host_cores": os.cpu_count()}
+        return out
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def run_reference(args, rank, world):
     """reference arm: the CPU port of the reference path on all host threads (rank 0 only)"""
     if rank != 0:
@@ -201,10 +275,19 @@ def run_reference(args, rank, world):
     if args.k < 0:
         args.k = 0  # configs[1]: -m 0
     cores = os.cpu_count() or 1
-    n = args.ref_sample or max(2000, 2500 * cores)
-    arena, offsets = hx_synth.gen_reads(n, seed=2)
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_port_run(arena, offsets, min(n, 500 * cores), pairs, args.k, cores)
+    # The GPU arm's own record count per step when the host gets through it in time (probe: 20 000 records; budget
+    # ~4 minutes for the whole run), else a bounded sample of the same generator and seed.
+    full = args.records
+    arena, offsets = hx_synth.gen_reads(full if not args.ref_sample else args.ref_sample, seed=2)
+    probe_n = min(len(offsets) - 1, 20_000)
+    cpu_port_run(arena, offsets, min(probe_n, 500 * cores), pairs, args.k, cores)  # warm-up (threads, page faults)
+    pb, pdt = cpu_port_run(arena, offsets, probe_n, pairs, args.k, cores)
+    n = len(offsets) - 1
+    if not args.ref_sample:
+        est_full = pdt * n / probe_n
+        if est_full * (args.steps + 0.2) > 240.0:
+            n = int(max(2000, min(n, probe_n * 240.0 / (args.steps + 0.2) / pdt)))
+    same_config = n == args.records
     times, bases = [], 0
     for _ in range(args.steps):
         bases, dt = cpu_port_run(arena, offsets, n, pairs, args.k, cores)
@@ -215,14 +298,48 @@ def run_reference(args, rank, world):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "c2: synthetic full-length 16S reads ~1.5 kb, 10 built-in regions, -m 0 "
-                                   f"(bounded sample of {n} records per step)", "records": n, "pairs": len(pairs),
-                       "k": args.k},
+                                   + (f"({n} records per step, the GPU arm's own count)" if same_config else
+                                      f"(bounded sample of {n} records per step)"), "records": n, "pairs": len(pairs),
+                       "k": args.k, "same_records_as_gpu_arm": same_config},
             "cpu_baseline": {"value": gb, "unit": "Gbases/s", "cores": cores, "kind": "port",
                              "sample": f"{n} records ({bases} bases) per step, {cores} threads; C port of the "
                                        "reference path (Rust toolchain absent: SURVEY.md §8c), Peq rebuilt per "
                                        "record x pair like utils.rs:301-302"},
             "e2e": {"value": gb, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_file_e2e:
+        line["file_e2e"] = reference_file_leg(arena, offsets, min(n, 60_000), pairs, args.k, cores)
     print(json.dumps(line), flush=True)
+
+
+def reference_file_leg(arena, offsets, n, pairs, k, cores):
+    """the reference's seam on the host: FASTA file in -> FASTA + GFF3 files out with the C port (parse, search on all
+    threads, format, write), on a bounded sample"""
+    import shutil
+    import hx_synth
+    from oracle import oracle as O
+    sub_o = np.ascontiguousarray(offsets[:n + 1])
+    bases = int(sub_o[-1])
+    work = scratch_dir(bases * 8 + (1 << 30))
+    if work is None:
+        return {"unavailable": "no scratch directory"}
+    try:
+        path = os.path.join(work, "in.fa")
+        hx_synth.write_fasta_file(path, arena[:bases], sub_o)
+        t0 = time.perf_counter()
+        buf = open(path, "rb").read()
+        a, o, ids = O.parse_fasta(buf)
+        res = O.run_batch(a, o, pairs, k, nthreads=cores, rebuild_per_record=True)
+        fa, gff = O.format_outputs(a, o, ids, pairs, res)
+        with open(os.path.join(work, "out.fa"), "wb") as f:
+            f.write(fa)
+        with open(os.path.join(work, "out.gff"), "wb") as f:
+            f.write(gff)
+        dt = time.perf_counter() - t0
+        return {"what": "C port: FASTA file -> parse -> search (all threads) -> format -> .fa + .gff files", "value": bases / dt / 1e9,
+                "unit": "Gbases/s", "records": n, "bases": bases, "seconds": dt, "cores": cores, "fasta_bytes": len(fa),
+                "gff_bytes": len(gff)}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
 
 
 def main():
@@ -342,6 +459,10 @@ def main():
         assert fast_res == d_out.cpu().numpy().tobytes(), "fast path and Myers path disagree"
 
     # ---- end-to-end leg ("e2e"): host arena in, host result table out, every step ----------------
+    # through the public entry point as shipped: library defaults, i.e. the small-k fast path is ON for -m 0..2
+    # (PCIe-bound either way; the result table is asserted equal to the Myers kernel's below)
+    ctx.set_option("fast_small_k", 1)
+    ctx.set_primers(pairs, args.k)
     h_arena = hx.pinned_empty(bases + 64)
     h_arena[:bases] = arena
     h_out_raw = hx.pinned_empty(n * npairs * 12)
@@ -377,10 +498,39 @@ def main():
         torch.cuda.synchronize()
         h2d_conc_ms = (time.perf_counter() - t0c) * 1e3 / 3
 
-    # results sanity: device-resident and host legs agree, every planted region found (k = 0)
+    # results sanity: device-resident (Myers) and host (library default) legs agree, every planted region found (k = 0)
     dev_res = d_out.cpu().numpy().view(hx.RESULT_DTYPE).reshape(n, npairs)
     assert dev_res.tobytes() == h_out.tobytes(), "device-resident and host legs disagree"
     found = int((h_out["flags"] & 4).astype(bool).sum())
+    import hashlib
+    table_sha = hashlib.sha256(h_out.tobytes()).hexdigest()
+    ctx.set_option("fast_small_k", 0)
+    ctx.set_primers(pairs, args.k)  # group_info() below describes the graded Myers configuration
+
+    # ---- one process, all N GPUs in one context (what `bin/hyperex --gpus N` ships): parity outside the timed region --
+    multidev = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            ns = min(n, 20_000)
+            so = np.ascontiguousarray(offsets[:ns + 1])
+            with hx.Context(tuple(range(world))) as mctx:
+                mctx.set_option("slab_bytes", 2 << 20)
+                mctx.set_primers(pairs, args.k)
+                mres = mctx.run_batch(arena[:int(so[-1])], so)
+            multidev = bool(mres.tobytes() == h_out[:ns].tobytes())
+        barrier()
+
+    # ---- file-level leg: the drop-in seam (FASTA file in, two files out), rank 0, a context over all N GPUs ----------
+    file_e2e = None
+    if not args.no_file_e2e and args.workload == "c2":
+        barrier()
+        if rank == 0:
+            try:
+                file_e2e = file_e2e_leg(hx, range(world), arena, offsets, pairs, args.k, max(1, args.file_steps), args.file_dir)
+            except Exception as e:  # pragma: no cover - reported, never hidden
+                file_e2e = {"error": str(e)}
+        barrier()
 
     # ---- max over ranks ---------------------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s * 1e3, myers_ms, fast_ms or 0.0, h2d_conc_ms], dtype=torch.float64, device="cuda")
@@ -461,7 +611,13 @@ def main():
                         "h2d_copy_all_ranks_at_once_ms": h2d_conc_ms_max,
                         "h2d_copy_all_ranks_at_once_gbs_total": total_bases / (h2d_conc_ms_max * 1e-3) / 1e9,
                         "frac_of_copy_all_ranks_at_once": h2d_conc_ms_max / (e2e_ms_max / args.steps)},
-                "gpu_launches": int(total_launches), "roofline": roofline, "clocks": clocks}
+                "gpu_launches": int(total_launches), "roofline": roofline, "clocks": clocks,
+                "result_table_sha256_rank0": table_sha}
+        line["e2e"]["path"] = "library defaults (fast_small_k = 1): result table asserted equal to the Myers kernel's"
+        if multidev is not None:
+            line["multidev_parity"] = multidev
+        if file_e2e is not None:
+            line["file_e2e"] = file_e2e
         if fast_ms_max > 0:
             fv = total_bases / (fast_ms_max * 1e-3) / 1e9
             line["fast_path"] = {"what": "library default for -m 0..2: Wu-Manber / Shift-Or automata, identical results "

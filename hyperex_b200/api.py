@@ -278,11 +278,21 @@ class Context:
         self._check(self._L.hx_kernel_time(self._h, C.byref(ms), C.byref(n), 1 if reset else 0))
         return ms.value, n.value
 
+    FILE_STATS = ("wall_s", "bases", "records", "batches", "chunk_s", "parse_s", "device_s", "write_s", "log_s",
+                  "fasta_bytes", "gff_bytes", "parsers", "lanes", "writers")
+
+    def file_stats(self) -> dict:
+        """hx_file_stats: where the time of the last get_hypervar_regions call went (stage seconds are summed over
+        the threads of a stage)"""
+        v = (C.c_double * len(self.FILE_STATS))()
+        self._check(self._L.hx_file_stats(self._h, v, len(self.FILE_STATS)))
+        return dict(zip(self.FILE_STATS, (float(x) for x in v)))
+
     def get_hypervar_regions(self, file: str, primers: Sequence[Sequence[str]], prefix: str, mismatch: int,
                              log=None):
-        """utils.rs:231-414: writes <prefix>.fa and <prefix>.gff; log(level, msg) gets warn!/error! lines"""
-        cb = _lib.LOG_FN((lambda lvl, msg, _u: log(lvl, msg.decode("utf-8", "replace"))) if log
-                         else (lambda lvl, msg, _u: None))
+        """utils.rs:231-414: writes <prefix>.fa and <prefix>.gff; log(level, msg) gets warn!/error! lines (log=None:
+        no callback at all, the result table then stays on the device)"""
+        cb = _lib.LOG_FN((lambda lvl, msg, _u: log(lvl, msg.decode("utf-8", "replace"))) if log else 0)
         fw = _cstrs([p[0] for p in primers])
         rv = _cstrs([p[1] for p in primers])
         self._check(self._L.hx_get_hypervar_regions(self._h, _b(file), len(primers), fw, rv, _b(prefix), mismatch, cb,

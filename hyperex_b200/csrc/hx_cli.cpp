@@ -37,12 +37,18 @@ void log_msg(Level lv, const char *target, const std::string &msg) {
     if (g_quiet && lv == INFO) return;  // quiet => LevelFilter::Warn (utils.rs:76-80)
     static const char *names[] = {"INFO", "WARN", "ERROR"};
     static const int colors[] = {32, 33, 31};
-    time_t t = time(nullptr);
-    struct tm tmv;
-    localtime_r(&t, &tmv);
-    char hms[16], date[16];
-    strftime(hms, sizeof hms, "%H:%M:%S", &tmv);
-    strftime(date, sizeof date, "%Y-%m-%d", &tmv);
+    // a run over a million reads prints a million lines: the time stamp is formatted once per second, and both
+    // streams are fully buffered (main sets 1 MB buffers; they are flushed at exit and before anything goes to stderr)
+    static time_t last = (time_t)-1;
+    static char hms[16], date[16];
+    const time_t t = time(nullptr);
+    if (t != last) {
+        struct tm tmv;
+        localtime_r(&t, &tmv);
+        strftime(hms, sizeof hms, "%H:%M:%S", &tmv);
+        strftime(date, sizeof date, "%Y-%m-%d", &tmv);
+        last = t;
+    }
     printf("[%s][\x1b[%dm%s\x1b[0m] %s\n", hms, colors[lv], names[lv], msg.c_str());
     if (g_logfile) fprintf(g_logfile, "[%s][%s][%s][%s] %s\n", date, hms, target, names[lv], msg.c_str());
 }
@@ -59,6 +65,7 @@ bool exists(const std::string &p) {
 }
 
 void usage_error(const std::string &msg) {
+    fflush(stdout);
     fprintf(stderr, "error: %s\n\nUsage: hyperex [options] [<FILE>]\n\nFor more information, try '--help'.\n", msg.c_str());
     exit(2);  // clap exits with status 2 on usage errors
 }
@@ -97,12 +104,15 @@ std::string read_stdin_to_temp_file() {
         const uint64_t *off;
         const char *const *ids;
         int64_t cnt;
-        while ((cnt = hx_fasta_next(r, 0, &arena, &off, &ids)) > 0)
+        while ((cnt = hx_fasta_next(r, 0, &arena, &off, &ids)) > 0) {
+            const char *const *descs = hx_fasta_descs(r);
             for (int64_t i = 0; i < cnt; ++i) {
-                fprintf(out, ">%s\n", ids[i]);
+                if (descs[i]) fprintf(out, ">%s %s\n", ids[i], descs[i]);
+                else fprintf(out, ">%s\n", ids[i]);
                 fwrite(arena + off[i], 1, (size_t)(off[i + 1] - off[i]), out);
                 fputc('\n', out);
             }
+        }
         hx_fasta_close(r);
     }
     if (out) fclose(out);
@@ -145,7 +155,13 @@ int main(int argc, char **argv) {
             mismatch = strtol(v.c_str(), &end, 10);
             if (v.empty() || *end || mismatch < 0 || mismatch > 255)
                 usage_error("invalid value '" + v + "' for '--mismatch <N>': not a u8");
-        } else if (is_opt(nullptr, "--gpus")) gpus = atoi(value("--gpus <N>").c_str());
+        } else if (is_opt(nullptr, "--gpus")) {
+            const std::string v = value("--gpus <N>");
+            char *end = nullptr;
+            const long g = strtol(v.c_str(), &end, 10);
+            if (v.empty() || *end || g < 1 || g > 64) usage_error("invalid value '" + v + "' for '--gpus <N>': expected 1..64");
+            gpus = (int)g;
+        }
         else if (is_opt(nullptr, "--region")) {
             has_region = true;
             if (a.find('=') != std::string::npos) regions.push_back(value("--region"));
@@ -161,6 +177,8 @@ int main(int argc, char **argv) {
     if (has_f != has_r) usage_error("the following required arguments were not provided: " +
                                     std::string(has_f ? "--reverse <STR>" : "--forward <STR>"));
     g_logfile = fopen("hyperex.log", "ab");
+    setvbuf(stdout, nullptr, _IOFBF, 1 << 20);
+    if (g_logfile) setvbuf(g_logfile, nullptr, _IOFBF, 1 << 20);
 
     // handle_input (utils.rs:416-442)
     std::string infile;
@@ -188,6 +206,7 @@ int main(int argc, char **argv) {
     std::vector<std::string> F, R;
     char **csv_f = nullptr, **csv_r = nullptr;
     int csv_n = 0;
+    size_t csv_longest = 0;
     auto add_region = [&](const char *name) {
         const char *f = nullptr, *r = nullptr;
         if (hx_region_to_primer(name, &f, &r) != HX_OK) return false;
@@ -211,6 +230,20 @@ int main(int argc, char **argv) {
                 R.push_back(csv_r[i]);
             }
             hx_free_primer_file(csv_f, csv_r, csv_n);
+            // validate_mismatch flattens EVERY field of every line (utils.rs:523-528), not just the two primers
+            if (FILE *cf = fopen(regions[0].c_str(), "rb")) {
+                size_t cur = 0;
+                for (int ch; (ch = fgetc(cf)) != EOF;) {
+                    if (ch == ',' || ch == '\n') {
+                        csv_longest = std::max(csv_longest, cur);
+                        cur = 0;
+                    } else if (ch != '\r') {
+                        ++cur;
+                    }
+                }
+                csv_longest = std::max(csv_longest, cur);
+                fclose(cf);
+            }
         } else {
             bool ok = true;
             for (const std::string &r : regions) ok = ok && add_region(r.c_str());
@@ -225,7 +258,7 @@ int main(int argc, char **argv) {
         for (uint32_t i = 0; i < n; ++i) add_region(names[i]);
     }
     // validate_mismatch (utils.rs:522-540)
-    size_t longest = 0;
+    size_t longest = csv_longest;
     for (size_t i = 0; i < F.size(); ++i) longest = std::max(longest, std::max(F[i].size(), R[i].size()));
     if (F.empty()) {
         fprintf(stderr, "Error: No primer sequences detected\n");

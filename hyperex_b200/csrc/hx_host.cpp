@@ -414,6 +414,7 @@ void HxhRecordBatch::clear() {
     ids.clear();
     id_off.assign(1, 0);
     descs.clear();
+    has_desc.clear();
     stop = false;
 }
 
@@ -425,7 +426,7 @@ bool HxhRecordBatch::reserve(size_t bytes) {  // contents are not preserved: cal
         arena = nullptr;
         arena_cap = 0;
     }
-    const size_t want = std::max(bytes + bytes / 4, (size_t)1 << 20);
+    const size_t want = std::max(bytes + bytes / 16, (size_t)1 << 20);  // chunks of one input are all about the same size
     uint8_t *p = (uint8_t *)hx_alloc_pinned(want);
     pinned = p != nullptr;
     if (!p) p = (uint8_t *)malloc(want);  // no CUDA device (CPU-only reader tests): plain memory
@@ -485,14 +486,20 @@ int hxh_parse_fasta_text(const uint8_t *p, size_t n, bool drop_last, bool keep_d
         b.ids.insert(b.ids.end(), (const char *)id_s, (const char *)ie);
         b.id_off.push_back(b.ids.size());
         b.offsets.push_back(used);
-        if (keep_desc) b.descs.emplace_back(has_desc ? std::string((const char *)ie + 1, (const char *)he) : std::string());
+        if (keep_desc) {
+            b.descs.emplace_back(has_desc ? std::string((const char *)ie + 1, (const char *)he) : std::string());
+            b.has_desc.push_back(has_desc ? 1 : 0);
+        }
     }
     if (drop_last && !b.stop) {  // the read that failed takes the record in progress with it and ends the iteration
         if (b.offsets.size() > 1) {
             b.offsets.pop_back();
             b.id_off.pop_back();
             b.ids.resize(b.id_off.back());
-            if (keep_desc) b.descs.pop_back();
+            if (keep_desc) {
+                b.descs.pop_back();
+                b.has_desc.pop_back();
+            }
         }
         b.stop = true;
     }
@@ -650,7 +657,7 @@ struct hx_fasta {
     HxhFastaReader reader;
     HxhRecordBatch batch;
     std::vector<char> id_cstr;  // ids with terminators, for the C strings handed out
-    std::vector<const char *> id_ptrs;
+    std::vector<const char *> id_ptrs, desc_ptrs;
 };
 
 extern "C" int hx_fasta_open(const char *path, hx_fasta **out) {
@@ -671,7 +678,7 @@ extern "C" int hx_fasta_open(const char *path, hx_fasta **out) {
 extern "C" int64_t hx_fasta_next(hx_fasta *r, size_t max_bytes, const uint8_t **arena, const uint64_t **offsets,
                                  const char *const **ids) {
     if (!r) return HX_ERR_ARG;
-    const int64_t n = r->reader.next_batch(r->batch, max_bytes ? max_bytes : ((size_t)256 << 20), false);
+    const int64_t n = r->reader.next_batch(r->batch, max_bytes ? max_bytes : ((size_t)256 << 20), true);
     if (n < 0) return n;
     const HxhRecordBatch &b = r->batch;
     r->id_cstr.clear();
@@ -683,11 +690,15 @@ extern "C" int64_t hx_fasta_next(hx_fasta *r, size_t max_bytes, const uint8_t **
         r->id_cstr.push_back('\0');
     }
     for (size_t s : starts) r->id_ptrs.push_back(r->id_cstr.data() + s);
+    r->desc_ptrs.clear();
+    for (int64_t i = 0; i < n; ++i) r->desc_ptrs.push_back(b.has_desc[i] ? b.descs[i].c_str() : nullptr);
     if (arena) *arena = b.arena;
     if (offsets) *offsets = b.offsets.data();
     if (ids) *ids = r->id_ptrs.data();
     return n;
 }
+
+extern "C" const char *const *hx_fasta_descs(hx_fasta *r) { return r ? r->desc_ptrs.data() : nullptr; }
 
 extern "C" void hx_fasta_close(hx_fasta *r) { delete r; }
 
@@ -733,11 +744,20 @@ bool pwrite_all(int fd, const char *p, size_t n, uint64_t off) {
     return true;
 }
 
-// Writes one block of bytes at a file offset on several threads at once (page-cache copies scale with threads;
-// one thread moves 2-4 GB/s).  The caller writes the first slice itself and returns when all slices are written.
+// Writes one block of bytes at a file offset on several threads at once.  Two ways:
+//   mapped (default)  the byte range of the file is mmap()ed MAP_SHARED and the threads copy into it, each one first
+//                     pre-faulting its slice with madvise(MADV_POPULATE_WRITE) — which reports "disk full" as an
+//                     error where a plain store would raise SIGBUS.  Page-cache pages are added under per-page locks,
+//                     so the copies of different threads run in parallel (measured on the 16-core B200 host, tmpfs:
+//                     see profiles/r02_file_e2e.md).
+//   pwrite            buffered write() takes the inode lock exclusively: any number of threads writing to ONE file move
+//                     what one thread moves (4.3 GB/s measured).  Used when the file cannot be mapped and with
+//                     HYPEREX_WRITE=pwrite.
+// The file must already be large enough (the byte range was reserved with ftruncate).  The caller copies the first
+// slice itself and returns when all slices are written.
 class WritePool {
   public:
-    explicit WritePool(int n_threads) {
+    WritePool(int n_threads, bool mapped) : mapped_(mapped) {
         for (int i = 0; i < n_threads; ++i) th_.emplace_back([this] { run(); });
     }
     ~WritePool() {
@@ -748,24 +768,23 @@ class WritePool {
         cv_.notify_all();
         for (std::thread &t : th_) t.join();
     }
+    bool mapped() const { return mapped_; }
     bool write(int fd, const char *p, size_t n, uint64_t off) {
-        const size_t min_slice = (size_t)1 << 20;
-        size_t parts = std::min<size_t>(th_.size() + 1, (n + min_slice - 1) / min_slice);
-        if (parts <= 1) return pwrite_all(fd, p, n, off);
-        const size_t slice = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
-        Call call;
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            for (size_t s = slice; s < n; s += slice) {
-                q_.push_back(Task{fd, p + s, std::min(slice, n - s), off + s, &call});
-                ++call.pending;
-            }
+        if (n == 0) return true;
+        char *map = nullptr;
+        uint64_t a0 = 0;
+        size_t map_len = 0;
+        if (mapped_) {
+            const uint64_t page = 4096;
+            a0 = off & ~(page - 1);
+            map_len = (size_t)(off + n - a0);
+            void *m = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)a0);
+            if (m == MAP_FAILED) return write_slices(fd, p, n, off, nullptr);  // not mappable: the write() path
+            map = (char *)m;
         }
-        cv_.notify_all();
-        bool ok = pwrite_all(fd, p, std::min(slice, n), off);
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [&] { return call.pending == 0; });
-        return ok && call.ok;
+        const bool ok = write_slices(fd, p, n, off, map ? map + (off - a0) : nullptr);
+        if (map) munmap(map, map_len);
+        return ok;
     }
 
   private:
@@ -778,8 +797,43 @@ class WritePool {
         const char *p;
         size_t n;
         uint64_t off;
+        char *dst;  // mapped destination of this slice, or NULL: pwrite
         Call *call;
     };
+    static bool do_task(const Task &t) {
+        if (!t.dst) return pwrite_all(t.fd, t.p, t.n, t.off);
+        // pre-fault whole pages of the slice; EINVAL = a kernel without MADV_POPULATE_WRITE (< 5.14): plain stores then
+        char *a = (char *)((uintptr_t)t.dst & ~(uintptr_t)4095);
+        const size_t len = (size_t)(t.dst + t.n - a);
+        while (madvise(a, len, MADV_POPULATE_WRITE) != 0) {
+            if (errno == EAGAIN || errno == EINTR) continue;
+            if (errno == EINVAL) break;
+            return false;  // EFAULT / ENOMEM: the store would have raised SIGBUS (no space left on the device)
+        }
+        memcpy(t.dst, t.p, t.n);
+        return true;
+    }
+    bool write_slices(int fd, const char *p, size_t n, uint64_t off, char *dst) {
+        const size_t min_slice = (size_t)1 << 20;
+        const size_t parts = std::min<size_t>(th_.size() + 1, (n + min_slice - 1) / min_slice);
+        if (parts <= 1) return do_task(Task{fd, p, n, off, dst, nullptr});
+        // slices end on page boundaries of the FILE so that two threads never fault the same page
+        const size_t slice = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
+        const size_t first = slice - (size_t)(off & 4095);
+        Call call;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t s = first; s < n; s += slice) {
+                q_.push_back(Task{fd, p + s, std::min(slice, n - s), off + s, dst ? dst + s : nullptr, &call});
+                ++call.pending;
+            }
+        }
+        cv_.notify_all();
+        const bool ok = do_task(Task{fd, p, std::min(first, n), off, dst, nullptr});
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return call.pending == 0; });
+        return ok && call.ok;
+    }
     void run() {
         for (;;) {
             Task t;
@@ -790,12 +844,13 @@ class WritePool {
                 t = q_.front();
                 q_.pop_front();
             }
-            const bool ok = pwrite_all(t.fd, t.p, t.n, t.off);
+            const bool ok = do_task(t);
             std::lock_guard<std::mutex> lk(mu_);
             if (!ok) t.call->ok = false;
             if (--t.call->pending == 0) done_cv_.notify_all();
         }
     }
+    const bool mapped_;
     std::vector<std::thread> th_;
     std::mutex mu_;
     std::condition_variable cv_, done_cv_;
@@ -960,6 +1015,17 @@ bool reserve_output(FileJob *J, uint64_t index, uint64_t fa_total, uint64_t gff_
     base[1] = J->file_pos[1];
     J->file_pos[0] += fa_total;
     J->file_pos[1] += gff_total;
+    if (J->writers->mapped()) {  // the mapped copies need the bytes to exist; sizes only ever grow, in batch order
+        if ((fa_total && ftruncate(J->fd[0], (off_t)J->file_pos[0]) != 0) || (gff_total && ftruncate(J->fd[1], (off_t)J->file_pos[1]) != 0)) {
+            if (J->rc == HX_OK) {
+                J->rc = HX_ERR_IO;
+                J->err = "cannot extend the output files";
+            }
+            J->abort = true;
+            J->cv.notify_all();
+            return false;
+        }
+    }
     J->out_turn = index + 1;
     J->cv.notify_all();
     return true;
@@ -1180,8 +1246,8 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
     // is assembled on the GPU and the host only writes it; HYPEREX_HOST_FORMAT=1 keeps the host formatter.
     J.device_text = env_int("HYPEREX_HOST_FORMAT", 0) == 0;
     const std::string fa_path = std::string(prefix) + ".fa", gff_path = std::string(prefix) + ".gff";
-    J.fd[0] = open(fa_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);  // fasta::Writer::to_file truncates (utils.rs:241)
-    J.fd[1] = open(gff_path.c_str(), O_WRONLY | O_CREAT, 0644);           // OpenOptions create+append (utils.rs:242-245)
+    J.fd[0] = open(fa_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);  // fasta::Writer::to_file truncates (utils.rs:241)
+    J.fd[1] = open(gff_path.c_str(), O_RDWR | O_CREAT, 0644);             // OpenOptions create+append (utils.rs:242-245)
     if (J.fd[0] < 0 || J.fd[1] < 0) {
         if (J.fd[0] >= 0) close(J.fd[0]);
         if (J.fd[1] >= 0) close(J.fd[1]);
@@ -1215,11 +1281,13 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
     // threads: HYPEREX_THREADS caps the parser and the writer pools (default: the machine's hardware threads)
     const int n_lanes = hxh_lane_count(ctx);
     const int hw = std::max(1, env_int("HYPEREX_THREADS", (int)std::thread::hardware_concurrency()));
-    const int n_parsers = std::max(1, std::min(16, hw - 1));
-    const int n_writers = std::max(1, std::min(16, hw - 1));
+    // (measured: parsing 1.5 GB of FASTA costs 0.3 thread-seconds in total, so a few parsers keep any number of lanes
+    // fed; every extra parser is one more pinned batch to allocate on the first call)
+    const int n_parsers = std::max(1, std::min(4, hw / 4));
+    const int n_writers = std::max(1, std::min(24, hw - 1));
     // chunk size: large enough to amortise the per-batch device round trip, small enough that every lane gets
     // several batches and the first / last batch (which nothing overlaps) stay short
-    size_t chunk_bytes = (size_t)32 << 20;
+    size_t chunk_bytes = (size_t)16 << 20;
     if (chunker.mapped()) {
         const size_t share = chunker.mapped_bytes() / ((size_t)n_lanes * 4) + 1;
         chunk_bytes = std::min(chunk_bytes, std::max<size_t>(share, (size_t)4 << 20));
@@ -1227,7 +1295,8 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
     if (env_int("HYPEREX_CHUNK_BYTES", 0) > 0) chunk_bytes = (size_t)env_int("HYPEREX_CHUNK_BYTES", 0);  // tests: many tiny batches
     HostCache *cache = host_cache_of(ctx);
     J.cache = cache;
-    WritePool writers(n_writers);
+    const char *wmode = getenv("HYPEREX_WRITE");
+    WritePool writers(n_writers, !(wmode && strcmp(wmode, "pwrite") == 0));
     J.writers = &writers;
     const int n_batches = n_parsers + n_lanes + 1;
     {

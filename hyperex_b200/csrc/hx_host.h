@@ -45,7 +45,8 @@ struct HxhRecordBatch {
     std::vector<uint64_t> offsets; // n + 1
     std::vector<char> ids;         // record ids back to back, no separators
     std::vector<uint64_t> id_off;  // n + 1
-    std::vector<std::string> descs; // only filled when the parser is asked to keep descriptions ("" = none)
+    std::vector<std::string> descs; // only filled when the parser is asked to keep descriptions
+    std::vector<uint8_t> has_desc;  // ... 0: the header had no description (rust-bio: desc == None), 1: it had (maybe "")
     bool stop = false;             // the reader's iteration ends after this batch (malformed / empty record)
     size_t n_records() const { return offsets.size() - 1; }
     void clear();

@@ -207,6 +207,9 @@ typedef struct hx_fasta hx_fasta;
 int hx_fasta_open(const char *path, hx_fasta **out);
 int64_t hx_fasta_next(hx_fasta *r, size_t max_bytes, const uint8_t **arena, const uint64_t **offsets,
                       const char *const **ids);
+/* descriptions of the records of the last hx_fasta_next batch: the header text after the first whitespace, NULL for
+ * a header without one (rust-bio Record::desc; fasta::Writer::write_record prints ">id desc", utils.rs:447-449) */
+const char *const *hx_fasta_descs(hx_fasta *r);
 void hx_fasta_close(hx_fasta *r);
 
 /* ---- the reference's seam itself ----------------------------------------------------- */

@@ -15,8 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "bin", "hyperex")
 
 
-def run(args, cwd, stdin=None):
-    return subprocess.run([BIN] + args, cwd=cwd, input=stdin, capture_output=True, timeout=300)
+def run(args, cwd, stdin=None, env=None):
+    return subprocess.run([BIN] + args, cwd=cwd, input=stdin, capture_output=True, timeout=300,
+                          env=dict(os.environ, **(env or {})))
 
 
 def test_default_regions_on_reference_fixture(tmp_path, golden_dir):
@@ -80,3 +81,28 @@ def test_usage_errors(tmp_path, golden_dir):
     r = run([fa, "-m", "30", "-p", "big"], tmp_path)                                  # utils.rs:522-540
     assert r.returncode == 1 and b"greater than length of longest primer" in r.stdout
     assert run(["--version"], tmp_path).stdout.strip() == b"hyperex 0.2.0"
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("gpus,host_format", [(1, 1), (2, 0), (2, 1)])
+def test_cli_host_formatter_and_gpus_flag(tmp_path, gpus, host_format):
+    """the two byte-writing branches (on-device text, HYPEREX_HOST_FORMAT=1) and `--gpus N` give the bytes of the
+    1-GPU default run, which test_flags_region_primers_csv_prefix_stdin compares with the oracle"""
+    if gpus > _n_gpus():
+        pytest.skip("needs two GPUs")
+    a, o = hx_synth.gen_reads_mutated(2000, seed=78, max_edits=2, revcomp_frac=0.3, lower_frac=0.3, rna_frac=0.1)
+    fasta = hx_synth.to_fasta(a, o, width=80)
+    (tmp_path / "in.fa").write_bytes(fasta)
+    env = {"HYPEREX_HOST_FORMAT": str(host_format), "HYPEREX_CHUNK_BYTES": "100000"}
+    r = run(["in.fa", "-m", "2", "-p", "x", "--gpus", str(gpus)], tmp_path, env=env)
+    assert r.returncode == 0, r.stderr
+    fa, gff, _ = O.get_hypervar_regions(fasta, O.default_pairs(), 2)
+    assert (tmp_path / "x.fa").read_bytes() == fa and (tmp_path / "x.gff").read_bytes() == gff
+    r1 = run(["in.fa", "-m", "2", "-p", "y"], tmp_path)
+    strip = lambda b: [ln.split(b"] ", 1)[-1] for ln in b.splitlines() if b"WARN" in ln or b"ERROR" in ln]
+    assert strip(r.stdout) == strip(r1.stdout) and len(strip(r.stdout)) > 100
+    assert run(["in.fa", "--gpus", "0"], tmp_path).returncode == 2 and run(["in.fa", "--gpus", "x"], tmp_path).returncode == 2

@@ -72,8 +72,11 @@ def test_find_all_end_capacity_is_reported_not_truncated_silently(ctx):
 
 
 # ---- config 1: the reference's own CPU-runnable case ----------------------------------------------
+@pytest.mark.parametrize("host_format", [0, 1])
 @pytest.mark.parametrize("k", [0, 2])
-def test_config1_bytes(ctx, golden_dir, tmp_path, k):
+def test_config1_bytes(ctx, golden_dir, tmp_path, k, host_format, monkeypatch):
+    # host_format = 1: the host formatter (HYPEREX_HOST_FORMAT=1) instead of the on-device text assembly
+    monkeypatch.setenv("HYPEREX_HOST_FORMAT", str(host_format))
     prefix = str(tmp_path / "hyperex_out")
     logs = []
     for f in ("test.fa", "test.fa.gz"):
@@ -408,10 +411,16 @@ def test_text_stream_chunks(ctx):
 
 
 # ---- file-level seam: FASTA in, FASTA + GFF3 bytes out ---------------------------------------------------
+@pytest.mark.parametrize("host_format,chunk", [(0, 0), (1, 0), (0, 20000), (1, 20000)])
 @pytest.mark.parametrize("k,codec", [(0, "plain"), (2, "gz"), (3, "xz")])
-def test_get_hypervar_regions_bytes(ctx, tmp_path, k, codec):
+def test_get_hypervar_regions_bytes(ctx, tmp_path, k, codec, host_format, chunk, monkeypatch):
+    """both formatters (on-device text / HYPEREX_HOST_FORMAT=1), as one batch and as ~30 batches that finish out of
+    order on the context's text lanes"""
     import gzip
     import lzma
+    monkeypatch.setenv("HYPEREX_HOST_FORMAT", str(host_format))
+    if chunk:
+        monkeypatch.setenv("HYPEREX_CHUNK_BYTES", str(chunk))
     a, o = hx_synth.gen_reads_mutated(400, seed=95 + k, max_edits=2, revcomp_frac=0.3, lower_frac=0.4, rna_frac=0.1)
     ids = [f"seq{i}" if i % 2 else f"seq{i} len={int(o[i + 1] - o[i])}" for i in range(400)]
     buf = hx_synth.to_fasta(a, o, ids, width=70 if k else 0, crlf=bool(k == 2))
@@ -421,10 +430,58 @@ def test_get_hypervar_regions_bytes(ctx, tmp_path, k, codec):
     prefix = str(tmp_path / "out")
     ctx.set_option("tile_len", 0)
     ctx.set_option("single_max", 0)
-    ctx.get_hypervar_regions(str(path), pairs, prefix, k)
-    fa, gff, _ = O.get_hypervar_regions(buf, pairs, k)
+    logs = []
+    ctx.get_hypervar_regions(str(path), pairs, prefix, k, log=lambda lvl, msg: logs.append((lvl, msg)))
+    fa, gff, res = O.get_hypervar_regions(buf, pairs, k)
     assert open(prefix + ".fa", "rb").read() == fa
     assert open(prefix + ".gff", "rb").read() == gff
+    st = ctx.file_stats()
+    assert st["records"] == 400 and st["fasta_bytes"] == len(fa) and st["gff_bytes"] == len(gff)
+    assert (st["batches"] > 10) == bool(chunk) or codec != "plain"
+    # the reference's warn!/error! lines arrive in record x pair order whatever lane ran the batch
+    n_expected = int((res["flags"][:, 0] & 8).astype(bool).sum())                    # error: unrecognized type
+    ok = ~(res["flags"][:, 0] & 8).astype(bool)
+    n_expected += int((np.diff(o.astype(np.int64))[ok] <= 1500).sum())               # warn: short sequence
+    n_expected += int(((res["flags"][ok] & 7) != 7).sum())                           # warn: one of the 4 not-found texts
+    assert len(logs) == n_expected
+    seen = [m.rsplit(" ", 1)[-1] for _, m in logs if " in sequence " in m and m.endswith(tuple("0123456789"))]
+    order = [int(x[3:]) for x in seen if x.startswith("seq")]
+    assert order == sorted(order)
+    # without a log callback the result table never leaves the device
+    ctx.get_hypervar_regions(str(path), pairs, prefix + "_nolog", k)
+    assert open(prefix + "_nolog.fa", "rb").read() == fa and open(prefix + "_nolog.gff", "rb").read() == gff
+
+
+# ---- several GPUs in one context (hx_create(dev_ids, n)): the shipped `--gpus N` path -------------------------
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif("_n_gpus() < 2", reason="needs two GPUs")
+@pytest.mark.parametrize("host_format", [0, 1])
+def test_multi_device_context_equals_single_device(ctx, tmp_path, host_format, monkeypatch):
+    monkeypatch.setenv("HYPEREX_HOST_FORMAT", str(host_format))
+    monkeypatch.setenv("HYPEREX_CHUNK_BYTES", "30000")
+    nd = min(_n_gpus(), 8)
+    a, o = hx_synth.gen_reads_mutated(3000, seed=31, max_edits=2, revcomp_frac=0.3, lower_frac=0.2, rna_frac=0.1)
+    pairs = hx.default_primers()
+    ref = O.run_batch(a, o, pairs, 2, nthreads=8)
+    buf = hx_synth.to_fasta(a, o, [f"seq{i}" for i in range(3000)], width=80)
+    path = tmp_path / "in.fa"
+    path.write_bytes(buf)
+    fa, gff, _ = O.get_hypervar_regions(buf, pairs, 2)
+    with hx.Context(tuple(range(nd))) as mctx:
+        mctx.set_option("slab_bytes", 1 << 20)  # many slabs so every device gets work
+        mctx.set_primers(pairs, 2)
+        assert mctx.run_batch(a, o).tobytes() == ref.tobytes()
+        logs = []
+        mctx.get_hypervar_regions(str(path), pairs, str(tmp_path / "m"), 2, log=lambda lvl, msg: logs.append(msg))
+        assert (tmp_path / "m.fa").read_bytes() == fa and (tmp_path / "m.gff").read_bytes() == gff
+        assert mctx.file_stats()["lanes"] == 2 * nd and mctx.file_stats()["batches"] > 2 * nd
+    logs1 = []
+    ctx.get_hypervar_regions(str(path), pairs, str(tmp_path / "s"), 2, log=lambda lvl, msg: logs1.append(msg))
+    assert logs == logs1 and (tmp_path / "s.fa").read_bytes() == fa
 
 
 # ---- full-size properties (BASELINE.json config 2 shape; the oracle is too slow at this size) -------------

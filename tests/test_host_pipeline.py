@@ -141,9 +141,27 @@ def test_pipeline_without_log_fn_and_single_lane(stub, tmp_path):
     path.write_bytes(buf)
     efa, egff, _ = O.get_hypervar_regions(buf, pairs, 1)
     for lanes in (1, 2, 7):
-        rc, fa, gff, lines, _s, err = run(stub, path, pairs, tmp_path / f"o{lanes}", 1, lanes=lanes, log=False,
-                                          env={"HYPEREX_CHUNK_BYTES": 5000})
-        assert rc == 0 and fa == efa and gff == egff and lines == [], err
+        for wmode in ("mmap", "pwrite"):  # both ways the write pool moves bytes into the files
+            rc, fa, gff, lines, _s, err = run(stub, path, pairs, tmp_path / f"o{lanes}{wmode}", 1, lanes=lanes, log=False,
+                                              env={"HYPEREX_CHUNK_BYTES": 5000, "HYPEREX_WRITE": wmode})
+            assert rc == 0 and fa == efa and gff == egff and lines == [], err
+
+
+def test_large_text_blocks_are_written_in_parallel_slices(stub, tmp_path):
+    """one batch whose text is several MB: the write pool cuts it into page-aligned slices written by different threads"""
+    a, o = hx_synth.gen_reads(1500, seed=21)
+    buf = hx_synth.to_fasta(a, o)
+    path = tmp_path / "in.fa"
+    path.write_bytes(buf)
+    pairs = O.default_pairs()
+    efa, egff, _ = O.get_hypervar_regions(buf, pairs, 0)
+    assert len(efa) > (8 << 20)
+    (tmp_path / "om.gff").write_bytes(b"x" * 1234)  # append at an odd offset: slices are aligned to FILE pages
+    for wmode, name in (("mmap", "om"), ("pwrite", "op")):
+        rc, fa, gff, _l, _s, err = run(stub, path, pairs, tmp_path / name, 0, lanes=2, log=False,
+                                          env={"HYPEREX_WRITE": wmode, "HYPEREX_HOST_FORMAT": 1})  # one write call per batch and file
+        assert rc == 0 and fa == efa, err
+        assert gff == (b"x" * 1234 if name == "om" else b"") + egff
 
 
 def test_pipeline_stops_where_the_reference_reader_stops(stub, tmp_path):

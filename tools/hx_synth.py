@@ -169,3 +169,16 @@ def to_fasta(arena, offsets, ids=None, width: int = 0, crlf: bool = False) -> by
         else:
             out.append(s + nl)
     return b"".join(out)
+
+
+def write_fasta_file(path: str, arena: np.ndarray, offsets: np.ndarray, prefix: str = "r") -> int:
+    """plain FASTA, one sequence line per record, ids <prefix><index>; returns the file size (bench.py's file_e2e input)"""
+    mv = memoryview(np.ascontiguousarray(arena))
+    off = [int(x) for x in offsets]
+    pre = prefix.encode()
+    with open(path, "wb", buffering=8 << 20) as f:
+        for i in range(len(off) - 1):
+            f.write(b">%s%d\n" % (pre, i))
+            f.write(mv[off[i]:off[i + 1]])
+            f.write(b"\n")
+        return f.tell()
