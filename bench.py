@@ -257,8 +257,8 @@ def file_e2e_leg(hx, devices, arena, offsets, pairs, k, steps, work_override="")
                "best": bases / min(times) / 1e9, "seconds": times, "records": n, "bases": bases,
                "input_bytes": in_bytes, "fasta_bytes": fa_bytes, "gff_bytes": gff_bytes, "dir": os.path.dirname(work),
                "sha256": {"fa": sha256_file(prefix + ".fa"), "gff": sha256_file(prefix + ".gff")},
-               "phases_of_best_call": {kk: stats[kk] for kk in ("wall_s", "chunk_s", "parse_s", "device_s", "write_s", "parsers",
-                                                              "lanes", "writers", "batches")},
+               "phases_of_best_call": {kk: stats[kk] for kk in ("wall_s", "setup_s", "chunk_s", "parse_s", "device_s", "write_s",
+                                                              "close_s", "parsers", "lanes", "writers", "batches")},
                "phases_note": "stage seconds are summed over the threads of the stage (pipeline: they overlap)",
                "host_cores": os.cpu_count()}
         return out

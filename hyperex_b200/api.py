@@ -279,7 +279,7 @@ class Context:
         return ms.value, n.value
 
     FILE_STATS = ("wall_s", "bases", "records", "batches", "chunk_s", "parse_s", "device_s", "write_s", "log_s",
-                  "fasta_bytes", "gff_bytes", "parsers", "lanes", "writers")
+                  "fasta_bytes", "gff_bytes", "parsers", "lanes", "writers", "setup_s", "close_s")
 
     def file_stats(self) -> dict:
         """hx_file_stats: where the time of the last get_hypervar_regions call went (stage seconds are summed over

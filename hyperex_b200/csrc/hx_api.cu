@@ -132,6 +132,7 @@ struct Device {
     TextLane lanes[HX_NLANE];
     uint8_t *d_tables = nullptr;
     uint8_t *d_tables_wm = nullptr;
+    uint8_t *d_tables_pk = nullptr;  // -m 0 packed tables (two 16-bit automata per word)
     uint64_t *d_vtables = nullptr;  // 64-bit verification tables of the suffix-filtered primers
     HxGroup *d_groups = nullptr;
     HxPairRef *d_pairs = nullptr;
@@ -158,7 +159,7 @@ struct hx_ctx {
     bool primers_set = false;
     // options
     int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1,
-            opt_long_filter = 1, opt_group_np_max = 0;
+            opt_long_filter = 1, opt_group_np_max = 0, opt_pack16 = 1;
     std::atomic<uint64_t> launches{0};
     std::mutex mu;  // guards err and timed: text lanes of one context run on several host threads
     DevPool find_pool;
@@ -375,6 +376,9 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
         a.wm_k = (ctx->opt_fast_small_k && !hg.word64 && !ctx->opt_text_tma && (ctx->k <= 1 || (ctx->k == 2 && hg.np <= 8)))
                      ? (int)ctx->k
                      : -1;
+        // -m 0: two <= 16-symbol Shift-Or automata per word when the planner found the group packable
+        a.tables_pk = D.d_tables_pk ? D.d_tables_pk + hg.pk_table_off : nullptr;
+        a.packed = (a.wm_k == 0 && ctx->opt_pack16 && hg.packed && D.d_tables_pk) ? 1 : 0;
         a.group = D.d_groups + gi;
         a.sum_f = S.sum_f.p;
         a.sum_r = S.sum_r.p;
@@ -382,7 +386,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
         a.pair_lo = S.pair_lo.p;
         a.tile_stride = pl.tile_cap;
         a.k = ctx->k;
-        a.variant = hg.longmask ? 0 : (int)ctx->opt_text_tma;  // suffix-filtered groups: vector-load text path only
+        a.variant = (hg.longmask || a.packed) ? 0 : (int)ctx->opt_text_tma;  // suffix-filtered groups: vector-load text path only
         a.two = 2;
         TimedLaunch tl;
         if (ctx->opt_time) {
@@ -415,12 +419,12 @@ int check_status(hx_ctx *ctx, const Slot &S) {
 
 // Host half of hx_set_primers (no CUDA): primer strings -> pattern groups, Peq tables, verification tables.
 struct PlanOpts {
-    int64_t fast_small_k, long_filter, group_np_max;
+    int64_t fast_small_k, long_filter, group_np_max, pack16;
 };
 struct PrimerPlan {
     std::vector<HxGroup> groups;
     std::vector<HxPairRef> refs;
-    std::vector<uint8_t> blob, blob_wm;
+    std::vector<uint8_t> blob, blob_wm, blob_pk;
     std::vector<uint64_t> vblob;  // [vslot][alphabet][256]
     uint32_t m_max = 0, n_slots = 0;
 };
@@ -651,6 +655,77 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
             }
         }
     }
+    // -m 0 pattern packing: a 32-bit group whose every pattern is either <= 16 symbols or has a 16-symbol
+    // suffix specific enough to serve as a filter gets a second table, two 16-bit Shift-Or automata per word.  The scan
+    // then steps half as many words (and loads half as many Peq bytes) per text byte; a pattern longer than 16 symbols
+    // reports candidates, verified against the rest of the primer in the drain (hx_verify_exact).  "Specific enough":
+    // the expected rate of chance candidates on random ACGT text, 2^-bits(suffix), stays below 2^-12 per position —
+    // every built-in primer has 24 bits or more.  pack16 = 2 skips the test (test-suite).
+    P.blob_pk.clear();
+    if (k == 0 && o.fast_small_k && o.pack16) {
+        auto suffix16_ok = [&](const std::string &pat) {
+            if (pat.size() <= 16 || o.pack16 >= 2) return true;
+            double bits = 0;
+            for (size_t i = pat.size() - 16; i < pat.size(); ++i) {
+                const char c = pat[i];
+                const int deg = strchr("RYSWKM", c) ? 2 : strchr("BDHV", c) ? 3 : c == 'N' ? 4 : 1;
+                bits += std::log2(4.0 / deg);
+            }
+            return bits >= 12.0;
+        };
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            HxGroup &g = groups[gi];
+            if (g.word64) continue;
+            bool ok = true;
+            for (int p = 0; p < g.np && ok; ++p) ok = suffix16_ok(gpats[gi][p].dna) && suffix16_ok(gpats[gi][p].rna);
+            if (!ok) continue;
+            g.packed = 1;
+            g.pk_longmask = 0;
+            const int nw = (g.np + 1) / 2, stride = hx_row_stride(nw, 4);
+            g.pk_table_off = (uint32_t)P.blob_pk.size();
+            P.blob_pk.resize(P.blob_pk.size() + 2 * (size_t)hx_table_bytes(nw, 4), 0);
+            for (int p = 0; p < g.np; ++p) {
+                const size_t full = gpats[gi][p].dna.size();
+                g.pk_m[p] = (uint8_t)std::min<size_t>(full, 16);
+                if (full > 16) {
+                    g.pk_longmask |= 1u << p;
+                    if (g.longmask >> p & 1u) {
+                        g.pk_vslot[p] = g.vslot[p];  // the 64-bit table of the whole primer exists already
+                    } else {
+                        g.pk_vslot[p] = (uint32_t)(vblob.size() / 512);
+                        for (int alpha = 0; alpha < 2; ++alpha) {
+                            uint64_t rows[256];
+                            peq_rows(alpha ? gpats[gi][p].rna : gpats[gi][p].dna, 64, rows);
+                            vblob.insert(vblob.end(), rows, rows + 256);
+                        }
+                    }
+                }
+            }
+            for (int alpha = 0; alpha < 2; ++alpha) {
+                uint8_t *tab = P.blob_pk.data() + g.pk_table_off + (size_t)alpha * hx_table_bytes(nw, 4);
+                for (int j = 0; j < nw; ++j) {
+                    uint64_t rows[2][256];
+                    uint32_t pmask[2] = {0xffffu, 0xffffu};  // a half without a pattern: all-ones in every row, never reports
+                    for (int h = 0; h < 2; ++h) {
+                        const int p = 2 * j + h;
+                        if (p >= g.np) {
+                            for (int b = 0; b < 256; ++b) rows[h][b] = 0;
+                            continue;
+                        }
+                        const std::string &full = alpha ? gpats[gi][p].rna : gpats[gi][p].dna;
+                        const std::string suf = full.size() > 16 ? full.substr(full.size() - 16) : full;
+                        peq_rows(suf, 16, rows[h]);  // top-aligned in 16 bits
+                        pmask[h] = (0xffffu << (16 - (int)suf.size())) & 0xffffu;
+                    }
+                    for (int b = 0; b < 256; ++b) {  // complemented inside the pattern bits, 0 in the unused low bits
+                        const uint32_t lo = ~(uint32_t)rows[0][b] & pmask[0], hi = ~(uint32_t)rows[1][b] & pmask[1];
+                        const uint32_t w = lo | (hi << 16);
+                        memcpy(tab + (size_t)b * stride + (size_t)j * 4, &w, 4);
+                    }
+                }
+            }
+        }
+    }
     for (uint32_t i = 0; i < n_pairs; ++i) {
         const HxGroup &g = groups[refs[i].pad];
         refs[i].f_slot += g.slot_base;
@@ -739,6 +814,7 @@ void hx_destroy(hx_ctx *ctx) {
         for (TextLane &L : D.lanes) L.release();
         if (D.d_tables) cudaFree(D.d_tables);
         if (D.d_tables_wm) cudaFree(D.d_tables_wm);
+        if (D.d_tables_pk) cudaFree(D.d_tables_pk);
         if (D.d_vtables) cudaFree(D.d_vtables);
         if (D.d_groups) cudaFree(D.d_groups);
         if (D.d_pairs) cudaFree(D.d_pairs);
@@ -757,6 +833,7 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     else if (n == "fast_small_k") ctx->opt_fast_small_k = value ? 1 : 0;
     else if (n == "long_filter") ctx->opt_long_filter = value < 0 ? 0 : (value > 2 ? 2 : value);  // read by hx_set_primers
     else if (n == "group_np_max") ctx->opt_group_np_max = value;         // read by hx_set_primers; 0 = automatic
+    else if (n == "pack16") ctx->opt_pack16 = value < 0 ? 0 : (value > 2 ? 2 : value);  // hx_set_primers builds, every scan reads
     else return fail(ctx, HX_ERR_ARG, "unknown option %s", name);
     return HX_OK;
 }
@@ -767,7 +844,7 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
     ctx->primers_set = false;
     PrimerPlan P;
     {
-        const PlanOpts o = {ctx->opt_fast_small_k, ctx->opt_long_filter, ctx->opt_group_np_max};
+        const PlanOpts o = {ctx->opt_fast_small_k, ctx->opt_long_filter, ctx->opt_group_np_max, ctx->opt_pack16};
         std::string err;
         const int rc = plan_primers(o, n_pairs, fwd, fwd_len, rev, rev_len, k, P, err);
         if (rc != HX_OK) return fail(ctx, rc, "%s", err.c_str());
@@ -783,10 +860,15 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
         HX_CUDA(ctx, cudaDeviceSynchronize());
         if (D.d_tables) cudaFree(D.d_tables);
         if (D.d_tables_wm) cudaFree(D.d_tables_wm);
+        if (D.d_tables_pk) cudaFree(D.d_tables_pk);
         if (D.d_vtables) cudaFree(D.d_vtables);
         if (D.d_groups) cudaFree(D.d_groups);
         if (D.d_pairs) cudaFree(D.d_pairs);
-        D.d_tables = nullptr; D.d_tables_wm = nullptr; D.d_vtables = nullptr; D.d_groups = nullptr; D.d_pairs = nullptr;
+        D.d_tables = nullptr; D.d_tables_wm = nullptr; D.d_tables_pk = nullptr; D.d_vtables = nullptr; D.d_groups = nullptr; D.d_pairs = nullptr;
+        if (!P.blob_pk.empty()) {
+            HX_CUDA(ctx, cudaMalloc((void **)&D.d_tables_pk, P.blob_pk.size()));
+            HX_CUDA(ctx, cudaMemcpy(D.d_tables_pk, P.blob_pk.data(), P.blob_pk.size(), cudaMemcpyHostToDevice));
+        }
         if (!vblob.empty()) {
             HX_CUDA(ctx, cudaMalloc((void **)&D.d_vtables, vblob.size() * sizeof(uint64_t)));
             HX_CUDA(ctx, cudaMemcpy(D.d_vtables, vblob.data(), vblob.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
@@ -1241,7 +1323,7 @@ int hx_plan_groups(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd
                    const uint32_t *rev_len, uint8_t k, int fast_small_k, int long_filter, int group_np_max,
                    uint32_t *n_groups, uint32_t *steps32_per_base, uint32_t *steps64_per_base, uint32_t *pair_group) {
     PrimerPlan P;
-    const PlanOpts o = {fast_small_k, long_filter, group_np_max};
+    const PlanOpts o = {fast_small_k, long_filter, group_np_max, 1};
     std::string err;
     const int rc = plan_primers(o, n_pairs, fwd, fwd_len, rev, rev_len, k, P, err);
     if (rc != HX_OK) return fail(nullptr, rc, "%s", err.c_str());
@@ -1263,7 +1345,7 @@ int hx_plan_peq_word(uint32_t n_pairs, const char *const *fwd, const uint32_t *f
                      int role, int alphabet, uint8_t byte, uint64_t *scan_word, uint64_t *wm_word, uint64_t *verify_word,
                      uint32_t *word_bits, uint32_t *m_scan, uint32_t *m_full) {
     PrimerPlan P;
-    const PlanOpts o = {fast_small_k, long_filter, group_np_max};
+    const PlanOpts o = {fast_small_k, long_filter, group_np_max, 1};
     std::string err;
     const int rc = plan_primers(o, n_pairs, fwd, fwd_len, rev, rev_len, k, P, err);
     if (rc != HX_OK) return fail(nullptr, rc, "%s", err.c_str());

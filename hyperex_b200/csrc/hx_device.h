@@ -49,6 +49,14 @@ struct HxGroup {
     uint32_t vslot[HX_MAX_NP32];              // suffix-filtered pattern: index of its 64-bit verification table
     uint32_t longmask;                        // bit p set: pattern p is the 32-symbol suffix of a longer primer; its
                                               // events are candidates, verified against the whole primer in the drain
+    // -m 0 pattern packing: two Shift-Or automata of <= 16 symbols per 32-bit word, pattern 2j in the low
+    // half of word j and pattern 2j + 1 in the high half.  A primer longer than 16 symbols is scanned as its last 16
+    // symbols and every candidate end is verified against the rest of the primer in the drain.
+    int32_t packed;                           // 1: the group has a packed table (hx_set_primers decided it pays)
+    uint32_t pk_table_off;                    // byte offset of the packed table in the packed blob
+    uint32_t pk_longmask;                     // bit p set: pattern p is the 16-symbol suffix of a longer primer
+    uint8_t pk_m[HX_MAX_NP32];                // scanned lengths (<= 16) in the packed table
+    uint32_t pk_vslot[HX_MAX_NP32];           // verification table of a packed pattern with pk_longmask set
 };
 
 // global pair -> where its summaries live (used by the pairing/combine kernel)
@@ -79,6 +87,8 @@ struct HxScanArgs {
     uint32_t n_pairs_total;
     const uint8_t *tables;     // Peq blob
     const uint8_t *tables_wm;  // complemented Peq blob of the small-k fast path (Shift-Or convention)
+    const uint8_t *tables_pk;  // -m 0 packed blob: two 16-bit complemented Peq half-words per 32-bit word
+    int32_t packed;            // 1: run the packed Shift-Or scan (wm_k == 0 and the group has a packed table)
     const uint64_t *vtables;   // [vslot][alphabet dna|rna][256] top-aligned 64-bit Peq words of the suffix-filtered primers
     int32_t wm_k;              // >= 0: run the Wu-Manber fast path with this many errors (32-bit groups only)
     const HxGroup *group;      // this launch's group (device memory)

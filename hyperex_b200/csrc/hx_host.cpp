@@ -744,15 +744,49 @@ bool pwrite_all(int fd, const char *p, size_t n, uint64_t off) {
     return true;
 }
 
+// An output file and, when it can be mapped, windows of it mapped MAP_SHARED for the whole call: mmap() / munmap()
+// take the process-wide mmap lock exclusively and stall every thread that is faulting pages in, so the file is not
+// mapped per block.  A window covers HX_WINDOW bytes of file offsets (mapping past the end of the file is allowed;
+// the bytes are only touched after ftruncate made them exist) and is created when the first block lands in it.
+struct OutFile {
+    static constexpr uint64_t HX_WINDOW = (uint64_t)1 << 36;
+    int fd = -1;
+    bool mappable = true;
+    std::mutex mu;
+    std::map<uint64_t, char *> windows;  // window index -> base address
+    // address of file offset `off` (the caller never crosses a window boundary); NULL: use pwrite
+    char *at(uint64_t off) {
+        if (!mappable) return nullptr;
+        const uint64_t w = off / HX_WINDOW;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = windows.find(w);
+        if (it == windows.end()) {
+            void *m = mmap(nullptr, HX_WINDOW, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)(w * HX_WINDOW));
+            if (m == MAP_FAILED) {
+                mappable = false;
+                return nullptr;
+            }
+            it = windows.emplace(w, (char *)m).first;
+        }
+        return it->second + (off - w * HX_WINDOW);
+    }
+    int close_all() {
+        for (auto &kv : windows) munmap(kv.second, HX_WINDOW);
+        windows.clear();
+        const int rc = fd >= 0 ? close(fd) : 0;
+        fd = -1;
+        return rc;
+    }
+};
+
 // Writes one block of bytes at a file offset on several threads at once.  Two ways:
-//   mapped (default)  the byte range of the file is mmap()ed MAP_SHARED and the threads copy into it, each one first
-//                     pre-faulting its slice with madvise(MADV_POPULATE_WRITE) — which reports "disk full" as an
-//                     error where a plain store would raise SIGBUS.  Page-cache pages are added under per-page locks,
-//                     so the copies of different threads run in parallel (measured on the 16-core B200 host, tmpfs:
-//                     see profiles/r02_file_e2e.md).
+//   mapped (default)  the threads copy into the mapped file, each one first pre-faulting its slice with
+//                     madvise(MADV_POPULATE_WRITE) — which reports "disk full" as an error where a plain store
+//                     would raise SIGBUS.  Page-cache pages are added under per-page locks, so the copies of
+//                     different threads run in parallel (measurements: profiles/r02_file_e2e.md).
 //   pwrite            buffered write() takes the inode lock exclusively: any number of threads writing to ONE file move
-//                     what one thread moves (4.3 GB/s measured).  Used when the file cannot be mapped and with
-//                     HYPEREX_WRITE=pwrite.
+//                     what one thread moves (4.3 GB/s measured on tmpfs).  Used when the file cannot be mapped and
+//                     with HYPEREX_WRITE=pwrite.
 // The file must already be large enough (the byte range was reserved with ftruncate).  The caller copies the first
 // slice itself and returns when all slices are written.
 class WritePool {
@@ -769,22 +803,15 @@ class WritePool {
         for (std::thread &t : th_) t.join();
     }
     bool mapped() const { return mapped_; }
-    bool write(int fd, const char *p, size_t n, uint64_t off) {
-        if (n == 0) return true;
-        char *map = nullptr;
-        uint64_t a0 = 0;
-        size_t map_len = 0;
-        if (mapped_) {
-            const uint64_t page = 4096;
-            a0 = off & ~(page - 1);
-            map_len = (size_t)(off + n - a0);
-            void *m = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)a0);
-            if (m == MAP_FAILED) return write_slices(fd, p, n, off, nullptr);  // not mappable: the write() path
-            map = (char *)m;
+    bool write(OutFile &f, const char *p, size_t n, uint64_t off) {
+        while (n) {  // a block that crosses a mapping window is written window by window
+            const size_t part = (size_t)std::min<uint64_t>(n, OutFile::HX_WINDOW - off % OutFile::HX_WINDOW);
+            if (!write_slices(f.fd, p, part, off, mapped_ ? f.at(off) : nullptr)) return false;
+            p += part;
+            n -= part;
+            off += part;
         }
-        const bool ok = write_slices(fd, p, n, off, map ? map + (off - a0) : nullptr);
-        if (map) munmap(map, map_len);
-        return ok;
+        return true;
     }
 
   private:
@@ -917,7 +944,7 @@ struct FileJob {
     hx_log_fn log_fn = nullptr;
     void *user = nullptr;
     bool device_text = true;
-    int fd[2] = {-1, -1};  // FASTA, GFF3
+    OutFile out[2];  // FASTA, GFF3
     std::vector<std::string> labels, fa_tail, gff_note;
     std::string tails_blob, gtails_blob;
     std::vector<uint32_t> tail_off, gtail_off;
@@ -1016,7 +1043,7 @@ bool reserve_output(FileJob *J, uint64_t index, uint64_t fa_total, uint64_t gff_
     J->file_pos[0] += fa_total;
     J->file_pos[1] += gff_total;
     if (J->writers->mapped()) {  // the mapped copies need the bytes to exist; sizes only ever grow, in batch order
-        if ((fa_total && ftruncate(J->fd[0], (off_t)J->file_pos[0]) != 0) || (gff_total && ftruncate(J->fd[1], (off_t)J->file_pos[1]) != 0)) {
+        if ((fa_total && ftruncate(J->out[0].fd, (off_t)J->file_pos[0]) != 0) || (gff_total && ftruncate(J->out[1].fd, (off_t)J->file_pos[1]) != 0)) {
             if (J->rc == HX_OK) {
                 J->rc = HX_ERR_IO;
                 J->err = "cannot extend the output files";
@@ -1040,7 +1067,7 @@ int sink_begin(void *user, uint64_t fa_total, uint64_t gff_total) {
 int sink_chunk(void *user, int kind, uint64_t off, const char *bytes, size_t n) {
     LaneSink *s = (LaneSink *)user;
     const double t0 = now_s();
-    const bool ok = s->J->writers->write(s->J->fd[kind], bytes, n, s->base[kind] + off);
+    const bool ok = s->J->writers->write(s->J->out[kind], bytes, n, s->base[kind] + off);
     s->t_write += now_s() - t0;
     return ok ? 0 : 1;
 }
@@ -1179,8 +1206,8 @@ void lane_thread(FileJob *J, int lane) {
             format_on_host(J, *b, res, fa_host, gff_host);
             uint64_t base[2];
             if (!reserve_output(J, index, fa_host.size(), gff_host.size(), base)) return;
-            const bool ok = J->writers->write(J->fd[0], fa_host.data(), fa_host.size(), base[0]) &&
-                            J->writers->write(J->fd[1], gff_host.data(), gff_host.size(), base[1]);
+            const bool ok = J->writers->write(J->out[0], fa_host.data(), fa_host.size(), base[0]) &&
+                            J->writers->write(J->out[1], gff_host.data(), gff_host.size(), base[1]);
             t_write = now_s() - tw;
             if (!ok) {
                 J->fail(HX_ERR_IO, "write error on the output files");
@@ -1246,18 +1273,18 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
     // is assembled on the GPU and the host only writes it; HYPEREX_HOST_FORMAT=1 keeps the host formatter.
     J.device_text = env_int("HYPEREX_HOST_FORMAT", 0) == 0;
     const std::string fa_path = std::string(prefix) + ".fa", gff_path = std::string(prefix) + ".gff";
-    J.fd[0] = open(fa_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);  // fasta::Writer::to_file truncates (utils.rs:241)
-    J.fd[1] = open(gff_path.c_str(), O_RDWR | O_CREAT, 0644);             // OpenOptions create+append (utils.rs:242-245)
-    if (J.fd[0] < 0 || J.fd[1] < 0) {
-        if (J.fd[0] >= 0) close(J.fd[0]);
-        if (J.fd[1] >= 0) close(J.fd[1]);
+    J.out[0].fd = open(fa_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);  // fasta::Writer::to_file truncates (utils.rs:241)
+    J.out[1].fd = open(gff_path.c_str(), O_RDWR | O_CREAT, 0644);           // OpenOptions create+append (utils.rs:242-245)
+    if (J.out[0].fd < 0 || J.out[1].fd < 0) {
+        J.out[0].close_all();
+        J.out[1].close_all();
         hxh_set_error(ctx, "cannot create the output files");
         return HX_ERR_IO;
     }
     {
         struct stat st;  // append: the GFF3 text starts at the current end of the file
-        J.file_pos[1] = fstat(J.fd[1], &st) == 0 ? (uint64_t)st.st_size : 0;
-        if (!pwrite_all(J.fd[1], "##gff-version 3\n", 16, J.file_pos[1])) rc = HX_ERR_IO;  // utils.rs:247
+        J.file_pos[1] = fstat(J.out[1].fd, &st) == 0 ? (uint64_t)st.st_size : 0;
+        if (!pwrite_all(J.out[1].fd, "##gff-version 3\n", 16, J.file_pos[1])) rc = HX_ERR_IO;  // utils.rs:247
         J.file_pos[1] += 16;
     }
     // per pair: everything of the FASTA header / GFF line that does not depend on the record
@@ -1284,7 +1311,7 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
     // (measured: parsing 1.5 GB of FASTA costs 0.3 thread-seconds in total, so a few parsers keep any number of lanes
     // fed; every extra parser is one more pinned batch to allocate on the first call)
     const int n_parsers = std::max(1, std::min(4, hw / 4));
-    const int n_writers = std::max(1, std::min(24, hw - 1));
+    const int n_writers = std::max(1, std::min(24, env_int("HYPEREX_WRITERS", hw - 1)));
     // chunk size: large enough to amortise the per-batch device round trip, small enough that every lane gets
     // several batches and the first / last batch (which nothing overlaps) stay short
     size_t chunk_bytes = (size_t)16 << 20;
@@ -1308,6 +1335,7 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
     std::vector<std::vector<uint8_t>> bufs(chunker.mapped() ? 0 : n_parsers + 2);
     for (auto &b : bufs) J.free_bufs.push_back(&b);
 
+    const double t_setup = now_s() - t_start;
     std::vector<std::thread> threads;
     if (rc == HX_OK) {
         for (int i = 0; i < n_parsers; ++i) threads.emplace_back(parser_thread, &J);
@@ -1351,10 +1379,13 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
     }
     if (rc == HX_OK) rc = J.rc;
     if (rc != HX_OK && !J.err.empty()) hxh_set_error(ctx, J.err.c_str());
-    if (close(J.fd[0]) != 0 && rc == HX_OK) rc = HX_ERR_IO;
-    if (close(J.fd[1]) != 0 && rc == HX_OK) rc = HX_ERR_IO;
+    const double t_close0 = now_s();
+    if (J.out[0].close_all() != 0 && rc == HX_OK) rc = HX_ERR_IO;
+    if (J.out[1].close_all() != 0 && rc == HX_OK) rc = HX_ERR_IO;
     const double wall = now_s() - t_start;
     double *s = cache->stats;
+    s[HX_FS_SETUP_S] = t_setup;
+    s[HX_FS_CLOSE_S] = now_s() - t_close0;
     s[HX_FS_WALL_S] = wall;
     s[HX_FS_BASES] = (double)J.n_bases;
     s[HX_FS_RECORDS] = (double)J.n_records;
@@ -1370,10 +1401,10 @@ extern "C" int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n
     s[HX_FS_WRITERS] = n_writers;
     if (getenv("HYPEREX_TIMING"))  // where the wall time of the file-level path goes (stage seconds are summed over threads)
         fprintf(stderr, "[hyperex timing] wall=%.3fs bases=%llu records=%llu batches=%llu | chunk=%.3fs parse=%.3fs/%d thr "
-                        "device=%.3fs/%d lanes write=%.3fs/%d thr log=%.3fs | fasta=%llu B gff=%llu B\n",
+                        "device=%.3fs/%d lanes write=%.3fs/%d thr log=%.3fs | setup=%.3fs unmap+close=%.3fs | fasta=%llu B gff=%llu B\n",
                 wall, (unsigned long long)J.n_bases, (unsigned long long)J.n_records, (unsigned long long)J.n_batches,
-                s[HX_FS_CHUNK_S], J.t_parse, n_parsers, J.t_device, n_lanes, J.t_write, n_writers, J.t_log,
-                (unsigned long long)J.file_pos[0], (unsigned long long)J.file_pos[1]);
+                s[HX_FS_CHUNK_S], J.t_parse, n_parsers, J.t_device, n_lanes, J.t_write, n_writers, J.t_log, t_setup,
+                s[HX_FS_CLOSE_S], (unsigned long long)J.file_pos[0], (unsigned long long)J.file_pos[1]);
     return rc;
 }
 

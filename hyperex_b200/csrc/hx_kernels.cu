@@ -475,13 +475,29 @@ __device__ __forceinline__ uint32_t hx_verify_long(const uint8_t *__restrict__ r
     return (uint32_t)s;
 }
 
-template <typename W, int NP, bool TMA, int KWM, bool LF>
-__global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((sizeof(W) * NP <= 32) ? 5 : 4)) * (128 / HX_THREADS))
+// Pattern packing at -m 0 (PK = true): a primer longer than 16 symbols is scanned as the Shift-Or automaton of its LAST
+// 16 symbols, so a candidate end `pos` means text[pos - 15 .. pos] matches that suffix exactly.  The primer occurs at
+// pos iff its first m - 16 symbols also match text[pos - m + 1 .. pos - 16]: vt (the top-aligned 64-bit Peq table of the
+// whole primer) has bit (64 - m + i) set in row b iff symbol i accepts the text byte b.
+__device__ __forceinline__ bool hx_verify_exact(const uint8_t *__restrict__ rec_text, uint32_t pos,
+                                                const uint64_t *__restrict__ vt, uint32_t m) {
+    if (pos + 1u < m) return false;  // the primer does not fit before pos
+    const uint8_t *t = rec_text + (pos + 1u - m);
+    uint64_t ok = 1;
+    for (uint32_t i = 0; i + 16u < m; ++i) ok &= __ldg(vt + t[i]) >> (64u - m + i);
+    return ok & 1ull;
+}
+
+template <typename W, int NP, bool TMA, int KWM, bool LF, bool PK = false>
+__global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <= 16) ? 8 : ((sizeof(W) * (PK ? NP / 2 : NP) <= 32) ? 5 : 4)) * (128 / HX_THREADS))
     hx_myers_pair_kernel(const HxScanArgs a) {
     constexpr bool WM = KWM >= 0;           // small-k fast path: Wu-Manber / Shift-Or automata instead of Myers
     constexpr int NR = WM ? KWM + 1 : 1;    // error levels 0..k
     constexpr int WB = sizeof(W);
-    constexpr int STRIDE = hx_row_stride(NP, WB);
+    // PK: NP is the (even) number of pattern halves; NW words hold them, two 16-bit automata each
+    static_assert(!PK || (KWM == 0 && sizeof(W) == 4 && NP % 2 == 0 && !TMA), "packing: -m 0, 32-bit words, whole words");
+    constexpr int NW = PK ? NP / 2 : NP;    // automaton words a thread steps per text byte
+    constexpr int STRIDE = hx_row_stride(NW, WB);
     constexpr int TBYTES = 256 * STRIDE;
     constexpr int SW = (NP + 3) / 4;  // score words of an event record
     constexpr int RW = 1 + SW;        // words of an event record: position + scores
@@ -519,16 +535,34 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
         single = a.tile_cnt[tl.rec] == 1u;
     }
 
-    W pv[NP], mv[NP];   // Myers state
+    W pv[NW], mv[NW];   // Myers state
     int s[NP];          // Myers biased score; for WM: filled on the rare path only
-    W rv[NR][NP];       // WM state: bit = 0 <=> prefix matches with <= d errors (Shift-Or convention)
+    W rv[NR][NW];       // WM state: bit = 0 <=> prefix matches with <= d errors (Shift-Or convention)
     uint64_t bestF[NP], bestR[NP];
     uint64_t phi[HX_MAX_GROUP_PAIRS];
     uint32_t plo[HX_MAX_GROUP_PAIRS];
     const int bias = (int)a.k + 1;
     __syncthreads();  // g is visible
+    if constexpr (PK) {
+        // a half starts with its pattern bits (the top m of the 16) set and the unused low bits clear; a half without
+        // a pattern (odd pattern count) stays all-ones: its table entries are all-ones too, it never reports
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
+        for (int j = 0; j < NW; ++j) {
+            const uint32_t lo = 2 * j < g.np ? (0xffffu << (16 - g.pk_m[2 * j])) & 0xffffu : 0xffffu;
+            const uint32_t hi = 2 * j + 1 < g.np ? (0xffffu << (16 - g.pk_m[2 * j + 1])) & 0xffffu : 0xffffu;
+            rv[0][j] = (W)(lo | (hi << 16));
+            pv[j] = 0;
+            mv[j] = 0;
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            s[p] = 0;
+            bestF[p] = HX_NONE64;
+            bestR[p] = HX_NONE64;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < (PK ? 0 : NP); ++p) {
         pv[p] = ~(W)0;
         mv[p] = 0;
         s[p] = (int)g.m[p] - bias;
@@ -572,7 +606,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
         const bool mine = alpha == pass;
         if (!__syncthreads_or(mine ? 1 : 0)) continue;  // no record of this alphabet in the CTA
         {
-            const uint4 *tsrc = reinterpret_cast<const uint4 *>(WM ? a.tables_wm : a.tables) + (size_t)pass * (TBYTES / 16);
+            const uint4 *tsrc = reinterpret_cast<const uint4 *>(PK ? a.tables_pk : WM ? a.tables_wm : a.tables) + (size_t)pass * (TBYTES / 16);
             uint4 *dst = reinterpret_cast<uint4 *>(smem);
             for (int i = threadIdx.x; i < TBYTES / 16; i += HX_THREADS) dst[i] = __ldg(tsrc + i);
         }
@@ -643,10 +677,21 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
                     for (int bi = 0; bi < UB; ++bi) {
                         const uint32_t byte = w & 0xffu;
                         w >>= 8;
-                        HxRow<W, NP> row;
+                        HxRow<W, NW> row;
                         row.load(tab + byte * STRIDE);
                         int any = 0;
-                        if constexpr (WM) {
+                        if constexpr (PK) {
+                            // two Shift-Or automata per word: R' = ((R << 1) & fence) | neq.  Shift-Or has no carries,
+                            // so the only coupling of the halves is the bit the shift moves from the low half's top
+                            // into the high half's bottom; the fence clears it (one LOP3 with the OR).
+                            W acc = ~(W)0;
+#pragma unroll
+                            for (int j = 0; j < NW; ++j) {
+                                rv[0][j] = ((rv[0][j] << 1) & (W)0xfffefffful) | row.eq(j);
+                                acc &= rv[0][j];
+                            }
+                            any = (~acc & (W)0x80008000ul) ? -1 : 0;
+                        } else if constexpr (WM) {
                             // Wu-Manber, Shift-Or form: row.eq(p) is the COMPLEMENTED Peq word
                             //   R0' = (R0 << 1) | neq
                             //   Rd' = ((Rd << 1) | neq) & R(d-1) & (R(d-1) << 1) & (R(d-1)' << 1)
@@ -681,7 +726,12 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
                             // ---- rare: some pattern has dist <= k here; record the event ----
                             const uint32_t pos = pos0 + (c << 4) + (wi << 2) + b0 + bi;
                             if (pos - tl.own_start < own_len) {
-                                if constexpr (WM) {
+                                if constexpr (PK) {
+                                    // biased score of a half: -1 (a hit at distance 0) when its top bit is clear, else 0
+#pragma unroll
+                                    for (int p = 0; p < NP; ++p)
+                                        s[p] = (int)((rv[0][p >> 1] >> ((p & 1) ? 31 : 15)) & 1u) - 1;
+                                } else if constexpr (WM) {
                                     // Exact distance of a hit = the lowest level whose top bit is 0.  "<= d errors"
                                     // implies "<= d + 1 errors", so the top bits are monotone over the levels and that
                                     // level is simply the NUMBER of levels whose top bit is set (k + 1, i.e. a biased
@@ -726,7 +776,17 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
                             const uint32_t neg = sw[j] & 0x80808080u;
                             hm |= (((neg >> 7) & 1u) | ((neg >> 14) & 2u) | ((neg >> 21) & 4u) | ((neg >> 28) & 8u)) << (4 * j);
                         }
-                        if constexpr (LF) {
+                        if constexpr (LF && PK) {
+                            // events of 16-symbol suffixes are candidates: the rest of the primer must match too
+                            uint32_t lm = hm & g.pk_longmask;
+                            const uint8_t *rec_text = a.arena + (a.offsets[tl.rec] - a.off_base);
+                            while (lm) {
+                                const int p = __ffs((int)lm) - 1;
+                                lm &= lm - 1;
+                                if (!hx_verify_exact(rec_text, pos, a.vtables + ((size_t)g.pk_vslot[p] * 2 + pass) * 256, g.mfull[p]))
+                                    hm &= ~(1u << p);
+                            }
+                        } else if constexpr (LF) {
                             // events of suffix-filtered patterns are candidates: exact distance of the whole primer
                             uint32_t lm = hm & g.longmask;
                             const uint8_t *rec_text = a.arena + (a.offsets[tl.rec] - a.off_base);  // only lanes with a tile hold events
@@ -816,6 +876,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
     }
     const size_t ts = a.tile_stride;
     for (int p = 0; p < NP; ++p) {
+        if (PK && p >= g.np) break;  // the padding half of an odd pattern count owns no summary slot
         a.sum_f[(size_t)(g.slot_base + p) * ts + tile_id] = bestF[p + dz];
         a.sum_r[(size_t)(g.slot_base + p) * ts + tile_id] = bestR[p + dz];
     }
@@ -825,20 +886,20 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * NP <= 16) ? 8 : ((si
     }
 }
 
-template <typename W, int NP, bool TMA, int KWM, bool LF = false>
+template <typename W, int NP, bool TMA, int KWM, bool LF = false, bool PK = false>
 static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
-    const int smem = hx_table_bytes(NP, sizeof(W)) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
+    const int smem = hx_table_bytes(PK ? NP / 2 : NP, sizeof(W)) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
     // per (instantiation, device) once; contexts on different host threads may race here, so the flags are atomic
     // (setting the attribute twice is harmless, skipping it is not)
     static std::atomic<bool> attr_done[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
-        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM, LF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
     }
     const uint32_t blocks = (tile_cap + HX_THREADS - 1) / HX_THREADS;
-    hx_myers_pair_kernel<W, NP, TMA, KWM, LF><<<blocks, HX_THREADS, smem, st>>>(a);
+    hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK><<<blocks, HX_THREADS, smem, st>>>(a);
     return 1;
 }
 
@@ -868,8 +929,20 @@ struct HxDispatch<W, 0> {
     static int run(int, bool, const HxScanArgs &, uint32_t, cudaStream_t) { return -1; }
 };
 
+// packed -m 0 scan: NW words = 2 * NW pattern halves
+template <int NW>
+static int hx_packed_dispatch(int nw, bool lf, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
+    if (nw == NW)
+        return lf ? hx_scan_launch_one<uint32_t, 2 * NW, false, 0, true, true>(a, cap, st)
+                  : hx_scan_launch_one<uint32_t, 2 * NW, false, 0, false, true>(a, cap, st);
+    if constexpr (NW > 1) return hx_packed_dispatch<NW - 1>(nw, lf, a, cap, st);
+    return -1;
+}
+
 int hx_launch_scan(const HxScanArgs &a, const HxGroup &hg, uint32_t tile_cap, cudaStream_t st) {
     if (tile_cap == 0) return 0;
+    if (a.packed && hg.packed && !hg.word64)
+        return hx_packed_dispatch<HX_MAX_NP32 / 2>((hg.np + 1) / 2, hg.pk_longmask != 0u, a, tile_cap, st);
     if (hg.word64) return HxDispatch<uint64_t, HX_MAX_NP64>::run(hg.np, false, a, tile_cap, st);
     return HxDispatch<uint32_t, HX_MAX_NP32>::run(hg.np, hg.longmask != 0u, a, tile_cap, st);
 }

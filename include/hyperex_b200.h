@@ -241,6 +241,8 @@ enum {
     HX_FS_PARSERS,       /* threads per stage */
     HX_FS_LANES,
     HX_FS_WRITERS,
+    HX_FS_SETUP_S,       /* hx_set_primers, opening the files, thread start */
+    HX_FS_CLOSE_S,       /* unmapping and closing the output files */
     HX_FILE_STATS_N
 };
 int hx_file_stats(hx_ctx *ctx, double *out, int n);

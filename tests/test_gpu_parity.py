@@ -31,6 +31,7 @@ def _run(ctx, arena, offsets, pairs, k, **opts):
     ctx.set_option("text_tma", opts.get("text_tma", 0))
     ctx.set_option("fast_small_k", opts.get("fast", 1))
     ctx.set_option("long_filter", opts.get("lf", 1))
+    ctx.set_option("pack16", opts.get("pack", 1))
     ctx.set_primers(pairs, k)
     return ctx.run_batch(arena, offsets)
 
@@ -113,10 +114,14 @@ def test_golden_batches(ctx, golden_dir, name, text_tma):
 
 
 # ---- seeded batches of the BASELINE.json shapes at oracle-friendly sizes -----------------------------
-@pytest.mark.parametrize("fast", [0, 1])
-def test_c2_reads_all_regions_k0(ctx, fast):
+@pytest.mark.parametrize("fast,pack", [(0, 1), (1, 0), (1, 1)])
+def test_c2_reads_all_regions_k0(ctx, fast, pack):
+    """fast 0: Myers; fast 1 + pack 0: Shift-Or, one automaton per word; fast 1 + pack 1 (library default): two
+    16-symbol suffix automata per word + verification of the rest of the primer"""
     a, o = hx_synth.gen_reads(3000, seed=22)
-    res = _run(ctx, a, o, hx.default_primers(), 0, fast=fast)
+    res = _run(ctx, a, o, hx.default_primers(), 0, fast=fast, pack=pack)
+    if fast and pack:
+        assert hx.plan_groups(hx.default_primers(), 0)[:3] == (1, 15, 0)
     _cmp(res, O.run_batch(a, o, O.default_pairs(), 0, nthreads=8), a, o, O.default_pairs(), 0)
     assert (res["flags"] & 7 == 7).all()
 
@@ -228,6 +233,51 @@ def test_long_primers_suffix_filter(ctx, k):
         assert ctx.group_info()[2] == 0 and n64 > 0   # the filter leaves no 64-bit automaton to step
 
 
+def test_pattern_packing_k0(ctx):
+    """-m 0, two Shift-Or automata of <= 16 symbols per word: primers of 1..64 nt around the 16-symbol boundary, sites
+    at record starts / ends, sites that match the 16-symbol suffix but not the rest of the primer (candidates the
+    verification must reject), degenerate suffixes, odd and even pattern counts, RNA and soft-masked records, windows"""
+    rng = np.random.default_rng(1616)
+    letters = "ACGT" * 6 + "MRWSYKVHDBN"
+    def prim(n, alphabet=letters):
+        return "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), n))
+    base = [[prim(15), prim(16)], [prim(17), prim(18)], [prim(24), prim(32)], [prim(33), prim(64)], [prim(1), prim(2)],
+            [prim(8, "ACGT") + "N" * 16, prim(20)],          # suffix of N: every position is a candidate
+            [prim(20, "ACGT"), "N" * 4 + prim(16, "ACGT")],
+            hx.region_to_primer("v4"), hx.region_to_primer("v3v4")]
+    for n_pairs in (1, 2, 5, len(base)):
+        pairs = base[:n_pairs] if n_pairs > 2 else base[2:2 + n_pairs]
+        recs = []
+        for i in range(120):
+            L = int(rng.integers(0, 600))
+            seq = bytearray(hx_synth.random_acgt(rng, L).tobytes())
+            for _s in range(int(rng.integers(0, 6))):
+                f, r = pairs[int(rng.integers(0, len(pairs)))]
+                site = f if rng.random() < 0.5 else O.to_reverse_complement(r, O.DNA).decode()
+                sb = bytearray(hx_synth._resolve(rng, site, 1)[0].tobytes())
+                if rng.random() < 0.4 and len(sb) > 16:       # damage the part in front of the 16-symbol suffix
+                    j = int(rng.integers(0, len(sb) - 16))
+                    sb[j] = ord("ACGT"[("ACGT".index(chr(sb[j])) + 1) % 4]) if chr(sb[j]) in "ACGT" else ord("A")
+                elif rng.random() < 0.2:
+                    sb = hx_synth._edit(rng, sb, 1)
+                if L >= len(sb):
+                    p = int(rng.choice([0, L - len(sb), int(rng.integers(0, L - len(sb) + 1))]))
+                    seq[p:p + len(sb)] = sb
+            a1 = np.frombuffer(bytes(seq), dtype=np.uint8).copy()
+            if i % 7 == 0:
+                a1[a1 == ord("T")] = ord("U")
+            if i % 5 == 0 and len(a1):
+                lo, hi = sorted(rng.integers(0, len(a1) + 1, size=2))
+                a1[lo:hi] |= 0x20
+            recs.append(a1)
+        a, o = hx_synth.pack(recs)
+        ref = O.run_batch(a, o, pairs, 0, nthreads=8)
+        assert (ref["flags"] & 4).any()
+        for tile in (0, 64, 4096):
+            for pack in (2, 1, 0):
+                _cmp(_run(ctx, a, o, pairs, 0, tile_len=tile, single_max=tile, fast=1, pack=pack), ref, a, o, pairs, 0)
+
+
 # ---- edge cases the domain has -------------------------------------------------------------------------
 def test_edge_records(ctx):
     recs = [b"", b"A", b"T", b"U", b"X", b"acgtn", b"ACGU" * 10 + b"T", b"N" * 50,
@@ -298,6 +348,9 @@ def test_random_primer_sets_fuzz(ctx, seed):
     for fast, tma, lf in ((0, 0, 1), (1, 0, 2), (0, 1, 1), (0, 0, 0)):
         _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, text_tma=tma, lf=lf), ref, a, o, pairs,
              k)
+    if k == 0:  # -m 0 pattern packing: off / forced for every group (degenerate 16-symbol suffixes included)
+        for pack in (0, 2):
+            _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=1, pack=pack), ref, a, o, pairs, k)
 
 
 def test_rna_records_use_rna_reverse_complement(ctx):

@@ -4,7 +4,7 @@
 # prof_classify.ncu-rep (--set full, one launch each).  tools/ncu_summary.py turns them into profiles/*.csv.
 set -u
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-ab"
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-ab --no-file-e2e"
 $CMD > gpurun_out/prof_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/prof_plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:hx_myers_pair -s 2 -c 1 -o gpurun_out/prof_myers -f $CMD > gpurun_out/ncu_full.log 2>&1
