@@ -498,6 +498,36 @@ def main():
         torch.cuda.synchronize()
         h2d_conc_ms = (time.perf_counter() - t0c) * 1e3 / 3
 
+    # ---- packed-arena leg ("e2e_packed"): 4-bit text (north_star "2-bit/ASCII arena"), half the bytes over PCIe ---------
+    # The packer (hx_pack_records, host, all threads) is timed on its own, and the leg is reported both without it (the
+    # arena arrives packed, e.g. from a parser that packs while it touches the bytes anyway) and with it inside the timed
+    # region every step.
+    pk = hx.pinned_empty(bases // 2 + 64)
+    fl = hx.pinned_empty(max(n, 1))
+    h_out2_raw = hx.pinned_empty(n * npairs * 12)
+    h_out2 = h_out2_raw.view(hx.RESULT_DTYPE).reshape(n, npairs)
+    hx.pack_records(h_arena[:bases], offsets, 0, pk, fl)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        hx.pack_records(h_arena[:bases], offsets, 0, pk, fl)
+    pack_s = (time.perf_counter() - t0) / 3
+    for _ in range(min(args.warmup, 2)):
+        ctx.run_batch_packed(pk, fl, offsets, out=h_out2)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.run_batch_packed(pk, fl, offsets, out=h_out2)
+    torch.cuda.synchronize()
+    e2e_packed_s = time.perf_counter() - t0
+    assert h_out2.tobytes() == h_out.tobytes(), "packed-arena and ASCII legs disagree"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hx.pack_records(h_arena[:bases], offsets, 0, pk, fl)
+        ctx.run_batch_packed(pk, fl, offsets, out=h_out2)
+    torch.cuda.synchronize()
+    e2e_packed_incl_s = time.perf_counter() - t0
+
     # results sanity: device-resident (Myers) and host (library default) legs agree, every planted region found (k = 0)
     dev_res = d_out.cpu().numpy().view(hx.RESULT_DTYPE).reshape(n, npairs)
     assert dev_res.tobytes() == h_out.tobytes(), "device-resident and host legs disagree"
@@ -533,12 +563,14 @@ def main():
         barrier()
 
     # ---- max over ranks ---------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s * 1e3, myers_ms, fast_ms or 0.0, h2d_conc_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, myers_ms, fast_ms or 0.0, h2d_conc_ms, e2e_packed_s * 1e3, e2e_packed_incl_s * 1e3,
+                      pack_s * 1e3], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(bases), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max, myers_ms_max, fast_ms_max, h2d_conc_ms_max = (float(x) for x in t.cpu())
+    (dev_ms_max, e2e_ms_max, myers_ms_max, fast_ms_max, h2d_conc_ms_max, e2e_pk_ms_max, e2e_pk_incl_ms_max,
+     pack_ms_max) = (float(x) for x in t.cpu())
     total_bases, total_launches = (float(x) for x in tot.cpu())
 
     if rank == 0:
@@ -614,6 +646,16 @@ def main():
                 "gpu_launches": int(total_launches), "roofline": roofline, "clocks": clocks,
                 "result_table_sha256_rank0": table_sha}
         line["e2e"]["path"] = "library defaults (fast_small_k = 1): result table asserted equal to the Myers kernel's"
+        line["e2e_packed"] = {
+            "what": "hx_run_batch_packed: pinned PACKED arena (4-bit codes, hx_pack_records) -> H2D -> kernels on nibble text -> D2H "
+                    "result table, every step; result table asserted equal to the ASCII leg's",
+            "value": total_bases * args.steps / (e2e_pk_ms_max * 1e-3) / 1e9, "unit": "Gbases/s",
+            "ms_per_step": e2e_pk_ms_max / args.steps, "h2d_bytes_per_step": int(bases // 2 + offsets.nbytes + n),
+            "d2h_bytes_per_step": int(n * npairs * 12), "pack_inside_timed_region": False,
+            "pack_ms": pack_ms_max, "pack_gbases_per_s": bases / (pack_ms_max * 1e-3) / 1e9, "pack_threads": os.cpu_count(),
+            "with_pack_inside_timed_region": {"value": total_bases * args.steps / (e2e_pk_incl_ms_max * 1e-3) / 1e9,
+                                              "ms_per_step": e2e_pk_incl_ms_max / args.steps,
+                                              "note": "pack then run, back to back on the host (not pipelined)"}}
         if multidev is not None:
             line["multidev_parity"] = multidev
         if file_e2e is not None:
@@ -635,6 +677,8 @@ def main():
         print(json.dumps(line), flush=True)
     hx.pinned_free(h_arena)
     hx.pinned_free(h_out_raw)
+    for buf in (pk, fl, h_out2_raw):
+        hx.pinned_free(buf)
     ctx.close()
     if world > 1:
         dist.barrier()

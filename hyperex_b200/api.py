@@ -102,6 +102,27 @@ def file_to_vec(filename: str):
     return out
 
 
+PACK_CODES = b"\0ACGTRYSWKMBDHVN"   # code -> letter; 'U' shares code 4 with 'T' (hx_pack_records)
+REC_HAS_U, REC_HAS_T, REC_NON_IUPAC = 1, 2, 4
+
+
+def pack_records(arena: np.ndarray, offsets: np.ndarray, n_threads: int = 0, packed: np.ndarray | None = None,
+                 rec_flags: np.ndarray | None = None):
+    """hx_pack_records: ASCII arena -> (packed u8[offsets[-1] // 2 + 1], rec_flags u8[n]); nibble i of packed = code of
+    base i (low nibble = even index).  Pure host code."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    if packed is None:
+        packed = np.zeros(int(offsets[-1]) // 2 + 1, dtype=np.uint8)
+    if rec_flags is None:
+        rec_flags = np.zeros(max(n, 1), dtype=np.uint8)
+    ap = arena.ctypes.data if arena is not None and arena.size else None
+    rc = _lib.load().hx_pack_records(ap, offsets.ctypes.data, n, packed.ctypes.data, rec_flags.ctypes.data, n_threads)
+    if rc != 0:
+        raise HyperexError(rc, "hx_pack_records: bad arguments")
+    return packed, rec_flags[:n]
+
+
 def read_fasta(path: str, max_bytes: int = 0):
     """fasta::Reader::new(read_file(path)).records() (utils.rs:237-238) -> iterator of
     (arena u8[], offsets u64[n+1], ids [str]) batches; arrays are copies"""
@@ -182,6 +203,17 @@ class Context:
             out = np.zeros((n, self.n_pairs), dtype=RESULT_DTYPE)
         ap = arena.ctypes.data if arena is not None and arena.size else None
         self._check(self._L.hx_run_batch(self._h, ap, offsets.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def run_batch_packed(self, packed: np.ndarray, rec_flags: np.ndarray, offsets: np.ndarray,
+                         out: np.ndarray | None = None) -> np.ndarray:
+        """hx_run_batch_packed on a packed HOST arena (pack_records) -> (n_records, n_pairs) structured array"""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        if out is None:
+            out = np.zeros((n, self.n_pairs), dtype=RESULT_DTYPE)
+        self._check(self._L.hx_run_batch_packed(self._h, packed.ctypes.data, rec_flags.ctypes.data if n else None,
+                                                offsets.ctypes.data, n, out.ctypes.data))
         return out
 
     def run_batch_fasta(self, arena: np.ndarray, offsets: np.ndarray, ids: Sequence[str], tails: Sequence[str]):

@@ -82,6 +82,7 @@ struct Slot {
     DevBuf<uint64_t> sum_f, sum_r, pair_hi;
     DevBuf<uint32_t> pair_lo;
     DevBuf<hx_result> out;
+    DevBuf<uint8_t> flags;         // packed text: per-record alphabet evidence gathered by the host packer
     uint32_t *h_status = nullptr;  // pinned: [0] ntiles, [1] overflow
     void release() {
         pool.release();
@@ -157,6 +158,7 @@ struct hx_ctx {
     std::vector<HxPairRef> pair_refs;
     std::vector<uint8_t> tables;
     bool primers_set = false;
+    bool packable = true;  // every primer symbol is one of ACGTURYSWKMBDHVN (or lower case, which matches nothing)
     // options
     int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1,
             opt_long_filter = 1, opt_group_np_max = 0, opt_pack16 = 1;
@@ -302,7 +304,7 @@ SlabPlan plan_slab(const hx_ctx *ctx, uint32_t n_records, uint64_t bytes) {
 // Carves the slot's device block for one slab (one cudaMalloc at most, and only when the slab needs more than any
 // before it).  io_bytes > 0: the slot also holds the arena copy, the offsets and the result table (host-buffer
 // entry points); 0: those live in caller-owned device memory (hx_run_batch_device).  The slot must be idle.
-int prepare_slab(hx_ctx *ctx, Slot &S, const SlabPlan &pl, uint32_t n_records, uint64_t io_bytes) {
+int prepare_slab(hx_ctx *ctx, Slot &S, const SlabPlan &pl, uint32_t n_records, uint64_t io_bytes, bool with_flags = false) {
     for (int pass = 0;; ++pass) {
         S.pool.reset();
         if (io_bytes) {
@@ -310,6 +312,7 @@ int prepare_slab(hx_ctx *ctx, Slot &S, const SlabPlan &pl, uint32_t n_records, u
             S.offsets.carve(S.pool, (size_t)n_records + 1);
             S.out.carve(S.pool, (size_t)n_records * ctx->n_pairs);
         }
+        if (with_flags) S.flags.carve(S.pool, (size_t)n_records + 16);
         S.rec_u32.carve(S.pool, (size_t)n_records * 4);
         S.scratch.carve(S.pool, 4 + 2 * HX_NBUCKETS);
         S.tiles.carve(S.pool, pl.tile_cap);
@@ -325,9 +328,11 @@ int prepare_slab(hx_ctx *ctx, Slot &S, const SlabPlan &pl, uint32_t n_records, u
 }
 
 // Enqueue the whole device path for one slab on `st` (after prepare_slab).  d_out receives n_records x n_pairs results.
+// d_flags != NULL: packed text (4-bit codes; offsets and off_base count symbols) with the host packer's per-record evidence.
 int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint8_t *d_arena, const uint64_t *d_offsets,
-                 uint64_t off_base, uint32_t n_records, hx_result *d_out, cudaStream_t st) {
+                 uint64_t off_base, uint32_t n_records, hx_result *d_out, cudaStream_t st, const uint8_t *d_flags = nullptr) {
     if (n_records == 0) return HX_OK;
+    const bool nib = d_flags != nullptr;
 
     uint32_t *rec_raw = S.rec_u32.p, *tile_first = rec_raw + n_records, *tile_cnt = tile_first + n_records;
     uint32_t *long_list = tile_cnt + n_records;
@@ -352,8 +357,11 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
     b.long_list = long_list;
     b.n_long = n_long;
     ctx->launches += hx_launch_tile_build(b, cursor, S.order.p, st);
-    ctx->launches += hx_launch_classify(d_arena, d_offsets, off_base, S.tiles.p, ntiles, pl.tile_cap, rec_raw, tile_cnt,
-                                        n_records, ntiles + 3, st);  // scratch[3] = n_plain (zeroed with the scratch block)
+    if (nib)  // the packer classified the records while it touched every byte anyway: no device pass over the text
+        ctx->launches += hx_launch_flags(d_flags, rec_raw, n_records, st);
+    else
+        ctx->launches += hx_launch_classify(d_arena, d_offsets, off_base, S.tiles.p, ntiles, pl.tile_cap, rec_raw, tile_cnt,
+                                            n_records, ntiles + 3, st);  // scratch[3] = n_plain (zeroed with the scratch block)
 
     for (size_t gi = 0; gi < ctx->groups.size(); ++gi) {
         const HxGroup &hg = ctx->groups[gi];
@@ -373,7 +381,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
         a.vtables = D.d_vtables;
         // small-k fast path: identical hits, fewer ALU operations; 32-bit groups, vector-load text path
         // (measured: at -m 2 the fast path only pays for narrow groups; wide groups run out of registers)
-        a.wm_k = (ctx->opt_fast_small_k && !hg.word64 && !ctx->opt_text_tma && (ctx->k <= 1 || (ctx->k == 2 && hg.np <= 8)))
+        a.wm_k = (ctx->opt_fast_small_k && !hg.word64 && (!ctx->opt_text_tma || nib) && (ctx->k <= 1 || (ctx->k == 2 && hg.np <= 8)))
                      ? (int)ctx->k
                      : -1;
         // -m 0: two <= 16-symbol Shift-Or automata per word when the planner found the group packable
@@ -386,7 +394,8 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
         a.pair_lo = S.pair_lo.p;
         a.tile_stride = pl.tile_cap;
         a.k = ctx->k;
-        a.variant = (hg.longmask || a.packed) ? 0 : (int)ctx->opt_text_tma;  // suffix-filtered groups: vector-load text path only
+        a.nib = nib ? 1 : 0;
+        a.variant = (hg.longmask || a.packed || nib) ? 0 : (int)ctx->opt_text_tma;  // suffix-filtered groups: vector-load text path only
         a.two = 2;
         TimedLaunch tl;
         if (ctx->opt_time) {
@@ -882,6 +891,13 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
         HX_CUDA(ctx, cudaMemcpy(D.d_groups, groups.data(), groups.size() * sizeof(HxGroup), cudaMemcpyHostToDevice));
         HX_CUDA(ctx, cudaMemcpy(D.d_pairs, refs.data(), refs.size() * sizeof(HxPairRef), cudaMemcpyHostToDevice));
     }
+    ctx->packable = true;
+    for (uint32_t i = 0; i < n_pairs; ++i)
+        for (const char *str : {fwd[i], rev[i]}) {
+            const size_t len = (str == fwd[i] ? fwd_len : rev_len) ? (str == fwd[i] ? fwd_len[i] : rev_len[i]) : strlen(str);
+            for (size_t j = 0; j < len; ++j)
+                if (!strchr("ACGTURYSWKMBDHVN", str[j]) && !(str[j] >= 'a' && str[j] <= 'z')) ctx->packable = false;
+        }
     ctx->n_pairs = n_pairs;
     ctx->k = k > 64 ? 64 : k;  // dist <= m <= 64: any larger bound accepts exactly the same hits
     ctx->m_max = m_max;
@@ -1151,9 +1167,16 @@ int hx_run_batch_text_stream(hx_ctx *ctx, const uint8_t *arena, const uint64_t *
                          want_gff ? gff_tail_off : nullptr, nullptr, text_len, nullptr, gff_len, &s);
 }
 
-int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out) {
-    if (!ctx) return HX_ERR_ARG;
+}  // extern "C"
+
+// hx_run_batch / hx_run_batch_packed: rec_flags != NULL means `arena` is a packed arena (4-bit codes, nibble i = base i)
+static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_flags, const uint64_t *offsets, uint32_t n_records,
+                          hx_result *out) {
+    const bool nib = rec_flags != nullptr;
     if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch: call hx_set_primers first");
+    if (nib && !ctx->packable)
+        return fail(ctx, HX_ERR_STATE, "hx_run_batch_packed: the primer set has symbols outside ACGTURYSWKMBDHVN, which packed text "
+                                       "cannot represent; use hx_run_batch");
     if (n_records == 0) return HX_OK;
     if (!offsets || !out) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL offsets/out");
     if (offsets[n_records] < offsets[0]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
@@ -1201,18 +1224,19 @@ int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uin
             if (rc != HX_OK) break;
         }
         // the host arena slice is copied with its 16-byte phase preserved so that device
-        // addresses keep the alignment of the arena offsets
-        const uint64_t base = offsets[r0] & ~15ull;
-        const uint64_t copy_bytes = offsets[r1] - base;
+        // addresses keep the alignment of the arena offsets (packed: 32 symbols = 16 bytes)
+        const uint64_t base = offsets[r0] & (nib ? ~31ull : ~15ull);
+        const uint64_t copy_bytes = nib ? (offsets[r1] + 1) / 2 - base / 2 : offsets[r1] - base;
         const SlabPlan pl = plan_slab(ctx, n, bytes);
-        rc = prepare_slab(ctx, S, pl, n, copy_bytes + 64);
+        rc = prepare_slab(ctx, S, pl, n, copy_bytes + 64, nib);
         if (rc != HX_OK) break;
         used[di * HX_NSLOT + si] = 1;  // from here on the slot's stream may hold work on caller memory
         if (copy_bytes)
-            HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.arena.p, arena + base, copy_bytes, cudaMemcpyHostToDevice, S.stream));
+            HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.arena.p, arena + (nib ? base / 2 : base), copy_bytes, cudaMemcpyHostToDevice, S.stream));
+        if (nib) HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.flags.p, rec_flags + r0, n, cudaMemcpyHostToDevice, S.stream));
         HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.offsets.p, offsets + r0, ((size_t)n + 1) * sizeof(uint64_t),
                                                cudaMemcpyHostToDevice, S.stream));
-        rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, base, n, S.out.p, S.stream);
+        rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, base, n, S.out.p, S.stream, nib ? S.flags.p : nullptr);
         if (rc != HX_OK) break;
         HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(out + (size_t)r0 * np, S.out.p, (size_t)n * np * sizeof(hx_result),
                                                cudaMemcpyDeviceToHost, S.stream));
@@ -1232,6 +1256,21 @@ int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uin
     }
     sync_timed(ctx);
     return rc;
+}
+
+extern "C" {
+
+int hx_run_batch(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out) {
+    if (!ctx) return HX_ERR_ARG;
+    return run_batch_impl(ctx, arena, nullptr, offsets, n_records, out);
+}
+
+int hx_run_batch_packed(hx_ctx *ctx, const uint8_t *packed, const uint8_t *rec_flags, const uint64_t *offsets,
+                        uint32_t n_records, hx_result *out) {
+    if (!ctx) return HX_ERR_ARG;
+    if (n_records && !rec_flags) return fail(ctx, HX_ERR_ARG, "hx_run_batch_packed: NULL rec_flags");
+    static const uint8_t none = 0;
+    return run_batch_impl(ctx, packed, n_records ? rec_flags : &none, offsets, n_records, out);
 }
 
 int64_t hx_find_all_end(hx_ctx *ctx, const char *pattern, uint32_t pattern_len, const uint8_t *text, uint64_t text_len,

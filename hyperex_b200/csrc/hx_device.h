@@ -89,6 +89,7 @@ struct HxScanArgs {
     const uint8_t *tables_wm;  // complemented Peq blob of the small-k fast path (Shift-Or convention)
     const uint8_t *tables_pk;  // -m 0 packed blob: two 16-bit complemented Peq half-words per 32-bit word
     int32_t packed;            // 1: run the packed Shift-Or scan (wm_k == 0 and the group has a packed table)
+    int32_t nib;               // 1: `arena` holds 4-bit codes (hx_run_batch_packed); offsets / off_base count symbols
     const uint64_t *vtables;   // [vslot][alphabet dna|rna][256] top-aligned 64-bit Peq words of the suffix-filtered primers
     int32_t wm_k;              // >= 0: run the Wu-Manber fast path with this many errors (32-bit groups only)
     const HxGroup *group;      // this launch's group (device memory)
@@ -125,6 +126,7 @@ int hx_launch_tile_build(const HxBuildArgs &a, uint32_t *cursor, uint32_t *order
 int hx_launch_classify(const uint8_t *arena, const uint64_t *offsets, uint64_t off_base, const HxTile *tiles,
                        const uint32_t *ntiles, uint32_t tile_cap, uint32_t *rec_raw, const uint32_t *tile_cnt,
                        uint32_t n_records, uint32_t *n_plain, cudaStream_t st);
+int hx_launch_flags(const uint8_t *flags, uint32_t *rec_raw, uint32_t n_records, cudaStream_t st);
 int hx_launch_scan(const HxScanArgs &a, const HxGroup &hostgroup, uint32_t tile_cap, cudaStream_t st);
 int hx_launch_combine(const uint32_t *tile_first, const uint32_t *tile_cnt, const uint32_t *rec_raw,
                       const HxPairRef *pairs, uint32_t n_pairs, uint32_t n_records, const uint64_t *sum_f,

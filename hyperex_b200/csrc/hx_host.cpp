@@ -12,7 +12,11 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
+#include <algorithm>
 #include <cerrno>
 #include <chrono>
 #include <cstdio>
@@ -203,6 +207,165 @@ void hx_free_primer_file(char **fwd, char **rev, int n) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// Packed arena (BASELINE.json north_star: "2-bit/ASCII arena in pinned memory"): 4-bit codes, two bases per byte.
+//   code 0        any byte that is not one of the 16 letters below (after to_ascii_uppercase, utils.rs:295)
+//   codes 1..15   A C G T|U R Y S W K M B D H V N
+// 'T' and 'U' share code 4: a record that holds both is alphabet None and is skipped (utils.rs:225-226), so inside a
+// record that is scanned the code is unambiguous and the device resolves it with the record's alphabet.  A byte
+// outside the 16 letters matches a primer symbol only if the primer holds that very byte (rust-bio build_64 + the
+// ambiguity table of utils.rs:251-263 list nothing else); hx_run_batch_packed refuses primer sets that do, so code
+// 0 — a text symbol that matches nothing — is exact.  While packing, the evidence sequence_type needs is gathered per
+// record (utils.rs:207-228): has 'U', has 'T', has a byte outside "ACGTRYSWKMBDHVN" + 'U'.
+// Nibble i of the packed buffer is base i of the arena (low nibble = even index), so the offsets array serves both.
+// ------------------------------------------------------------------------------------
+namespace {
+
+struct PackTables {
+    uint8_t code[256];  // byte -> 4-bit code
+    uint8_t flag[256];  // byte -> HX_REC_* evidence bits
+    PackTables() {
+        static const char letters[] = "ACGTRYSWKMBDHVN";
+        for (int b = 0; b < 256; ++b) {
+            const int u = (b >= 'a' && b <= 'z') ? b - 32 : b;
+            const char *q = (u && u < 128) ? strchr(letters, u) : nullptr;
+            code[b] = q ? (uint8_t)(q - letters + 1) : (u == 'U' ? 4 : 0);
+            flag[b] = (uint8_t)((u == 'U' ? HX_REC_HAS_U : 0) | (u == 'T' ? HX_REC_HAS_T : 0) | ((!q && u != 'U') ? HX_REC_NON_IUPAC : 0));
+        }
+    }
+};
+const PackTables &pack_tables() {
+    static const PackTables t;
+    return t;
+}
+
+#if defined(__x86_64__)
+// 64 bases -> 32 packed bytes per trip, straight from the ASCII text (src and dst start on an even base); returns the
+// number of bases consumed (a multiple of 64) and ORs the evidence bits into f
+__attribute__((target("avx2"))) size_t pack_avx2(const uint8_t *src, size_t n, uint8_t *dst, uint32_t &f) {
+    // letter index (byte & 0x1f, 1..26) -> code through two 16-entry shuffles; everything that is not a letter -> 0
+    //                 idx:  0  A  B  C  D  E  F  G  H  I  J  K  L  M  N  O
+    const __m256i lut_lo = _mm256_setr_epi8(0, 1, 11, 2, 12, 0, 0, 3, 13, 0, 0, 9, 0, 10, 15, 0, 0, 1, 11, 2, 12, 0, 0, 3, 13, 0, 0, 9, 0, 10, 15, 0);
+    //                 idx:  P  Q  R  S  T  U  V  W  X  Y  Z
+    const __m256i lut_hi = _mm256_setr_epi8(0, 0, 5, 7, 4, 4, 14, 8, 0, 6, 0, 0, 0, 0, 0, 0, 0, 0, 5, 7, 4, 4, 14, 8, 0, 6, 0, 0, 0, 0, 0, 0);
+    const __m256i m_df = _mm256_set1_epi8((char)0xdf), m_0f = _mm256_set1_epi8(0x0f), m_10 = _mm256_set1_epi8(0x10);
+    const __m256i c_40 = _mm256_set1_epi8(0x40), c_5b = _mm256_set1_epi8(0x5b), c_T = _mm256_set1_epi8('T'), c_U = _mm256_set1_epi8('U');
+    const __m256i mult = _mm256_set1_epi16(0x1001), zero = _mm256_setzero_si256();  // bytes (1, 16): low + 16 * high
+    __m256i any_t = zero, any_u = zero, any_bad = zero;
+#define HX_CODES32(p, out)                                                                                                     \
+    {                                                                                                                          \
+        const __m256i x = _mm256_loadu_si256((const __m256i *)(p));                                                            \
+        const __m256i u = _mm256_and_si256(x, m_df); /* letters: upper case; a non-letter never becomes a letter */          \
+        const __m256i letter = _mm256_and_si256(_mm256_cmpgt_epi8(u, c_40), _mm256_cmpgt_epi8(c_5b, u));                       \
+        const __m256i idx = _mm256_and_si256(u, m_0f);                                                                         \
+        const __m256i is_hi = _mm256_cmpeq_epi8(_mm256_and_si256(u, m_10), m_10);                                              \
+        out = _mm256_and_si256(_mm256_blendv_epi8(_mm256_shuffle_epi8(lut_lo, idx), _mm256_shuffle_epi8(lut_hi, idx), is_hi), \
+                               letter);                                                                                        \
+        any_t = _mm256_or_si256(any_t, _mm256_cmpeq_epi8(u, c_T)); /* 'T' / 't' (0x54 / 0x74): both fold to 0x54 */          \
+        any_u = _mm256_or_si256(any_u, _mm256_cmpeq_epi8(u, c_U));                                                             \
+        any_bad = _mm256_or_si256(any_bad, _mm256_cmpeq_epi8(out, zero));                                                      \
+    }
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        __m256i c0, c1;
+        HX_CODES32(src + i, c0);
+        HX_CODES32(src + i + 32, c1);
+        const __m256i a = _mm256_maddubs_epi16(c0, mult), b = _mm256_maddubs_epi16(c1, mult);
+        _mm256_storeu_si256((__m256i *)(dst + i / 2), _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xd8));
+    }
+#undef HX_CODES32
+    f |= (_mm256_movemask_epi8(any_t) ? HX_REC_HAS_T : 0u) | (_mm256_movemask_epi8(any_u) ? HX_REC_HAS_U : 0u) |
+         (_mm256_movemask_epi8(any_bad) ? HX_REC_NON_IUPAC : 0u);
+    return i;
+}
+#endif
+
+bool have_avx2() {
+#if defined(__x86_64__)
+    static const bool v = __builtin_cpu_supports("avx2");
+    return v;
+#else
+    return false;
+#endif
+}
+
+// Packs records [r0, r1) of the arena.  A thread owns the packed bytes whose LOW nibble lies in its base range
+// [offsets[r0], offsets[r1]): when the range ends on an odd base, the byte's high nibble is the first base of the next
+// record, read from the arena (zero past the end of the batch); when it starts on an odd base, that first nibble was
+// written by the owner of the byte before it.  Evidence bits are per record regardless of who writes the nibble.
+void pack_range(const uint8_t *arena, const uint64_t *offsets, uint32_t r0, uint32_t r1, uint64_t arena_end, uint8_t *packed,
+                uint8_t *rec_flags) {
+    const bool avx2 = have_avx2();
+    const PackTables &t = pack_tables();
+    bool skip_first = (offsets[r0] & 1) != 0;  // the range starts on an odd base: its nibble has an owner already
+    int carry = -1;                            // code of an even base whose partner (the next base) is still to come
+    uint64_t last = offsets[r0];
+    for (uint32_t r = r0; r < r1; ++r) {
+        uint64_t b = offsets[r];
+        const uint64_t e = offsets[r + 1];
+        uint32_t f = 0;
+        if (skip_first && b < e) {  // evidence only
+            f |= t.flag[arena[b]];
+            ++b;
+            skip_first = false;
+        }
+        if (carry >= 0 && b < e) {  // b is odd: completes the pending byte
+            packed[b / 2] = (uint8_t)(carry | (t.code[arena[b]] << 4));
+            f |= t.flag[arena[b]];
+            ++b;
+            carry = -1;
+        }
+#if defined(__x86_64__)
+        if (avx2 && b < e) b += pack_avx2(arena + b, (size_t)(e - b), packed + b / 2, f);  // b is even here
+#endif
+        for (; b + 2 <= e; b += 2) {
+            packed[b / 2] = (uint8_t)(t.code[arena[b]] | (t.code[arena[b + 1]] << 4));
+            f |= t.flag[arena[b]] | t.flag[arena[b + 1]];
+        }
+        if (b < e) {
+            carry = t.code[arena[b]];
+            f |= t.flag[arena[b]];
+        }
+        rec_flags[r] = (uint8_t)f;
+        last = e;
+    }
+    if (carry >= 0)  // odd tail: the high nibble is the base after the range (it belongs to the next record, if any)
+        packed[(last - 1) / 2] = (uint8_t)(carry | ((last < arena_end ? t.code[arena[last]] : 0) << 4));
+}
+
+}  // namespace
+
+extern "C" int hx_pack_records(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint8_t *packed,
+                               uint8_t *rec_flags, int n_threads) {
+    if (!offsets || (n_records && (!packed || !rec_flags))) return HX_ERR_ARG;
+    if (n_records == 0) return HX_OK;
+    if (offsets[n_records] < offsets[0] || (offsets[n_records] > offsets[0] && !arena)) return HX_ERR_ARG;
+    for (uint32_t r = 0; r < n_records; ++r)
+        if (offsets[r + 1] < offsets[r]) return HX_ERR_ARG;
+    const uint64_t end = offsets[n_records];
+    if (offsets[0] & 1) {  // the batch starts on an odd base: nobody before it owns that byte
+        const uint64_t b = offsets[0];
+        packed[b / 2] = (uint8_t)((b < end ? pack_tables().code[arena[b]] : 0) << 4);
+    }
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nt, (end - offsets[0]) / (1 << 20) + 1));
+    if (nt == 1) {
+        pack_range(arena, offsets, 0, n_records, end, packed, rec_flags);
+        return HX_OK;
+    }
+    std::vector<std::thread> th;
+    uint32_t r0 = 0;
+    for (int t = 0; t < nt; ++t) {  // record ranges of about equal bases
+        const uint64_t target = offsets[0] + (end - offsets[0]) * (uint64_t)(t + 1) / (uint64_t)nt;
+        uint32_t r1 = t + 1 == nt ? n_records : (uint32_t)(std::lower_bound(offsets + r0, offsets + n_records + 1, target) - offsets);
+        r1 = std::min(std::max(r1, r0), n_records);
+        if (r1 > r0) th.emplace_back(pack_range, arena, offsets, r0, r1, end, packed, rec_flags);
+        r0 = r1;
+    }
+    for (std::thread &t : th) t.join();
+    return HX_OK;
+}
 
 // ------------------------------------------------------------------------------------
 // byte sources: niffler 2.7.0 magic-number sniffing (call site utils.rs:148-154)

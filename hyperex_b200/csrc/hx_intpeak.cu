@@ -10,6 +10,7 @@
 //   10..13 the Myers step itself (variants 0..3 of hx_kernels.cu) on register operands:
 //            result is in word-steps, not instructions.
 #include "../../include/hyperex_b200.h"
+#include "../../include/hyperex_b200_bench.h"
 
 #include <cuda_runtime.h>
 #include <stdint.h>

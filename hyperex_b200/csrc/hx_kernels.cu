@@ -347,6 +347,19 @@ int hx_launch_classify(const uint8_t *arena, const uint64_t *offsets, uint64_t o
     return 3;
 }
 
+// packed text: the host packer's per-record evidence (HX_REC_* of include/hyperex_b200.h == HX_RAW_*) becomes rec_raw
+__global__ void __launch_bounds__(256) hx_flags_kernel(const uint8_t *__restrict__ flags, uint32_t *__restrict__ rec_raw,
+                                                       uint32_t n_records) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_records) rec_raw[r] = flags[r] & (HX_RAW_U | HX_RAW_T | HX_RAW_NONIUPAC);
+}
+
+int hx_launch_flags(const uint8_t *flags, uint32_t *rec_raw, uint32_t n_records, cudaStream_t st) {
+    if (n_records == 0) return 0;
+    hx_flags_kernel<<<(n_records + 255) / 256, 256, 0, st>>>(flags, rec_raw, n_records);
+    return 1;
+}
+
 // ------------------------------------------------------------------------------------
 // The Myers step (rust-bio 1.6.0 Myers::step).  The pattern is
 // TOP-ALIGNED in the word: bit (i + BITS - m) belongs to pattern position i, so `bound` is
@@ -459,6 +472,21 @@ __device__ __forceinline__ void hx_mbar_wait(uint32_t mbar, uint32_t parity) {
 }
 __device__ __forceinline__ void hx_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Packed text (NIB = true, hx_run_batch_packed): nibble i of the arena is base i; codes of include/hyperex_b200.h.
+// hx_code_byte gives the text byte a code stands for under the record's alphabet (code 4 is 'T' in a DNA record and 'U'
+// in an RNA record; code 0, "none of the 16 letters", is the null byte whose Peq rows are empty).
+__device__ __forceinline__ uint32_t hx_code_byte(uint32_t code, int rna) {
+    // "\0ACGTRYSWKMBDHVN" as four little-endian words
+    const uint32_t w = code < 4u ? 0x47434100u : code < 8u ? 0x53595254u : code < 12u ? 0x424d4b57u : 0x4e564844u;
+    const uint32_t b = (w >> (8u * (code & 3u))) & 0xffu;
+    return (rna && code == 4u) ? (uint32_t)'U' : b;
+}
+template <bool NIB>
+__device__ __forceinline__ uint32_t hx_text_byte(const uint8_t *__restrict__ text, uint64_t i, int rna) {
+    if constexpr (!NIB) return text[i];
+    return hx_code_byte((text[i >> 1] >> (4u * (uint32_t)(i & 1ull))) & 0xfu, rna);
+}
+
 // Suffix filter (LF = true): a primer longer than 32 symbols is scanned as the 32-bit automaton of its LAST 32
 // symbols.  An alignment of the whole primer ending at text position j with <= k edits contains an alignment of
 // that suffix ending at j with <= k edits, so {j : dist_suffix(j) <= k} is a superset of the primer's hits and a
@@ -466,12 +494,15 @@ __device__ __forceinline__ void hx_fence_proxy_async() { asm volatile("fence.pro
 // warp-synchronous drain: a fresh 64-bit automaton of the whole primer over the m + k text bytes that end at j
 // reports the exact distance whenever it is <= k, and never <= k otherwise (the window-restart property of
 // DESIGN.md §3.1; at the record start the scan is the full scan).  Returns the unbiased distance at `pos`.
-__device__ __forceinline__ uint32_t hx_verify_long(const uint8_t *__restrict__ rec_text, uint32_t pos,
-                                                   const uint64_t *__restrict__ vt, uint32_t m, uint32_t k) {
+template <bool NIB>
+__device__ __forceinline__ uint32_t hx_verify_long(const uint8_t *__restrict__ text, uint64_t rec0, uint32_t pos,
+                                                   const uint64_t *__restrict__ vt, uint32_t m, uint32_t k, int rna) {
+    // text + rec0 (bytes, or nibbles when NIB) is the record's first symbol
     const uint32_t span = m + k - 1u;
     uint64_t pv = ~0ull, mv = 0ull;
     int s = (int)m;
-    for (uint32_t i = pos >= span ? pos - span : 0u; i <= pos; ++i) hx_step(__ldg(vt + rec_text[i]), pv, mv, s);
+    for (uint32_t i = pos >= span ? pos - span : 0u; i <= pos; ++i)
+        hx_step(__ldg(vt + hx_text_byte<NIB>(text, rec0 + i, rna)), pv, mv, s);
     return (uint32_t)s;
 }
 
@@ -479,18 +510,27 @@ __device__ __forceinline__ uint32_t hx_verify_long(const uint8_t *__restrict__ r
 // 16 symbols, so a candidate end `pos` means text[pos - 15 .. pos] matches that suffix exactly.  The primer occurs at
 // pos iff its first m - 16 symbols also match text[pos - m + 1 .. pos - 16]: vt (the top-aligned 64-bit Peq table of the
 // whole primer) has bit (64 - m + i) set in row b iff symbol i accepts the text byte b.
-__device__ __forceinline__ bool hx_verify_exact(const uint8_t *__restrict__ rec_text, uint32_t pos,
-                                                const uint64_t *__restrict__ vt, uint32_t m) {
+template <bool NIB>
+__device__ __forceinline__ bool hx_verify_exact(const uint8_t *__restrict__ text, uint64_t rec0, uint32_t pos,
+                                                const uint64_t *__restrict__ vt, uint32_t m, int rna) {
     if (pos + 1u < m) return false;  // the primer does not fit before pos
-    const uint8_t *t = rec_text + (pos + 1u - m);
+    const uint64_t t0 = rec0 + (pos + 1u - m);
     uint64_t ok = 1;
-    for (uint32_t i = 0; i + 16u < m; ++i) ok &= __ldg(vt + t[i]) >> (64u - m + i);
+    for (uint32_t i = 0; i + 16u < m; ++i) ok &= __ldg(vt + hx_text_byte<NIB>(text, t0 + i, rna)) >> (64u - m + i);
     return ok & 1ull;
 }
 
-template <typename W, int NP, bool TMA, int KWM, bool LF, bool PK = false>
+template <typename W, int NP, bool TMA, int KWM, bool LF, bool PK = false, bool NIB = false>
 __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <= 16) ? 8 : ((sizeof(W) * (PK ? NP / 2 : NP) <= 32) ? 5 : 4)) * (128 / HX_THREADS))
     hx_myers_pair_kernel(const HxScanArgs a) {
+    // NIB: the arena holds 4-bit codes (hx_run_batch_packed); a 16-byte chunk is 32 symbols and the shared-memory
+    // Peq table has 16 rows, gathered from the 256-row table of the record alphabet
+    static_assert(!NIB || !TMA, "packed text: vector-load text path only");
+    constexpr int SYM_BITS = NIB ? 4 : 8;            // bits per text symbol
+    constexpr int SPW = 32 / SYM_BITS;               // symbols per 32-bit word
+    constexpr int CSH = NIB ? 5 : 4;                 // log2(symbols per 16-byte chunk)
+    constexpr uint32_t SPC = 1u << CSH;              // symbols per chunk
+    constexpr int NROWS = NIB ? 16 : 256;
     constexpr bool WM = KWM >= 0;           // small-k fast path: Wu-Manber / Shift-Or automata instead of Myers
     constexpr int NR = WM ? KWM + 1 : 1;    // error levels 0..k
     constexpr int WB = sizeof(W);
@@ -498,7 +538,8 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     static_assert(!PK || (KWM == 0 && sizeof(W) == 4 && NP % 2 == 0 && !TMA), "packing: -m 0, 32-bit words, whole words");
     constexpr int NW = PK ? NP / 2 : NP;    // automaton words a thread steps per text byte
     constexpr int STRIDE = hx_row_stride(NW, WB);
-    constexpr int TBYTES = 256 * STRIDE;
+    constexpr int TBYTES = 256 * STRIDE;   // one alphabet's table in global memory
+    constexpr int SBYTES = NROWS * STRIDE; // ... and what of it is staged in shared memory
     constexpr int SW = (NP + 3) / 4;  // score words of an event record
     constexpr int RW = 1 + SW;        // words of an event record: position + scores
     extern __shared__ __align__(16) uint8_t smem[];
@@ -507,7 +548,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     // per-thread text pipeline (TMA variant): two HX_CH-byte stages, each with its own mbarrier
     // (count 1): the thread arms the barrier with the byte count, issues one TMA bulk copy
     // global -> shared and later waits for the phase; no cross-thread synchronisation is involved.
-    uint8_t *const txt = smem + TBYTES;
+    uint8_t *const txt = smem + SBYTES;
     const uint32_t stage0 = hx_smem_u32(txt + (size_t)threadIdx.x * HX_CH);
     const uint32_t stage1 = stage0 + HX_THREADS * HX_CH;
     const uint32_t mbar0 = hx_smem_u32(txt + 2 * HX_THREADS * HX_CH + (size_t)threadIdx.x * 8);
@@ -582,11 +623,13 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     }
     const int dz = (int)a.two - 2;  // run-time zero: keeps the pairing state in local memory, not registers
 
-    const uint64_t a0 = have ? a.offsets[tl.rec] - a.off_base + tl.own_start - tl.warm : 0ull;
-    const uint64_t ab = a0 & ~15ull;
+    // (symbol indices; with packed text a symbol is a nibble and the arena address is index / 2)
+    const uint64_t rec0 = have ? a.offsets[tl.rec] - a.off_base : 0ull;
+    const uint64_t a0 = rec0 + tl.own_start - tl.warm;
+    const uint64_t ab = a0 & ~(uint64_t)(SPC - 1u);
     const uint32_t lead = (uint32_t)(a0 - ab);
-    const uint32_t pos0 = tl.own_start - tl.warm - lead;  // record position of chunk 0 byte 0 (may wrap)
-    const uint8_t *src = a.arena + ab;
+    const uint32_t pos0 = tl.own_start - tl.warm - lead;  // record position of chunk 0 symbol 0 (may wrap)
+    const uint8_t *src = a.arena + (NIB ? ab >> 1 : ab);
     // UB text bytes are processed per trip of the innermost loop (narrow groups amortise the loop
     // overhead over more bytes; wide groups keep the hot loop small).
 #ifndef HX_WM_UB24
@@ -599,6 +642,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
 #endif
     constexpr int UB = WM ? ((KWM == 0 || NP * (KWM + 1) <= 16) ? 4 : (NP * (KWM + 1) <= 24 ? HX_WM_UB24 : HX_WM_UBWIDE))
                           : (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
+    static_assert(SPW % UB == 0, "text symbols per trip must divide the word");
     uint32_t cnt = 0;  // records in this lane's queue
     const uint64_t pol = hx_policy_evict_first();
 
@@ -608,12 +652,18 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
         {
             const uint4 *tsrc = reinterpret_cast<const uint4 *>(PK ? a.tables_pk : WM ? a.tables_wm : a.tables) + (size_t)pass * (TBYTES / 16);
             uint4 *dst = reinterpret_cast<uint4 *>(smem);
-            for (int i = threadIdx.x; i < TBYTES / 16; i += HX_THREADS) dst[i] = __ldg(tsrc + i);
+            if constexpr (NIB) {  // row of code c = row of the byte the code stands for in this alphabet
+                constexpr int R16 = STRIDE / 16;
+                for (int i = threadIdx.x; i < SBYTES / 16; i += HX_THREADS)
+                    dst[i] = __ldg(tsrc + (size_t)hx_code_byte((uint32_t)(i / R16), pass) * R16 + i % R16);
+            } else {
+                for (int i = threadIdx.x; i < TBYTES / 16; i += HX_THREADS) dst[i] = __ldg(tsrc + i);
+            }
         }
         __syncthreads();
         const uint8_t *tab = smem;
         const uint32_t own_len = mine ? tl.own_len : 0u;  // a lane that is not scanning owns nothing
-        const uint32_t nchunks = mine ? (lead + tl.warm + tl.own_len + 15u) >> 4 : 0u;
+        const uint32_t nchunks = mine ? (lead + tl.warm + tl.own_len + (SPC - 1u)) >> CSH : 0u;
         const uint32_t nchunks_w = __reduce_max_sync(0xffffffffu, nchunks);
 
         const bool mask_lead = nchunks && tl.own_start == tl.warm && lead;
@@ -659,9 +709,9 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                 uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
                 for (int wi = 0; wi < 4; ++wi) {
-                    const int z = (int)lead - 4 * wi;  // bytes of this word to clear
-                    if (z >= 4) w[wi] = 0;
-                    else if (z > 0) w[wi] &= 0xffffffffu << (8 * z);
+                    const int z = (int)lead - SPW * wi;  // symbols of this word to clear
+                    if (z >= SPW) w[wi] = 0;
+                    else if (z > 0) w[wi] &= 0xffffffffu << (SYM_BITS * z);
                 }
                 cur = make_uint4(w[0], w[1], w[2], w[3]);
             }
@@ -672,11 +722,11 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                 cur.y = cur.z;
                 cur.z = cur.w;
 #pragma unroll 1
-                for (int b0 = 0; b0 < 4; b0 += UB) {
+                for (int b0 = 0; b0 < SPW; b0 += UB) {
 #pragma unroll
                     for (int bi = 0; bi < UB; ++bi) {
-                        const uint32_t byte = w & 0xffu;
-                        w >>= 8;
+                        const uint32_t byte = w & ((1u << SYM_BITS) - 1u);
+                        w >>= SYM_BITS;
                         HxRow<W, NW> row;
                         row.load(tab + byte * STRIDE);
                         int any = 0;
@@ -724,7 +774,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                         }
                         if (any < 0) {
                             // ---- rare: some pattern has dist <= k here; record the event ----
-                            const uint32_t pos = pos0 + (c << 4) + (wi << 2) + b0 + bi;
+                            const uint32_t pos = pos0 + (c << CSH) + wi * SPW + b0 + bi;
                             if (pos - tl.own_start < own_len) {
                                 if constexpr (PK) {
                                     // biased score of a half: -1 (a hit at distance 0) when its top bit is clear, else 0
@@ -779,22 +829,21 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                         if constexpr (LF && PK) {
                             // events of 16-symbol suffixes are candidates: the rest of the primer must match too
                             uint32_t lm = hm & g.pk_longmask;
-                            const uint8_t *rec_text = a.arena + (a.offsets[tl.rec] - a.off_base);
                             while (lm) {
                                 const int p = __ffs((int)lm) - 1;
                                 lm &= lm - 1;
-                                if (!hx_verify_exact(rec_text, pos, a.vtables + ((size_t)g.pk_vslot[p] * 2 + pass) * 256, g.mfull[p]))
+                                if (!hx_verify_exact<NIB>(a.arena, rec0, pos, a.vtables + ((size_t)g.pk_vslot[p] * 2 + pass) * 256,
+                                                          g.mfull[p], pass))
                                     hm &= ~(1u << p);
                             }
                         } else if constexpr (LF) {
                             // events of suffix-filtered patterns are candidates: exact distance of the whole primer
-                            uint32_t lm = hm & g.longmask;
-                            const uint8_t *rec_text = a.arena + (a.offsets[tl.rec] - a.off_base);  // only lanes with a tile hold events
+                            uint32_t lm = hm & g.longmask;  // (only lanes with a tile hold events)
                             while (lm) {
                                 const int p = __ffs((int)lm) - 1;
                                 lm &= lm - 1;
-                                const uint32_t d = hx_verify_long(rec_text, pos, a.vtables + ((size_t)g.vslot[p] * 2 + pass) * 256,
-                                                                  g.mfull[p], a.k);
+                                const uint32_t d = hx_verify_long<NIB>(a.arena, rec0, pos, a.vtables + ((size_t)g.vslot[p] * 2 + pass) * 256,
+                                                                       g.mfull[p], a.k, pass);
                                 const uint32_t sh = 8u * (p & 3);
                                 if (d > a.k) hm &= ~(1u << p);
 #pragma unroll
@@ -886,20 +935,20 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     }
 }
 
-template <typename W, int NP, bool TMA, int KWM, bool LF = false, bool PK = false>
+template <typename W, int NP, bool TMA, int KWM, bool LF = false, bool PK = false, bool NIB = false>
 static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
-    const int smem = hx_table_bytes(PK ? NP / 2 : NP, sizeof(W)) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
+    const int smem = hx_table_bytes(PK ? NP / 2 : NP, sizeof(W)) / (NIB ? 16 : 1) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
     // per (instantiation, device) once; contexts on different host threads may race here, so the flags are atomic
     // (setting the attribute twice is harmless, skipping it is not)
     static std::atomic<bool> attr_done[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
-        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
     }
     const uint32_t blocks = (tile_cap + HX_THREADS - 1) / HX_THREADS;
-    hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK><<<blocks, HX_THREADS, smem, st>>>(a);
+    hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB><<<blocks, HX_THREADS, smem, st>>>(a);
     return 1;
 }
 
@@ -907,6 +956,16 @@ template <typename W, int NP>
 struct HxDispatch {
     static int run(int np, bool lf, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
         if (np == NP) {
+            if (a.nib) {  // packed text: one variant per algorithm (the suffix-filter code path covers groups without one)
+                if constexpr (sizeof(W) == 4) {
+                    if (a.wm_k == 0) return hx_scan_launch_one<W, NP, false, 0, true, false, true>(a, cap, st);
+                    if (a.wm_k == 1) return hx_scan_launch_one<W, NP, false, 1, true, false, true>(a, cap, st);
+                    if (a.wm_k == 2) return hx_scan_launch_one<W, NP, false, 2, true, false, true>(a, cap, st);
+                    return hx_scan_launch_one<W, NP, false, -1, true, false, true>(a, cap, st);
+                } else {
+                    return hx_scan_launch_one<W, NP, false, -1, false, false, true>(a, cap, st);
+                }
+            }
             if constexpr (sizeof(W) == 4) {
                 if (lf) {  // group with suffix-filtered primers: vector-load text path only
                     if (a.wm_k == 0) return hx_scan_launch_one<W, NP, false, 0, true>(a, cap, st);
@@ -932,9 +991,11 @@ struct HxDispatch<W, 0> {
 // packed -m 0 scan: NW words = 2 * NW pattern halves
 template <int NW>
 static int hx_packed_dispatch(int nw, bool lf, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
-    if (nw == NW)
+    if (nw == NW) {
+        if (a.nib) return hx_scan_launch_one<uint32_t, 2 * NW, false, 0, true, true, true>(a, cap, st);
         return lf ? hx_scan_launch_one<uint32_t, 2 * NW, false, 0, true, true>(a, cap, st)
                   : hx_scan_launch_one<uint32_t, 2 * NW, false, 0, false, true>(a, cap, st);
+    }
     if constexpr (NW > 1) return hx_packed_dispatch<NW - 1>(nw, lf, a, cap, st);
     return -1;
 }

@@ -123,6 +123,27 @@ int hx_run_batch_text_stream(hx_ctx *ctx, const uint8_t *arena, const uint64_t *
                              const uint32_t *fa_tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
                              hx_text_sink sink, void *user, uint64_t *text_len, uint64_t *gff_len);
 
+/* ---- packed arena (BASELINE.json north_star: "2-bit/ASCII arena in pinned memory") ------------------------------
+ * Four bits per base, two bases per byte: nibble i of `packed` is base i of the arena (low nibble = even index), so
+ * the same offsets array describes both.  Codes: 0 = any byte outside the 16 letters, 1..15 = A C G T|U R Y S W K M B
+ * D H V N after to_ascii_uppercase (utils.rs:295).  'T' and 'U' share a code: a record that holds both is alphabet
+ * None and is skipped (utils.rs:225-226), so within a scanned record the code is unambiguous.  rec_flags[r] receives
+ * the evidence utils.rs:207-228 (sequence_type) needs, HX_REC_* below, so the device does not have to look at the
+ * text again to classify it.  Pure host code (AVX2 when the CPU has it), n_threads <= 0: all hardware threads.
+ * packed must hold offsets[n_records] / 2 + 1 bytes (it is indexed like the arena, from offset 0). */
+#define HX_REC_HAS_U 1u
+#define HX_REC_HAS_T 2u
+#define HX_REC_NON_IUPAC 4u
+int hx_pack_records(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint8_t *packed,
+                    uint8_t *rec_flags, int n_threads);
+
+/* hx_run_batch on a packed arena: half the bytes cross PCIe, the device scans nibbles and skips its own
+ * classification pass.  Same result table, bit for bit.  A byte outside the 16 letters can only ever match a primer
+ * symbol that is that very byte; a primer set with such symbols (anything but ACGTURYSWKMBDHVN) cannot be matched
+ * on packed text and the call fails with HX_ERR_STATE — use hx_run_batch. */
+int hx_run_batch_packed(hx_ctx *ctx, const uint8_t *packed, const uint8_t *rec_flags, const uint64_t *offsets,
+                        uint32_t n_records, hx_result *out);
+
 /* Same, for an arena already resident in device memory of the context's device `dev_slot`
  * (index into dev_ids).  d_arena must be 16-byte aligned and readable up to the next
  * multiple of 16 bytes past offsets[n_records]; d_out is device memory.  Work is enqueued on
@@ -171,12 +192,6 @@ uint64_t hx_launch_count(const hx_ctx *ctx);
  * on the launching stream since the last reset, and the number of launches timed; only
  * collected after hx_set_option(ctx, "time_kernels", 1). */
 int hx_kernel_time(hx_ctx *ctx, double *myers_ms, uint64_t *myers_launches, int reset);
-
-/* Measurement helper (hx_intpeak.cu): measured throughput, in 1e9 lane-operations per second, of one
- * integer instruction class on `device` (variant 0 LOP3, 1 IADD3, 2 SHF, 3 IMAD, 4 LOP3+IMAD 1:1,
- * 5 IMAD.HI, 6 LOP3+IADD3, 7 LOP3+IMAD 2:1) or of the bare Myers step on register operands (10-12:
- * step variants 0-2, in word-steps).  This is the integer-ALU roofline denominator of bench.py. */
-int hx_int_peak(int device, int variant, int iters, double *gops);
 
 /* ---- host helpers that shape the output bytes (pure host code) ---------------------- */
 /* utils.rs:207-228: 0 dna, 1 rna, 2 none */

@@ -33,6 +33,9 @@ def _run(ctx, arena, offsets, pairs, k, **opts):
     ctx.set_option("long_filter", opts.get("lf", 1))
     ctx.set_option("pack16", opts.get("pack", 1))
     ctx.set_primers(pairs, k)
+    if opts.get("packed"):  # 4-bit packed arena (hx_pack_records + hx_run_batch_packed)
+        pk, fl = hx.pack_records(arena, offsets, opts.get("pack_threads", 3))
+        return ctx.run_batch_packed(pk, fl, offsets)
     return ctx.run_batch(arena, offsets)
 
 
@@ -278,6 +281,52 @@ def test_pattern_packing_k0(ctx):
                 _cmp(_run(ctx, a, o, pairs, 0, tile_len=tile, single_max=tile, fast=1, pack=pack), ref, a, o, pairs, 0)
 
 
+# ---- packed arena (north_star "2-bit/ASCII arena"): 4-bit text through hx_pack_records + hx_run_batch_packed --------
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_packed_arena_equals_oracle(ctx, k):
+    """soft-masked, RNA, both strands, garbage bytes (code 0), windows; every scan algorithm on the nibble text path"""
+    a, o = hx_synth.gen_reads_mutated(1500, seed=440 + k, max_edits=3, revcomp_frac=0.4, lower_frac=0.3, rna_frac=0.15)
+    a = a.copy()
+    rng = np.random.default_rng(k)
+    for r in rng.integers(0, 1500, 60):       # garbage inside records: 'X', '-', a digit, a high byte
+        if o[r + 1] > o[r]:
+            a[int(rng.integers(int(o[r]), int(o[r + 1])))] = int(rng.choice([ord("X"), ord("-"), ord("7"), 200]))
+    pairs = hx.default_primers()
+    ref = O.run_batch(a, o, pairs, k, nthreads=8)
+    assert (ref["flags"] & 8).any() and (ref["flags"] & 16).any() and (ref["flags"] & 4).any()
+    for tile in ((0, 0), (4096, 4096), (96, 96)):
+        for fast in (0, 1):
+            _cmp(_run(ctx, a, o, pairs, k, tile_len=tile[0], single_max=tile[1], fast=fast, packed=1), ref, a, o, pairs, k)
+    _cmp(_run(ctx, a, o, pairs, k, packed=1, slab_bytes=50_000, pack_threads=8), ref, a, o, pairs, k)
+    # an arena whose first record starts at an odd offset
+    a2 = np.concatenate([np.frombuffer(b"GTGCCAG", np.uint8), a])
+    o2 = o + np.uint64(7)
+    _cmp(_run(ctx, a2, o2, pairs, k, packed=1, slab_bytes=30_000), ref, a2, o2, pairs, k)
+
+
+def test_packed_arena_contigs_long_primers_and_refusal(ctx):
+    a, o = hx_synth.gen_contigs(3, seed=45, length=300_000)
+    pairs = hx.default_primers()
+    ref = O.run_batch(a, o, pairs, 3, nthreads=8)
+    _cmp(_run(ctx, a, o, pairs, 3, packed=1), ref, a, o, pairs, 3)
+    _cmp(_run(ctx, a, o, pairs, 3, packed=1, tile_len=1024, single_max=1500), ref, a, o, pairs, 3)
+    # primers of 33..64 nt: suffix filter + verification read the text as nibbles too; 64-bit groups
+    a, o = hx_synth.gen_reads(300, seed=46)
+    pairs = hx_synth.gen_primer_pairs(12, seed=5, builtins=hx.default_primers())
+    assert max(len(x) for p in pairs for x in p) > 32
+    for k, lf in ((2, 1), (2, 0), (0, 1), (9, 1)):
+        ref = O.run_batch(a, o, pairs, k, nthreads=8)
+        _cmp(_run(ctx, a, o, pairs, k, packed=1, lf=lf), ref, a, o, pairs, k)
+    # a primer symbol outside ACGTURYSWKMBDHVN cannot be matched on packed text: refused, never approximated
+    ctx.set_primers([["ACGTXACGT", "GGCC"]], 0)
+    pk, fl = hx.pack_records(a, o)
+    with pytest.raises(hx.HyperexError) as e:
+        ctx.run_batch_packed(pk, fl, o)
+    assert e.value.code == -4 and "packed" in str(e.value)
+    ctx.set_primers([["acgtACGT", "GGCC"]], 0)   # lower-case primer symbols match nothing in either mode
+    _cmp(ctx.run_batch_packed(pk, fl, o), O.run_batch(a, o, [["acgtACGT", "GGCC"]], 0), a, o)
+
+
 # ---- edge cases the domain has -------------------------------------------------------------------------
 def test_edge_records(ctx):
     recs = [b"", b"A", b"T", b"U", b"X", b"acgtn", b"ACGU" * 10 + b"T", b"N" * 50,
@@ -295,6 +344,9 @@ def test_edge_records(ctx):
             _cmp(_run(ctx, a, o, pairs, k, tile_len=16, single_max=16, text_tma=tma), ref, a, o, pairs, k)
         _cmp(_run(ctx, a, o, pairs, k, fast=0), ref, a, o, pairs, k)
         _cmp(_run(ctx, a, o, pairs, k, tile_len=16, single_max=16, fast=0), ref, a, o, pairs, k)
+        for fast in (0, 1):
+            _cmp(_run(ctx, a, o, pairs, k, packed=1, fast=fast), ref, a, o, pairs, k)
+            _cmp(_run(ctx, a, o, pairs, k, tile_len=16, single_max=16, packed=1, fast=fast), ref, a, o, pairs, k)
 
 
 def test_k_at_least_pattern_length_every_position_hits(ctx):
@@ -351,6 +403,10 @@ def test_random_primer_sets_fuzz(ctx, seed):
     if k == 0:  # -m 0 pattern packing: off / forced for every group (degenerate 16-symbol suffixes included)
         for pack in (0, 2):
             _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=1, pack=pack), ref, a, o, pairs, k)
+    # the packed arena (4-bit text): Myers, the fast paths, suffix filters; slabs cut at unaligned record starts
+    for fast, lf, pack in ((0, 1, 1), (1, 2, 2), (1, 1, 1), (0, 0, 0)):
+        _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, lf=lf, pack=pack, packed=1,
+                  slab_bytes=int(rng.choice([1, 3000, 128 << 20]))), ref, a, o, pairs, k)
 
 
 def test_rna_records_use_rna_reverse_complement(ctx):

@@ -21,6 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "hyperex_b200.h")).read()
+    assert "hx_int_peak" not in header  # the microbenchmark is a bench-only export with its own header
+    header += open(os.path.join(ROOT, "include", "hyperex_b200_bench.h")).read()
     declared = set(re.findall(r"\b(hx_[a-z_0-9]+)\s*\(", header)) - {"hx_log_fn"}
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in sorted(declared):
@@ -253,3 +255,65 @@ def test_plan_groups_rejects_what_set_primers_rejects():
         with pytest.raises(hx.HyperexError) as e:
             hx.plan_groups(bad, 0)
         assert e.value.code == -1
+
+
+# ---- packed arena (hx_pack_records; pure host code) -----------------------------------------------------------
+def _pack_model(arena, offsets):
+    """numpy model of the packed layout: nibble i = code of base i, per-record evidence bits"""
+    code = np.zeros(256, np.uint8)
+    for c, ch in enumerate(hx.PACK_CODES):
+        if c:
+            code[ch] = c
+            code[ch | 0x20] = c
+    code[ord("U")] = code[ord("u")] = 4
+    end = int(offsets[-1])
+    full = np.zeros(end // 2 * 2 + 2, np.uint8)
+    lo = int(offsets[0])
+    full[lo:end] = code[arena[lo:end]]
+    packed = (full[0::2] | (full[1::2] << 4)).astype(np.uint8)
+    flags = np.zeros(len(offsets) - 1, np.uint8)
+    up = arena.copy()
+    low = (up >= ord("a")) & (up <= ord("z"))
+    up[low] -= 32
+    for r in range(len(offsets) - 1):
+        seg = up[int(offsets[r]):int(offsets[r + 1])]
+        f = (hx.REC_HAS_U if (seg == ord("U")).any() else 0) | (hx.REC_HAS_T if (seg == ord("T")).any() else 0)
+        if ((code[seg] == 0)).any():
+            f |= hx.REC_NON_IUPAC
+        flags[r] = f
+    return packed, flags
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_pack_records_equals_the_model(threads):
+    rng = np.random.default_rng(77 + threads)
+    alphabet = np.frombuffer(b"ACGT" * 12 + b"acgtnNRYSWKMBDHVUuXx-*.019 \t@[`{" + bytes([0, 1, 127, 128, 200, 255]), np.uint8)
+    for trial in range(60):
+        n = int(rng.integers(0, 50))
+        lens = rng.integers(0, 3000 if trial % 3 else 40, n)
+        if trial == 7:
+            lens = np.array([0, 0, 1, 0, 1, 1, 0, 2, 0], dtype=np.int64)   # empty records at odd offsets
+        if trial == 8:
+            lens = np.array([3_000_001, 5, 1_500_000], dtype=np.int64)    # several threads inside one record range
+        start = int(rng.integers(0, 5))
+        offsets = np.zeros(len(lens) + 1, np.uint64)
+        offsets[0] = start
+        offsets[1:] = start + np.cumsum(lens)
+        arena = alphabet[rng.integers(0, len(alphabet), int(offsets[-1]) + 3)]
+        if trial % 4 == 0:  # clean reads: mostly ACGT, the vector path's common case
+            arena = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(offsets[-1]) + 3)].copy()
+        packed, flags = hx.pack_records(arena, offsets, threads)
+        mp, mf = _pack_model(arena, offsets)
+        lo, hi = int(offsets[0]), int(offsets[-1])
+        # every nibble inside [offsets[0], offsets[-1]) is defined; compare nibble-wise
+        got = np.stack([packed & 15, packed >> 4], 1).reshape(-1)[lo:hi]
+        exp = np.stack([mp & 15, mp >> 4], 1).reshape(-1)[lo:hi]
+        assert (got == exp).all(), trial
+        assert (flags == mf).all(), trial
+    # the evidence reproduces sequence_type (utils.rs:207-228)
+    for s in ("ATCGATCGATCG", "ATCGMTGCAATCG", "AGCUUUGCA", "GUUUUAACCCAAM", "ATCXXXRMGU", "acgn", "ACGX", "", "T", "u"):
+        a = np.frombuffer(s.encode(), np.uint8)
+        _p, f = hx.pack_records(a, np.array([0, len(a)], np.uint64), 1)
+        u, t, bad = bool(f[0] & hx.REC_HAS_U), bool(f[0] & hx.REC_HAS_T), bool(f[0] & hx.REC_NON_IUPAC)
+        st = 1 if (u and not t) else 0 if (t and not u) else (2 if (u and t) else (2 if bad else 0))
+        assert st == O.sequence_type(s), s
