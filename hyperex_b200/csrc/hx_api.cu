@@ -381,12 +381,11 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
         a.vtables = D.d_vtables;
         // small-k fast path: identical hits, fewer ALU operations; 32-bit groups, vector-load text path
         // (measured: at -m 2 the fast path only pays for narrow groups; wide groups run out of registers)
-        a.wm_k = (ctx->opt_fast_small_k && !hg.word64 && (!ctx->opt_text_tma || nib) && (ctx->k <= 1 || (ctx->k == 2 && hg.np <= 8)))
-                     ? (int)ctx->k
-                     : -1;
-        // -m 0: two <= 16-symbol Shift-Or automata per word when the planner found the group packable
+        // ... and two <= 16-symbol automata per word when the planner found the group packable
+        const bool fast_ok = ctx->opt_fast_small_k && !hg.word64 && (!ctx->opt_text_tma || nib) && ctx->k <= 2;
         a.tables_pk = D.d_tables_pk ? D.d_tables_pk + hg.pk_table_off : nullptr;
-        a.packed = (a.wm_k == 0 && ctx->opt_pack16 && hg.packed && D.d_tables_pk) ? 1 : 0;
+        a.packed = (fast_ok && ctx->opt_pack16 && hg.packed && D.d_tables_pk) ? 1 : 0;
+        a.wm_k = (fast_ok && (a.packed || ctx->k <= 1 || hg.np <= 8)) ? (int)ctx->k : -1;
         a.group = D.d_groups + gi;
         a.sum_f = S.sum_f.p;
         a.sum_r = S.sum_r.p;
@@ -499,6 +498,28 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
         pp[i].is_long = (F[i].size() > 32 || R[i].size() > 32) && !(filter && suffix_ok(F[i]) && suffix_ok(rd));
         m_max = std::max<uint32_t>(m_max, (uint32_t)std::max(F[i].size(), R[i].size()));
     }
+    // Small-k pattern packing: on the Shift-Or / Wu-Manber path (-m 0..2) two automata of <= 16 symbols
+    // share a 32-bit word.  A primer longer than 16 symbols is scanned as its last 16 symbols and every candidate end is
+    // verified against the whole primer in the drain (exact match of the rest at -m 0, hx_verify_long otherwise), so the
+    // suffix must be specific enough: the expected rate of chance candidates on random ACGT text, 2^-bits(suffix) x
+    // (number of k-edit neighbourhoods of a 16-mer), stays below 1e-3 per position — every built-in primer qualifies at
+    // -m 0..2.  The whole 32-bit class packs or none of it does (pack16 = 2 skips the test: test-suite).
+    auto suffix16_ok = [&](const std::string &pat) {
+        if (pat.size() <= 16 || o.pack16 >= 2) return true;
+        double bits = 0;
+        for (size_t i = pat.size() - 16; i < pat.size(); ++i) {
+            const char c = pat[i];
+            const int deg = strchr("RYSWKM", c) ? 2 : strchr("BDHV", c) ? 3 : c == 'N' ? 4 : 1;
+            bits += std::log2(4.0 / deg);
+        }
+        double nb = k ? 20.0 : 1.0;  // indels on top of substitutions
+        for (int i = 0; i < (int)k; ++i) nb *= (16.0 - i) / (i + 1) * 3.0;
+        return bits >= std::log2(nb / 1e-3);
+    };
+    bool pack_class = k <= 2 && o.fast_small_k && o.pack16;
+    for (uint32_t i = 0; i < n_pairs && pack_class; ++i)
+        if (!pp[i].is_long)
+            pack_class = suffix16_ok(pp[i].f.dna) && suffix16_ok(pp[i].f.rna) && suffix16_ok(pp[i].r.dna) && suffix16_ok(pp[i].r.rna);
     // Grouping, short (32-bit words) and long (64-bit words) pairs separately.  Pairs that share a pattern (27F and
     // 1492Rmod serve three built-in regions each) should land in the same group, or the shared automaton is stepped
     // once per group: pairs are first joined into the connected components of the "shares a pattern" relation, whole
@@ -520,7 +541,8 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
         int np_max = want_long ? HX_MAX_NP64 : HX_MAX_NP32;
         // -m 2 on the Wu-Manber path: three bit-vectors per automaton, so only groups of <= 8 patterns stay in
         // registers (measured per 1.5 Gbases: config 5 108.7 -> 84.8 ms, built-in regions as 8 + 7 automata 14.3 -> 11.4 ms)
-        if (!want_long && k == 2 && o.fast_small_k) np_max = 8;
+        // (packed, 16 automata are 8 words: the same 24 registers of state)
+        if (!want_long && k == 2 && o.fast_small_k && !pack_class) np_max = 8;
         if (o.group_np_max >= 2) np_max = std::min<int>(np_max, (int)o.group_np_max);
         // connected components over the pairs of this class (union-find on pattern ids)
         std::vector<int> parent(pat_id.size());
@@ -664,30 +686,12 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
             }
         }
     }
-    // -m 0 pattern packing: a 32-bit group whose every pattern is either <= 16 symbols or has a 16-symbol
-    // suffix specific enough to serve as a filter gets a second table, two 16-bit Shift-Or automata per word.  The scan
-    // then steps half as many words (and loads half as many Peq bytes) per text byte; a pattern longer than 16 symbols
-    // reports candidates, verified against the rest of the primer in the drain (hx_verify_exact).  "Specific enough":
-    // the expected rate of chance candidates on random ACGT text, 2^-bits(suffix), stays below 2^-12 per position —
-    // every built-in primer has 24 bits or more.  pack16 = 2 skips the test (test-suite).
+    // packed tables of the 32-bit groups (see pack_class above): two 16-bit automata per word, pattern 2j in the low half
     P.blob_pk.clear();
-    if (k == 0 && o.fast_small_k && o.pack16) {
-        auto suffix16_ok = [&](const std::string &pat) {
-            if (pat.size() <= 16 || o.pack16 >= 2) return true;
-            double bits = 0;
-            for (size_t i = pat.size() - 16; i < pat.size(); ++i) {
-                const char c = pat[i];
-                const int deg = strchr("RYSWKM", c) ? 2 : strchr("BDHV", c) ? 3 : c == 'N' ? 4 : 1;
-                bits += std::log2(4.0 / deg);
-            }
-            return bits >= 12.0;
-        };
+    if (pack_class) {
         for (size_t gi = 0; gi < groups.size(); ++gi) {
             HxGroup &g = groups[gi];
             if (g.word64) continue;
-            bool ok = true;
-            for (int p = 0; p < g.np && ok; ++p) ok = suffix16_ok(gpats[gi][p].dna) && suffix16_ok(gpats[gi][p].rna);
-            if (!ok) continue;
             g.packed = 1;
             g.pk_longmask = 0;
             const int nw = (g.np + 1) / 2, stride = hx_row_stride(nw, 4);

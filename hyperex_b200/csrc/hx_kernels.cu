@@ -496,10 +496,13 @@ __device__ __forceinline__ uint32_t hx_text_byte(const uint8_t *__restrict__ tex
 // DESIGN.md §3.1; at the record start the scan is the full scan).  Returns the unbiased distance at `pos`.
 template <bool NIB>
 __device__ __forceinline__ uint32_t hx_verify_long(const uint8_t *__restrict__ text, uint64_t rec0, uint32_t pos,
-                                                   const uint64_t *__restrict__ vt, uint32_t m, uint32_t k, int rna) {
-    // text + rec0 (bytes, or nibbles when NIB) is the record's first symbol
+                                                   const uint64_t *__restrict__ vt, uint32_t m, uint32_t k, int rna,
+                                                   uint64_t &pv, uint64_t &mv) {
+    // text + rec0 (bytes, or nibbles when NIB) is the record's first symbol; pv / mv leave with the automaton's state
+    // after `pos`, so that the caller can continue it to pos + 1
     const uint32_t span = m + k - 1u;
-    uint64_t pv = ~0ull, mv = 0ull;
+    pv = ~0ull;
+    mv = 0ull;
     int s = (int)m;
     for (uint32_t i = pos >= span ? pos - span : 0u; i <= pos; ++i)
         hx_step(__ldg(vt + hx_text_byte<NIB>(text, rec0 + i, rna)), pv, mv, s);
@@ -535,7 +538,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     constexpr int NR = WM ? KWM + 1 : 1;    // error levels 0..k
     constexpr int WB = sizeof(W);
     // PK: NP is the (even) number of pattern halves; NW words hold them, two 16-bit automata each
-    static_assert(!PK || (KWM == 0 && sizeof(W) == 4 && NP % 2 == 0 && !TMA), "packing: -m 0, 32-bit words, whole words");
+    static_assert(!PK || (KWM >= 0 && sizeof(W) == 4 && NP % 2 == 0 && !TMA), "packing: Shift-Or / Wu-Manber, 32-bit words, whole words");
     constexpr int NW = PK ? NP / 2 : NP;    // automaton words a thread steps per text byte
     constexpr int STRIDE = hx_row_stride(NW, WB);
     constexpr int TBYTES = 256 * STRIDE;   // one alphabet's table in global memory
@@ -587,11 +590,16 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     if constexpr (PK) {
         // a half starts with its pattern bits (the top m of the 16) set and the unused low bits clear; a half without
         // a pattern (odd pattern count) stays all-ones: its table entries are all-ones too, it never reports
+        // (level d starts with its d lowest pattern bits cleared: a prefix of length <= d matches with <= d deletions)
 #pragma unroll
         for (int j = 0; j < NW; ++j) {
-            const uint32_t lo = 2 * j < g.np ? (0xffffu << (16 - g.pk_m[2 * j])) & 0xffffu : 0xffffu;
-            const uint32_t hi = 2 * j + 1 < g.np ? (0xffffu << (16 - g.pk_m[2 * j + 1])) & 0xffffu : 0xffffu;
-            rv[0][j] = (W)(lo | (hi << 16));
+#pragma unroll
+            for (int d = 0; d < NR; ++d) {
+                const int ml = g.pk_m[2 * j], mh = g.pk_m[2 * j + 1];
+                const uint32_t lo = 2 * j < g.np ? (d < ml ? (0xffffu << (16 - ml + d)) & 0xffffu : 0u) : 0xffffu;
+                const uint32_t hi = 2 * j + 1 < g.np ? (d < mh ? (0xffffu << (16 - mh + d)) & 0xffffu : 0u) : 0xffffu;
+                rv[d][j] = (W)(lo | (hi << 16));
+            }
             pv[j] = 0;
             mv[j] = 0;
         }
@@ -640,7 +648,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
 #ifndef HX_WM_UBWIDE
 #define HX_WM_UBWIDE 2  // ... and beyond 24 (15 automata at -m 1): 2 is 7 % faster than 1 (2.62 -> 2.44 ms per 0.45 Gbases)
 #endif
-    constexpr int UB = WM ? ((KWM == 0 || NP * (KWM + 1) <= 16) ? 4 : (NP * (KWM + 1) <= 24 ? HX_WM_UB24 : HX_WM_UBWIDE))
+    constexpr int UB = WM ? ((KWM == 0 || NW * (KWM + 1) <= 16) ? 4 : (NW * (KWM + 1) <= 24 ? HX_WM_UB24 : HX_WM_UBWIDE))
                           : (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
     static_assert(SPW % UB == 0, "text symbols per trip must divide the word");
     uint32_t cnt = 0;  // records in this lane's queue
@@ -734,11 +742,27 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                             // two Shift-Or automata per word: R' = ((R << 1) & fence) | neq.  Shift-Or has no carries,
                             // so the only coupling of the halves is the bit the shift moves from the low half's top
                             // into the high half's bottom; the fence clears it (one LOP3 with the OR).
+                            // The Wu-Manber levels (see below) use the same fenced shift for R(d-1) << 1; the other
+                            // shifted terms are ANDed with it, which clears their stray bit as well.
+                            constexpr W FENCE = (W)0xfffefffful;
                             W acc = ~(W)0;
 #pragma unroll
                             for (int j = 0; j < NW; ++j) {
-                                rv[0][j] = ((rv[0][j] << 1) & (W)0xfffefffful) | row.eq(j);
-                                acc &= rv[0][j];
+                                const W n = row.eq(j);
+                                W prev_old = rv[0][j], prev_old_s = (prev_old << 1) & FENCE;
+                                W prev_new = prev_old_s | n;
+                                rv[0][j] = prev_new;
+#pragma unroll
+                                for (int d = 1; d < NR; ++d) {
+                                    const W cur_old = rv[d][j];
+                                    const W cur_old_s = d + 1 < NR ? (W)((cur_old << 1) & FENCE) : (W)(cur_old << 1);
+                                    const W cur_new = ((cur_old_s | n) & prev_old_s) & prev_old & (prev_new << 1);
+                                    rv[d][j] = cur_new;
+                                    prev_old = cur_old;
+                                    prev_old_s = cur_old_s;
+                                    prev_new = cur_new;
+                                }
+                                acc &= prev_new;
                             }
                             any = (~acc & (W)0x80008000ul) ? -1 : 0;
                         } else if constexpr (WM) {
@@ -777,10 +801,14 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                             const uint32_t pos = pos0 + (c << CSH) + wi * SPW + b0 + bi;
                             if (pos - tl.own_start < own_len) {
                                 if constexpr (PK) {
-                                    // biased score of a half: -1 (a hit at distance 0) when its top bit is clear, else 0
+                                    // biased score of a half: the number of levels whose top bit is set, minus k + 1
 #pragma unroll
-                                    for (int p = 0; p < NP; ++p)
-                                        s[p] = (int)((rv[0][p >> 1] >> ((p & 1) ? 31 : 15)) & 1u) - 1;
+                                    for (int p = 0; p < NP; ++p) {
+                                        int sp = -bias;
+#pragma unroll
+                                        for (int d = 0; d < NR; ++d) sp += (int)((rv[d][p >> 1] >> ((p & 1) ? 31 : 15)) & 1u);
+                                        s[p] = sp;
+                                    }
                                 } else if constexpr (WM) {
                                     // Exact distance of a hit = the lowest level whose top bit is 0.  "<= d errors"
                                     // implies "<= d + 1 errors", so the top bits are monotone over the levels and that
@@ -815,6 +843,13 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                 // ---- warp-synchronous drain: all lanes process their queued events together ----
                 const bool last_word = (c + 1 == nchunks_w) && wi == 3;
                 if (__any_sync(0xffffffffu, cnt > HX_QCAP - 4 || (last_word && cnt))) {
+                    // verification automaton of the last candidate (LF): a true site of a filtered primer yields up
+                    // to 2k + 1 candidates at consecutive ends, and the next one costs a single step when the
+                    // automaton that verified this one is kept (a longer warm-up leaves the distance exact)
+                    uint64_t v_pv = 0, v_mv = 0;
+                    int v_s = 0, v_pat = -1;
+                    uint32_t v_pos = 0;
+                    (void)v_pv; (void)v_mv; (void)v_s; (void)v_pat; (void)v_pos;
                     for (uint32_t i = 0; i < cnt; ++i) {
                         const uint32_t *r = queue[i];
                         const uint32_t pos = r[0];
@@ -826,7 +861,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                             const uint32_t neg = sw[j] & 0x80808080u;
                             hm |= (((neg >> 7) & 1u) | ((neg >> 14) & 2u) | ((neg >> 21) & 4u) | ((neg >> 28) & 8u)) << (4 * j);
                         }
-                        if constexpr (LF && PK) {
+                        if constexpr (LF && PK && KWM == 0) {
                             // events of 16-symbol suffixes are candidates: the rest of the primer must match too
                             uint32_t lm = hm & g.pk_longmask;
                             while (lm) {
@@ -838,12 +873,21 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                             }
                         } else if constexpr (LF) {
                             // events of suffix-filtered patterns are candidates: exact distance of the whole primer
-                            uint32_t lm = hm & g.longmask;  // (only lanes with a tile hold events)
+                            uint32_t lm = hm & (PK ? g.pk_longmask : g.longmask);  // (only lanes with a tile hold events)
                             while (lm) {
                                 const int p = __ffs((int)lm) - 1;
                                 lm &= lm - 1;
-                                const uint32_t d = hx_verify_long<NIB>(a.arena, rec0, pos, a.vtables + ((size_t)g.vslot[p] * 2 + pass) * 256,
-                                                                       g.mfull[p], a.k, pass);
+                                const uint64_t *vt = a.vtables + ((size_t)(PK ? g.pk_vslot[p] : g.vslot[p]) * 2 + pass) * 256;
+                                uint32_t d;
+                                if (v_pat == p && v_pos + 1u == pos) {
+                                    hx_step(__ldg(vt + hx_text_byte<NIB>(a.arena, rec0 + pos, pass)), v_pv, v_mv, v_s);
+                                    d = (uint32_t)v_s;
+                                } else {
+                                    d = hx_verify_long<NIB>(a.arena, rec0, pos, vt, g.mfull[p], a.k, pass, v_pv, v_mv);
+                                    v_s = (int)d;
+                                    v_pat = p;
+                                }
+                                v_pos = pos;
                                 const uint32_t sh = 8u * (p & 3);
                                 if (d > a.k) hm &= ~(1u << p);
 #pragma unroll
@@ -988,22 +1032,27 @@ struct HxDispatch<W, 0> {
     static int run(int, bool, const HxScanArgs &, uint32_t, cudaStream_t) { return -1; }
 };
 
-// packed -m 0 scan: NW words = 2 * NW pattern halves
-template <int NW>
+// packed small-k scan: NW words = 2 * NW pattern halves
+template <int NW, int K>
 static int hx_packed_dispatch(int nw, bool lf, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
     if (nw == NW) {
-        if (a.nib) return hx_scan_launch_one<uint32_t, 2 * NW, false, 0, true, true, true>(a, cap, st);
-        return lf ? hx_scan_launch_one<uint32_t, 2 * NW, false, 0, true, true>(a, cap, st)
-                  : hx_scan_launch_one<uint32_t, 2 * NW, false, 0, false, true>(a, cap, st);
+        if (a.nib) return hx_scan_launch_one<uint32_t, 2 * NW, false, K, true, true, true>(a, cap, st);
+        return lf ? hx_scan_launch_one<uint32_t, 2 * NW, false, K, true, true>(a, cap, st)
+                  : hx_scan_launch_one<uint32_t, 2 * NW, false, K, false, true>(a, cap, st);
     }
-    if constexpr (NW > 1) return hx_packed_dispatch<NW - 1>(nw, lf, a, cap, st);
+    if constexpr (NW > 1) return hx_packed_dispatch<NW - 1, K>(nw, lf, a, cap, st);
     return -1;
 }
 
 int hx_launch_scan(const HxScanArgs &a, const HxGroup &hg, uint32_t tile_cap, cudaStream_t st) {
     if (tile_cap == 0) return 0;
-    if (a.packed && hg.packed && !hg.word64)
-        return hx_packed_dispatch<HX_MAX_NP32 / 2>((hg.np + 1) / 2, hg.pk_longmask != 0u, a, tile_cap, st);
+    if (a.packed && hg.packed && !hg.word64) {
+        const int nw = (hg.np + 1) / 2;
+        const bool lf = hg.pk_longmask != 0u;
+        if (a.wm_k == 0) return hx_packed_dispatch<HX_MAX_NP32 / 2, 0>(nw, lf, a, tile_cap, st);
+        if (a.wm_k == 1) return hx_packed_dispatch<HX_MAX_NP32 / 2, 1>(nw, lf, a, tile_cap, st);
+        if (a.wm_k == 2) return hx_packed_dispatch<HX_MAX_NP32 / 2, 2>(nw, lf, a, tile_cap, st);
+    }
     if (hg.word64) return HxDispatch<uint64_t, HX_MAX_NP64>::run(hg.np, false, a, tile_cap, st);
     return HxDispatch<uint32_t, HX_MAX_NP32>::run(hg.np, hg.longmask != 0u, a, tile_cap, st);
 }

@@ -134,7 +134,9 @@ def test_c2_reads_all_regions_k0(ctx, fast, pack):
 def test_c3_degenerate_primers_both_strands(ctx, k, fast):
     a, o = hx_synth.gen_reads_mutated(1500, seed=30 + k, max_edits=3, revcomp_frac=0.5)
     pairs = [hx.region_to_primer("v3v4"), hx.region_to_primer("v4v5")]
-    _cmp(_run(ctx, a, o, pairs, k, fast=fast), O.run_batch(a, o, pairs, k, nthreads=8), a, o, pairs, k)
+    ref = O.run_batch(a, o, pairs, k, nthreads=8)
+    for pack in ((1, 0) if fast else (1,)):
+        _cmp(_run(ctx, a, o, pairs, k, fast=fast, pack=pack), ref, a, o, pairs, k)
 
 
 @pytest.mark.parametrize("k", [0, 1, 2])
@@ -144,7 +146,8 @@ def test_all_regions_mutated_small_k_fast_path(ctx, k):
     pairs = hx.default_primers()
     ref = O.run_batch(a, o, pairs, k, nthreads=8)
     for tile in ((4096, 4096), (128, 128)):
-        _cmp(_run(ctx, a, o, pairs, k, tile_len=tile[0], single_max=tile[1], fast=1), ref, a, o, pairs, k)
+        for pack in (1, 0):  # two 16-symbol suffix automata per word + verification (library default) / one per word
+            _cmp(_run(ctx, a, o, pairs, k, tile_len=tile[0], single_max=tile[1], fast=1, pack=pack), ref, a, o, pairs, k)
 
 
 @pytest.mark.parametrize("text_tma", [0, 1])
@@ -236,11 +239,12 @@ def test_long_primers_suffix_filter(ctx, k):
         assert ctx.group_info()[2] == 0 and n64 > 0   # the filter leaves no 64-bit automaton to step
 
 
-def test_pattern_packing_k0(ctx):
-    """-m 0, two Shift-Or automata of <= 16 symbols per word: primers of 1..64 nt around the 16-symbol boundary, sites
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_pattern_packing(ctx, k):
+    """-m 0..2, two Shift-Or / Wu-Manber automata of <= 16 symbols per word: primers of 1..64 nt around the 16-symbol boundary, sites
     at record starts / ends, sites that match the 16-symbol suffix but not the rest of the primer (candidates the
     verification must reject), degenerate suffixes, odd and even pattern counts, RNA and soft-masked records, windows"""
-    rng = np.random.default_rng(1616)
+    rng = np.random.default_rng(1616 + k)
     letters = "ACGT" * 6 + "MRWSYKVHDBN"
     def prim(n, alphabet=letters):
         return "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), n))
@@ -261,8 +265,8 @@ def test_pattern_packing_k0(ctx):
                 if rng.random() < 0.4 and len(sb) > 16:       # damage the part in front of the 16-symbol suffix
                     j = int(rng.integers(0, len(sb) - 16))
                     sb[j] = ord("ACGT"[("ACGT".index(chr(sb[j])) + 1) % 4]) if chr(sb[j]) in "ACGT" else ord("A")
-                elif rng.random() < 0.2:
-                    sb = hx_synth._edit(rng, sb, 1)
+                elif rng.random() < 0.4:
+                    sb = hx_synth._edit(rng, sb, int(rng.integers(1, k + 3)))
                 if L >= len(sb):
                     p = int(rng.choice([0, L - len(sb), int(rng.integers(0, L - len(sb) + 1))]))
                     seq[p:p + len(sb)] = sb
@@ -274,11 +278,12 @@ def test_pattern_packing_k0(ctx):
                 a1[lo:hi] |= 0x20
             recs.append(a1)
         a, o = hx_synth.pack(recs)
-        ref = O.run_batch(a, o, pairs, 0, nthreads=8)
+        ref = O.run_batch(a, o, pairs, k, nthreads=8)
         assert (ref["flags"] & 4).any()
         for tile in (0, 64, 4096):
             for pack in (2, 1, 0):
-                _cmp(_run(ctx, a, o, pairs, 0, tile_len=tile, single_max=tile, fast=1, pack=pack), ref, a, o, pairs, 0)
+                _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=1, pack=pack), ref, a, o, pairs, k)
+            _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=1, pack=2, packed=1), ref, a, o, pairs, k)
 
 
 # ---- packed arena (north_star "2-bit/ASCII arena"): 4-bit text through hx_pack_records + hx_run_batch_packed --------
@@ -291,6 +296,15 @@ def test_packed_arena_equals_oracle(ctx, k):
     for r in rng.integers(0, 1500, 60):       # garbage inside records: 'X', '-', a digit, a high byte
         if o[r + 1] > o[r]:
             a[int(rng.integers(int(o[r]), int(o[r + 1])))] = int(rng.choice([ord("X"), ord("-"), ord("7"), 200]))
+    for r in rng.integers(0, 1500, 40):       # 'U' in a DNA record / garbage in a record without T or U: alphabet None
+        if o[r + 1] > o[r] + 10:
+            a[int(o[r]) + 5] = ord("U") if r % 2 else ord("u")
+    for r in rng.integers(0, 1500, 20):
+        seg = a[int(o[r]):int(o[r + 1])]
+        seg[(seg | 0x20) == ord("t")] = ord("A")
+        seg[(seg | 0x20) == ord("u")] = ord("A")
+        if len(seg):
+            seg[len(seg) // 2] = ord("X") if r % 2 else ord("N")
     pairs = hx.default_primers()
     ref = O.run_batch(a, o, pairs, k, nthreads=8)
     assert (ref["flags"] & 8).any() and (ref["flags"] & 16).any() and (ref["flags"] & 4).any()
@@ -400,7 +414,7 @@ def test_random_primer_sets_fuzz(ctx, seed):
     for fast, tma, lf in ((0, 0, 1), (1, 0, 2), (0, 1, 1), (0, 0, 0)):
         _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, text_tma=tma, lf=lf), ref, a, o, pairs,
              k)
-    if k == 0:  # -m 0 pattern packing: off / forced for every group (degenerate 16-symbol suffixes included)
+    if k <= 2:  # small-k pattern packing: off / forced for every group (degenerate 16-symbol suffixes included)
         for pack in (0, 2):
             _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=1, pack=pack), ref, a, o, pairs, k)
     # the packed arena (4-bit text): Myers, the fast paths, suffix filters; slabs cut at unaligned record starts
