@@ -494,18 +494,25 @@ __device__ __forceinline__ uint32_t hx_text_byte(const uint8_t *__restrict__ tex
 // warp-synchronous drain: a fresh 64-bit automaton of the whole primer over the m + k text bytes that end at j
 // reports the exact distance whenever it is <= k, and never <= k otherwise (the window-restart property of
 // DESIGN.md §3.1; at the record start the scan is the full scan).  Returns the unbiased distance at `pos`.
-template <bool NIB>
+// VW = uint32_t when the whole primer has <= 32 symbols: the upper half of its top-aligned 64-bit Peq word is then the
+// top-aligned 32-bit word, and the automaton costs half the instructions.
+template <typename VW>
+__device__ __forceinline__ VW hx_vrow(const uint64_t *__restrict__ vt, uint32_t byte) {
+    if constexpr (sizeof(VW) == 8) return __ldg(vt + byte);
+    else return __ldg(reinterpret_cast<const uint32_t *>(vt) + 2u * byte + 1u);
+}
+template <bool NIB, typename VW>
 __device__ __forceinline__ uint32_t hx_verify_long(const uint8_t *__restrict__ text, uint64_t rec0, uint32_t pos,
                                                    const uint64_t *__restrict__ vt, uint32_t m, uint32_t k, int rna,
-                                                   uint64_t &pv, uint64_t &mv) {
+                                                   VW &pv, VW &mv) {
     // text + rec0 (bytes, or nibbles when NIB) is the record's first symbol; pv / mv leave with the automaton's state
     // after `pos`, so that the caller can continue it to pos + 1
     const uint32_t span = m + k - 1u;
-    pv = ~0ull;
-    mv = 0ull;
+    pv = ~(VW)0;
+    mv = 0;
     int s = (int)m;
     for (uint32_t i = pos >= span ? pos - span : 0u; i <= pos; ++i)
-        hx_step(__ldg(vt + hx_text_byte<NIB>(text, rec0 + i, rna)), pv, mv, s);
+        hx_step(hx_vrow<VW>(vt, hx_text_byte<NIB>(text, rec0 + i, rna)), pv, mv, s);
     return (uint32_t)s;
 }
 
@@ -543,11 +550,16 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     constexpr int STRIDE = hx_row_stride(NW, WB);
     constexpr int TBYTES = 256 * STRIDE;   // one alphabet's table in global memory
     constexpr int SBYTES = NROWS * STRIDE; // ... and what of it is staged in shared memory
-    constexpr int SW = (NP + 3) / 4;  // score words of an event record
-    constexpr int RW = 1 + SW;        // words of an event record: position + scores
+    constexpr int SW = (NP + 3) / 4;  // score words of an event: the NP biased scores as bytes
+    // words of a queued event record: position + scores; packed automata queue the level bits of their words instead
+    // (cheaper to produce on the divergent hit path; the warp-synchronous drain turns them into scores)
+    constexpr int RW = PK ? 1 + NW : 1 + SW;
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ HxGroup g;
-    uint32_t queue[HX_QCAP][RW];  // event records; indexed dynamically => local memory
+    // A word of text can add one event per symbol before the queue is looked at again (4 bytes, or 8 nibbles of packed
+    // text): the drain starts while a whole word still fits.
+    constexpr int QCAP = NIB ? HX_QCAP + 8 : HX_QCAP;
+    uint32_t queue[QCAP][RW];  // event records; indexed dynamically => local memory
     // per-thread text pipeline (TMA variant): two HX_CH-byte stages, each with its own mbarrier
     // (count 1): the thread arms the barrier with the byte count, issues one TMA bulk copy
     // global -> shared and later waits for the phase; no cross-thread synchronisation is involved.
@@ -801,14 +813,20 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                             const uint32_t pos = pos0 + (c << CSH) + wi * SPW + b0 + bi;
                             if (pos - tl.own_start < own_len) {
                                 if constexpr (PK) {
-                                    // biased score of a half: the number of levels whose top bit is set, minus k + 1
+                                    // This path runs once per hit position and lane with the other 31 lanes idle (a read
+                                    // with 15 primer sites makes a warp take it for a third of its text bytes), so it only
+                                    // queues what the drain needs: per word, the top bit of both halves at every level,
+                                    // level d at bit 31 - d / 15 - d.
+                                    uint32_t *r = queue[cnt];
+                                    r[0] = pos;
 #pragma unroll
-                                    for (int p = 0; p < NP; ++p) {
-                                        int sp = -bias;
+                                    for (int j = 0; j < NW; ++j) {
+                                        uint32_t lv = NR == 1 ? (uint32_t)rv[0][j] : (uint32_t)rv[0][j] & 0x80008000u;
 #pragma unroll
-                                        for (int d = 0; d < NR; ++d) sp += (int)((rv[d][p >> 1] >> ((p & 1) ? 31 : 15)) & 1u);
-                                        s[p] = sp;
+                                        for (int d = 1; d < NR; ++d) lv |= ((uint32_t)rv[d][j] & 0x80008000u) >> d;
+                                        r[1 + j] = lv;
                                     }
+                                    ++cnt;
                                 } else if constexpr (WM) {
                                     // Exact distance of a hit = the lowest level whose top bit is 0.  "<= d errors"
                                     // implies "<= d + 1 errors", so the top bits are monotone over the levels and that
@@ -824,6 +842,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                                         s[p] = sp;
                                     }
                                 }
+                                if constexpr (!PK) {
                                 uint32_t *r = queue[cnt];
                                 r[0] = pos;
 #pragma unroll
@@ -836,13 +855,14 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                                         __byte_perm(__byte_perm(b0_, b1_, 0x0040), __byte_perm(b2_, b3_, 0x0040), 0x5410);
                                 }
                                 ++cnt;
+                                }
                             }
                         }
                     }
                 }
                 // ---- warp-synchronous drain: all lanes process their queued events together ----
                 const bool last_word = (c + 1 == nchunks_w) && wi == 3;
-                if (__any_sync(0xffffffffu, cnt > HX_QCAP - 4 || (last_word && cnt))) {
+                if (__any_sync(0xffffffffu, cnt > (uint32_t)(QCAP - SPW) || (last_word && cnt))) {
                     // verification automaton of the last candidate (LF): a true site of a filtered primer yields up
                     // to 2k + 1 candidates at consecutive ends, and the next one costs a single step when the
                     // automaton that verified this one is kept (a longer warm-up leaves the distance exact)
@@ -855,11 +875,24 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                         const uint32_t pos = r[0];
                         uint32_t sw[SW];
                         uint32_t hm = 0;  // bit p: pattern p hit (its biased score byte is negative)
+                        if constexpr (PK) {
+                            // distance of a half = the number of levels whose top bit is set (monotone over the levels)
 #pragma unroll
-                        for (int j = 0; j < SW; ++j) {
-                            sw[j] = r[1 + j];
-                            const uint32_t neg = sw[j] & 0x80808080u;
-                            hm |= (((neg >> 7) & 1u) | ((neg >> 14) & 2u) | ((neg >> 21) & 4u) | ((neg >> 28) & 8u)) << (4 * j);
+                            for (int j = 0; j < SW; ++j) sw[j] = 0;
+#pragma unroll
+                            for (int p = 0; p < NP; ++p) {
+                                const uint32_t lv = (r[1 + (p >> 1)] >> ((p & 1) ? 32 - NR : 16 - NR)) & ((1u << NR) - 1u);
+                                const int sc = __popc(lv) - bias;
+                                hm |= (sc < 0 ? 1u : 0u) << p;
+                                sw[p >> 2] |= ((uint32_t)sc & 0xffu) << (8 * (p & 3));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < SW; ++j) {
+                                sw[j] = r[1 + j];
+                                const uint32_t neg = sw[j] & 0x80808080u;
+                                hm |= (((neg >> 7) & 1u) | ((neg >> 14) & 2u) | ((neg >> 21) & 4u) | ((neg >> 28) & 8u)) << (4 * j);
+                            }
                         }
                         if constexpr (LF && PK && KWM == 0) {
                             // events of 16-symbol suffixes are candidates: the rest of the primer must match too
@@ -878,12 +911,25 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                                 const int p = __ffs((int)lm) - 1;
                                 lm &= lm - 1;
                                 const uint64_t *vt = a.vtables + ((size_t)(PK ? g.pk_vslot[p] : g.vslot[p]) * 2 + pass) * 256;
+                                const uint32_t mfull = g.mfull[p];
                                 uint32_t d;
-                                if (v_pat == p && v_pos + 1u == pos) {
-                                    hx_step(__ldg(vt + hx_text_byte<NIB>(a.arena, rec0 + pos, pass)), v_pv, v_mv, v_s);
+                                if (mfull <= 32u) {  // 32-bit verification automaton in the low halves of the kept state
+                                    uint32_t pv32 = (uint32_t)v_pv, mv32 = (uint32_t)v_mv;
+                                    if (v_pat == p && v_pos + 1u == pos) {
+                                        hx_step(hx_vrow<uint32_t>(vt, hx_text_byte<NIB>(a.arena, rec0 + pos, pass)), pv32, mv32, v_s);
+                                        d = (uint32_t)v_s;
+                                    } else {
+                                        d = hx_verify_long<NIB, uint32_t>(a.arena, rec0, pos, vt, mfull, a.k, pass, pv32, mv32);
+                                        v_s = (int)d;
+                                        v_pat = p;
+                                    }
+                                    v_pv = pv32;
+                                    v_mv = mv32;
+                                } else if (v_pat == p && v_pos + 1u == pos) {
+                                    hx_step(hx_vrow<uint64_t>(vt, hx_text_byte<NIB>(a.arena, rec0 + pos, pass)), v_pv, v_mv, v_s);
                                     d = (uint32_t)v_s;
                                 } else {
-                                    d = hx_verify_long<NIB>(a.arena, rec0, pos, vt, g.mfull[p], a.k, pass, v_pv, v_mv);
+                                    d = hx_verify_long<NIB, uint64_t>(a.arena, rec0, pos, vt, mfull, a.k, pass, v_pv, v_mv);
                                     v_s = (int)d;
                                     v_pat = p;
                                 }

@@ -279,7 +279,7 @@ def test_pattern_packing(ctx, k):
             recs.append(a1)
         a, o = hx_synth.pack(recs)
         ref = O.run_batch(a, o, pairs, k, nthreads=8)
-        assert (ref["flags"] & 4).any()
+        assert (ref["flags"] & 3).any() and (n_pairs < len(base) or (ref["flags"] & 4).any())
         for tile in (0, 64, 4096):
             for pack in (2, 1, 0):
                 _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=1, pack=pack), ref, a, o, pairs, k)
