@@ -743,6 +743,36 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                 cur.z = cur.w;
 #pragma unroll 1
                 for (int b0 = 0; b0 < SPW; b0 += UB) {
+                    if constexpr (PK && NR == 1) {
+                        // Fast trip: step the UB symbols without looking for hits one by one (4 branches, their
+                        // reconvergence points and compares were 12 % of the loop), only OR-ing the hit bits together.
+                        // When a lane does see a hit, the trip is replayed symbol by symbol from the kept state.
+                        W keep[NW];
+#pragma unroll
+                        for (int j = 0; j < NW; ++j) keep[j] = rv[0][j];
+                        uint32_t wf = w;
+                        W hit = 0;
+#pragma unroll
+                        for (int bi = 0; bi < UB; ++bi) {
+                            const uint32_t byte = wf & ((1u << SYM_BITS) - 1u);
+                            wf >>= SYM_BITS;
+                            HxRow<W, NW> row;
+                            row.load(tab + byte * STRIDE);
+                            W acc = ~(W)0;
+#pragma unroll
+                            for (int j = 0; j < NW; ++j) {
+                                rv[0][j] = ((rv[0][j] << 1) & (W)0xfffefffful) | row.eq(j);
+                                acc &= rv[0][j];
+                            }
+                            hit |= ~acc;
+                        }
+                        if (!(hit & (W)0x80008000ul)) {
+                            w = wf;
+                            continue;
+                        }
+#pragma unroll
+                        for (int j = 0; j < NW; ++j) rv[0][j] = keep[j];
+                    }
 #pragma unroll
                     for (int bi = 0; bi < UB; ++bi) {
                         const uint32_t byte = w & ((1u << SYM_BITS) - 1u);
