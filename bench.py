@@ -537,6 +537,18 @@ def main():
     ctx.set_option("fast_small_k", 0)
     ctx.set_primers(pairs, args.k)  # group_info() below describes the graded Myers configuration
 
+    # ---- one batch sharded over the N ranks (hyperex_b200/shard.py: contiguous record ranges, result tables gathered on
+    # rank 0 in input order, no collective on the data path): equal to the same batch on one GPU ------------------------
+    sharded = None
+    if world > 1:
+        from hyperex_b200 import shard
+        gloo = dist.new_group(backend="gloo")  # the gather of the small result tables is host-side plumbing (CPU tensors)
+        sa, so = hx_synth.gen_reads(24_000, seed=99)
+        part = shard.run_sharded(lambda aa, oo: ctx.run_batch(aa, oo), sa, so, rank, world, npairs, hx.RESULT_DTYPE, group=gloo)
+        if rank == 0:
+            sharded = bool(part.tobytes() == ctx.run_batch(sa, so).tobytes())
+        dist.barrier(group=gloo)
+
     # ---- one process, all N GPUs in one context (what `bin/hyperex --gpus N` ships): parity outside the timed region --
     multidev = None
     if world > 1:
@@ -656,6 +668,8 @@ def main():
             "with_pack_inside_timed_region": {"value": total_bases * args.steps / (e2e_pk_incl_ms_max * 1e-3) / 1e9,
                                               "ms_per_step": e2e_pk_incl_ms_max / args.steps,
                                               "note": "pack then run, back to back on the host (not pipelined)"}}
+        if sharded is not None:
+            line["sharded_parity"] = sharded
         if multidev is not None:
             line["multidev_parity"] = multidev
         if file_e2e is not None:

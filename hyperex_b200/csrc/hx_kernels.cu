@@ -40,6 +40,13 @@ __device__ __forceinline__ uint32_t hx_w32(const uint4 &v, int i) {
     return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
 }
 
+// a & b & c as ONE LOP3 whose shape the compiler keeps (plain C is re-associated into long chains)
+__device__ __forceinline__ uint32_t hx_and3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __device__ __forceinline__ uint4 hx_ldg16(const uint8_t *p) {
     return __ldg(reinterpret_cast<const uint4 *>(p));
 }
@@ -399,10 +406,14 @@ struct HxRow {
     static constexpr int WB = sizeof(W);
     static constexpr int NV = (NP * WB + 15) / 16;
     uint4 v[NV];
-    __device__ __forceinline__ void load(const uint8_t *row) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(row);
+    // row = 32-bit shared-space address of the Peq row: explicit ld.shared (a generic pointer makes ptxas rebuild the
+    // CTA's shared window base inside the hot loop of the wider kernels: S2R SR_CgaCtaId + LEA per trip)
+    __device__ __forceinline__ void load(uint32_t row) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = p[i];
+        for (int i = 0; i < NV; ++i)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                         : "r"(row + 16u * i));
     }
     __device__ __forceinline__ W eq(int p) const {
         if (WB == 4) return (W)hx_w32(v[p >> 2], p & 3);
@@ -530,8 +541,17 @@ __device__ __forceinline__ bool hx_verify_exact(const uint8_t *__restrict__ text
     return ok & 1ull;
 }
 
+#ifndef HX_PREFETCH2
+#define HX_PREFETCH2 0  // experiment: two 16-byte text chunks in flight per thread instead of one
+#endif
+#ifndef HX_WI_UNROLL
+#define HX_WI_UNROLL ((PK && NR == 1) ? 4 : 1)  // see the loop over the four text words of a chunk
+#endif
+#ifndef HX_PK_MINB
+#define HX_PK_MINB 5    // resident CTAs per SM the packed kernels (8 words of state) are compiled for
+#endif
 template <typename W, int NP, bool TMA, int KWM, bool LF, bool PK = false, bool NIB = false>
-__global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <= 16) ? 8 : ((sizeof(W) * (PK ? NP / 2 : NP) <= 32) ? 5 : 4)) * (128 / HX_THREADS))
+__global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <= 16) ? 8 : ((sizeof(W) * (PK ? NP / 2 : NP) <= 32) ? (PK ? HX_PK_MINB : 5) : 4)) * (128 / HX_THREADS))
     hx_myers_pair_kernel(const HxScanArgs a) {
     // NIB: the arena holds 4-bit codes (hx_run_batch_packed); a 16-byte chunk is 32 symbols and the shared-memory
     // Peq table has 16 rows, gathered from the 256-row table of the record alphabet
@@ -663,6 +683,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     constexpr int UB = WM ? ((KWM == 0 || NW * (KWM + 1) <= 16) ? 4 : (NW * (KWM + 1) <= 24 ? HX_WM_UB24 : HX_WM_UBWIDE))
                           : (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
     static_assert(SPW % UB == 0, "text symbols per trip must divide the word");
+    constexpr int WI_UNROLL = HX_WI_UNROLL;
     uint32_t cnt = 0;  // records in this lane's queue
     const uint64_t pol = hx_policy_evict_first();
 
@@ -681,7 +702,10 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
             }
         }
         __syncthreads();
-        const uint8_t *tab = smem;
+        // CTA-relative shared-space address of the table, taken from the symbol: converting the generic pointer instead
+        // makes ptxas rebuild the cluster-form address (S2R SR_CgaCtaId + LEA) inside the hot loop of the wider kernels
+        uint32_t tab;
+        asm("mov.u32 %0, smem;" : "=r"(tab));
         const uint32_t own_len = mine ? tl.own_len : 0u;  // a lane that is not scanning owns nothing
         const uint32_t nchunks = mine ? (lead + tl.warm + tl.own_len + (SPC - 1u)) >> CSH : 0u;
         const uint32_t nchunks_w = __reduce_max_sync(0xffffffffu, nchunks);
@@ -697,11 +721,17 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
             }
         };
         uint4 nxt = make_uint4(0, 0, 0, 0);  // one 16-byte chunk in flight (two measured slower: more registers)
+#if HX_PREFETCH2
+        uint4 nxt2 = make_uint4(0, 0, 0, 0);
+#endif
         if constexpr (TMA) {
             issue(0);
             issue(1);
         } else {
             if (nchunks) nxt = hx_ldg16_stream(src, pol);
+#if HX_PREFETCH2
+            if (nchunks > 1) nxt2 = hx_ldg16_stream(src + 16ull, pol);
+#endif
         }
 
         for (uint32_t c = 0; c < nchunks_w; ++c) {
@@ -721,7 +751,12 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                 }
             } else {
                 cur = nxt;
+#if HX_PREFETCH2
+                nxt = nxt2;
+                nxt2 = (c + 2 < nchunks) ? hx_ldg16_stream(src + 16ull * (c + 2), pol) : make_uint4(0, 0, 0, 0);
+#else
                 nxt = (c + 1 < nchunks) ? hx_ldg16_stream(src + 16ull * (c + 1), pol) : make_uint4(0, 0, 0, 0);
+#endif
             }
             if (c == 0 && mask_lead) {
                 // The scan starts at the record start: bytes before it belong to the previous record.
@@ -735,12 +770,12 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                 }
                 cur = make_uint4(w[0], w[1], w[2], w[3]);
             }
-#pragma unroll 1
+            // The four words of a chunk: a rolled loop rotates them through cur.x, and ptxas then makes the rotation wait
+            // for the chunk that is being prefetched (measured: 7 % of all stall samples of the packed -m 0 kernel, the
+            // prefetch hid nothing).  HX_WI_UNROLL words are therefore taken straight from their registers.
+#pragma unroll(WI_UNROLL)
             for (int wi = 0; wi < 4; ++wi) {
-                uint32_t w = cur.x;
-                cur.x = cur.y;
-                cur.y = cur.z;
-                cur.z = cur.w;
+                uint32_t w = hx_w32(cur, wi);
 #pragma unroll 1
                 for (int b0 = 0; b0 < SPW; b0 += UB) {
                     if constexpr (PK && NR == 1) {
@@ -751,21 +786,25 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
 #pragma unroll
                         for (int j = 0; j < NW; ++j) keep[j] = rv[0][j];
                         uint32_t wf = w;
-                        W hit = 0;
+                        uint32_t accb[UB];  // per symbol: AND of the NW words, as a tree (a 32-word AND chain is 16 dependent LOP3)
 #pragma unroll
                         for (int bi = 0; bi < UB; ++bi) {
                             const uint32_t byte = wf & ((1u << SYM_BITS) - 1u);
                             wf >>= SYM_BITS;
                             HxRow<W, NW> row;
                             row.load(tab + byte * STRIDE);
-                            W acc = ~(W)0;
+                            uint32_t t3[(NW + 2) / 3];
 #pragma unroll
-                            for (int j = 0; j < NW; ++j) {
-                                rv[0][j] = ((rv[0][j] << 1) & (W)0xfffefffful) | row.eq(j);
-                                acc &= rv[0][j];
-                            }
-                            hit |= ~acc;
+                            for (int j = 0; j < NW; ++j) rv[0][j] = ((rv[0][j] << 1) & (W)0xfffefffful) | row.eq(j);
+#pragma unroll
+                            for (int j = 0; j < (NW + 2) / 3; ++j)
+                                t3[j] = hx_and3((uint32_t)rv[0][3 * j], 3 * j + 1 < NW ? (uint32_t)rv[0][3 * j + 1] : ~0u,
+                                                3 * j + 2 < NW ? (uint32_t)rv[0][3 * j + 2] : ~0u);
+                            accb[bi] = hx_and3(t3[0], (NW + 2) / 3 > 1 ? t3[(NW + 2) / 3 > 1 ? 1 : 0] : ~0u,
+                                               (NW + 2) / 3 > 2 ? t3[(NW + 2) / 3 > 2 ? 2 : 0] : ~0u);
                         }
+                        static_assert(NW <= 9 && UB <= 4, "AND tree of the fast trip");
+                        const uint32_t hit = ~hx_and3(hx_and3(accb[0], accb[UB > 1 ? 1 : 0], accb[UB > 2 ? 2 : 0]), accb[UB > 3 ? 3 : 0], ~0u);
                         if (!(hit & (W)0x80008000ul)) {
                             w = wf;
                             continue;
