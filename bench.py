@@ -575,9 +575,11 @@ def main():
         barrier()
 
     # ---- max over ranks ---------------------------------------------------------------------------
+    torch.cuda.set_device(local)
+    dev_local = torch.device("cuda", local)
     t = torch.tensor([dev_ms, e2e_s * 1e3, myers_ms, fast_ms or 0.0, h2d_conc_ms, e2e_packed_s * 1e3, e2e_packed_incl_s * 1e3,
-                      pack_s * 1e3], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(bases), float(launches)], dtype=torch.float64, device="cuda")
+                      pack_s * 1e3], dtype=torch.float64, device=dev_local)
+    tot = torch.tensor([float(bases), float(launches)], dtype=torch.float64, device=dev_local)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)

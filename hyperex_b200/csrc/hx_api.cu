@@ -175,6 +175,33 @@ struct hx_ctx {
 
 namespace {
 
+// The entry points select the context's devices on the calling thread; the caller's current device is put back on the
+// way out (a host that also drives CUDA itself — torch, another library — must not find it changed).
+// Only a device whose primary context is alive is restored: cudaSetDevice would otherwise CREATE a context (0.4 s and a
+// few hundred MB) on a device the caller never used, e.g. device 0 for a context made on device 3 alone.
+bool primary_ctx_active(int dev) {
+    typedef int (*fn_t)(int, unsigned int *, int *);  // CUresult cuDevicePrimaryCtxGetState(CUdevice, unsigned *, int *)
+    static const fn_t fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuDevicePrimaryCtxGetState", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (fn_t)p;
+    }();
+    unsigned int flags = 0;
+    int active = 0;
+    return fn && fn(dev, &flags, &active) == 0 && active;
+}
+struct DeviceGuard {
+    int dev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (dev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != dev && primary_ctx_active(dev)) cudaSetDevice(dev);
+    }
+};
+
 int fail(hx_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
@@ -759,6 +786,7 @@ int hx_abi_version(void) { return HX_ABI_VERSION; }
 const char *hx_last_error(const hx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int hx_create(hx_ctx **out, const int *dev_ids, int n_dev) {
+    DeviceGuard device_guard;
     if (!out || n_dev < 1) return fail(nullptr, HX_ERR_ARG, "hx_create: bad arguments");
     *out = nullptr;
     int count = 0;
@@ -814,6 +842,7 @@ int hx_create(hx_ctx **out, const int *dev_ids, int n_dev) {
 }
 
 void hx_destroy(hx_ctx *ctx) {
+    DeviceGuard device_guard;
     if (!ctx) return;
     sync_timed(ctx);
     if (ctx->host_cache && ctx->host_cache_free) ctx->host_cache_free(ctx->host_cache);  // pinned memory: before the devices go
@@ -853,6 +882,7 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
 
 int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len,
                    const char *const *rev, const uint32_t *rev_len, uint8_t k) {
+    DeviceGuard device_guard;
     if (!ctx) return HX_ERR_ARG;
     ctx->primers_set = false;
     PrimerPlan P;
@@ -915,6 +945,7 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
 
 int hx_run_batch_device(hx_ctx *ctx, int dev_slot, const uint8_t *d_arena, const uint64_t *d_offsets,
                         uint32_t n_records, uint64_t arena_bytes, hx_result *d_out, void *stream) {
+    DeviceGuard device_guard;
     if (!ctx) return HX_ERR_ARG;
     if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch_device: call hx_set_primers first");
     if (dev_slot < 0 || dev_slot >= (int)ctx->devs.size() || (n_records && (!d_arena || !d_offsets || !d_out)))
@@ -986,6 +1017,7 @@ static int run_text_lane(hx_ctx *ctx, int lane_id, const uint8_t *arena, const u
                          const uint32_t *tail_off, const char *gff_tails, const uint32_t *gff_tail_off,
                          const char **text, uint64_t *text_len, const char **gff_text, uint64_t *gff_len,
                          const HxhTextSink *sink) {
+    DeviceGuard device_guard;
     if (!ctx) return HX_ERR_ARG;
     const bool want_gff = gff_tails && gff_tail_off;
     if (text) *text = nullptr;
@@ -1176,6 +1208,7 @@ int hx_run_batch_text_stream(hx_ctx *ctx, const uint8_t *arena, const uint64_t *
 // hx_run_batch / hx_run_batch_packed: rec_flags != NULL means `arena` is a packed arena (4-bit codes, nibble i = base i)
 static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_flags, const uint64_t *offsets, uint32_t n_records,
                           hx_result *out) {
+    DeviceGuard device_guard;
     const bool nib = rec_flags != nullptr;
     if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch: call hx_set_primers first");
     if (nib && !ctx->packable)
@@ -1279,6 +1312,7 @@ int hx_run_batch_packed(hx_ctx *ctx, const uint8_t *packed, const uint8_t *rec_f
 
 int64_t hx_find_all_end(hx_ctx *ctx, const char *pattern, uint32_t pattern_len, const uint8_t *text, uint64_t text_len,
                         uint8_t k, int fold_case, uint64_t *out_end, uint8_t *out_dist, uint64_t cap) {
+    DeviceGuard device_guard;
     if (!ctx) return HX_ERR_ARG;
     if (!pattern || pattern_len == 0 || pattern_len > 64)
         return fail(ctx, HX_ERR_ARG, "hx_find_all_end: pattern length must be 1..64");
@@ -1414,6 +1448,7 @@ int hx_plan_peq_word(uint32_t n_pairs, const char *const *fwd, const uint32_t *f
 }
 
 int hx_kernel_time(hx_ctx *ctx, double *myers_ms, uint64_t *myers_launches, int reset) {
+    DeviceGuard device_guard;
     if (!ctx) return HX_ERR_ARG;
     sync_timed(ctx);
     if (myers_ms) *myers_ms = ctx->myers_ms;
@@ -1442,6 +1477,7 @@ int hxh_run_text_lane(hx_ctx *ctx, int lane, const uint8_t *arena, const uint64_
 // result table only, on the lane's own device and stream (the host-formatter path of the file-level driver)
 int hxh_run_batch_lane(hx_ctx *ctx, int lane, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
                        hx_result *out) {
+    DeviceGuard device_guard;
     if (!ctx) return HX_ERR_ARG;
     if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch: call hx_set_primers first");
     if (lane < 0 || lane >= (int)ctx->devs.size() * HX_NLANE) return fail(ctx, HX_ERR_ARG, "hx_run_batch: bad lane");

@@ -406,8 +406,15 @@ struct HxRow {
     static constexpr int WB = sizeof(W);
     static constexpr int NV = (NP * WB + 15) / 16;
     uint4 v[NV];
-    // row = 32-bit shared-space address of the Peq row: explicit ld.shared (a generic pointer makes ptxas rebuild the
-    // CTA's shared window base inside the hot loop of the wider kernels: S2R SR_CgaCtaId + LEA per trip)
+    __device__ __forceinline__ void load(const uint8_t *row) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(row);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = p[i];
+    }
+    // row = 32-bit shared-space address of the Peq row: explicit ld.shared.  With a generic pointer ptxas rebuilt the CTA's
+    // shared window base inside the hot loop of the packed -m 0 kernel (S2R SR_CgaCtaId + LEA per trip) and gave the S2R
+    // the scoreboard of the text prefetch, so every trip waited for the chunk in flight (ncu: 20 % of all stall samples).
+    // Measured per kernel: +4 % for packed -m 0, -1 % for Myers and -3 % for the Wu-Manber levels, which keep the pointer.
     __device__ __forceinline__ void load(uint32_t row) {
 #pragma unroll
         for (int i = 0; i < NV; ++i)
@@ -704,8 +711,14 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
         __syncthreads();
         // CTA-relative shared-space address of the table, taken from the symbol: converting the generic pointer instead
         // makes ptxas rebuild the cluster-form address (S2R SR_CgaCtaId + LEA) inside the hot loop of the wider kernels
-        uint32_t tab;
-        asm("mov.u32 %0, smem;" : "=r"(tab));
+        uint32_t tab_s;
+        asm("mov.u32 %0, smem;" : "=r"(tab_s));
+        const uint8_t *const tab_g = smem;
+        // packed -m 0: shared-space address; everything else: the generic pointer (see HxRow::load)
+        const auto tab = [&] {
+            if constexpr (PK && NR == 1) return tab_s;
+            else return tab_g;
+        }();
         const uint32_t own_len = mine ? tl.own_len : 0u;  // a lane that is not scanning owns nothing
         const uint32_t nchunks = mine ? (lead + tl.warm + tl.own_len + (SPC - 1u)) >> CSH : 0u;
         const uint32_t nchunks_w = __reduce_max_sync(0xffffffffu, nchunks);
