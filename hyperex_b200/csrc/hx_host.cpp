@@ -933,6 +933,24 @@ struct OutFile {
         }
         return it->second + (off - w * HX_WINDOW);
     }
+    // The bytes [off, off + n) are written: drop their page-table entries now (the pages stay in the page cache).  For a
+    // shared file mapping MADV_DONTNEED only takes the mmap lock shared, so lanes release their own batches concurrently
+    // instead of leaving 1.7 M entries to one munmap at the end (0.24 s of a 1.1 s call for 7 GB of output).
+    void release(uint64_t off, uint64_t n) {
+        if (!mappable || n < 2 * 4096) return;
+        const uint64_t a = (off + 4095) & ~(uint64_t)4095, e = (off + n) & ~(uint64_t)4095;
+        for (uint64_t p = a; p < e;) {
+            const uint64_t w = p / HX_WINDOW, stop = std::min(e, (w + 1) * HX_WINDOW);
+            char *base = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                auto it = windows.find(w);
+                if (it != windows.end()) base = it->second;
+            }
+            if (base) madvise(base + (p - w * HX_WINDOW), (size_t)(stop - p), MADV_DONTNEED);
+            p = stop;
+        }
+    }
     int close_all() {
         for (auto &kv : windows) munmap(kv.second, HX_WINDOW);
         windows.clear();
@@ -1191,7 +1209,7 @@ void parser_thread(FileJob *J) {
 struct LaneSink {  // HxhTextSink of one batch
     FileJob *J;
     uint64_t index;
-    uint64_t base[2];
+    uint64_t base[2], total[2];
     bool begun;
     double t_write;
 };
@@ -1224,6 +1242,8 @@ bool reserve_output(FileJob *J, uint64_t index, uint64_t fa_total, uint64_t gff_
 int sink_begin(void *user, uint64_t fa_total, uint64_t gff_total) {
     LaneSink *s = (LaneSink *)user;
     s->begun = true;
+    s->total[0] = fa_total;
+    s->total[1] = gff_total;
     return reserve_output(s->J, s->index, fa_total, gff_total, s->base) ? 0 : 1;
 }
 
@@ -1350,7 +1370,7 @@ void lane_thread(FileJob *J, int lane) {
             uint64_t base[2];
             if (!reserve_output(J, index, 0, 0, base)) return;
         } else if (J->device_text) {
-            LaneSink sink{J, index, {0, 0}, false, 0.0};
+            LaneSink sink{J, index, {0, 0}, {0, 0}, false, 0.0};
             const HxhTextSink hs{sink_begin, sink_chunk, &sink};
             rc = hxh_run_text_lane(J->ctx, lane, b->arena, b->offsets.data(), n, res, b->ids.data(), b->id_off.data(),
                                    J->tails_blob.data(), J->tail_off.data(), J->gtails_blob.data(), J->gtail_off.data(), &hs);
@@ -1358,6 +1378,12 @@ void lane_thread(FileJob *J, int lane) {
             if (rc != HX_OK) {
                 J->fail(rc, hx_last_error(J->ctx));
                 return;
+            }
+            if (sink.begun) {
+                const double tr = now_s();
+                J->out[0].release(sink.base[0], sink.total[0]);
+                J->out[1].release(sink.base[1], sink.total[1]);
+                t_write += now_s() - tr;
             }
         } else {
             rc = hxh_run_batch_lane(J->ctx, lane, b->arena, b->offsets.data(), n, res);
@@ -1371,6 +1397,8 @@ void lane_thread(FileJob *J, int lane) {
             if (!reserve_output(J, index, fa_host.size(), gff_host.size(), base)) return;
             const bool ok = J->writers->write(J->out[0], fa_host.data(), fa_host.size(), base[0]) &&
                             J->writers->write(J->out[1], gff_host.data(), gff_host.size(), base[1]);
+            J->out[0].release(base[0], fa_host.size());
+            J->out[1].release(base[1], gff_host.size());
             t_write = now_s() - tw;
             if (!ok) {
                 J->fail(HX_ERR_IO, "write error on the output files");

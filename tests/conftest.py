@@ -24,6 +24,24 @@ def pytest_sessionstart(session):
         __graft_entry__.build()
 
 
+def pytest_collection_modifyitems(config, items):
+    """Without a CUDA device the gpu-marked tests are skipped (a plain `pytest` on a CPU box must not fail in them);
+    on a GPU box nothing is skipped here, and a broken device path fails loudly in the tests themselves."""
+    if not any("gpu" in it.keywords for it in items):
+        return
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (there is no CPU fallback)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
