@@ -173,16 +173,17 @@ def load_peaks():
 
 def load_traffic(bases):
     """dram__bytes_read.sum + dram__bytes_write.sum of hx_myers_pair_kernel from the committed ncu capture of
-    this same command (profiles/r01_ncu_traffic.json, written from the .ncu-rep by tools/ncu_summary.py); only
+    this same command (profiles/r02_ncu_traffic.json, written by tools/ncu_summary.py from the ncu export); only
     reported when the capture was taken on the same number of bases per launch."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        if int(t["bases_per_launch"]) == int(bases):
-            return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "dram_bytes_read": t["dram_bytes_read"],
-                    "dram_bytes_write": t["dram_bytes_write"], "algorithmic_bytes": int(bases),
-                    "source": t.get("source", "profiles/r01_ncu_traffic.json")}
-    except Exception:
-        pass
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if int(t["bases_per_launch"]) == int(bases):
+                return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "dram_bytes_read": t["dram_bytes_read"],
+                        "dram_bytes_write": t["dram_bytes_write"], "algorithmic_bytes": int(bases),
+                        "source": t.get("source", "") + f" [profiles/{name}]"}
+        except Exception:
+            continue
     return None
 
 
@@ -678,10 +679,29 @@ def main():
             line["file_e2e"] = file_e2e
         if fast_ms_max > 0:
             fv = total_bases / (fast_ms_max * 1e-3) / 1e9
-            line["fast_path"] = {"what": "library default for -m 0..2: Wu-Manber / Shift-Or automata, identical results "
-                                         "(asserted), not counted as Myers GCUPS", "value": fv, "unit": "Gbases/s",
+            line["fast_path"] = {"what": "library default for -m 0..2: Shift-Or / Wu-Manber automata, two <= 16-symbol automata per "
+                                         "word + verification (DESIGN.md 3.5, 3.8), identical results (asserted), not counted as "
+                                         "Myers GCUPS; ms_per_step is the whole device step (tile build, classify, scan, combine)",
+                                 "value": fv, "unit": "Gbases/s",
                                  "ms_per_step": fast_ms_max, "speedup_vs_myers": dev_ms_max / args.steps / fast_ms_max,
                                  "groups": fast_groups[0], "automata_per_base": fast_groups[1] + fast_groups[2]}
+            # per text byte and thread, packed kernel of 8 words (SASS of the hot loop / ncu source page, profiles/r02_sass_*,
+            # r02_hot_*): ALU-pipe instructions, FMA-pipe instructions (IMAD.IADD shifts), LDS.128 of Peq rows
+            mix = {0: (17.25, 9.75, 2.0), 1: (40.0, 21.0, 2.0), 2: (64.0, 35.0, 2.0)}.get(args.k)
+            if mix and args.workload == "c2":
+                sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+                lds_peak = 148 * sm_hz * 128 / (mix[2] * 16)  # bases/s the 128 B/clk/SM shared-memory pipe allows
+                issue_peak = 148 * 4 * sm_hz * 32 / (mix[0] + mix[1] + mix[2] + 1.0)
+                line["fast_path"]["roofline"] = {
+                    "alu_ops_per_base": mix[0], "fma_ops_per_base": mix[1], "lds128_per_base": mix[2],
+                    "alu": {"achieved": fv * mix[0] / 1e3, "peak": alu_peak, "unit": "Tint-op/s (ALU pipe)",
+                            "frac": fv * mix[0] / 1e3 / alu_peak},
+                    "lds": {"achieved": fv, "peak": lds_peak / 1e9, "unit": "Gbases/s at 128 B/clk/SM", "frac": fv * 1e9 / lds_peak},
+                    "issue": {"achieved": fv, "peak": issue_peak / 1e9, "unit": "Gbases/s at 1 warp-instruction/clk/SMSP",
+                              "frac": fv * 1e9 / issue_peak},
+                    "note": "no pipe is saturated: the scan is bound by latency at 5 resident CTAs (20 warps) per SM, see "
+                            "profiles/r02_ncu_shiftor_k0_packed.csv; the fractions include the tile-build / classify / combine "
+                            "kernels of the step in the time"}
         if not args.no_cpu_baseline:
             ns = min(args.cpu_sample, n)
             cb, cdt = cpu_port_run(arena, offsets, ns, pairs, args.k, 1)

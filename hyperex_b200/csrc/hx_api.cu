@@ -493,7 +493,7 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
             return pfail(err, HX_ERR_ARG, "hx_set_primers: pair %u: NUL byte inside a primer", i);
     }
     // unique patterns per pair: forward as given; reverse = reverse complement per alphabet (utils.rs:299)
-    struct PairPat { PatternKey f, r; bool is_long; };
+    struct PairPat { PatternKey f, r; bool is_long; int cls; };  // cls: 0 packable 32-bit, 1 other 32-bit, 2 64-bit
     std::vector<PairPat> pp(n_pairs);
     uint32_t m_max = 0;
     // Suffix filter (hx_kernels.cu: hx_verify_long): primers of 33..64 symbols are scanned as the 32-bit automaton of
@@ -530,7 +530,7 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
     // verified against the whole primer in the drain (exact match of the rest at -m 0, hx_verify_long otherwise), so the
     // suffix must be specific enough: the expected rate of chance candidates on random ACGT text, 2^-bits(suffix) x
     // (number of k-edit neighbourhoods of a 16-mer), stays below 1e-3 per position — every built-in primer qualifies at
-    // -m 0..2.  The whole 32-bit class packs or none of it does (pack16 = 2 skips the test: test-suite).
+    // -m 0..2 (pack16 = 2 skips the test: test-suite).
     auto suffix16_ok = [&](const std::string &pat) {
         if (pat.size() <= 16 || o.pack16 >= 2) return true;
         double bits = 0;
@@ -543,10 +543,12 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
         for (int i = 0; i < (int)k; ++i) nb *= (16.0 - i) / (i + 1) * 3.0;
         return bits >= std::log2(nb / 1e-3);
     };
-    bool pack_class = k <= 2 && o.fast_small_k && o.pack16;
-    for (uint32_t i = 0; i < n_pairs && pack_class; ++i)
-        if (!pp[i].is_long)
-            pack_class = suffix16_ok(pp[i].f.dna) && suffix16_ok(pp[i].f.rna) && suffix16_ok(pp[i].r.dna) && suffix16_ok(pp[i].r.rna);
+    // Pairs whose two patterns qualify form their own grouping class, so one vague primer in a CSV does not unpack the rest.
+    const bool packing = k <= 2 && o.fast_small_k && o.pack16;
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        const bool ok16 = packing && suffix16_ok(pp[i].f.dna) && suffix16_ok(pp[i].f.rna) && suffix16_ok(pp[i].r.dna) && suffix16_ok(pp[i].r.rna);
+        pp[i].cls = pp[i].is_long ? 2 : (ok16 ? 0 : 1);
+    }
     // Grouping, short (32-bit words) and long (64-bit words) pairs separately.  Pairs that share a pattern (27F and
     // 1492Rmod serve three built-in regions each) should land in the same group, or the shared automaton is stepped
     // once per group: pairs are first joined into the connected components of the "shares a pattern" relation, whole
@@ -563,13 +565,13 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
         fid[i] = pat_id.emplace(std::make_pair(pp[i].f.dna, pp[i].f.rna), (int)pat_id.size()).first->second;
         rid[i] = pat_id.emplace(std::make_pair(pp[i].r.dna, pp[i].r.rna), (int)pat_id.size()).first->second;
     }
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool want_long = pass == 1;
+    for (int pass = 0; pass < 3; ++pass) {
+        const bool want_long = pass == 2;
         int np_max = want_long ? HX_MAX_NP64 : HX_MAX_NP32;
         // -m 2 on the Wu-Manber path: three bit-vectors per automaton, so only groups of <= 8 patterns stay in
         // registers (measured per 1.5 Gbases: config 5 108.7 -> 84.8 ms, built-in regions as 8 + 7 automata 14.3 -> 11.4 ms)
         // (packed, 16 automata are 8 words: the same 24 registers of state)
-        if (!want_long && k == 2 && o.fast_small_k && !pack_class) np_max = 8;
+        if (pass == 1 && k == 2 && o.fast_small_k) np_max = 8;
         if (o.group_np_max >= 2) np_max = std::min<int>(np_max, (int)o.group_np_max);
         // connected components over the pairs of this class (union-find on pattern ids)
         std::vector<int> parent(pat_id.size());
@@ -579,10 +581,10 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
             return x;
         };
         for (uint32_t i = 0; i < n_pairs; ++i)
-            if (pp[i].is_long == want_long) parent[root(fid[i])] = root(rid[i]);
+            if (pp[i].cls == pass) parent[root(fid[i])] = root(rid[i]);
         std::map<int, std::vector<uint32_t>> comps;  // root -> pairs, ascending
         for (uint32_t i = 0; i < n_pairs; ++i)
-            if (pp[i].is_long == want_long) comps[root(fid[i])].push_back(i);
+            if (pp[i].cls == pass) comps[root(fid[i])].push_back(i);
         // items = whole components, or the pair-order pieces of one that is too large for a group
         struct Item { std::vector<uint32_t> pairs; std::vector<int> pats; uint32_t first; };
         std::vector<Item> items;
@@ -628,6 +630,7 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
             HxGroup g;
             memset(&g, 0, sizeof g);
             g.word64 = want_long ? 1 : 0;
+            g.packed = pass == 0 ? 1 : 0;
             groups.push_back(g);
             gpats.emplace_back();
             const int cur = (int)groups.size() - 1;
@@ -713,13 +716,12 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
             }
         }
     }
-    // packed tables of the 32-bit groups (see pack_class above): two 16-bit automata per word, pattern 2j in the low half
+    // packed tables of the groups of class 0: two 16-bit automata per word, pattern 2j in the low half
     P.blob_pk.clear();
-    if (pack_class) {
+    {
         for (size_t gi = 0; gi < groups.size(); ++gi) {
             HxGroup &g = groups[gi];
-            if (g.word64) continue;
-            g.packed = 1;
+            if (!g.packed) continue;
             g.pk_longmask = 0;
             const int nw = (g.np + 1) / 2, stride = hx_row_stride(nw, 4);
             g.pk_table_off = (uint32_t)P.blob_pk.size();

@@ -204,12 +204,15 @@ def test_builtin_regions_are_one_group_of_15_automata():
     # and the 15 automata stay one group (8 words x 3 levels of state) ...
     assert hx.plan_groups(pairs, 2)[:3] == (1, 15, 0)
     assert hx.plan_groups(pairs, 2, fast_small_k=False)[:3] == (1, 15, 0)
-    # ... unless a primer's last 16 symbols are too degenerate to filter with: then nothing packs and -m 2 falls back
-    # to groups of <= 8 unpacked automata; primers shared between regions (27F x3, 341F x2, 1492Rmod x3) stay together,
-    # so the split costs no duplicated automaton
+    # A pair with a primer whose last 16 symbols are too degenerate to filter with forms its own, unpacked class: it does
+    # not unpack the others.
     vague = pairs + [["ACGTACGTAC" + "N" * 14, "TTGACATTGACAGGT"]]
     g, s32, s64, pg = hx.plan_groups(vague, 2)
-    assert (g, s32, s64) == (3, 17, 0)
+    assert (g, s32, s64) == (2, 17, 0) and len(set(pg[:10])) == 1 and pg[10] != pg[0]
+    # Unpacked automata at -m 2 run in groups of <= 8 (three bit-vectors each); primers shared between regions
+    # (27F x3, 341F x2, 1492Rmod x3) stay together, so the split costs no duplicated automaton.
+    g, s32, s64, pg = hx.plan_groups([[f + "N" * 16, r] for f, r in pairs], 2, long_filter=2)
+    assert s32 == 15 and g == 2
     grp = dict(zip(hx.supported_regions(), pg))
     assert grp["v1v2"] == grp["v1v3"] == grp["v1v9"] == grp["v6v9"] == grp["v7v9"] and grp["v3v4"] == grp["v3v5"]
 
