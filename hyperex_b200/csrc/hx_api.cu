@@ -14,6 +14,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -29,6 +30,7 @@ namespace {
 
 constexpr int HX_NSLOT = 3;  // pipeline depth per device (H2D / scan / D2H overlap)
 constexpr int HX_NLANE = 2;  // text lanes per device (see TextLane)
+constexpr int HX_NSTAGE = 4; // pinned staging buffers per device of the pack-on-the-way path (see PackStage)
 
 std::string g_create_error;
 
@@ -84,7 +86,11 @@ struct Slot {
     DevBuf<hx_result> out;
     DevBuf<uint8_t> flags;         // packed text: per-record alphabet evidence gathered by the host packer
     uint32_t *h_status = nullptr;  // pinned: [0] ntiles, [1] overflow
+    cudaEvent_t done_ev = nullptr; // blocking-sync event after the slab's last copy (pack-on-the-way path: a spinning wait
+                                   // would take a core from the packer)
     void release() {
+        if (done_ev) cudaEventDestroy(done_ev);
+        done_ev = nullptr;
         pool.release();
         if (h_status) cudaFreeHost(h_status);
         if (stream) cudaStreamDestroy(stream);
@@ -127,9 +133,18 @@ struct TextLane {
     }
 };
 
+// pinned staging of hx_run_batch with pack_h2d: one slab as 4-bit codes followed by its rec_flags; `ev` marks the end of the
+// host->device copies that read it
+struct PackStage {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+};
+
 struct Device {
     int dev = 0;
     Slot slots[HX_NSLOT];
+    PackStage stage[HX_NSTAGE];
     TextLane lanes[HX_NLANE];
     uint8_t *d_tables = nullptr;
     uint8_t *d_tables_wm = nullptr;
@@ -161,7 +176,7 @@ struct hx_ctx {
     bool packable = true;  // every primer symbol is one of ACGTURYSWKMBDHVN (or lower case, which matches nothing)
     // options
     int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1,
-            opt_long_filter = 1, opt_group_np_max = 0, opt_pack16 = 1;
+            opt_long_filter = 1, opt_group_np_max = 0, opt_pack16 = 1, opt_pack_h2d = -1, opt_pack_threads = 0;
     std::atomic<uint64_t> launches{0};
     std::mutex mu;  // guards err and timed: text lanes of one context run on several host threads
     DevPool find_pool;
@@ -856,6 +871,10 @@ void hx_destroy(hx_ctx *ctx) {
         cudaDeviceSynchronize();
         for (Slot &S : D.slots) S.release();
         for (TextLane &L : D.lanes) L.release();
+        for (PackStage &G : D.stage) {
+            if (G.p) cudaFreeHost(G.p);
+            if (G.ev) cudaEventDestroy(G.ev);
+        }
         if (D.d_tables) cudaFree(D.d_tables);
         if (D.d_tables_wm) cudaFree(D.d_tables_wm);
         if (D.d_tables_pk) cudaFree(D.d_tables_pk);
@@ -878,6 +897,8 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     else if (n == "long_filter") ctx->opt_long_filter = value < 0 ? 0 : (value > 2 ? 2 : value);  // read by hx_set_primers
     else if (n == "group_np_max") ctx->opt_group_np_max = value;         // read by hx_set_primers; 0 = automatic
     else if (n == "pack16") ctx->opt_pack16 = value < 0 ? 0 : (value > 2 ? 2 : value);  // hx_set_primers builds, every scan reads
+    else if (n == "pack_h2d") ctx->opt_pack_h2d = value < 0 ? -1 : (value ? 1 : 0);
+    else if (n == "pack_threads") ctx->opt_pack_threads = std::max<int64_t>(value, 0);
     else return fail(ctx, HX_ERR_ARG, "unknown option %s", name);
     return HX_OK;
 }
@@ -1207,35 +1228,60 @@ int hx_run_batch_text_stream(hx_ctx *ctx, const uint8_t *arena, const uint64_t *
 
 }  // extern "C"
 
-// hx_run_batch / hx_run_batch_packed: rec_flags != NULL means `arena` is a packed arena (4-bit codes, nibble i = base i)
+// hx_run_batch / hx_run_batch_packed: rec_flags != NULL means `arena` is a packed arena (4-bit codes, nibble i = base i).
+// An ASCII arena may still cross PCIe packed (option pack_h2d): a producer thread packs slab after slab into a ring of
+// pinned staging buffers with all host threads while this thread enqueues the copies and kernels of the slabs that are
+// ready, and the device runs its nibble-text kernels.  The bytes per base over PCIe halve; the caller's buffers and the
+// result table are what they were.
+namespace {
+struct SlabCut {
+    uint32_t r0, r1;
+    uint64_t base, copy_bytes;
+};
+
+// producer <-> issuer hand-over of the pack-on-the-way path
+struct PackPipe {
+    std::mutex m;
+    std::condition_variable cv;
+    int64_t packed_upto = -1;    // slabs [0, packed_upto] are packed (producer -> issuer)
+    int64_t recorded_upto = -1;  // the H2D-done events of slabs [0, recorded_upto] are recorded (issuer -> producer)
+    bool abort = false, failed = false;
+};
+}  // namespace
+
 static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_flags, const uint64_t *offsets, uint32_t n_records,
                           hx_result *out) {
     DeviceGuard device_guard;
-    const bool nib = rec_flags != nullptr;
+    const bool packed_in = rec_flags != nullptr;
     if (!ctx->primers_set) return fail(ctx, HX_ERR_STATE, "hx_run_batch: call hx_set_primers first");
-    if (nib && !ctx->packable)
+    if (packed_in && !ctx->packable)
         return fail(ctx, HX_ERR_STATE, "hx_run_batch_packed: the primer set has symbols outside ACGTURYSWKMBDHVN, which packed text "
                                        "cannot represent; use hx_run_batch");
     if (n_records == 0) return HX_OK;
     if (!offsets || !out) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL offsets/out");
     if (offsets[n_records] < offsets[0]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
     if (offsets[n_records] > offsets[0] && !arena) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL arena");
+    // pack on the way: always / never / automatic = when the batch is large enough for the pipeline to fill and the
+    // host has the threads to pack faster than the link copies (measured: profiles/r02_pack_h2d.md)
+    const int pack_threads = ctx->opt_pack_threads > 0 ? (int)ctx->opt_pack_threads : (int)std::thread::hardware_concurrency();
+    const bool pack_otf = !packed_in && ctx->packable &&
+                          (ctx->opt_pack_h2d == 1 ||
+                           (ctx->opt_pack_h2d < 0 && offsets[n_records] - offsets[0] >= ((uint64_t)64 << 20) && pack_threads >= 8));
+    const bool nib = packed_in || pack_otf;
     const size_t np = ctx->n_pairs;
     const int ndev = (int)ctx->devs.size();
-    // Slab size: opt_slab_bytes for large batches; a batch of only a few slabs is cut finer (>= 8 slabs per device,
-    // >= 8 MB each) so that the first copy and the last kernel, which nothing overlaps, stay short and every
+    // Slab size: opt_slab_bytes for large batches (half of it when the slabs are packed on the way: the packed slab is
+    // what crosses the link, and a finer pipeline fills sooner); a batch of only a few slabs is cut finer (>= 8 slabs per
+    // device, >= 8 MB each) so that the first copy and the last kernel, which nothing overlaps, stay short and every
     // device of the context gets work.
-    uint64_t slab_bytes = (uint64_t)ctx->opt_slab_bytes;
+    uint64_t slab_bytes = std::max<uint64_t>((uint64_t)ctx->opt_slab_bytes / (pack_otf ? 2 : 1), 1);
     {
         const uint64_t share = (offsets[n_records] - offsets[0]) / (8ull * ndev) + 1;
         slab_bytes = std::min(slab_bytes, std::max<uint64_t>(share, (uint64_t)8 << 20));
     }
-    // per (device, slot): the slab it last ran, so its status word can be checked before reuse
-    std::vector<int> used(ndev * HX_NSLOT, 0);
-    uint32_t r0 = 0;
-    uint64_t slab_idx = 0;
-    int rc = HX_OK;
-    while (r0 < n_records && rc == HX_OK) {
+    // ---- cut the batch into slabs (records only; nothing is enqueued yet, so an error can simply return) ----
+    std::vector<SlabCut> cuts;
+    for (uint32_t r0 = 0; r0 < n_records;) {
         // largest r1 with offsets[r1] - offsets[r0] <= this slab's size (at least one record).  The last slabs of
         // a batch taper (half of what is left per device, >= 8 MB): only the kernels and the result copy of the very
         // last slab are not hidden under a host->device copy, so that slab should be small.
@@ -1243,44 +1289,128 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
         const uint64_t limit = offsets[r0] + std::min(slab_bytes, std::max<uint64_t>(left / 2, (uint64_t)8 << 20));
         uint32_t r1 = (uint32_t)(std::upper_bound(offsets + r0 + 1, offsets + n_records + 1, limit) - offsets) - 1;
         if (r1 <= r0) r1 = r0 + 1;
-        bool monotone = true;  // cheap sanity: monotone offsets inside the slab edges
-        for (uint32_t i = r0; i < r1 && monotone; ++i) monotone = offsets[i + 1] >= offsets[i];
-        if (!monotone) {
-            rc = fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
-            break;  // never return from inside the loop: earlier slabs' copies still use the caller's arena and out
+        for (uint32_t i = r0; i < r1; ++i)  // cheap sanity: monotone offsets inside the slab edges
+            if (offsets[i + 1] < offsets[i]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
+        // the host arena slice is copied with its 16-byte phase preserved so that device addresses keep the alignment of
+        // the arena offsets (packed: 32 symbols = 16 bytes; packed on the way: 128 symbols, the staging buffer then takes
+        // the packer's 64-byte stores aligned)
+        const uint64_t base = offsets[r0] & (pack_otf ? ~127ull : nib ? ~31ull : ~15ull);
+        const uint64_t copy_bytes = nib ? (offsets[r1] + 1) / 2 - base / 2 : offsets[r1] - base;
+        cuts.push_back({r0, r1, base, copy_bytes});
+        r0 = r1;
+    }
+    const int64_t n_slabs = (int64_t)cuts.size();
+    // per (device, slot): the slab it last ran, so its status word can be checked before reuse
+    std::vector<int> used(ndev * HX_NSLOT, 0);
+    int rc = HX_OK;
+
+    // ---- pack on the way: staging ring + producer thread ----
+    PackPipe pipe;
+    std::thread producer;
+    auto stage_of = [&](int64_t j) -> PackStage & { return ctx->devs[j % ndev].stage[(j / ndev) % HX_NSTAGE]; };
+    auto flags_off = [](const SlabCut &c) { return ((size_t)c.copy_bytes + 63) & ~(size_t)63; };
+    if (pack_otf) {
+        size_t need = 0;
+        for (const SlabCut &c : cuts) need = std::max(need, flags_off(c) + (c.r1 - c.r0) + 64);
+        for (int64_t j = 0; j < std::min<int64_t>(n_slabs, (int64_t)ndev * HX_NSTAGE) && rc == HX_OK; ++j) {
+            PackStage &G = stage_of(j);
+            if (cudaSetDevice(ctx->devs[j % ndev].dev) != cudaSuccess) rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaSetDevice failed");
+            if (rc == HX_OK && !G.ev && cudaEventCreateWithFlags(&G.ev, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
+                rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaEventCreate failed");
+            if (rc == HX_OK && G.cap < need) {
+                if (G.p) cudaFreeHost(G.p);
+                G.p = nullptr;
+                G.cap = 0;
+                const size_t want = need + need / 8;
+                if (cudaHostAlloc((void **)&G.p, want, cudaHostAllocDefault) != cudaSuccess)
+                    rc = fail(ctx, HX_ERR_NOMEM, "hx_run_batch: cannot allocate %zu bytes of pinned staging", want);
+                else G.cap = want;
+            }
         }
-        const uint32_t n = r1 - r0;
-        const uint64_t bytes = offsets[r1] - offsets[r0];
-        const int di = (int)(slab_idx % ndev);
-        const int si = (int)((slab_idx / ndev) % HX_NSLOT);
+        if (rc != HX_OK) return rc;  // nothing enqueued yet
+        producer = std::thread([&] {
+            for (int64_t j = 0; j < n_slabs; ++j) {
+                const SlabCut &c = cuts[j];
+                PackStage &G = stage_of(j);
+                const int64_t prev = j - (int64_t)ndev * HX_NSTAGE;  // the slab that used this staging buffer before
+                if (prev >= 0) {
+                    {
+                        std::unique_lock<std::mutex> g(pipe.m);
+                        pipe.cv.wait(g, [&] { return pipe.abort || pipe.recorded_upto >= prev; });
+                        if (pipe.abort) return;
+                    }
+                    if (cudaEventSynchronize(G.ev) != cudaSuccess) {
+                        std::lock_guard<std::mutex> g(pipe.m);
+                        pipe.failed = true;
+                        pipe.cv.notify_all();
+                        return;
+                    }
+                }
+                const int prc = hxh_pack_slab(arena, offsets + c.r0, c.r1 - c.r0, G.p, c.base, G.p + flags_off(c), pack_threads);
+                std::lock_guard<std::mutex> g(pipe.m);
+                if (prc != HX_OK) pipe.failed = true;
+                else pipe.packed_upto = j;
+                pipe.cv.notify_all();
+                if (prc != HX_OK || pipe.abort) return;
+            }
+        });
+    }
+
+    for (int64_t j = 0; j < n_slabs && rc == HX_OK; ++j) {
+        const SlabCut &c = cuts[j];
+        const uint32_t r0 = c.r0, n = c.r1 - c.r0;
+        const uint64_t bytes = offsets[c.r1] - offsets[c.r0];
+        const int di = (int)(j % ndev);
+        const int si = (int)((j / ndev) % HX_NSLOT);
         Device &D = ctx->devs[di];
         Slot &S = D.slots[si];
         HX_CUDA_BREAK(ctx, rc, cudaSetDevice(D.dev));
         if (used[di * HX_NSLOT + si]) {
             // buffers of this slot may be regrown below: wait for its previous slab and check it
-            HX_CUDA_BREAK(ctx, rc, cudaStreamSynchronize(S.stream));
+            if (pack_otf) HX_CUDA_BREAK(ctx, rc, cudaEventSynchronize(S.done_ev))
+            else HX_CUDA_BREAK(ctx, rc, cudaStreamSynchronize(S.stream));
             rc = check_status(ctx, S);
             if (rc != HX_OK) break;
         }
-        // the host arena slice is copied with its 16-byte phase preserved so that device
-        // addresses keep the alignment of the arena offsets (packed: 32 symbols = 16 bytes)
-        const uint64_t base = offsets[r0] & (nib ? ~31ull : ~15ull);
-        const uint64_t copy_bytes = nib ? (offsets[r1] + 1) / 2 - base / 2 : offsets[r1] - base;
+        if (pack_otf && !S.done_ev) HX_CUDA_BREAK(ctx, rc, cudaEventCreateWithFlags(&S.done_ev, cudaEventDisableTiming | cudaEventBlockingSync));
         const SlabPlan pl = plan_slab(ctx, n, bytes);
-        rc = prepare_slab(ctx, S, pl, n, copy_bytes + 64, nib);
+        rc = prepare_slab(ctx, S, pl, n, c.copy_bytes + 64, nib);
         if (rc != HX_OK) break;
+        const uint8_t *h_src = arena + (nib ? c.base / 2 : c.base), *h_flags = packed_in ? rec_flags + r0 : nullptr;
+        if (pack_otf) {
+            std::unique_lock<std::mutex> g(pipe.m);
+            pipe.cv.wait(g, [&] { return pipe.failed || pipe.packed_upto >= j; });
+            if (pipe.failed) {
+                rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: packing a slab failed");
+                break;
+            }
+            h_src = stage_of(j).p;
+            h_flags = h_src + flags_off(c);
+        }
         used[di * HX_NSLOT + si] = 1;  // from here on the slot's stream may hold work on caller memory
-        if (copy_bytes)
-            HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.arena.p, arena + (nib ? base / 2 : base), copy_bytes, cudaMemcpyHostToDevice, S.stream));
-        if (nib) HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.flags.p, rec_flags + r0, n, cudaMemcpyHostToDevice, S.stream));
+        if (c.copy_bytes) HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.arena.p, h_src, c.copy_bytes, cudaMemcpyHostToDevice, S.stream));
+        if (nib) HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.flags.p, h_flags, n, cudaMemcpyHostToDevice, S.stream));
+        if (pack_otf) {  // the staging buffer is free again once these copies are done
+            HX_CUDA_BREAK(ctx, rc, cudaEventRecord(stage_of(j).ev, S.stream));
+            std::lock_guard<std::mutex> g(pipe.m);
+            pipe.recorded_upto = j;
+            pipe.cv.notify_all();
+        }
         HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.offsets.p, offsets + r0, ((size_t)n + 1) * sizeof(uint64_t),
                                                cudaMemcpyHostToDevice, S.stream));
-        rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, base, n, S.out.p, S.stream, nib ? S.flags.p : nullptr);
+        rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, c.base, n, S.out.p, S.stream, nib ? S.flags.p : nullptr);
         if (rc != HX_OK) break;
         HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(out + (size_t)r0 * np, S.out.p, (size_t)n * np * sizeof(hx_result),
                                                cudaMemcpyDeviceToHost, S.stream));
-        r0 = r1;
-        ++slab_idx;
+        if (pack_otf) HX_CUDA_BREAK(ctx, rc, cudaEventRecord(S.done_ev, S.stream));
+    }
+    if (producer.joinable()) {
+        {
+            std::lock_guard<std::mutex> g(pipe.m);
+            if (rc != HX_OK) pipe.abort = true;
+            pipe.cv.notify_all();
+        }
+        producer.join();
     }
     // epilogue on every path: drain each (device, slot) stream that was used, so that no copy from the caller's arena
     // or into the caller's table is in flight when this function returns, and the slots are idle for the next call

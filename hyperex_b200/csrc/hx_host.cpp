@@ -17,6 +17,7 @@
 #endif
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <chrono>
 #include <cstdio>
@@ -24,6 +25,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -222,16 +224,17 @@ void hx_free_primer_file(char **fwd, char **rev, int n) {
 // ------------------------------------------------------------------------------------
 namespace {
 
+// byte -> 4-bit code in the low nibble, HX_REC_* evidence bits in bits 4..6
 struct PackTables {
-    uint8_t code[256];  // byte -> 4-bit code
-    uint8_t flag[256];  // byte -> HX_REC_* evidence bits
+    uint8_t lut[256];
     PackTables() {
         static const char letters[] = "ACGTRYSWKMBDHVN";
         for (int b = 0; b < 256; ++b) {
             const int u = (b >= 'a' && b <= 'z') ? b - 32 : b;
             const char *q = (u && u < 128) ? strchr(letters, u) : nullptr;
-            code[b] = q ? (uint8_t)(q - letters + 1) : (u == 'U' ? 4 : 0);
-            flag[b] = (uint8_t)((u == 'U' ? HX_REC_HAS_U : 0) | (u == 'T' ? HX_REC_HAS_T : 0) | ((!q && u != 'U') ? HX_REC_NON_IUPAC : 0));
+            const int code = q ? (int)(q - letters + 1) : (u == 'U' ? 4 : 0);
+            const int flag = (u == 'U' ? HX_REC_HAS_U : 0) | (u == 'T' ? HX_REC_HAS_T : 0) | ((!q && u != 'U') ? HX_REC_NON_IUPAC : 0);
+            lut[b] = (uint8_t)(code | (flag << 4));
         }
     }
 };
@@ -240,130 +243,370 @@ const PackTables &pack_tables() {
     return t;
 }
 
+// The packer is a STREAM over bases, not over records: nibble i is base i whatever record it belongs to, so a thread
+// packs its base range [start, stop) in whole vector blocks (64 bases with AVX2, 128 with AVX-512 VBMI; block starts are
+// absolute multiples of the block size, so the packed stores are aligned whenever `packed` is) and only the evidence
+// bits are per record.  A cursor walks the records alongside: blocks that lie inside one record — 22 of 23 for 1.5 kb
+// reads — OR their table bytes into a vector accumulator; a block that holds record ends turns the three evidence bits
+// into bit masks over its bases and splits them at the ends.  A record is finalised (rec_flags[r] stored) by the thread
+// whose range holds its last base; what a thread saw of a record that ends later is handed to the merge after the join.
+struct PackCursor {
+    const uint64_t *off;
+    uint32_t n;
+    uint8_t *rec_flags;
+    uint32_t cur;           // record that holds the next base
+    uint64_t e;             // its end (UINT64_MAX past the last record)
+    uint32_t acc = 0;       // evidence of `cur` so far (HX_REC_* bits)
+    int64_t first_final = -1;
+    void seek(uint64_t start) {
+        // last r with off[r] <= start: empty records that end at `start` belong to whoever holds base start - 1
+        cur = (uint32_t)(std::upper_bound(off, off + n + 1, start) - off) - 1;
+        e = cur < n ? off[cur + 1] : UINT64_MAX;
+    }
+    void finalize() {  // `cur` ends here
+        rec_flags[cur] = (uint8_t)acc;
+        if (first_final < 0) first_final = cur;
+        acc = 0;
+        ++cur;
+        e = cur < n ? off[cur + 1] : UINT64_MAX;
+    }
+};
+
+// bases [p, q) one by one (heads and tails of a thread's range); q is even or the end of the batch
+void pack_scalar(const uint8_t *arena, uint64_t p, uint64_t q, uint8_t *packed, PackCursor &c) {
+    const uint8_t *lut = pack_tables().lut;
+    for (uint64_t i = p; i < q; ++i) {
+        while (c.e <= i) c.finalize();
+        const uint8_t v = lut[arena[i]];
+        c.acc |= v >> 4;
+        if (i & 1) packed[i >> 1] = (uint8_t)((packed[i >> 1] & 0x0f) | (v << 4));
+        else packed[i >> 1] = (uint8_t)(v & 0x0f);  // the high nibble follows, or stays 0 at the end of the batch
+    }
+    while (c.e <= q) c.finalize();
+}
+
+inline uint32_t seg_any(const uint64_t *m, int words, uint32_t a, uint32_t b) {  // any bit of m in [a, b)?
+    uint64_t r = 0;
+    for (int w = 0; w < words; ++w) {
+        const uint32_t lo = (uint32_t)w * 64u, hi = lo + 64u;
+        if (b <= lo || a >= hi) continue;
+        uint64_t mask = ~0ull;
+        if (a > lo) mask &= ~0ull << (a - lo);
+        if (b < hi) mask &= ~0ull >> (hi - b);
+        r |= m[w] & mask;
+    }
+    return r != 0;
+}
+
+// record ends inside the block [p, p + bases): mU / mT / mB hold one bit per base of the block
+inline void pack_split(PackCursor &c, uint64_t p, uint32_t bases, const uint64_t *mU, const uint64_t *mT, const uint64_t *mB,
+                       uint32_t vec_acc) {
+    const int words = (int)(bases / 64u);
+    c.acc |= vec_acc;
+    uint32_t pos = 0;
+    while (c.e <= p + bases) {
+        const uint32_t end = (uint32_t)(c.e - p);
+        if (end > pos)
+            c.acc |= (seg_any(mU, words, pos, end) ? HX_REC_HAS_U : 0u) | (seg_any(mT, words, pos, end) ? HX_REC_HAS_T : 0u) |
+                     (seg_any(mB, words, pos, end) ? HX_REC_NON_IUPAC : 0u);
+        pos = end;
+        c.finalize();
+    }
+    if (pos < bases)
+        c.acc |= (seg_any(mU, words, pos, bases) ? HX_REC_HAS_U : 0u) | (seg_any(mT, words, pos, bases) ? HX_REC_HAS_T : 0u) |
+                 (seg_any(mB, words, pos, bases) ? HX_REC_NON_IUPAC : 0u);
+}
+
 #if defined(__x86_64__)
-// 64 bases -> 32 packed bytes per trip, straight from the ASCII text (src and dst start on an even base); returns the
-// number of bases consumed (a multiple of 64) and ORs the evidence bits into f
-__attribute__((target("avx2"))) size_t pack_avx2(const uint8_t *src, size_t n, uint8_t *dst, uint32_t &f) {
-    // letter index (byte & 0x1f, 1..26) -> code through two 16-entry shuffles; everything that is not a letter -> 0
-    //                 idx:  0  A  B  C  D  E  F  G  H  I  J  K  L  M  N  O
-    const __m256i lut_lo = _mm256_setr_epi8(0, 1, 11, 2, 12, 0, 0, 3, 13, 0, 0, 9, 0, 10, 15, 0, 0, 1, 11, 2, 12, 0, 0, 3, 13, 0, 0, 9, 0, 10, 15, 0);
-    //                 idx:  P  Q  R  S  T  U  V  W  X  Y  Z
-    const __m256i lut_hi = _mm256_setr_epi8(0, 0, 5, 7, 4, 4, 14, 8, 0, 6, 0, 0, 0, 0, 0, 0, 0, 0, 5, 7, 4, 4, 14, 8, 0, 6, 0, 0, 0, 0, 0, 0);
-    const __m256i m_df = _mm256_set1_epi8((char)0xdf), m_0f = _mm256_set1_epi8(0x0f), m_10 = _mm256_set1_epi8(0x10);
-    const __m256i c_40 = _mm256_set1_epi8(0x40), c_5b = _mm256_set1_epi8(0x5b), c_T = _mm256_set1_epi8('T'), c_U = _mm256_set1_epi8('U');
-    const __m256i mult = _mm256_set1_epi16(0x1001), zero = _mm256_setzero_si256();  // bytes (1, 16): low + 16 * high
-    __m256i any_t = zero, any_u = zero, any_bad = zero;
-#define HX_CODES32(p, out)                                                                                                     \
-    {                                                                                                                          \
-        const __m256i x = _mm256_loadu_si256((const __m256i *)(p));                                                            \
-        const __m256i u = _mm256_and_si256(x, m_df); /* letters: upper case; a non-letter never becomes a letter */          \
-        const __m256i letter = _mm256_and_si256(_mm256_cmpgt_epi8(u, c_40), _mm256_cmpgt_epi8(c_5b, u));                       \
-        const __m256i idx = _mm256_and_si256(u, m_0f);                                                                         \
-        const __m256i is_hi = _mm256_cmpeq_epi8(_mm256_and_si256(u, m_10), m_10);                                              \
-        out = _mm256_and_si256(_mm256_blendv_epi8(_mm256_shuffle_epi8(lut_lo, idx), _mm256_shuffle_epi8(lut_hi, idx), is_hi), \
-                               letter);                                                                                        \
-        any_t = _mm256_or_si256(any_t, _mm256_cmpeq_epi8(u, c_T)); /* 'T' / 't' (0x54 / 0x74): both fold to 0x54 */          \
-        any_u = _mm256_or_si256(any_u, _mm256_cmpeq_epi8(u, c_U));                                                             \
-        any_bad = _mm256_or_si256(any_bad, _mm256_cmpeq_epi8(out, zero));                                                      \
+__attribute__((target("avx2"))) inline uint32_t pack_reduce_avx2(__m256i vacc) {  // OR of the evidence bits of all bytes
+    alignas(32) uint64_t w[4];
+    _mm256_store_si256((__m256i *)w, vacc);
+    uint64_t r = w[0] | w[1] | w[2] | w[3];
+    r |= r >> 32;
+    r |= r >> 16;
+    r |= r >> 8;
+    return (uint32_t)(r >> 4) & 7u;
+}
+__attribute__((target("avx512f,avx512bw,avx512vbmi"))) inline uint32_t pack_reduce_avx512(__m512i vacc) {
+    return (_mm512_test_epi8_mask(vacc, _mm512_set1_epi8(HX_REC_HAS_U << 4)) ? HX_REC_HAS_U : 0u) |
+           (_mm512_test_epi8_mask(vacc, _mm512_set1_epi8(HX_REC_HAS_T << 4)) ? HX_REC_HAS_T : 0u) |
+           (_mm512_test_epi8_mask(vacc, _mm512_set1_epi8(HX_REC_NON_IUPAC << 4)) ? HX_REC_NON_IUPAC : 0u);
+}
+// 64 bases per trip.  Table byte of a base: letters (0x40..0x7f) through two 16-entry shuffles on the low five bits, which
+// also folds the case; everything else is "not one of the 16" (code 0, HX_REC_NON_IUPAC).
+__attribute__((target("avx2"))) void pack_blocks_avx2(const uint8_t *arena, uint64_t p, uint64_t q, uint8_t *packed, PackCursor &c, bool nt) {
+    const uint8_t *lut = pack_tables().lut;
+    alignas(32) uint8_t t_lo[32], t_hi[32];
+    for (int i = 0; i < 16; ++i) {
+        t_lo[i] = t_lo[16 + i] = lut[0x40 + i];  // '@' A..O
+        t_hi[i] = t_hi[16 + i] = lut[0x50 + i];  // P..Z [ \ ] ^ _
     }
-    size_t i = 0;
-    for (; i + 64 <= n; i += 64) {
-        __m256i c0, c1;
-        HX_CODES32(src + i, c0);
-        HX_CODES32(src + i + 32, c1);
-        const __m256i a = _mm256_maddubs_epi16(c0, mult), b = _mm256_maddubs_epi16(c1, mult);
-        _mm256_storeu_si256((__m256i *)(dst + i / 2), _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xd8));
+    const __m256i lut_lo = _mm256_load_si256((const __m256i *)t_lo), lut_hi = _mm256_load_si256((const __m256i *)t_hi);
+    const __m256i m_0f = _mm256_set1_epi8(0x0f), m_c0 = _mm256_set1_epi8((char)0xc0), c_40 = _mm256_set1_epi8(0x40);
+    const __m256i mult = _mm256_set1_epi16(0x1001);  // bytes (1, 16): low code + 16 * high code
+    __m256i vacc = _mm256_setzero_si256();
+    for (; p + 64 <= q; p += 64) {
+        __m256i o[2];
+        for (int h = 0; h < 2; ++h) {
+            const __m256i x = _mm256_loadu_si256((const __m256i *)(arena + p + 32 * h));
+            const __m256i idx = _mm256_and_si256(x, m_0f);
+            const __m256i t = _mm256_blendv_epi8(_mm256_shuffle_epi8(lut_lo, idx), _mm256_shuffle_epi8(lut_hi, idx),
+                                                 _mm256_slli_epi16(x, 3));  // bit 4 of the byte selects P..Z
+            const __m256i letter = _mm256_cmpeq_epi8(_mm256_and_si256(x, m_c0), c_40);
+            o[h] = _mm256_blendv_epi8(c_40, t, letter);  // 0x40 = code 0 + HX_REC_NON_IUPAC << 4
+        }
+        if (c.e > p + 64) {
+            vacc = _mm256_or_si256(vacc, _mm256_or_si256(o[0], o[1]));
+        } else {  // record ends inside the block: evidence of the record's finished blocks, then the split of this one
+            const uint32_t va = pack_reduce_avx2(vacc);
+            vacc = _mm256_setzero_si256();
+            const uint64_t mU = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(o[0], 3)) | ((uint64_t)(uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(o[1], 3)) << 32);
+            const uint64_t mT = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(o[0], 2)) | ((uint64_t)(uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(o[1], 2)) << 32);
+            const uint64_t mB = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(o[0], 1)) | ((uint64_t)(uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(o[1], 1)) << 32);
+            pack_split(c, p, 64, &mU, &mT, &mB, va);
+        }
+        const __m256i a = _mm256_maddubs_epi16(_mm256_and_si256(o[0], m_0f), mult), b = _mm256_maddubs_epi16(_mm256_and_si256(o[1], m_0f), mult);
+        const __m256i v = _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xd8);
+        if (nt) _mm256_stream_si256((__m256i *)(packed + p / 2), v);
+        else _mm256_storeu_si256((__m256i *)(packed + p / 2), v);
     }
-#undef HX_CODES32
-    f |= (_mm256_movemask_epi8(any_t) ? HX_REC_HAS_T : 0u) | (_mm256_movemask_epi8(any_u) ? HX_REC_HAS_U : 0u) |
-         (_mm256_movemask_epi8(any_bad) ? HX_REC_NON_IUPAC : 0u);
-    return i;
+    if (nt) _mm_sfence();
+    // hand the vector accumulator to the cursor (the open record goes on in the scalar tail or in the next thread)
+    c.acc |= pack_reduce_avx2(vacc);
+}
+
+// 128 bases per trip: one VPERMI2B looks a 7-bit byte up in the 128-entry table, bytes >= 0x80 are masked to 0x40
+__attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_blocks_avx512(const uint8_t *arena, uint64_t p, uint64_t q, uint8_t *packed,
+                                                                                PackCursor &c, bool nt) {
+    const uint8_t *lut = pack_tables().lut;
+    const __m512i tab0 = _mm512_loadu_si512(lut), tab1 = _mm512_loadu_si512(lut + 64);
+    const __m512i c_40 = _mm512_set1_epi8(0x40), m_0f = _mm512_set1_epi8(0x0f), mult = _mm512_set1_epi16(0x1001);
+    const __m512i bU = _mm512_set1_epi8(HX_REC_HAS_U << 4), bT = _mm512_set1_epi8(HX_REC_HAS_T << 4), bB = _mm512_set1_epi8(HX_REC_NON_IUPAC << 4);
+    __m512i vacc = _mm512_setzero_si512();
+    for (; p + 128 <= q; p += 128) {
+        const __m512i x0 = _mm512_loadu_si512(arena + p), x1 = _mm512_loadu_si512(arena + p + 64);
+        const __m512i o0 = _mm512_mask_mov_epi8(_mm512_permutex2var_epi8(tab0, x0, tab1), _mm512_movepi8_mask(x0), c_40);
+        const __m512i o1 = _mm512_mask_mov_epi8(_mm512_permutex2var_epi8(tab0, x1, tab1), _mm512_movepi8_mask(x1), c_40);
+        if (c.e > p + 128) {
+            vacc = _mm512_ternarylogic_epi64(vacc, o0, o1, 0xfe);
+        } else {
+            const uint64_t mU[2] = {_mm512_test_epi8_mask(o0, bU), _mm512_test_epi8_mask(o1, bU)};
+            const uint64_t mT[2] = {_mm512_test_epi8_mask(o0, bT), _mm512_test_epi8_mask(o1, bT)};
+            const uint64_t mB[2] = {_mm512_test_epi8_mask(o0, bB), _mm512_test_epi8_mask(o1, bB)};
+            pack_split(c, p, 128, mU, mT, mB, pack_reduce_avx512(vacc));
+            vacc = _mm512_setzero_si512();
+        }
+        const __m512i a = _mm512_maddubs_epi16(_mm512_and_si512(o0, m_0f), mult), b = _mm512_maddubs_epi16(_mm512_and_si512(o1, m_0f), mult);
+        const __m512i v = _mm512_inserti64x4(_mm512_castsi256_si512(_mm512_cvtepi16_epi8(a)), _mm512_cvtepi16_epi8(b), 1);
+        if (nt) _mm512_stream_si512((__m512i *)(packed + p / 2), v);
+        else _mm512_storeu_si512(packed + p / 2, v);
+    }
+    if (nt) _mm_sfence();
+    c.acc |= pack_reduce_avx512(vacc);
 }
 #endif
 
-bool have_avx2() {
+int pack_isa() {  // 0 scalar, 1 AVX2, 2 AVX-512 VBMI; HYPEREX_PACK_ISA caps it (tests run every level the CPU has)
 #if defined(__x86_64__)
-    static const bool v = __builtin_cpu_supports("avx2");
-    return v;
+    static const int v = [] {
+        int isa = 0;
+        if (__builtin_cpu_supports("avx2")) isa = 1;
+        if (isa == 1 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi")) isa = 2;
+        return isa;
+    }();
+    const char *cap = getenv("HYPEREX_PACK_ISA");
+    return cap ? std::min(v, atoi(cap)) : v;
 #else
-    return false;
+    return 0;
 #endif
 }
 
-// Packs records [r0, r1) of the arena.  A thread owns the packed bytes whose LOW nibble lies in its base range
-// [offsets[r0], offsets[r1]): when the range ends on an odd base, the byte's high nibble is the first base of the next
-// record, read from the arena (zero past the end of the batch); when it starts on an odd base, that first nibble was
-// written by the owner of the byte before it.  Evidence bits are per record regardless of who writes the nibble.
-void pack_range(const uint8_t *arena, const uint64_t *offsets, uint32_t r0, uint32_t r1, uint64_t arena_end, uint8_t *packed,
-                uint8_t *rec_flags) {
-    const bool avx2 = have_avx2();
-    const PackTables &t = pack_tables();
-    bool skip_first = (offsets[r0] & 1) != 0;  // the range starts on an odd base: its nibble has an owner already
-    int carry = -1;                            // code of an even base whose partner (the next base) is still to come
-    uint64_t last = offsets[r0];
-    for (uint32_t r = r0; r < r1; ++r) {
-        uint64_t b = offsets[r];
-        const uint64_t e = offsets[r + 1];
-        uint32_t f = 0;
-        if (skip_first && b < e) {  // evidence only
-            f |= t.flag[arena[b]];
-            ++b;
-            skip_first = false;
-        }
-        if (carry >= 0 && b < e) {  // b is odd: completes the pending byte
-            packed[b / 2] = (uint8_t)(carry | (t.code[arena[b]] << 4));
-            f |= t.flag[arena[b]];
-            ++b;
-            carry = -1;
-        }
-#if defined(__x86_64__)
-        if (avx2 && b < e) b += pack_avx2(arena + b, (size_t)(e - b), packed + b / 2, f);  // b is even here
-#endif
-        for (; b + 2 <= e; b += 2) {
-            packed[b / 2] = (uint8_t)(t.code[arena[b]] | (t.code[arena[b + 1]] << 4));
-            f |= t.flag[arena[b]] | t.flag[arena[b + 1]];
-        }
-        if (b < e) {
-            carry = t.code[arena[b]];
-            f |= t.flag[arena[b]];
-        }
-        rec_flags[r] = (uint8_t)f;
-        last = e;
+struct PackPart {  // what one thread reports to the merge
+    int64_t first_final = -1;
+    uint32_t open_rec = 0, open_acc = 0;
+};
+
+// bases [start, stop) of the batch; interior range edges are multiples of 128 bases
+void pack_range(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint64_t start, uint64_t stop, uint8_t *packed,
+                uint8_t *rec_flags, int isa, bool stream_stores, PackPart *part) {
+    PackCursor c{offsets, n_records, rec_flags, 0, 0};
+    c.seek(start);
+    const uint64_t blk = isa == 2 ? 128 : 64;
+    uint64_t p = start;
+    const uint64_t head_end = std::min(stop, (start + blk - 1) / blk * blk);
+    if (isa == 0 || head_end > p) {
+        const uint64_t q = isa == 0 ? stop : head_end;
+        pack_scalar(arena, p, q, packed, c);
+        p = q;
     }
-    if (carry >= 0)  // odd tail: the high nibble is the base after the range (it belongs to the next record, if any)
-        packed[(last - 1) / 2] = (uint8_t)(carry | ((last < arena_end ? t.code[arena[last]] : 0) << 4));
+    const uint64_t body_end = p + (stop - p) / blk * blk;
+#if defined(__x86_64__)
+    if (body_end > p) {
+        // large outputs bypass the cache (no read-for-ownership of the packed lines; the next reader is a DMA engine or
+        // another pass long after); the block stores are 64- / 32-byte aligned whenever the buffer is
+        const bool nt = stream_stores && (((uintptr_t)(packed + p / 2)) & (blk / 2 - 1)) == 0;
+        if (isa == 2) pack_blocks_avx512(arena, p, body_end, packed, c, nt);
+        else pack_blocks_avx2(arena, p, body_end, packed, c, nt);
+        p = body_end;
+    }
+#endif
+    if (stop > p) pack_scalar(arena, p, stop, packed, c);
+    while (c.e <= stop) c.finalize();  // records (also empty ones) that end exactly at the end of the range
+    part->first_final = c.first_final;
+    part->open_rec = c.cur;
+    part->open_acc = c.acc;
 }
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------
+// A small persistent pool for data-parallel host loops that run once per slab (packing a slab takes about a
+// millisecond: starting threads for it would cost as much as the work).  One pool per process, created on first use;
+// callers are serialised.
+// ------------------------------------------------------------------------------------
+namespace {
+class HxhPool {
+  public:
+    static HxhPool &get() {
+        static HxhPool *p = new HxhPool();  // never destroyed: worker threads must not outlive their state at exit
+        return *p;
+    }
+    int size() const { return (int)workers_.size() + 1; }
+    // runs fn(i) for i in [0, n) on up to `threads` threads (the caller is one of them)
+    void run(int n, int threads, const std::function<void(int)> &fn) {
+        if (n <= 0) return;
+        if (n == 1 || threads <= 1 || workers_.empty()) {
+            for (int i = 0; i < n; ++i) fn(i);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(call_);
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0);
+            done_ = 0;
+            want_ = std::min((int)workers_.size(), threads - 1);
+            woken_ = 0;
+            epoch_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        work(true);
+        std::unique_lock<std::mutex> g(m_);
+        cv_done_.wait(g, [&] { return done_ == n_ && active_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    HxhPool() {
+        const int hw = (int)std::thread::hardware_concurrency();
+        for (int i = 0; i + 1 < std::max(1, hw); ++i) workers_.emplace_back([this] { loop(); });
+        for (std::thread &t : workers_) t.detach();
+    }
+    void work(bool caller) {
+        int mine = 0;
+        for (;;) {
+            const int i = next_.fetch_add(1);
+            if (i >= n_) break;
+            (*fn_)(i);
+            ++mine;
+        }
+        std::lock_guard<std::mutex> g(m_);
+        done_ += mine;
+        if (!caller) --active_;
+        if (done_ == n_ && active_ == 0) cv_done_.notify_all();
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            // a caller that packs slab after slab comes back within microseconds: look for the next call for a moment
+            // before going to sleep (a futex wake-up of 15 sleepers costs more than packing a small slab)
+            for (int spin = 0; spin < 4000 && epoch_.load(std::memory_order_acquire) == seen; ++spin) {
+#if defined(__x86_64__)
+                _mm_pause();
+#endif
+            }
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
+                seen = epoch_.load(std::memory_order_acquire);
+                if (woken_ >= want_ || fn_ == nullptr) continue;  // enough helpers for this call
+                ++woken_;
+                ++active_;
+            }
+            work(false);
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex call_, m_;
+    std::condition_variable cv_, cv_done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_ = 0, done_ = 0, want_ = 0, woken_ = 0, active_ = 0;
+    std::atomic<int> next_{0};
+    std::atomic<uint64_t> epoch_{0};
+};
+}  // namespace
+
 extern "C" int hx_pack_records(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint8_t *packed,
                                uint8_t *rec_flags, int n_threads) {
+    return hxh_pack_slab(arena, offsets, n_records, packed, 0, rec_flags, n_threads);
+}
+
+// hx_pack_records into a buffer whose first byte is packed byte `packed_base / 2` of the batch (packed_base even and
+// <= offsets[0]): the staging buffer of one host->device slab (hx_run_batch with pack_h2d)
+int hxh_pack_slab(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint8_t *packed, uint64_t packed_base,
+                  uint8_t *rec_flags, int n_threads) {
     if (!offsets || (n_records && (!packed || !rec_flags))) return HX_ERR_ARG;
+    if ((packed_base & 1) || (n_records && packed_base > offsets[0])) return HX_ERR_ARG;
+    packed = (uint8_t *)((uintptr_t)packed - (uintptr_t)(packed_base / 2));  // indexed by absolute base / 2 below
     if (n_records == 0) return HX_OK;
     if (offsets[n_records] < offsets[0] || (offsets[n_records] > offsets[0] && !arena)) return HX_ERR_ARG;
     for (uint32_t r = 0; r < n_records; ++r)
         if (offsets[r + 1] < offsets[r]) return HX_ERR_ARG;
-    const uint64_t end = offsets[n_records];
-    if (offsets[0] & 1) {  // the batch starts on an odd base: nobody before it owns that byte
-        const uint64_t b = offsets[0];
-        packed[b / 2] = (uint8_t)((b < end ? pack_tables().code[arena[b]] : 0) << 4);
-    }
+    const uint64_t begin = offsets[0], end = offsets[n_records];
+    if (begin & 1) packed[begin / 2] = 0;  // the batch starts on an odd base: nobody owns the low nibble of its first byte
+    if (end & 1) packed[end / 2] = 0;      // ... and the high nibble of its last byte when it ends on one
+    // leading empty records end before the first base: no range finalises them
+    for (uint32_t r = 0; r < n_records && offsets[r + 1] == begin; ++r) rec_flags[r] = 0;
+    if (end == begin) return HX_OK;
+    const int isa = pack_isa();
     int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-    nt = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nt, (end - offsets[0]) / (1 << 20) + 1));
-    if (nt == 1) {
-        pack_range(arena, offsets, 0, n_records, end, packed, rec_flags);
-        return HX_OK;
+    // The batch is cut into ranges of about `grain` bases at multiples of 128 (whole vector blocks, aligned packed
+    // stores) that the threads take one after the other.  Small ranges taken in order rather than one large range per
+    // thread: threads that stream through addresses a fixed large distance apart were measured to run at 1/T of their
+    // single-thread rate on some hosts (same DRAM banks in lockstep); neighbours do not, and they balance the load.
+    const char *grain_env = getenv("HYPEREX_PACK_GRAIN");  // tests cut finer
+    const uint64_t grain = std::max<uint64_t>(grain_env ? strtoull(grain_env, nullptr, 10) : (1u << 20), 128);
+    const int np = (int)std::min<uint64_t>((end - begin + grain - 1) / grain, 1u << 20);
+    nt = std::max(1, std::min(nt, np));
+    std::vector<uint64_t> cut(np + 1);
+    for (int t = 0; t <= np; ++t) {
+        const uint64_t x = begin + (uint64_t)((__uint128_t)(end - begin) * (uint64_t)t / (uint64_t)np);
+        cut[t] = t == 0 ? begin : t == np ? end : std::min<uint64_t>(end, std::max<uint64_t>(begin, x & ~(uint64_t)127));
     }
-    std::vector<std::thread> th;
-    uint32_t r0 = 0;
-    for (int t = 0; t < nt; ++t) {  // record ranges of about equal bases
-        const uint64_t target = offsets[0] + (end - offsets[0]) * (uint64_t)(t + 1) / (uint64_t)nt;
-        uint32_t r1 = t + 1 == nt ? n_records : (uint32_t)(std::lower_bound(offsets + r0, offsets + n_records + 1, target) - offsets);
-        r1 = std::min(std::max(r1, r0), n_records);
-        if (r1 > r0) th.emplace_back(pack_range, arena, offsets, r0, r1, end, packed, rec_flags);
-        r0 = r1;
+    const char *nt_env = getenv("HYPEREX_PACK_NT");  // A/B switch: 0 keeps ordinary stores
+    const bool stream_stores = nt_env ? atoi(nt_env) != 0 : (end - begin) >= ((uint64_t)8 << 20);
+    std::vector<PackPart> parts(np);
+    HxhPool::get().run(np, nt, [&](int t) {
+        if (cut[t + 1] > cut[t]) pack_range(arena, offsets, n_records, cut[t], cut[t + 1], packed, rec_flags, isa, stream_stores, &parts[t]);
+        else parts[t].first_final = -2;  // empty range
+    });
+    // merge: a record that spans range edges is finalised by the range that holds its last base; OR in what the ranges
+    // before it saw of it
+    uint32_t open_rec = UINT32_MAX, open_acc = 0;
+    for (int t = 0; t < np; ++t) {
+        if (parts[t].first_final == -2) continue;
+        if (parts[t].first_final >= 0) {
+            if ((uint32_t)parts[t].first_final == open_rec) rec_flags[open_rec] |= (uint8_t)open_acc;
+            open_rec = parts[t].open_rec;
+            open_acc = parts[t].open_acc;
+        } else if (parts[t].open_rec == open_rec) {
+            open_acc |= parts[t].open_acc;
+        } else {
+            open_rec = parts[t].open_rec;
+            open_acc = parts[t].open_acc;
+        }
     }
-    for (std::thread &t : th) t.join();
     return HX_OK;
 }
 

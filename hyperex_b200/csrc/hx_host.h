@@ -33,6 +33,9 @@ int hxh_run_text_lane(hx_ctx *ctx, int lane, const uint8_t *arena, const uint64_
 // hx_run_batch (result table only) on the lane's device
 int hxh_run_batch_lane(hx_ctx *ctx, int lane, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
                        hx_result *out);
+// hx_pack_records (include/hyperex_b200.h) into a buffer that starts at packed byte packed_base / 2 of the batch
+int hxh_pack_slab(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint8_t *packed, uint64_t packed_base,
+                  uint8_t *rec_flags, int n_threads);
 // slot for host-side state the driver keeps in the context across calls (freed with free_fn by hx_destroy)
 void **hxh_host_cache(hx_ctx *ctx, void (*free_fn)(void *));
 void hxh_set_error(hx_ctx *ctx, const char *msg);

@@ -32,6 +32,9 @@ def _run(ctx, arena, offsets, pairs, k, **opts):
     ctx.set_option("fast_small_k", opts.get("fast", 1))
     ctx.set_option("long_filter", opts.get("lf", 1))
     ctx.set_option("pack16", opts.get("pack", 1))
+    # 1: hx_run_batch packs every slab to 4 bits per base on its way to the device (ASCII in, nibble-text kernels)
+    ctx.set_option("pack_h2d", opts.get("pack_h2d", -1))
+    ctx.set_option("pack_threads", opts.get("pack_threads", 0))
     ctx.set_primers(pairs, k)
     if opts.get("packed"):  # 4-bit packed arena (hx_pack_records + hx_run_batch_packed)
         pk, fl = hx.pack_records(arena, offsets, opts.get("pack_threads", 3))
@@ -312,10 +315,14 @@ def test_packed_arena_equals_oracle(ctx, k):
         for fast in (0, 1):
             _cmp(_run(ctx, a, o, pairs, k, tile_len=tile[0], single_max=tile[1], fast=fast, packed=1), ref, a, o, pairs, k)
     _cmp(_run(ctx, a, o, pairs, k, packed=1, slab_bytes=50_000, pack_threads=8), ref, a, o, pairs, k)
+    # ASCII in, packed on the way (pack_h2d): one slab, many slabs cut at unaligned / odd record starts
+    for slab, th in ((128 << 20, 0), (50_000, 3), (1, 2), (333_333, 8)):
+        _cmp(_run(ctx, a, o, pairs, k, pack_h2d=1, slab_bytes=slab, pack_threads=th), ref, a, o, pairs, k)
     # an arena whose first record starts at an odd offset
     a2 = np.concatenate([np.frombuffer(b"GTGCCAG", np.uint8), a])
     o2 = o + np.uint64(7)
     _cmp(_run(ctx, a2, o2, pairs, k, packed=1, slab_bytes=30_000), ref, a2, o2, pairs, k)
+    _cmp(_run(ctx, a2, o2, pairs, k, pack_h2d=1, slab_bytes=30_000), ref, a2, o2, pairs, k)
 
 
 def test_packed_arena_contigs_long_primers_and_refusal(ctx):
@@ -324,6 +331,7 @@ def test_packed_arena_contigs_long_primers_and_refusal(ctx):
     ref = O.run_batch(a, o, pairs, 3, nthreads=8)
     _cmp(_run(ctx, a, o, pairs, 3, packed=1), ref, a, o, pairs, 3)
     _cmp(_run(ctx, a, o, pairs, 3, packed=1, tile_len=1024, single_max=1500), ref, a, o, pairs, 3)
+    _cmp(_run(ctx, a, o, pairs, 3, pack_h2d=1, slab_bytes=200_000), ref, a, o, pairs, 3)
     # primers of 33..64 nt: suffix filter + verification read the text as nibbles too; 64-bit groups
     a, o = hx_synth.gen_reads(300, seed=46)
     pairs = hx_synth.gen_primer_pairs(12, seed=5, builtins=hx.default_primers())
@@ -339,6 +347,11 @@ def test_packed_arena_contigs_long_primers_and_refusal(ctx):
     assert e.value.code == -4 and "packed" in str(e.value)
     ctx.set_primers([["acgtACGT", "GGCC"]], 0)   # lower-case primer symbols match nothing in either mode
     _cmp(ctx.run_batch_packed(pk, fl, o), O.run_batch(a, o, [["acgtACGT", "GGCC"]], 0), a, o)
+    # ... and hx_run_batch with pack_h2d forced simply keeps the ASCII path for such a primer set
+    a = a.copy()
+    a[int(o[5]) + 3:int(o[5]) + 12] = np.frombuffer(b"ACGTXACGT", np.uint8)
+    px = [["ACGTXACGT", "GGCC"], ["ACGTNACGT", "GGCC"]]
+    _cmp(_run(ctx, a, o, px, 1, pack_h2d=1), O.run_batch(a, o, px, 1), a, o, px, 1)
 
 
 # ---- edge cases the domain has -------------------------------------------------------------------------
@@ -421,6 +434,8 @@ def test_random_primer_sets_fuzz(ctx, seed):
     for fast, lf, pack in ((0, 1, 1), (1, 2, 2), (1, 1, 1), (0, 0, 0)):
         _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, lf=lf, pack=pack, packed=1,
                   slab_bytes=int(rng.choice([1, 3000, 128 << 20]))), ref, a, o, pairs, k)
+    _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, pack_h2d=1, pack_threads=int(rng.integers(1, 9)),
+              slab_bytes=int(rng.choice([1, 3000, 128 << 20]))), ref, a, o, pairs, k)
 
 
 def test_rna_records_use_rna_reverse_complement(ctx):
@@ -446,6 +461,7 @@ def test_slab_pipeline_and_unaligned_offsets(ctx):
     ref = O.run_batch(a, o, pairs, 2, nthreads=8)
     for slab in (1, 4096, 50_000, 1 << 20):
         _cmp(_run(ctx, a, o, pairs, 2, slab_bytes=slab), ref, a, o, pairs, 2)
+        _cmp(_run(ctx, a, o, pairs, 2, slab_bytes=slab, pack_h2d=1), ref, a, o, pairs, 2)
     # an arena whose first record does not start at offset 0
     pad = 7
     a2 = np.concatenate([np.frombuffer(b"GTGCCAG", np.uint8), a])

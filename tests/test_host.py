@@ -291,8 +291,13 @@ def _pack_model(arena, offsets):
     return packed, flags
 
 
+@pytest.mark.parametrize("isa", [0, 1, 2])       # scalar / AVX2 / AVX-512 VBMI (capped at what this CPU has)
+@pytest.mark.parametrize("grain", [0, 192, 4096])  # bases per range the threads take: default (1 Mi) / finer than a record
 @pytest.mark.parametrize("threads", [1, 3, 8])
-def test_pack_records_equals_the_model(threads):
+def test_pack_records_equals_the_model(threads, grain, isa, monkeypatch):
+    monkeypatch.setenv("HYPEREX_PACK_ISA", str(isa))
+    if grain:
+        monkeypatch.setenv("HYPEREX_PACK_GRAIN", str(grain))
     rng = np.random.default_rng(77 + threads)
     alphabet = np.frombuffer(b"ACGT" * 12 + b"acgtnNRYSWKMBDHVUuXx-*.019 \t@[`{" + bytes([0, 1, 127, 128, 200, 255]), np.uint8)
     for trial in range(60):
@@ -301,7 +306,11 @@ def test_pack_records_equals_the_model(threads):
         if trial == 7:
             lens = np.array([0, 0, 1, 0, 1, 1, 0, 2, 0], dtype=np.int64)   # empty records at odd offsets
         if trial == 8:
+            if grain == 192:
+                continue
             lens = np.array([3_000_001, 5, 1_500_000], dtype=np.int64)    # several threads inside one record range
+        if trial == 9:
+            lens = np.array([700, 0, 0, 129, 127, 1, 0, 128, 256, 0, 63, 65, 640, 0], dtype=np.int64)  # ends on / next to block edges
         start = int(rng.integers(0, 5))
         offsets = np.zeros(len(lens) + 1, np.uint64)
         offsets[0] = start
