@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -30,7 +31,6 @@ namespace {
 
 constexpr int HX_NSLOT = 3;  // pipeline depth per device (H2D / scan / D2H overlap)
 constexpr int HX_NLANE = 2;  // text lanes per device (see TextLane)
-constexpr int HX_NSTAGE = 4; // pinned staging buffers per device of the pack-on-the-way path (see PackStage)
 
 std::string g_create_error;
 
@@ -133,18 +133,32 @@ struct TextLane {
     }
 };
 
-// pinned staging of hx_run_batch with pack_h2d: one slab as 4-bit codes followed by its rec_flags; `ev` marks the end of the
-// host->device copies that read it
-struct PackStage {
-    uint8_t *p = nullptr;
-    size_t cap = 0;
-    cudaEvent_t ev = nullptr;
+// Pinned staging of hx_run_batch with pack_h2d.  The packed text goes through a RING of small piece buffers (a few MiB
+// each): small enough to stay in the host's last-level cache between the packer's stores and the DMA engine's reads, so
+// the packed bytes cost no DRAM traffic (whole-slab staging buffers were measured: the packer drops from 91 to 73
+// Gbases/s while the copies of the slabs before it read host memory, profiles/r02_pack_h2d.md).  The ring belongs to the
+// context (portable pinned memory, any device copies from it); every device has one event per ring buffer, which marks
+// the end of the host->device copy that read it.
+constexpr int HX_NRING = 8;  // piece buffers per device of the context
+struct PackRing {
+    uint8_t *p = nullptr;       // n_buf buffers of buf_bytes
+    size_t buf_bytes = 0;
+    int n_buf = 0;
+    uint8_t *flags = nullptr;   // rec_flags of the whole batch (final slab by slab)
+    size_t flags_cap = 0;
+    void release() {
+        if (p) cudaFreeHost(p);
+        if (flags) cudaFreeHost(flags);
+        p = flags = nullptr;
+        buf_bytes = flags_cap = 0;
+        n_buf = 0;
+    }
 };
 
 struct Device {
     int dev = 0;
     Slot slots[HX_NSLOT];
-    PackStage stage[HX_NSTAGE];
+    std::vector<cudaEvent_t> ring_ev;  // per ring buffer of the context: end of this device's copy out of it
     TextLane lanes[HX_NLANE];
     uint8_t *d_tables = nullptr;
     uint8_t *d_tables_wm = nullptr;
@@ -176,10 +190,11 @@ struct hx_ctx {
     bool packable = true;  // every primer symbol is one of ACGTURYSWKMBDHVN (or lower case, which matches nothing)
     // options
     int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1,
-            opt_long_filter = 1, opt_group_np_max = 0, opt_pack16 = 1, opt_pack_h2d = -1, opt_pack_threads = 0;
+            opt_long_filter = 1, opt_group_np_max = 0, opt_pack16 = 1, opt_pack_h2d = -1, opt_pack_threads = 0, opt_pack_piece_bytes = 4ll << 20;
     std::atomic<uint64_t> launches{0};
     std::mutex mu;  // guards err and timed: text lanes of one context run on several host threads
     DevPool find_pool;
+    PackRing pack_ring;
     // host-side state the file-level driver (hx_host.cpp) keeps across calls: pinned record batches etc.
     void *host_cache = nullptr;
     void (*host_cache_free)(void *) = nullptr;
@@ -271,6 +286,14 @@ void peq_rows(const std::string &pat, int bits, uint64_t rows[256]) {
         for (uint8_t b : accepts[(uint8_t)pat[i]]) up[b] |= 1ull << (i + bits - m);
     rows[0] = 0;
     for (int b = 1; b < 256; ++b) rows[b] = up[(b >= 'a' && b <= 'z') ? b - 32 : b];
+}
+
+inline void hx_cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
 }
 
 // Like HX_CUDA, for loops that must not return while earlier asynchronous copies still use caller memory: records the
@@ -866,15 +889,14 @@ void hx_destroy(hx_ctx *ctx) {
     ctx->host_cache = nullptr;
     if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].dev);
     ctx->find_pool.release();
+    ctx->pack_ring.release();
     for (Device &D : ctx->devs) {
         cudaSetDevice(D.dev);
         cudaDeviceSynchronize();
         for (Slot &S : D.slots) S.release();
         for (TextLane &L : D.lanes) L.release();
-        for (PackStage &G : D.stage) {
-            if (G.p) cudaFreeHost(G.p);
-            if (G.ev) cudaEventDestroy(G.ev);
-        }
+        for (cudaEvent_t e : D.ring_ev)
+            if (e) cudaEventDestroy(e);
         if (D.d_tables) cudaFree(D.d_tables);
         if (D.d_tables_wm) cudaFree(D.d_tables_wm);
         if (D.d_tables_pk) cudaFree(D.d_tables_pk);
@@ -899,6 +921,7 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     else if (n == "pack16") ctx->opt_pack16 = value < 0 ? 0 : (value > 2 ? 2 : value);  // hx_set_primers builds, every scan reads
     else if (n == "pack_h2d") ctx->opt_pack_h2d = value < 0 ? -1 : (value ? 1 : 0);
     else if (n == "pack_threads") ctx->opt_pack_threads = std::max<int64_t>(value, 0);
+    else if (n == "pack_piece_bytes") ctx->opt_pack_piece_bytes = std::min<int64_t>(std::max<int64_t>(value, 4096), 256ll << 20) & ~(int64_t)63;
     else return fail(ctx, HX_ERR_ARG, "unknown option %s", name);
     return HX_OK;
 }
@@ -1239,13 +1262,20 @@ struct SlabCut {
     uint64_t base, copy_bytes;
 };
 
-// producer <-> issuer hand-over of the pack-on-the-way path
-struct PackPipe {
-    std::mutex m;
-    std::condition_variable cv;
-    int64_t packed_upto = -1;    // slabs [0, packed_upto] are packed (producer -> issuer)
-    int64_t recorded_upto = -1;  // the H2D-done events of slabs [0, recorded_upto] are recorded (issuer -> producer)
-    bool abort = false, failed = false;
+// A piece of a slab on the pack-on-the-way path: bases [p, q) of the batch, packed range by range into ring buffer
+// `slot` and copied from there to byte dst_off of the slab's arena
+struct PackPiece {
+    int64_t slab;
+    uint64_t p, q, al;  // al: the base the first byte of the ring buffer stands for (p rounded down to the slab's base)
+    uint64_t dst_off, bytes;
+    int slot;
+    int64_t first_range, n_ranges;
+    bool last_of_slab;
+};
+struct PackRange {
+    uint64_t p, q;
+    int64_t piece;
+    bool slab_first;
 };
 }  // namespace
 
@@ -1304,57 +1334,114 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
     std::vector<int> used(ndev * HX_NSLOT, 0);
     int rc = HX_OK;
 
-    // ---- pack on the way: staging ring + producer thread ----
-    PackPipe pipe;
-    std::thread producer;
-    auto stage_of = [&](int64_t j) -> PackStage & { return ctx->devs[j % ndev].stage[(j / ndev) % HX_NSTAGE]; };
-    auto flags_off = [](const SlabCut &c) { return ((size_t)c.copy_bytes + 63) & ~(size_t)63; };
+    // ---- pack on the way ----
+    // Every slab is cut into pieces (one ring buffer each) and every piece into ranges of 128 Ki bases.  The packer threads
+    // take the ranges of the WHOLE batch in order from one counter (one fork / join per call) and only wait when the ring
+    // buffer of their range is still being read by an earlier copy; this thread issues the copy of a piece as soon as its
+    // last range is done, frees ring buffers as their copies complete, and finishes a slab (evidence merge, rec_flags,
+    // offsets, kernels, result copy) after its last piece.
+    std::vector<PackPiece> pieces;
+    std::vector<PackRange> ranges;
+    std::vector<int64_t> first_piece;  // per slab
+    std::vector<HxhPackPart> parts;
+    std::unique_ptr<std::atomic<int>[]> piece_done;  // ranges of the piece that are packed
+    std::atomic<int64_t> next_range{0}, allowed_piece{0};
+    std::atomic<bool> pack_abort{false};
+    std::thread packer;
+    PackRing &R = ctx->pack_ring;
+    int64_t oldest = 0;  // first piece whose copy is not known to be complete
+    auto piece_ev = [&](int64_t g) -> cudaEvent_t { return ctx->devs[pieces[g].slab % ndev].ring_ev[pieces[g].slot]; };
+    int64_t issued = 0;  // pieces whose copies are enqueued
+    auto poll_ring = [&] {
+        while (oldest < issued && cudaEventQuery(piece_ev(oldest)) == cudaSuccess) ++oldest;
+        allowed_piece.store(oldest + R.n_buf, std::memory_order_release);
+    };
     if (pack_otf) {
-        size_t need = 0;
-        for (const SlabCut &c : cuts) need = std::max(need, flags_off(c) + (c.r1 - c.r0) + 64);
-        for (int64_t j = 0; j < std::min<int64_t>(n_slabs, (int64_t)ndev * HX_NSTAGE) && rc == HX_OK; ++j) {
-            PackStage &G = stage_of(j);
-            if (cudaSetDevice(ctx->devs[j % ndev].dev) != cudaSuccess) rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaSetDevice failed");
-            if (rc == HX_OK && !G.ev && cudaEventCreateWithFlags(&G.ev, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
-                rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaEventCreate failed");
-            if (rc == HX_OK && G.cap < need) {
-                if (G.p) cudaFreeHost(G.p);
-                G.p = nullptr;
-                G.cap = 0;
-                const size_t want = need + need / 8;
-                if (cudaHostAlloc((void **)&G.p, want, cudaHostAllocDefault) != cudaSuccess)
-                    rc = fail(ctx, HX_ERR_NOMEM, "hx_run_batch: cannot allocate %zu bytes of pinned staging", want);
-                else G.cap = want;
+        const uint64_t piece_bases = 2ull * (uint64_t)ctx->opt_pack_piece_bytes;  // a multiple of 128
+        const uint64_t range_bases = 128u << 10;
+        const int n_buf = HX_NRING * ndev;
+        for (int64_t j = 0; j < n_slabs; ++j) {
+            const SlabCut &c = cuts[j];
+            const uint64_t begin = offsets[c.r0], end = offsets[c.r1];
+            first_piece.push_back((int64_t)pieces.size());
+            for (uint64_t al = c.base;; al += piece_bases) {
+                PackPiece P;
+                P.slab = j;
+                P.al = al;
+                P.p = std::max(al, begin);
+                P.q = std::max(P.p, std::min(end, al + piece_bases));
+                P.dst_off = (al - c.base) / 2;
+                P.bytes = P.q > P.al ? (P.q + 1) / 2 - P.al / 2 : 0;
+                P.slot = (int)(pieces.size() % (size_t)n_buf);
+                P.first_range = (int64_t)ranges.size();
+                for (uint64_t x = P.p; x < P.q;) {  // range edges at multiples of 128 (whole vector blocks)
+                    const uint64_t y = std::min(P.q, (x + range_bases) & ~(uint64_t)127);
+                    ranges.push_back({x, y, (int64_t)pieces.size(), x == begin});
+                    x = y;
+                }
+                P.n_ranges = (int64_t)ranges.size() - P.first_range;
+                P.last_of_slab = al + piece_bases >= end;
+                pieces.push_back(P);
+                if (P.last_of_slab) break;
             }
         }
-        if (rc != HX_OK) return rc;  // nothing enqueued yet
-        producer = std::thread([&] {
-            for (int64_t j = 0; j < n_slabs; ++j) {
-                const SlabCut &c = cuts[j];
-                PackStage &G = stage_of(j);
-                const int64_t prev = j - (int64_t)ndev * HX_NSTAGE;  // the slab that used this staging buffer before
-                if (prev >= 0) {
-                    {
-                        std::unique_lock<std::mutex> g(pipe.m);
-                        pipe.cv.wait(g, [&] { return pipe.abort || pipe.recorded_upto >= prev; });
-                        if (pipe.abort) return;
-                    }
-                    if (cudaEventSynchronize(G.ev) != cudaSuccess) {
-                        std::lock_guard<std::mutex> g(pipe.m);
-                        pipe.failed = true;
-                        pipe.cv.notify_all();
-                        return;
-                    }
-                }
-                const int prc = hxh_pack_slab(arena, offsets + c.r0, c.r1 - c.r0, G.p, c.base, G.p + flags_off(c), pack_threads);
-                std::lock_guard<std::mutex> g(pipe.m);
-                if (prc != HX_OK) pipe.failed = true;
-                else pipe.packed_upto = j;
-                pipe.cv.notify_all();
-                if (prc != HX_OK || pipe.abort) return;
+        parts.resize(ranges.size());
+        piece_done.reset(new std::atomic<int>[pieces.size()]);
+        for (size_t g = 0; g < pieces.size(); ++g) piece_done[g].store(0, std::memory_order_relaxed);
+        // ring + flags + events (first call, or a larger piece size / batch than before)
+        const size_t buf_bytes = (size_t)ctx->opt_pack_piece_bytes + 64;
+        if (R.n_buf != n_buf || R.buf_bytes != buf_bytes) {
+            if (R.p) cudaFreeHost(R.p);
+            R.p = nullptr;
+            R.n_buf = 0;
+            if (cudaHostAlloc((void **)&R.p, buf_bytes * (size_t)n_buf, cudaHostAllocPortable) != cudaSuccess)
+                return fail(ctx, HX_ERR_NOMEM, "hx_run_batch: cannot allocate %zu bytes of pinned staging", buf_bytes * (size_t)n_buf);
+            R.n_buf = n_buf;
+            R.buf_bytes = buf_bytes;
+        }
+        if (R.flags_cap < (size_t)n_records + 64) {
+            if (R.flags) cudaFreeHost(R.flags);
+            R.flags = nullptr;
+            R.flags_cap = 0;
+            const size_t want = (size_t)n_records + (size_t)n_records / 4 + 64;
+            if (cudaHostAlloc((void **)&R.flags, want, cudaHostAllocPortable) != cudaSuccess)
+                return fail(ctx, HX_ERR_NOMEM, "hx_run_batch: cannot allocate %zu bytes of pinned staging", want);
+            R.flags_cap = want;
+        }
+        for (Device &D : ctx->devs) {
+            if ((int)D.ring_ev.size() >= n_buf) continue;
+            if (cudaSetDevice(D.dev) != cudaSuccess) return fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaSetDevice failed");
+            while ((int)D.ring_ev.size() < n_buf) {
+                cudaEvent_t e = nullptr;
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaEventCreate failed");
+                D.ring_ev.push_back(e);
             }
+        }
+        // records that end before the first base of the batch: no range finalises them
+        for (uint32_t r = 0; r < n_records && offsets[r + 1] == offsets[0]; ++r) R.flags[r] = 0;
+        allowed_piece.store(n_buf);
+        const int workers = std::max(1, pack_threads - 1);  // this thread issues; it polls, so it is not idle
+        packer = std::thread([&, workers] {
+            hxh_parallel_run(workers, workers, [&](int) {
+                for (;;) {
+                    const int64_t i = next_range.fetch_add(1, std::memory_order_relaxed);
+                    if (i >= (int64_t)ranges.size() || pack_abort.load(std::memory_order_relaxed)) return;
+                    const PackRange &rg = ranges[i];
+                    while (rg.piece >= allowed_piece.load(std::memory_order_acquire)) {  // the ring buffer is still being read
+                        if (pack_abort.load(std::memory_order_relaxed)) return;
+                        hx_cpu_relax();
+                    }
+                    const PackPiece &P = pieces[rg.piece];
+                    uint8_t *buf = R.p + (size_t)P.slot * R.buf_bytes;
+                    // ordinary stores: the buffer is meant to stay in the cache until the DMA engine has read it
+                    hxh_pack_range(arena, offsets, n_records, rg.p, rg.q, (uint8_t *)((uintptr_t)buf - (uintptr_t)(P.al / 2)), R.flags, false,
+                                   rg.slab_first, &parts[i]);
+                    piece_done[rg.piece].fetch_add(1, std::memory_order_release);
+                }
+            });
         });
     }
+    uint32_t merge_open_rec = UINT32_MAX, merge_open_acc = 0;
 
     for (int64_t j = 0; j < n_slabs && rc == HX_OK; ++j) {
         const SlabCut &c = cuts[j];
@@ -1367,34 +1454,50 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
         HX_CUDA_BREAK(ctx, rc, cudaSetDevice(D.dev));
         if (used[di * HX_NSLOT + si]) {
             // buffers of this slot may be regrown below: wait for its previous slab and check it
-            if (pack_otf) HX_CUDA_BREAK(ctx, rc, cudaEventSynchronize(S.done_ev))
-            else HX_CUDA_BREAK(ctx, rc, cudaStreamSynchronize(S.stream));
+            if (pack_otf) {  // keep freeing ring buffers while waiting
+                cudaError_t q;
+                while ((q = cudaEventQuery(S.done_ev)) == cudaErrorNotReady) {
+                    poll_ring();
+                    hx_cpu_relax();
+                }
+                HX_CUDA_BREAK(ctx, rc, q);
+            } else {
+                HX_CUDA_BREAK(ctx, rc, cudaStreamSynchronize(S.stream));
+            }
             rc = check_status(ctx, S);
             if (rc != HX_OK) break;
         }
-        if (pack_otf && !S.done_ev) HX_CUDA_BREAK(ctx, rc, cudaEventCreateWithFlags(&S.done_ev, cudaEventDisableTiming | cudaEventBlockingSync));
+        if (pack_otf && !S.done_ev) HX_CUDA_BREAK(ctx, rc, cudaEventCreateWithFlags(&S.done_ev, cudaEventDisableTiming));
         const SlabPlan pl = plan_slab(ctx, n, bytes);
         rc = prepare_slab(ctx, S, pl, n, c.copy_bytes + 64, nib);
         if (rc != HX_OK) break;
-        const uint8_t *h_src = arena + (nib ? c.base / 2 : c.base), *h_flags = packed_in ? rec_flags + r0 : nullptr;
+        used[di * HX_NSLOT + si] = 1;  // from here on the slot's stream may hold work on caller memory
         if (pack_otf) {
-            std::unique_lock<std::mutex> g(pipe.m);
-            pipe.cv.wait(g, [&] { return pipe.failed || pipe.packed_upto >= j; });
-            if (pipe.failed) {
-                rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: packing a slab failed");
+            // piece by piece as the packer threads finish them, then the rec_flags
+            cudaError_t e = cudaSuccess;
+            for (int64_t g = first_piece[j]; e == cudaSuccess; ++g) {
+                const PackPiece &P = pieces[g];
+                while (piece_done[g].load(std::memory_order_acquire) < (int)P.n_ranges) {
+                    poll_ring();
+                    hx_cpu_relax();
+                }
+                if (P.bytes) e = cudaMemcpyAsync(S.arena.p + P.dst_off, R.p + (size_t)P.slot * R.buf_bytes, P.bytes, cudaMemcpyHostToDevice, S.stream);
+                if (e == cudaSuccess) e = cudaEventRecord(piece_ev(g), S.stream);
+                issued = g + 1;
+                if (P.last_of_slab) break;
+            }
+            if (e != cudaSuccess) {
+                rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: %s", cudaGetErrorString(e));
                 break;
             }
-            h_src = stage_of(j).p;
-            h_flags = h_src + flags_off(c);
-        }
-        used[di * HX_NSLOT + si] = 1;  // from here on the slot's stream may hold work on caller memory
-        if (c.copy_bytes) HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.arena.p, h_src, c.copy_bytes, cudaMemcpyHostToDevice, S.stream));
-        if (nib) HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.flags.p, h_flags, n, cudaMemcpyHostToDevice, S.stream));
-        if (pack_otf) {  // the staging buffer is free again once these copies are done
-            HX_CUDA_BREAK(ctx, rc, cudaEventRecord(stage_of(j).ev, S.stream));
-            std::lock_guard<std::mutex> g(pipe.m);
-            pipe.recorded_upto = j;
-            pipe.cv.notify_all();
+            const PackPiece &P0 = pieces[first_piece[j]], &P1 = pieces[issued - 1];
+            hxh_pack_merge(R.flags, parts.data() + P0.first_range, (size_t)(P1.first_range + P1.n_ranges - P0.first_range), merge_open_rec,
+                           merge_open_acc);
+            HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.flags.p, R.flags + r0, n, cudaMemcpyHostToDevice, S.stream));
+        } else {
+            const uint8_t *h_src = arena + (nib ? c.base / 2 : c.base);
+            if (c.copy_bytes) HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.arena.p, h_src, c.copy_bytes, cudaMemcpyHostToDevice, S.stream));
+            if (nib) HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.flags.p, rec_flags + r0, n, cudaMemcpyHostToDevice, S.stream));
         }
         HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.offsets.p, offsets + r0, ((size_t)n + 1) * sizeof(uint64_t),
                                                cudaMemcpyHostToDevice, S.stream));
@@ -1404,13 +1507,9 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
                                                cudaMemcpyDeviceToHost, S.stream));
         if (pack_otf) HX_CUDA_BREAK(ctx, rc, cudaEventRecord(S.done_ev, S.stream));
     }
-    if (producer.joinable()) {
-        {
-            std::lock_guard<std::mutex> g(pipe.m);
-            if (rc != HX_OK) pipe.abort = true;
-            pipe.cv.notify_all();
-        }
-        producer.join();
+    if (packer.joinable()) {
+        if (rc != HX_OK) pack_abort.store(true);  // threads waiting for a ring buffer leave; otherwise every range is packed
+        packer.join();
     }
     // epilogue on every path: drain each (device, slot) stream that was used, so that no copy from the caller's arena
     // or into the caller's table is in flight when this function returns, and the slots are idle for the next call

@@ -421,10 +421,7 @@ int pack_isa() {  // 0 scalar, 1 AVX2, 2 AVX-512 VBMI; HYPEREX_PACK_ISA caps it 
 #endif
 }
 
-struct PackPart {  // what one thread reports to the merge
-    int64_t first_final = -1;
-    uint32_t open_rec = 0, open_acc = 0;
-};
+typedef HxhPackPart PackPart;  // what one range reports to the merge (hx_host.h)
 
 // bases [start, stop) of the batch; interior range edges are multiples of 128 bases
 void pack_range(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint64_t start, uint64_t stop, uint8_t *packed,
@@ -552,49 +549,21 @@ extern "C" int hx_pack_records(const uint8_t *arena, const uint64_t *offsets, ui
     return hxh_pack_slab(arena, offsets, n_records, packed, 0, rec_flags, n_threads);
 }
 
-// hx_pack_records into a buffer whose first byte is packed byte `packed_base / 2` of the batch (packed_base even and
-// <= offsets[0]): the staging buffer of one host->device slab (hx_run_batch with pack_h2d)
-int hxh_pack_slab(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint8_t *packed, uint64_t packed_base,
-                  uint8_t *rec_flags, int n_threads) {
-    if (!offsets || (n_records && (!packed || !rec_flags))) return HX_ERR_ARG;
-    if ((packed_base & 1) || (n_records && packed_base > offsets[0])) return HX_ERR_ARG;
-    packed = (uint8_t *)((uintptr_t)packed - (uintptr_t)(packed_base / 2));  // indexed by absolute base / 2 below
-    if (n_records == 0) return HX_OK;
-    if (offsets[n_records] < offsets[0] || (offsets[n_records] > offsets[0] && !arena)) return HX_ERR_ARG;
-    for (uint32_t r = 0; r < n_records; ++r)
-        if (offsets[r + 1] < offsets[r]) return HX_ERR_ARG;
-    const uint64_t begin = offsets[0], end = offsets[n_records];
-    if (begin & 1) packed[begin / 2] = 0;  // the batch starts on an odd base: nobody owns the low nibble of its first byte
-    if (end & 1) packed[end / 2] = 0;      // ... and the high nibble of its last byte when it ends on one
-    // leading empty records end before the first base: no range finalises them
-    for (uint32_t r = 0; r < n_records && offsets[r + 1] == begin; ++r) rec_flags[r] = 0;
-    if (end == begin) return HX_OK;
-    const int isa = pack_isa();
-    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-    // The batch is cut into ranges of about `grain` bases at multiples of 128 (whole vector blocks, aligned packed
-    // stores) that the threads take one after the other.  Small ranges taken in order rather than one large range per
-    // thread: threads that stream through addresses a fixed large distance apart were measured to run at 1/T of their
-    // single-thread rate on some hosts (same DRAM banks in lockstep); neighbours do not, and they balance the load.
-    const char *grain_env = getenv("HYPEREX_PACK_GRAIN");  // tests cut finer
-    const uint64_t grain = std::max<uint64_t>(grain_env ? strtoull(grain_env, nullptr, 10) : (1u << 20), 128);
-    const int np = (int)std::min<uint64_t>((end - begin + grain - 1) / grain, 1u << 20);
-    nt = std::max(1, std::min(nt, np));
-    std::vector<uint64_t> cut(np + 1);
-    for (int t = 0; t <= np; ++t) {
-        const uint64_t x = begin + (uint64_t)((__uint128_t)(end - begin) * (uint64_t)t / (uint64_t)np);
-        cut[t] = t == 0 ? begin : t == np ? end : std::min<uint64_t>(end, std::max<uint64_t>(begin, x & ~(uint64_t)127));
+// ---- the packer's building blocks for a caller that schedules the ranges itself (hx_run_batch with pack_h2d) ----------
+void hxh_pack_range(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint64_t p, uint64_t q, uint8_t *packed_virtual,
+                    uint8_t *rec_flags, bool stream_stores, bool clear_low_nibble, HxhPackPart *part) {
+    if (q <= p) {
+        part->first_final = -2;  // empty range
+        return;
     }
-    const char *nt_env = getenv("HYPEREX_PACK_NT");  // A/B switch: 0 keeps ordinary stores
-    const bool stream_stores = nt_env ? atoi(nt_env) != 0 : (end - begin) >= ((uint64_t)8 << 20);
-    std::vector<PackPart> parts(np);
-    HxhPool::get().run(np, nt, [&](int t) {
-        if (cut[t + 1] > cut[t]) pack_range(arena, offsets, n_records, cut[t], cut[t + 1], packed, rec_flags, isa, stream_stores, &parts[t]);
-        else parts[t].first_final = -2;  // empty range
-    });
-    // merge: a record that spans range edges is finalised by the range that holds its last base; OR in what the ranges
-    // before it saw of it
-    uint32_t open_rec = UINT32_MAX, open_acc = 0;
-    for (int t = 0; t < np; ++t) {
+    if (clear_low_nibble && (p & 1)) packed_virtual[p / 2] = 0;
+    pack_range(arena, offsets, n_records, p, q, packed_virtual, rec_flags, pack_isa(), stream_stores, part);
+}
+
+void hxh_pack_merge(uint8_t *rec_flags, const HxhPackPart *parts, size_t n, uint32_t &open_rec, uint32_t &open_acc) {
+    // a record that spans range edges is finalised by the range that holds its last base; OR in what the ranges before
+    // it saw of it
+    for (size_t t = 0; t < n; ++t) {
         if (parts[t].first_final == -2) continue;
         if (parts[t].first_final >= 0) {
             if ((uint32_t)parts[t].first_final == open_rec) rec_flags[open_rec] |= (uint8_t)open_acc;
@@ -607,6 +576,75 @@ int hxh_pack_slab(const uint8_t *arena, const uint64_t *offsets, uint32_t n_reco
             open_acc = parts[t].open_acc;
         }
     }
+}
+
+void hxh_parallel_run(int n, int threads, const std::function<void(int)> &fn) { HxhPool::get().run(n, threads, fn); }
+
+// hx_pack_records in pieces (hx_host.h): begin validates and settles the records that end before the first base; a
+// piece packs the base range [p, q) — p is `begin` or a multiple of 128, q is `end` or a multiple of 128, pieces follow
+// each other without gaps — into packed_virtual[i / 2] for base i and folds the evidence of the records into rec_flags;
+// after the last piece every rec_flags entry is final.
+int hxh_pack_begin(HxhPackJob &J, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint8_t *rec_flags) {
+    if (!offsets || (n_records && !rec_flags)) return HX_ERR_ARG;
+    J.arena = arena;
+    J.offsets = offsets;
+    J.n_records = n_records;
+    J.rec_flags = rec_flags;
+    J.begin = J.end = n_records ? offsets[0] : 0;
+    J.open_rec = UINT32_MAX;
+    J.open_acc = 0;
+    if (n_records == 0) return HX_OK;
+    if (offsets[n_records] < offsets[0] || (offsets[n_records] > offsets[0] && !arena)) return HX_ERR_ARG;
+    for (uint32_t r = 0; r < n_records; ++r)
+        if (offsets[r + 1] < offsets[r]) return HX_ERR_ARG;
+    J.end = offsets[n_records];
+    // leading empty records end before the first base: no range finalises them
+    for (uint32_t r = 0; r < n_records && offsets[r + 1] == J.begin; ++r) rec_flags[r] = 0;
+    return HX_OK;
+}
+
+void hxh_pack_piece(HxhPackJob &J, uint64_t p, uint64_t q, uint8_t *packed_virtual, int n_threads, bool stream_stores) {
+    if (q <= p) return;
+    uint8_t *packed = packed_virtual;
+    if (p == J.begin && (p & 1)) packed[p / 2] = 0;  // the batch starts on an odd base: nobody owns the low nibble of that byte
+    const int isa = pack_isa();
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    // The piece is cut into ranges of about `grain` bases at multiples of 128 (whole vector blocks, aligned packed
+    // stores) that the threads take one after the other.  Small ranges taken in order rather than one large range per
+    // thread: neighbours balance the load, and threads that stream through addresses a fixed large distance apart were
+    // seen to slow each other down.
+    const char *grain_env = getenv("HYPEREX_PACK_GRAIN");  // tests cut finer
+    uint64_t grain = std::max<uint64_t>(grain_env ? strtoull(grain_env, nullptr, 10) : (1u << 20), 128);
+    if (!grain_env) grain = std::min<uint64_t>(grain, std::max<uint64_t>((q - p) / (4ull * (uint64_t)nt), 64u << 10));  // small pieces: 4 ranges per thread
+    const int np = (int)std::min<uint64_t>((q - p + grain - 1) / grain, 1u << 20);
+    nt = std::max(1, std::min(nt, np));
+    std::vector<uint64_t> cut(np + 1);
+    for (int t = 0; t <= np; ++t) {
+        const uint64_t x = p + (uint64_t)((__uint128_t)(q - p) * (uint64_t)t / (uint64_t)np);
+        cut[t] = t == 0 ? p : t == np ? q : std::min<uint64_t>(q, std::max<uint64_t>(p, x & ~(uint64_t)127));
+    }
+    std::vector<PackPart> parts(np);
+    HxhPool::get().run(np, nt, [&](int t) {
+        if (cut[t + 1] > cut[t])
+            pack_range(J.arena, J.offsets, J.n_records, cut[t], cut[t + 1], packed, J.rec_flags, isa, stream_stores, &parts[t]);
+        else parts[t].first_final = -2;  // empty range
+    });
+    hxh_pack_merge(J.rec_flags, parts.data(), parts.size(), J.open_rec, J.open_acc);
+}
+
+// hx_pack_records into a buffer whose first byte is packed byte `packed_base / 2` of the batch (packed_base even and
+// <= offsets[0])
+int hxh_pack_slab(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint8_t *packed, uint64_t packed_base,
+                  uint8_t *rec_flags, int n_threads) {
+    if (n_records && !packed) return HX_ERR_ARG;
+    if ((packed_base & 1) || (n_records && offsets && packed_base > offsets[0])) return HX_ERR_ARG;
+    HxhPackJob J;
+    const int rc = hxh_pack_begin(J, arena, offsets, n_records, rec_flags);
+    if (rc != HX_OK || J.end == J.begin) return rc;
+    const char *nt_env = getenv("HYPEREX_PACK_NT");  // A/B switch: 0 keeps ordinary stores
+    // large outputs bypass the cache: no read-for-ownership of the packed lines, and the next reader is far away
+    const bool stream_stores = nt_env ? atoi(nt_env) != 0 : (J.end - J.begin) >= ((uint64_t)8 << 20);
+    hxh_pack_piece(J, J.begin, J.end, (uint8_t *)((uintptr_t)packed - (uintptr_t)(packed_base / 2)), n_threads, stream_stores);
     return HX_OK;
 }
 

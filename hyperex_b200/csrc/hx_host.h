@@ -4,6 +4,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -33,7 +34,31 @@ int hxh_run_text_lane(hx_ctx *ctx, int lane, const uint8_t *arena, const uint64_
 // hx_run_batch (result table only) on the lane's device
 int hxh_run_batch_lane(hx_ctx *ctx, int lane, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records,
                        hx_result *out);
-// hx_pack_records (include/hyperex_b200.h) into a buffer that starts at packed byte packed_base / 2 of the batch
+// The packer's building blocks (hx_host.cpp): one range of bases [p, q) — edges at multiples of 128, or where a slab or the
+// batch begins / ends — packed into packed_virtual[i / 2] for base i; ranges are independent of each other (any thread,
+// any order), the per-record evidence is completed by merging the parts in range order.
+struct HxhPackPart {
+    int64_t first_final = -1;  // first record this range finalised (-1: none, -2: empty range)
+    uint32_t open_rec = 0, open_acc = 0;
+};
+void hxh_pack_range(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint64_t p, uint64_t q, uint8_t *packed_virtual,
+                    uint8_t *rec_flags, bool stream_stores, bool clear_low_nibble, HxhPackPart *part);
+void hxh_pack_merge(uint8_t *rec_flags, const HxhPackPart *parts, size_t n, uint32_t &open_rec, uint32_t &open_acc);
+// fn(i) for i in [0, n) on up to `threads` threads of the process-wide pool (the caller is one of them)
+void hxh_parallel_run(int n, int threads, const std::function<void(int)> &fn);
+// hx_pack_records (include/hyperex_b200.h) in pieces, for a caller that ships the packed bytes while they are produced
+// (hx_run_batch with pack_h2d): see hx_host.cpp
+struct HxhPackJob {
+    const uint8_t *arena = nullptr;
+    const uint64_t *offsets = nullptr;
+    uint32_t n_records = 0;
+    uint8_t *rec_flags = nullptr;
+    uint64_t begin = 0, end = 0;      // base range of the records
+    uint32_t open_rec = 0, open_acc = 0;  // the record the last piece left open and its evidence so far
+};
+int hxh_pack_begin(HxhPackJob &J, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint8_t *rec_flags);
+void hxh_pack_piece(HxhPackJob &J, uint64_t p, uint64_t q, uint8_t *packed_virtual, int n_threads, bool stream_stores);
+// ... and in one go, into a buffer that starts at packed byte packed_base / 2 of the batch
 int hxh_pack_slab(const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, uint8_t *packed, uint64_t packed_base,
                   uint8_t *rec_flags, int n_threads);
 // slot for host-side state the driver keeps in the context across calls (freed with free_fn by hx_destroy)

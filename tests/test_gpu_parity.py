@@ -35,6 +35,7 @@ def _run(ctx, arena, offsets, pairs, k, **opts):
     # 1: hx_run_batch packs every slab to 4 bits per base on its way to the device (ASCII in, nibble-text kernels)
     ctx.set_option("pack_h2d", opts.get("pack_h2d", -1))
     ctx.set_option("pack_threads", opts.get("pack_threads", 0))
+    ctx.set_option("pack_piece_bytes", opts.get("pack_piece", 4 << 20))  # ring buffer size of that path
     ctx.set_primers(pairs, k)
     if opts.get("packed"):  # 4-bit packed arena (hx_pack_records + hx_run_batch_packed)
         pk, fl = hx.pack_records(arena, offsets, opts.get("pack_threads", 3))
@@ -316,13 +317,16 @@ def test_packed_arena_equals_oracle(ctx, k):
             _cmp(_run(ctx, a, o, pairs, k, tile_len=tile[0], single_max=tile[1], fast=fast, packed=1), ref, a, o, pairs, k)
     _cmp(_run(ctx, a, o, pairs, k, packed=1, slab_bytes=50_000, pack_threads=8), ref, a, o, pairs, k)
     # ASCII in, packed on the way (pack_h2d): one slab, many slabs cut at unaligned / odd record starts
-    for slab, th in ((128 << 20, 0), (50_000, 3), (1, 2), (333_333, 8)):
-        _cmp(_run(ctx, a, o, pairs, k, pack_h2d=1, slab_bytes=slab, pack_threads=th), ref, a, o, pairs, k)
+    # and slabs that go through the ring of piece buffers many times over
+    for slab, th, piece in ((128 << 20, 0, 4 << 20), (50_000, 3, 4096), (1, 2, 4096), (333_333, 8, 8192), (128 << 20, 5, 4096),
+                            (128 << 20, 0, 65536)):
+        _cmp(_run(ctx, a, o, pairs, k, pack_h2d=1, slab_bytes=slab, pack_threads=th, pack_piece=piece), ref, a, o, pairs, k)
     # an arena whose first record starts at an odd offset
     a2 = np.concatenate([np.frombuffer(b"GTGCCAG", np.uint8), a])
     o2 = o + np.uint64(7)
     _cmp(_run(ctx, a2, o2, pairs, k, packed=1, slab_bytes=30_000), ref, a2, o2, pairs, k)
     _cmp(_run(ctx, a2, o2, pairs, k, pack_h2d=1, slab_bytes=30_000), ref, a2, o2, pairs, k)
+    _cmp(_run(ctx, a2, o2, pairs, k, pack_h2d=1, pack_piece=4096), ref, a2, o2, pairs, k)
 
 
 def test_packed_arena_contigs_long_primers_and_refusal(ctx):
@@ -332,6 +336,7 @@ def test_packed_arena_contigs_long_primers_and_refusal(ctx):
     _cmp(_run(ctx, a, o, pairs, 3, packed=1), ref, a, o, pairs, 3)
     _cmp(_run(ctx, a, o, pairs, 3, packed=1, tile_len=1024, single_max=1500), ref, a, o, pairs, 3)
     _cmp(_run(ctx, a, o, pairs, 3, pack_h2d=1, slab_bytes=200_000), ref, a, o, pairs, 3)
+    _cmp(_run(ctx, a, o, pairs, 3, pack_h2d=1, pack_piece=16384), ref, a, o, pairs, 3)
     # primers of 33..64 nt: suffix filter + verification read the text as nibbles too; 64-bit groups
     a, o = hx_synth.gen_reads(300, seed=46)
     pairs = hx_synth.gen_primer_pairs(12, seed=5, builtins=hx.default_primers())
@@ -435,7 +440,8 @@ def test_random_primer_sets_fuzz(ctx, seed):
         _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, lf=lf, pack=pack, packed=1,
                   slab_bytes=int(rng.choice([1, 3000, 128 << 20]))), ref, a, o, pairs, k)
     _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, pack_h2d=1, pack_threads=int(rng.integers(1, 9)),
-              slab_bytes=int(rng.choice([1, 3000, 128 << 20]))), ref, a, o, pairs, k)
+              slab_bytes=int(rng.choice([1, 3000, 128 << 20])), pack_piece=int(rng.choice([4096, 8192, 4 << 20]))), ref, a, o,
+         pairs, k)
 
 
 def test_rna_records_use_rna_reverse_complement(ctx):

@@ -71,9 +71,10 @@ def main():
         ctx.set_primers(pairs, k)
         h_out = hx.pinned_empty(n * len(pairs) * 12).view(hx.RESULT_DTYPE).reshape(n, len(pairs))
         ref = None
-        for mode, threads, slab_mb, nt in [(0, 0, 128, 1), (1, 0, 256, 1), (1, 0, 128, 1), (1, 0, 64, 1), (1, 0, 32, 1), (1, 0, 128, 0),
-                                           (1, 15, 128, 1), (1, 12, 128, 1), (1, 8, 128, 1), (-1, 0, 128, 1)]:
-            os.environ["HYPEREX_PACK_NT"] = str(nt)
+        for mode, threads, slab_mb, piece_kb in [(0, 0, 128, 4096), (1, 0, 128, 4096), (1, 0, 128, 1024), (1, 0, 128, 2048), (1, 0, 128, 8192),
+                                                 (1, 0, 128, 16384), (1, 0, 128, 65536), (1, 0, 256, 4096), (1, 0, 64, 4096), (1, 12, 128, 4096),
+                                                 (1, 8, 128, 4096), (1, 4, 128, 4096), (-1, 0, 128, 4096)]:
+            ctx.set_option("pack_piece_bytes", piece_kb << 10)
             ctx.set_option("pack_h2d", mode)
             ctx.set_option("pack_threads", threads)
             ctx.set_option("slab_bytes", slab_mb << 20)
@@ -88,7 +89,7 @@ def main():
                 ref = h_out.tobytes()
             assert h_out.tobytes() == ref, "pack_h2d changed the result table"
             ts.sort()
-            out["run_batch"].append({"pack_h2d": mode, "pack_threads": threads, "slab_mb": slab_mb, "nt_stores": nt, "ms_median": ts[2] * 1e3,
+            out["run_batch"].append({"pack_h2d": mode, "pack_threads": threads, "slab_mb": slab_mb, "piece_kb": piece_kb, "ms_median": ts[2] * 1e3,
                                      "ms_min": ts[0] * 1e3, "gbases_per_s_median": bases / ts[2] / 1e9})
     print(json.dumps(out, indent=1))
 
