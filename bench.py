@@ -62,6 +62,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=60_000, help="records of the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=0, help="records per step of the reference arm (0: auto)")
     ap.add_argument("--slab-mb", type=int, default=0, help="host->device pipeline granule of the e2e leg (0: library default)")
+    ap.add_argument("--pack-h2d", type=int, default=-1, choices=[-1, 0, 1],
+                    help="hx_run_batch of the e2e leg: -1 library default (automatic), 0 ASCII slabs, 1 slabs packed to 4 bits per "
+                         "base on their way to the device")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ab", action="store_true", help="skip the TMA / LDG text-path A/B")
     ap.add_argument("--no-file-e2e", action="store_true", help="skip the file-level leg (FASTA file in, two files out)")
@@ -468,14 +471,30 @@ def main():
     h_arena[:bases] = arena
     h_out_raw = hx.pinned_empty(n * npairs * 12)
     h_out = h_out_raw.view(hx.RESULT_DTYPE).reshape(n, npairs)
-    for _ in range(min(args.warmup, 2)):
-        ctx.run_batch(h_arena[:bases], offsets, out=h_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.run_batch(h_arena[:bases], offsets, out=h_out)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    # a rank shares the host's threads with the other ranks of the job: the packer of the packed-on-the-way path gets its share
+    pack_threads = max(1, (os.cpu_count() or 1) // world)
+    ctx.set_option("pack_threads", pack_threads)
+
+    def e2e_leg(pack_h2d):
+        """args.steps timed hx_run_batch calls, host arena -> host result table; returns (seconds, hx_batch_stats, sha-able bytes)"""
+        ctx.set_option("pack_h2d", pack_h2d)
+        for _ in range(min(args.warmup, 2)):
+            ctx.run_batch(h_arena[:bases], offsets, out=h_out)
+        barrier()
+        t0_ = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.run_batch(h_arena[:bases], offsets, out=h_out)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0_, ctx.batch_stats(), h_out.tobytes()
+
+    # `e2e` = the library default (pack_h2d automatic: ASCII slabs packed to 4 bits per base on the way when this process has
+    # the host threads for it); the two forced modes are timed next to it so that the line always shows both
+    e2e_s, e2e_stats, e2e_bytes = e2e_leg(args.pack_h2d)
+    e2e_ascii_s, ascii_stats, ascii_bytes = e2e_leg(0)
+    e2e_otw_s, otw_stats, otw_bytes = e2e_leg(1)
+    assert e2e_bytes == ascii_bytes == otw_bytes, "pack_h2d changed the result table"
+    ctx.set_option("pack_h2d", args.pack_h2d)
+    ctx.run_batch(h_arena[:bases], offsets, out=h_out)
     clocks = sampler.stop()
     # context for e2e: the same arena as one plain pinned -> device copy (what PCIe alone costs), outside the timed region
     t_arena = torch.from_numpy(h_arena[:bases])
@@ -579,13 +598,13 @@ def main():
     torch.cuda.set_device(local)
     dev_local = torch.device("cuda", local)
     t = torch.tensor([dev_ms, e2e_s * 1e3, myers_ms, fast_ms or 0.0, h2d_conc_ms, e2e_packed_s * 1e3, e2e_packed_incl_s * 1e3,
-                      pack_s * 1e3], dtype=torch.float64, device=dev_local)
+                      pack_s * 1e3, e2e_ascii_s * 1e3, e2e_otw_s * 1e3], dtype=torch.float64, device=dev_local)
     tot = torch.tensor([float(bases), float(launches)], dtype=torch.float64, device=dev_local)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     (dev_ms_max, e2e_ms_max, myers_ms_max, fast_ms_max, h2d_conc_ms_max, e2e_pk_ms_max, e2e_pk_incl_ms_max,
-     pack_ms_max) = (float(x) for x in t.cpu())
+     pack_ms_max, e2e_ascii_ms_max, e2e_otw_ms_max) = (float(x) for x in t.cpu())
     total_bases, total_launches = (float(x) for x in tot.cpu())
 
     if rank == 0:
@@ -650,17 +669,29 @@ def main():
                            "parallelism": f"records sharded over {world} GPU(s), no collective",
                            "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
                 "e2e": {"value": e2e, "unit": "Gbases/s", "gcups": e2e * cells, "ms_per_step": e2e_ms_max / args.steps,
-                        "h2d_bytes_per_step": int(bases + offsets.nbytes), "d2h_bytes_per_step": int(n * npairs * 12),
+                        "h2d_bytes_per_step": e2e_stats["h2d_bytes"], "d2h_bytes_per_step": e2e_stats["d2h_bytes"],
                         "timer": "host wall clock around hx_run_batch (synchronous), max over ranks",
+                        "packed_on_the_way": e2e_stats["packed_text"], "pack_threads": e2e_stats["pack_threads"],
+                        "slabs": e2e_stats["slabs"],
+                        "ascii_slabs": {"value": total_bases * args.steps / (e2e_ascii_ms_max * 1e-3) / 1e9, "unit": "Gbases/s",
+                                        "ms_per_step": e2e_ascii_ms_max / args.steps, "h2d_bytes_per_step": ascii_stats["h2d_bytes"],
+                                        "what": "pack_h2d = 0: the arena crosses PCIe as it is, one byte per base"},
+                        "packed_slabs": {"value": total_bases * args.steps / (e2e_otw_ms_max * 1e-3) / 1e9, "unit": "Gbases/s",
+                                         "ms_per_step": e2e_otw_ms_max / args.steps, "h2d_bytes_per_step": otw_stats["h2d_bytes"],
+                                         "pack_threads": otw_stats["pack_threads"],
+                                         "what": "pack_h2d = 1: every slab is packed to 4 bits per base by the host threads (inside the "
+                                                 "timed call) while the slabs before it are copied and scanned"},
                         "h2d_copy_alone_ms": h2d_only_ms,
                         "h2d_copy_alone_gbs": bases / (h2d_only_ms * 1e-3) / 1e9,
                         "frac_of_copy_alone": h2d_only_ms / (e2e_ms_max / args.steps),
+                        "copy_alone_note": "one plain pinned -> device copy of the ASCII arena; a packed path can beat it (half the bytes)",
                         "h2d_copy_all_ranks_at_once_ms": h2d_conc_ms_max,
                         "h2d_copy_all_ranks_at_once_gbs_total": total_bases / (h2d_conc_ms_max * 1e-3) / 1e9,
                         "frac_of_copy_all_ranks_at_once": h2d_conc_ms_max / (e2e_ms_max / args.steps)},
                 "gpu_launches": int(total_launches), "roofline": roofline, "clocks": clocks,
                 "result_table_sha256_rank0": table_sha}
-        line["e2e"]["path"] = "library defaults (fast_small_k = 1): result table asserted equal to the Myers kernel's"
+        line["e2e"]["path"] = ("library defaults (fast_small_k = 1, pack_h2d automatic; --pack-h2d %d given): result table asserted "
+                               "equal to the Myers kernel's and equal between the ASCII and packed paths" % args.pack_h2d)
         line["e2e_packed"] = {
             "what": "hx_run_batch_packed: pinned PACKED arena (4-bit codes, hx_pack_records) -> H2D -> kernels on nibble text -> D2H "
                     "result table, every step; result table asserted equal to the ASCII leg's",

@@ -19,7 +19,7 @@ EXPORTS = [
     "hx_kernel_time", "hx_sequence_type", "hx_to_complement", "hx_to_reverse_complement", "hx_primers_to_region",
     "hx_region_to_primer", "hx_supported_regions", "hx_file_to_vec", "hx_free_primer_file",
     "hx_get_hypervar_regions", "hx_fasta_open", "hx_fasta_next", "hx_fasta_close", "hx_int_peak", "hx_group_info", "hx_plan_groups", "hx_plan_peq_word", "hx_run_batch_fasta", "hx_run_batch_text",
-    "hx_run_batch_text_stream", "hx_file_stats", "hx_fasta_descs", "hx_pack_records", "hx_run_batch_packed",
+    "hx_run_batch_text_stream", "hx_file_stats", "hx_batch_stats", "hx_fasta_descs", "hx_pack_records", "hx_run_batch_packed",
 ]
 
 LOG_FN = C.CFUNCTYPE(None, C.c_int, C.c_char_p, C.c_void_p)
@@ -93,6 +93,7 @@ def load():
     L.hx_run_batch_text.argtypes = [vp, vp, vp, C.c_uint32, vp, cp, vp, cp, vp, cp, vp, C.POINTER(vp), C.POINTER(C.c_uint64),
                                     C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.hx_file_stats.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+    L.hx_batch_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
     L.hx_pack_records.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_int]
     L.hx_run_batch_packed.argtypes = [vp, vp, vp, vp, C.c_uint32, vp]
     _lib = L

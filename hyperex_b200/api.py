@@ -205,6 +205,12 @@ class Context:
         self._check(self._L.hx_run_batch(self._h, ap, offsets.ctypes.data, n, out.ctypes.data))
         return out
 
+    def batch_stats(self) -> dict:
+        """hx_batch_stats: what the last run_batch / run_batch_packed call moved"""
+        v = (C.c_uint64 * 5)()
+        self._check(self._L.hx_batch_stats(self._h, v, 5))
+        return {"h2d_bytes": int(v[0]), "d2h_bytes": int(v[1]), "packed_text": bool(v[2]), "slabs": int(v[3]), "pack_threads": int(v[4])}
+
     def run_batch_packed(self, packed: np.ndarray, rec_flags: np.ndarray, offsets: np.ndarray,
                          out: np.ndarray | None = None) -> np.ndarray:
         """hx_run_batch_packed on a packed HOST arena (pack_records) -> (n_records, n_pairs) structured array"""

@@ -195,6 +195,7 @@ struct hx_ctx {
     std::mutex mu;  // guards err and timed: text lanes of one context run on several host threads
     DevPool find_pool;
     PackRing pack_ring;
+    uint64_t batch_stats[5] = {0, 0, 0, 0, 0};  // hx_batch_stats
     // host-side state the file-level driver (hx_host.cpp) keeps across calls: pinned record batches etc.
     void *host_cache = nullptr;
     void (*host_cache_free)(void *) = nullptr;
@@ -1291,12 +1292,14 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
     if (!offsets || !out) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL offsets/out");
     if (offsets[n_records] < offsets[0]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
     if (offsets[n_records] > offsets[0] && !arena) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL arena");
-    // pack on the way: always / never / automatic = when the batch is large enough for the pipeline to fill and the
-    // host has the threads to pack faster than the link copies (measured: profiles/r02_pack_h2d.md)
+    // pack on the way: always / never / automatic = when the batch is large enough for the pipeline to fill and the host
+    // has the threads to pack faster than the link copies ASCII: measured on the 16-thread B200 host, 8 packer threads tie
+    // with the plain copy (52 Gbases/s), 12 give 68, 16 give 82 (profiles/r02_pack_h2d.md).  The packer serves all the
+    // devices of the context, each of which could copy ASCII at link speed, so the bar is per device.
     const int pack_threads = ctx->opt_pack_threads > 0 ? (int)ctx->opt_pack_threads : (int)std::thread::hardware_concurrency();
     const bool pack_otf = !packed_in && ctx->packable &&
-                          (ctx->opt_pack_h2d == 1 ||
-                           (ctx->opt_pack_h2d < 0 && offsets[n_records] - offsets[0] >= ((uint64_t)64 << 20) && pack_threads >= 8));
+                          (ctx->opt_pack_h2d == 1 || (ctx->opt_pack_h2d < 0 && offsets[n_records] - offsets[0] >= ((uint64_t)64 << 20) &&
+                                                      pack_threads >= 10 * (int)ctx->devs.size()));
     const bool nib = packed_in || pack_otf;
     const size_t np = ctx->n_pairs;
     const int ndev = (int)ctx->devs.size();
@@ -1330,6 +1333,15 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
         r0 = r1;
     }
     const int64_t n_slabs = (int64_t)cuts.size();
+    {
+        uint64_t h2d = 0;
+        for (const SlabCut &c : cuts) h2d += c.copy_bytes + ((uint64_t)(c.r1 - c.r0) + 1) * sizeof(uint64_t) + (nib ? c.r1 - c.r0 : 0);
+        ctx->batch_stats[0] = h2d;
+        ctx->batch_stats[1] = (uint64_t)n_records * np * sizeof(hx_result);
+        ctx->batch_stats[2] = nib ? 1 : 0;
+        ctx->batch_stats[3] = (uint64_t)n_slabs;
+        ctx->batch_stats[4] = pack_otf ? (uint64_t)pack_threads : 0;
+    }
     // per (device, slot): the slab it last ran, so its status word can be checked before reuse
     std::vector<int> used(ndev * HX_NSLOT, 0);
     int rc = HX_OK;
@@ -1613,6 +1625,12 @@ void *hx_alloc_pinned(size_t bytes) {
 
 void hx_free_pinned(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+int hx_batch_stats(const hx_ctx *ctx, uint64_t *out, int n) {
+    if (!ctx || !out || n < 0) return HX_ERR_ARG;
+    for (int i = 0; i < n && i < 5; ++i) out[i] = ctx->batch_stats[i];
+    return HX_OK;
 }
 
 uint64_t hx_launch_count(const hx_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }

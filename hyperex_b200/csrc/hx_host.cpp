@@ -317,6 +317,18 @@ inline void pack_split(PackCursor &c, uint64_t p, uint32_t bases, const uint64_t
                  (seg_any(mB, words, pos, bases) ? HX_REC_NON_IUPAC : 0u);
 }
 
+// Software prefetch distance of the vector loops in bytes (HYPEREX_PACK_PF; < 0: into all cache levels, > 0: with the
+// non-temporal hint, 0: none).  A core streams 9-10 GB/s of text with the hardware prefetcher alone and 14 GB/s when it
+// also asks 2 KB ahead (16 threads of the B200 host: 76-89 -> 103-111 Gbases/s); the non-temporal hint measured slower
+// (profiles/r02_pack_h2d.md).
+int pack_prefetch() {
+    static const int v = [] {
+        const char *e = getenv("HYPEREX_PACK_PF");
+        return e ? atoi(e) : -2048;
+    }();
+    return v;
+}
+
 #if defined(__x86_64__)
 __attribute__((target("avx2"))) inline uint32_t pack_reduce_avx2(__m256i vacc) {  // OR of the evidence bits of all bytes
     alignas(32) uint64_t w[4];
@@ -345,7 +357,10 @@ __attribute__((target("avx2"))) void pack_blocks_avx2(const uint8_t *arena, uint
     const __m256i m_0f = _mm256_set1_epi8(0x0f), m_c0 = _mm256_set1_epi8((char)0xc0), c_40 = _mm256_set1_epi8(0x40);
     const __m256i mult = _mm256_set1_epi16(0x1001);  // bytes (1, 16): low code + 16 * high code
     __m256i vacc = _mm256_setzero_si256();
+    const int pf = pack_prefetch();
     for (; p + 64 <= q; p += 64) {
+        if (pf > 0) _mm_prefetch((const char *)(arena + p + pf), _MM_HINT_NTA);
+        else if (pf < 0) _mm_prefetch((const char *)(arena + p - pf), _MM_HINT_T0);
         __m256i o[2];
         for (int h = 0; h < 2; ++h) {
             const __m256i x = _mm256_loadu_si256((const __m256i *)(arena + p + 32 * h));
@@ -383,7 +398,15 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_blocks_avx512(c
     const __m512i c_40 = _mm512_set1_epi8(0x40), m_0f = _mm512_set1_epi8(0x0f), mult = _mm512_set1_epi16(0x1001);
     const __m512i bU = _mm512_set1_epi8(HX_REC_HAS_U << 4), bT = _mm512_set1_epi8(HX_REC_HAS_T << 4), bB = _mm512_set1_epi8(HX_REC_NON_IUPAC << 4);
     __m512i vacc = _mm512_setzero_si512();
+    const int pf = pack_prefetch();
     for (; p + 128 <= q; p += 128) {
+        if (pf > 0) {  // the text is read once: ask for it ahead of the hardware prefetcher, without keeping it in the caches
+            _mm_prefetch((const char *)(arena + p + pf), _MM_HINT_NTA);
+            _mm_prefetch((const char *)(arena + p + pf + 64), _MM_HINT_NTA);
+        } else if (pf < 0) {
+            _mm_prefetch((const char *)(arena + p - pf), _MM_HINT_T0);
+            _mm_prefetch((const char *)(arena + p - pf + 64), _MM_HINT_T0);
+        }
         const __m512i x0 = _mm512_loadu_si512(arena + p), x1 = _mm512_loadu_si512(arena + p + 64);
         const __m512i o0 = _mm512_mask_mov_epi8(_mm512_permutex2var_epi8(tab0, x0, tab1), _mm512_movepi8_mask(x0), c_40);
         const __m512i o1 = _mm512_mask_mov_epi8(_mm512_permutex2var_epi8(tab0, x1, tab1), _mm512_movepi8_mask(x1), c_40);

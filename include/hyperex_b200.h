@@ -80,7 +80,13 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
  * 32 symbols are so degenerate (mostly N) that too many positions would be candidates; 2: filter those too; 0: such
  * primers are stepped as 64-bit automata over the whole text), "group_np_max" (read by hx_set_primers; cap on the
  * automata one scan thread steps per text byte, 0 = automatic: 16 with 32-bit words, 8 with 64-bit words and on the
- * Wu-Manber path at -m 2). */
+ * Wu-Manber path at -m 2), "pack_h2d" (hx_run_batch only: 1 = the host threads pack every slab of the caller's ASCII
+ * arena to 4 bits per base while it is on its way to the device — see hx_pack_records for the code — so half the bytes
+ * cross PCIe and the device runs its packed-text kernels; identical results; 0 = ASCII slabs; -1, default = automatic:
+ * batches >= 64 MB on hosts with >= 10 packer threads per device of the context, never for a primer set that packed text
+ * cannot represent), "pack_threads" (host threads of that path, 0 = all hardware threads; a process that shares the host
+ * with other ranks passes its share), "pack_piece_bytes" (size of the pinned ring buffers the packed text goes through,
+ * default 4 MiB: small enough to stay in the last-level cache between the packer's stores and the DMA reads). */
 int hx_set_option(hx_ctx *ctx, const char *name, int64_t value);
 
 /* Replaces the record loop body utils.rs:270-351 (sequence_type, to_ascii_uppercase, both
@@ -261,6 +267,12 @@ enum {
     HX_FILE_STATS_N
 };
 int hx_file_stats(hx_ctx *ctx, double *out, int n);
+
+/* What the last hx_run_batch / hx_run_batch_packed call of this context moved: out[0] bytes copied host -> device
+ * (text, offsets, rec_flags), out[1] bytes copied device -> host (the result table), out[2] 1 when the text crossed
+ * PCIe as 4-bit codes (a packed arena, or an ASCII arena packed on the way: option pack_h2d), out[3] slabs,
+ * out[4] host threads that packed (0: none).  n = entries of out (fewer are fine). */
+int hx_batch_stats(const hx_ctx *ctx, uint64_t *out, int n);
 
 #ifdef __cplusplus
 }
