@@ -380,7 +380,7 @@ int prepare_slab(hx_ctx *ctx, Slot &S, const SlabPlan &pl, uint32_t n_records, u
         }
         if (with_flags) S.flags.carve(S.pool, (size_t)n_records + 16);
         S.rec_u32.carve(S.pool, (size_t)n_records * 4);
-        S.scratch.carve(S.pool, 4 + 2 * HX_NBUCKETS);
+        S.scratch.carve(S.pool, 4 + 2 * HX_NBUCKETS + 2);
         S.tiles.carve(S.pool, pl.tile_cap);
         S.order.carve(S.pool, pl.tile_cap);
         S.sum_f.carve(S.pool, (size_t)ctx->n_slots * pl.tile_cap);
@@ -403,7 +403,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
     uint32_t *rec_raw = S.rec_u32.p, *tile_first = rec_raw + n_records, *tile_cnt = tile_first + n_records;
     uint32_t *long_list = tile_cnt + n_records;
     uint32_t *ntiles = S.scratch.p, *overflow = ntiles + 1, *n_long = ntiles + 2, *hist = ntiles + 4, *cursor = hist + HX_NBUCKETS;
-    HX_CUDA(ctx, cudaMemsetAsync(S.scratch.p, 0, (4 + 2 * HX_NBUCKETS) * sizeof(uint32_t), st));
+    HX_CUDA(ctx, cudaMemsetAsync(S.scratch.p, 0, (4 + 2 * HX_NBUCKETS + 2) * sizeof(uint32_t), st));
     HX_CUDA(ctx, cudaMemsetAsync(rec_raw, 0, (size_t)n_records * sizeof(uint32_t), st));
 
     HxBuildArgs b;
@@ -432,9 +432,13 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
     for (size_t gi = 0; gi < ctx->groups.size(); ++gi) {
         const HxGroup &hg = ctx->groups[gi];
         HxScanArgs a;
-        a.arena = d_arena;
+        // the scan kernels fetch whole 32-byte sectors: hand them a sector-aligned base.  d_arena is 16-byte aligned, so
+        // the bytes in front of it belong to the same sector (same allocation); off_base moves with it (wrapping
+        // arithmetic: rec0 = offsets[r] - off_base), counted in symbols for packed text
+        const uint64_t mis = (uint64_t)((uintptr_t)d_arena & 31u);
+        a.arena = d_arena - mis;
         a.offsets = d_offsets;
-        a.off_base = off_base;
+        a.off_base = off_base - (nib ? 2 * mis : mis);
         a.tiles = S.tiles.p;
         a.order = S.order.p;
         a.ntiles = ntiles;
@@ -462,6 +466,7 @@ int enqueue_slab(hx_ctx *ctx, Device &D, Slot &S, const SlabPlan &pl, const uint
         a.nib = nib ? 1 : 0;
         a.variant = (hg.longmask || a.packed || nib) ? 0 : (int)ctx->opt_text_tma;  // suffix-filtered groups: vector-load text path only
         a.two = 2;
+        a.sched = cursor + HX_NBUCKETS;  // batch counters of the persistent scan grid (zeroed with the scratch block)
         TimedLaunch tl;
         if (ctx->opt_time) {
             tl.dev = D.dev;

@@ -101,6 +101,7 @@ struct HxScanArgs {
     uint32_t k;
     int32_t variant;           // text path: 0 per-thread LDG.128 + prefetch, 1 TMA bulk copies into shared memory
     uint32_t two;              // == 2, passed at run time (a constant ptxas cannot fold)
+    uint32_t *sched;           // {next batch, CTAs that left}: both 0 at launch, zeroed again by the last CTA to leave
 };
 
 struct HxBuildArgs {

@@ -20,6 +20,8 @@
 #include "hx_device.h"
 
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <atomic>
@@ -59,7 +61,7 @@ __device__ __forceinline__ uint4 hx_ldg16(const uint8_t *p) {
 #endif
 __device__ __forceinline__ uint64_t hx_policy_evict_first() {
     uint64_t pol = 0;
-#if HX_LDPOL == 2
+#if HX_LDPOL >= 2 || HX_CHUNK32
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 #endif
     return pol;
@@ -68,6 +70,18 @@ __device__ __forceinline__ uint4 hx_ldg16_stream(const uint8_t *p, uint64_t pol)
 #if HX_LDPOL == 2
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+#elif HX_LDPOL == 3  // text leaves the L2 first (it is read once), but still allocates in the L1 (two 16-byte loads per sector)
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+#elif HX_LDPOL == 4  // ... and stays in the L1 until its second half has been read
+    uint4 v;
+    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(p), "l"(pol));
     return v;
@@ -82,6 +96,14 @@ __device__ __forceinline__ uint4 hx_ldg16_stream(const uint8_t *p, uint64_t pol)
     (void)pol;
     return hx_ldg16(p);
 #endif
+}
+
+// One whole 32-byte sector per thread: LDG.E.256, no L1 allocation (every byte of the sector is in registers after
+// this one load), first to leave the L2 (the scan reads text exactly once).  p must be 32-byte aligned.
+__device__ __forceinline__ void hx_ldg32_stream(const uint8_t *p, uint64_t pol, uint4 &lo, uint4 &hi) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p), "l"(pol));
 }
 
 // ------------------------------------------------------------------------------------
@@ -463,7 +485,6 @@ struct HxRow {
 #ifndef HX_CH
 #define HX_CH 128   // bytes per text stage of one thread (two stages in flight)
 #endif
-#define HX_CPS (HX_CH / 16)  // 16-byte chunks per stage
 
 // ---- TMA (cp.async.bulk) + mbarrier primitives; SASS: UBLKCP / SYNCS ----
 __device__ __forceinline__ uint32_t hx_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -548,9 +569,6 @@ __device__ __forceinline__ bool hx_verify_exact(const uint8_t *__restrict__ text
     return ok & 1ull;
 }
 
-#ifndef HX_PREFETCH2
-#define HX_PREFETCH2 0  // experiment: two 16-byte text chunks in flight per thread instead of one
-#endif
 #ifndef HX_WI_UNROLL
 #define HX_WI_UNROLL ((PK && NR == 1) ? 4 : 1)  // see the loop over the four text words of a chunk
 #endif
@@ -565,7 +583,18 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     static_assert(!NIB || !TMA, "packed text: vector-load text path only");
     constexpr int SYM_BITS = NIB ? 4 : 8;            // bits per text symbol
     constexpr int SPW = 32 / SYM_BITS;               // symbols per 32-bit word
-    constexpr int CSH = NIB ? 5 : 4;                 // log2(symbols per 16-byte chunk)
+    // Text chunk = what a thread fetches per load: 16 bytes (LDG.128, allocating in the L1: the second half of the
+    // 32-byte sector is an L1 hit or an L2 hit).  HX_CHUNK32=1 builds the Myers kernels on ASCII text with one 256-bit,
+    // non-allocating, L2-evict-first load per 32-byte sector instead (hx_ldg32_stream).  Measured (profiles/
+    // r02_traffic_experiments.md): 13.9 vs 13.5 ms, and DRAM reads go UP (3.6 vs 2.3 GB per 1.5 GB of text): DRAM is
+    // read 64 bytes at a time and an evict-first sector does not survive in the L2 until its thread comes back for it.
+#ifndef HX_CHUNK32
+#define HX_CHUNK32 0
+#endif
+    constexpr int NH = (HX_CHUNK32 && KWM < 0 && !NIB) ? 2 : 1;  // 16-byte halves per chunk
+    constexpr int CHB = 16 * NH;                     // bytes per chunk
+    constexpr int CPS = HX_CH / CHB;                 // chunks per TMA stage
+    constexpr int CSH = (NIB ? 5 : 4) + (NH - 1);    // log2(symbols per chunk)
     constexpr uint32_t SPC = 1u << CSH;              // symbols per chunk
     constexpr int NROWS = NIB ? 16 : 256;
     constexpr bool WM = KWM >= 0;           // small-k fast path: Wu-Manber / Shift-Or automata instead of Myers
@@ -604,9 +633,33 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     }
     if (threadIdx.x < sizeof(HxGroup) / 4)
         reinterpret_cast<uint32_t *>(&g)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.group)[threadIdx.x];
+    __syncthreads();  // g is visible
 
+    // Persistent CTAs: the grid is at most what the device holds at once (hx_scan_launch_one), and every CTA walks
+    // batches of HX_THREADS tiles (longest tiles first).  What this buys: a thread's event queue and pairing state (local
+    // memory) are the SAME addresses for every tile it scans, so they stay in the L1/L2 instead of being written back to
+    // DRAM and fetched again once per tile (ncu, round 1: 0.75 GB each way per 1.5 GB of text), and the Peq table is
+    // staged once per CTA, not once per batch.
+    //   a.sched != NULL  the next batch comes from a device-wide counter (CTAs drift apart like hardware-scheduled ones;
+    //                    the last CTA to leave zeroes the counters for the next launch on the stream)
+    //   a.sched == NULL  round r hands batch r * gridDim.x + j to CTA j, in alternating direction
     const uint32_t ntiles = min(*a.ntiles, a.tile_stride);
-    const uint32_t t = blockIdx.x * HX_THREADS + threadIdx.x;
+    const uint32_t nbatches = (ntiles + HX_THREADS - 1u) / HX_THREADS;
+    __shared__ uint32_t s_batch;
+    uint32_t round = 0;
+    const auto next_batch = [&]() -> uint32_t {
+        if (a.sched) {
+            __syncthreads();  // everybody has read s_batch
+            if (threadIdx.x == 0) s_batch = gridDim.x + atomicAdd(a.sched, 1u);
+            __syncthreads();
+            return s_batch;
+        }
+        ++round;
+        return round * gridDim.x + ((round & 1u) ? gridDim.x - 1u - blockIdx.x : blockIdx.x);
+    };
+    int staged = -1;  // alphabet whose table is in shared memory
+    for (uint32_t batch = blockIdx.x; batch < nbatches; batch = next_batch()) {
+    const uint32_t t = batch * HX_THREADS + threadIdx.x;
     const bool have = t < ntiles;
     const uint32_t tile_id = have ? a.order[t] : 0u;
     HxTile tl = {0u, 0u, 0u, 0u};
@@ -625,7 +678,6 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     uint64_t phi[HX_MAX_GROUP_PAIRS];
     uint32_t plo[HX_MAX_GROUP_PAIRS];
     const int bias = (int)a.k + 1;
-    __syncthreads();  // g is visible
     if constexpr (PK) {
         // a half starts with its pattern bits (the top m of the 16) set and the unused low bits clear; a half without
         // a pattern (odd pattern count) stays all-ones: its table entries are all-ones too, it never reports
@@ -697,7 +749,8 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     for (int pass = 0; pass < 2; ++pass) {
         const bool mine = alpha == pass;
         if (!__syncthreads_or(mine ? 1 : 0)) continue;  // no record of this alphabet in the CTA
-        {
+        if (staged != pass) {  // (every scan of the table in shared memory ended before the barrier above)
+            staged = pass;
             const uint4 *tsrc = reinterpret_cast<const uint4 *>(PK ? a.tables_pk : WM ? a.tables_wm : a.tables) + (size_t)pass * (TBYTES / 16);
             uint4 *dst = reinterpret_cast<uint4 *>(smem);
             if constexpr (NIB) {  // row of code c = row of the byte the code stands for in this alphabet
@@ -707,8 +760,8 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
             } else {
                 for (int i = threadIdx.x; i < TBYTES / 16; i += HX_THREADS) dst[i] = __ldg(tsrc + i);
             }
+            __syncthreads();
         }
-        __syncthreads();
         // CTA-relative shared-space address of the table, taken from the symbol: converting the generic pointer instead
         // makes ptxas rebuild the cluster-form address (S2R SR_CgaCtaId + LEA) inside the hot loop of the wider kernels
         uint32_t tab_s;
@@ -724,65 +777,77 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
         const uint32_t nchunks_w = __reduce_max_sync(0xffffffffu, nchunks);
 
         const bool mask_lead = nchunks && tl.own_start == tl.warm && lead;
-        const uint32_t nstages = (nchunks + HX_CPS - 1u) / HX_CPS;
+        const uint32_t nstages = (nchunks + CPS - 1u) / CPS;
         auto issue = [&](uint32_t st) {
             if (st < nstages) {
-                const uint32_t bytes = min((uint32_t)HX_CH, (nchunks - HX_CPS * st) * 16u);
+                const uint32_t bytes = min((uint32_t)HX_CH, (nchunks - CPS * st) * (uint32_t)CHB);
                 const uint32_t mb = (st & 1u) ? mbar1 : mbar0;
                 hx_mbar_expect_tx(mb, bytes);
                 hx_bulk_g2s((st & 1u) ? stage1 : stage0, src + (size_t)st * HX_CH, bytes, mb);
             }
         };
-        uint4 nxt = make_uint4(0, 0, 0, 0);  // one 16-byte chunk in flight (two measured slower: more registers)
-#if HX_PREFETCH2
-        uint4 nxt2 = make_uint4(0, 0, 0, 0);
-#endif
+        // one chunk in flight (two measured slower: more registers)
+        uint4 nxt[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) nxt[h] = make_uint4(0, 0, 0, 0);
+        const auto fetch = [&](uint32_t c) {
+            if constexpr (NH == 2) hx_ldg32_stream(src + (uint64_t)CHB * c, pol, nxt[0], nxt[NH - 1]);
+            else nxt[0] = hx_ldg16_stream(src + (uint64_t)CHB * c, pol);
+        };
         if constexpr (TMA) {
             issue(0);
             issue(1);
         } else {
-            if (nchunks) nxt = hx_ldg16_stream(src, pol);
-#if HX_PREFETCH2
-            if (nchunks > 1) nxt2 = hx_ldg16_stream(src + 16ull, pol);
-#endif
+            if (nchunks) fetch(0);
         }
 
         for (uint32_t c = 0; c < nchunks_w; ++c) {
-            uint4 cur = make_uint4(0, 0, 0, 0);
-            const uint32_t st = c / HX_CPS, cc = c % HX_CPS;
+            uint4 chunk[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) chunk[h] = make_uint4(0, 0, 0, 0);
+            const uint32_t st = c / CPS, cc = c % CPS;
             if constexpr (TMA) {
                 if (c < nchunks) {
                     if (cc == 0) {
                         if (st & 1u) hx_mbar_wait(mbar1, uses1++ & 1u);
                         else hx_mbar_wait(mbar0, uses0++ & 1u);
                     }
-                    const uint32_t sa = ((st & 1u) ? stage1 : stage0) + cc * 16u;
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(cur.x), "=r"(cur.y), "=r"(cur.z), "=r"(cur.w)
-                                 : "r"(sa)
-                                 : "memory");
+                    const uint32_t sa = ((st & 1u) ? stage1 : stage0) + cc * (uint32_t)CHB;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h)
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(chunk[h].x), "=r"(chunk[h].y), "=r"(chunk[h].z), "=r"(chunk[h].w)
+                                     : "r"(sa + 16u * h)
+                                     : "memory");
                 }
             } else {
-                cur = nxt;
-#if HX_PREFETCH2
-                nxt = nxt2;
-                nxt2 = (c + 2 < nchunks) ? hx_ldg16_stream(src + 16ull * (c + 2), pol) : make_uint4(0, 0, 0, 0);
-#else
-                nxt = (c + 1 < nchunks) ? hx_ldg16_stream(src + 16ull * (c + 1), pol) : make_uint4(0, 0, 0, 0);
-#endif
+#pragma unroll
+                for (int h = 0; h < NH; ++h) chunk[h] = nxt[h];
+                if (c + 1 < nchunks) {
+                    fetch(c + 1);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) nxt[h] = make_uint4(0, 0, 0, 0);
+                }
             }
             if (c == 0 && mask_lead) {
                 // The scan starts at the record start: bytes before it belong to the previous record.
                 // Byte 0 selects the all-zero Peq row, under which a fresh automaton stays fresh.
-                uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-                for (int wi = 0; wi < 4; ++wi) {
-                    const int z = (int)lead - SPW * wi;  // symbols of this word to clear
-                    if (z >= SPW) w[wi] = 0;
-                    else if (z > 0) w[wi] &= 0xffffffffu << (SYM_BITS * z);
+                for (int h = 0; h < NH; ++h) {
+                    uint32_t w[4] = {chunk[h].x, chunk[h].y, chunk[h].z, chunk[h].w};
+#pragma unroll
+                    for (int wi = 0; wi < 4; ++wi) {
+                        const int z = (int)lead - SPW * (4 * h + wi);  // symbols of this word to clear
+                        if (z >= SPW) w[wi] = 0;
+                        else if (z > 0) w[wi] &= 0xffffffffu << (SYM_BITS * z);
+                    }
+                    chunk[h] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
-                cur = make_uint4(w[0], w[1], w[2], w[3]);
             }
+#pragma unroll 1
+            for (int h = 0; h < NH; ++h) {
+            const uint4 cur = (NH == 2 && h) ? chunk[NH - 1] : chunk[0];
             // The four words of a chunk: a rolled loop rotates them through cur.x, and ptxas then makes the rotation wait
             // for the chunk that is being prefetched (measured: 7 % of all stall samples of the packed -m 0 kernel, the
             // prefetch hid nothing).  HX_WI_UNROLL words are therefore taken straight from their registers.
@@ -892,7 +957,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                         }
                         if (any < 0) {
                             // ---- rare: some pattern has dist <= k here; record the event ----
-                            const uint32_t pos = pos0 + (c << CSH) + wi * SPW + b0 + bi;
+                            const uint32_t pos = pos0 + (c << CSH) + (4 * h + wi) * SPW + b0 + bi;
                             if (pos - tl.own_start < own_len) {
                                 if constexpr (PK) {
                                     // This path runs once per hit position and lane with the other 31 lanes idle (a read
@@ -943,7 +1008,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                     }
                 }
                 // ---- warp-synchronous drain: all lanes process their queued events together ----
-                const bool last_word = (c + 1 == nchunks_w) && wi == 3;
+                const bool last_word = (c + 1 == nchunks_w) && h == NH - 1 && wi == 3;
                 if (__any_sync(0xffffffffu, cnt > (uint32_t)(QCAP - SPW) || (last_word && cnt))) {
                     // verification automaton of the last candidate (LF): a true site of a filtered primer yields up
                     // to 2k + 1 candidates at consecutive ends, and the next one costs a single step when the
@@ -1062,17 +1127,17 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                     cnt = 0;
                 }
             }
+            }  // halves of the chunk
             if constexpr (TMA) {
-                if (cc == HX_CPS - 1u && c < nchunks) {
+                if (cc == CPS - 1u && c < nchunks) {
                     hx_fence_proxy_async();  // my reads of this stage precede the TMA write that refills it
                     issue(st + 2u);
                 }
             }
         }
-        __syncthreads();  // the table may be replaced by the next pass
     }
 
-    if (!have || alpha == 2) return;
+    if (!have || alpha == 2) continue;
     if (single) {
         // the tile is the whole record: final result of utils.rs:312-351 for every pair of the group
         uint32_t *out = reinterpret_cast<uint32_t *>(a.out) + (size_t)tl.rec * a.n_pairs_total * 3;
@@ -1093,7 +1158,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
             o[1] = r_end;
             o[2] = flags | (comb << 8);
         }
-        return;
+        continue;
     }
     const size_t ts = a.tile_stride;
     for (int p = 0; p < NP; ++p) {
@@ -1105,6 +1170,11 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
         a.pair_hi[(size_t)g.pair_global[q] * ts + tile_id] = phi[q + dz];
         a.pair_lo[(size_t)g.pair_global[q] * ts + tile_id] = plo[q + dz];
     }
+    }  // batches of this CTA
+    if (a.sched && threadIdx.x == 0 && atomicAdd(a.sched + 1, 1u) == gridDim.x - 1u) {
+        a.sched[0] = 0u;  // every CTA has taken its last batch number: nobody reads the counters any more
+        a.sched[1] = 0u;
+    }
 }
 
 template <typename W, int NP, bool TMA, int KWM, bool LF = false, bool PK = false, bool NIB = false>
@@ -1112,14 +1182,30 @@ static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream
     const int smem = hx_table_bytes(PK ? NP / 2 : NP, sizeof(W)) / (NIB ? 16 : 1) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
     // per (instantiation, device) once; contexts on different host threads may race here, so the flags are atomic
     // (setting the attribute twice is harmless, skipping it is not)
-    static std::atomic<bool> attr_done[64];
+    // max_ctas: what the device holds at once (CTAs per SM x SMs) — the kernel's CTAs are persistent and walk the batches
+    static std::atomic<int> max_ctas[64];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
+    int resident = dev < 64 ? max_ctas[dev].load(std::memory_order_acquire) : 0;
+    if (resident <= 0) {
         cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
+        int per_sm = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB>, HX_THREADS, smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident = per_sm > 0 && sms > 0 ? per_sm * sms : 1 << 30;
+        if (dev < 64) max_ctas[dev].store(resident, std::memory_order_release);
     }
-    const uint32_t blocks = (tile_cap + HX_THREADS - 1) / HX_THREADS;
+    // HYPEREX_SCAN_GRID=full: one CTA per batch, as before (A/B of the persistent grid; same kernel, one round per CTA)
+    static const bool full_grid = [] { const char *e = getenv("HYPEREX_SCAN_GRID"); return e && !strcmp(e, "full"); }();
+    const uint32_t nb = (tile_cap + HX_THREADS - 1) / HX_THREADS;
+    const uint32_t blocks = full_grid ? nb : std::min<uint32_t>(nb, (uint32_t)resident);
+    static const bool static_rounds = [] { const char *e = getenv("HYPEREX_SCAN_GRID"); return e && !strcmp(e, "static"); }();
+    if (full_grid || static_rounds) {
+        HxScanArgs b = a;
+        b.sched = nullptr;
+        hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB><<<blocks, HX_THREADS, smem, st>>>(b);
+        return 1;
+    }
     hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB><<<blocks, HX_THREADS, smem, st>>>(a);
     return 1;
 }
