@@ -196,6 +196,12 @@ struct hx_ctx {
     DevPool find_pool;
     PackRing pack_ring;
     uint64_t batch_stats[5] = {0, 0, 0, 0, 0};  // hx_batch_stats
+    // pack_h2d = automatic: the first four large batches alternate ASCII / packed-on-the-way slabs, the last two of them
+    // are timed, and the faster mode serves every later call (run_batch_impl)
+    struct {
+        int calls = 0, decided = -1;
+        double rate[2] = {0, 0};  // bases per second of the timed ASCII / packed call
+    } auto_pack;
     // host-side state the file-level driver (hx_host.cpp) keeps across calls: pinned record batches etc.
     void *host_cache = nullptr;
     void (*host_cache_free)(void *) = nullptr;
@@ -925,8 +931,13 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     else if (n == "long_filter") ctx->opt_long_filter = value < 0 ? 0 : (value > 2 ? 2 : value);  // read by hx_set_primers
     else if (n == "group_np_max") ctx->opt_group_np_max = value;         // read by hx_set_primers; 0 = automatic
     else if (n == "pack16") ctx->opt_pack16 = value < 0 ? 0 : (value > 2 ? 2 : value);  // hx_set_primers builds, every scan reads
-    else if (n == "pack_h2d") ctx->opt_pack_h2d = value < 0 ? -1 : (value ? 1 : 0);
-    else if (n == "pack_threads") ctx->opt_pack_threads = std::max<int64_t>(value, 0);
+    else if (n == "pack_h2d") {
+        ctx->opt_pack_h2d = value < 0 ? -1 : (value ? 1 : 0);
+        ctx->auto_pack = {};  // automatic: measure again
+    } else if (n == "pack_threads") {
+        ctx->opt_pack_threads = std::max<int64_t>(value, 0);
+        ctx->auto_pack = {};
+    }
     else if (n == "pack_piece_bytes") ctx->opt_pack_piece_bytes = std::min<int64_t>(std::max<int64_t>(value, 4096), 256ll << 20) & ~(int64_t)63;
     else return fail(ctx, HX_ERR_ARG, "unknown option %s", name);
     return HX_OK;
@@ -1297,14 +1308,19 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
     if (!offsets || !out) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL offsets/out");
     if (offsets[n_records] < offsets[0]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
     if (offsets[n_records] > offsets[0] && !arena) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL arena");
-    // pack on the way: always / never / automatic = when the batch is large enough for the pipeline to fill and the host
-    // has the threads to pack faster than the link copies ASCII: measured on the 16-thread B200 host, 8 packer threads tie
-    // with the plain copy (52 Gbases/s), 12 give 68, 16 give 82 (profiles/r02_pack_h2d.md).  The packer serves all the
-    // devices of the context, each of which could copy ASCII at link speed, so the bar is per device.
+    // pack on the way: always / never / automatic.  Whether packing pays is a property of the host, not of the library:
+    // on a 16-thread B200 host one process gets 76 Gbases/s packed against 53 ASCII, on a 24-thread host shared by two
+    // processes (one GPU each) 26 against 51 per process (profiles/r02_pack_h2d_auto.md) — a process cannot see what its
+    // siblings do to the memory system.  So automatic = measure: batches large enough for the pipeline to fill (>= 64 MB),
+    // with at least 4 packer threads per device, alternate ASCII, packed, ASCII, packed; the third and fourth call are
+    // timed (buffers exist, pages are mapped) and packing serves the later calls iff it was at least 5 % faster.
     const int pack_threads = ctx->opt_pack_threads > 0 ? (int)ctx->opt_pack_threads : (int)std::thread::hardware_concurrency();
+    const bool pack_probe = !packed_in && ctx->packable && ctx->opt_pack_h2d < 0 && ctx->auto_pack.decided < 0 &&
+                            offsets[n_records] - offsets[0] >= ((uint64_t)64 << 20) && pack_threads >= 4 * (int)ctx->devs.size();
     const bool pack_otf = !packed_in && ctx->packable &&
-                          (ctx->opt_pack_h2d == 1 || (ctx->opt_pack_h2d < 0 && offsets[n_records] - offsets[0] >= ((uint64_t)64 << 20) &&
-                                                      pack_threads >= 10 * (int)ctx->devs.size()));
+                          (ctx->opt_pack_h2d == 1 ||
+                           (ctx->opt_pack_h2d < 0 && (pack_probe ? (ctx->auto_pack.calls & 1) != 0 : ctx->auto_pack.decided == 1)));
+    const auto t_call = std::chrono::steady_clock::now();
     const bool nib = packed_in || pack_otf;
     const size_t np = ctx->n_pairs;
     const int ndev = (int)ctx->devs.size();
@@ -1540,6 +1556,12 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
         }
     }
     sync_timed(ctx);
+    if (pack_probe && rc == HX_OK) {
+        auto &ap = ctx->auto_pack;
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call).count();
+        if (ap.calls >= 2) ap.rate[pack_otf ? 1 : 0] = (double)(offsets[n_records] - offsets[0]) / std::max(sec, 1e-9);
+        if (++ap.calls == 4) ap.decided = ap.rate[1] > 1.05 * ap.rate[0] ? 1 : 0;
+    }
     return rc;
 }
 

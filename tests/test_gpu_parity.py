@@ -329,6 +329,35 @@ def test_packed_arena_equals_oracle(ctx, k):
     _cmp(_run(ctx, a2, o2, pairs, k, pack_h2d=1, pack_piece=4096), ref, a2, o2, pairs, k)
 
 
+def test_pack_h2d_automatic_measures_both_modes(ctx):
+    """pack_h2d = -1: the first four large batches go ASCII, packed, ASCII, packed (hx_batch_stats says which), the library
+    then keeps one mode; every call returns the same table.  Small batches and hosts without packer threads stay ASCII."""
+    a, o = hx_synth.gen_reads(48_000, seed=77)  # ~72 MB: above the 64 MB bar
+    assert int(o[-1]) >= 64 << 20
+    pairs = hx.default_primers()
+    first = _run(ctx, a, o, pairs, 0, pack_h2d=-1, pack_threads=4)
+    seen = [ctx.batch_stats()["packed_text"]]
+    for _ in range(5):
+        res = ctx.run_batch(a, o)
+        seen.append(ctx.batch_stats()["packed_text"])
+        assert res.tobytes() == first.tobytes()
+    assert seen[:4] == [False, True, False, True] and seen[4] == seen[5]
+    _cmp(first[:300], O.run_batch(a[:int(o[300])], o[:301], pairs, 0, nthreads=8), a, o, pairs, 0)
+    ctx.set_option("pack_h2d", -1)  # measures again
+    ctx.run_batch(a, o)
+    ctx.run_batch(a, o)
+    assert ctx.batch_stats()["packed_text"]
+    ctx.set_option("pack_threads", 3)  # fewer than 4 packer threads per device: never packed
+    for _ in range(2):
+        ctx.run_batch(a, o)
+        assert not ctx.batch_stats()["packed_text"]
+    ctx.set_option("pack_threads", 8)
+    n = 2000  # a small batch never is
+    for _ in range(2):
+        ctx.run_batch(a[:int(o[n])], o[:n + 1])
+        assert not ctx.batch_stats()["packed_text"]
+
+
 def test_packed_arena_contigs_long_primers_and_refusal(ctx):
     a, o = hx_synth.gen_contigs(3, seed=45, length=300_000)
     pairs = hx.default_primers()
