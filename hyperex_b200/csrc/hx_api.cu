@@ -136,7 +136,7 @@ struct TextLane {
 // Pinned staging of hx_run_batch with pack_h2d.  The packed text goes through a RING of small piece buffers (a few MiB
 // each): small enough to stay in the host's last-level cache between the packer's stores and the DMA engine's reads, so
 // the packed bytes cost no DRAM traffic (whole-slab staging buffers were measured: the packer drops from 91 to 73
-// Gbases/s while the copies of the slabs before it read host memory, profiles/r02_pack_h2d.md).  The ring belongs to the
+// Gbases/s while the copies of the slabs before it read host memory, profiles/r02_pack_h2d_auto.md, r02_pack_h2d_ab_ring.json).  The ring belongs to the
 // context (portable pinned memory, any device copies from it); every device has one event per ring buffer, which marks
 // the end of the host->device copy that read it.
 constexpr int HX_NRING = 8;  // piece buffers per device of the context

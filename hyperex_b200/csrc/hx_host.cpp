@@ -320,7 +320,7 @@ inline void pack_split(PackCursor &c, uint64_t p, uint32_t bases, const uint64_t
 // Software prefetch distance of the vector loops in bytes (HYPEREX_PACK_PF; < 0: into all cache levels, > 0: with the
 // non-temporal hint, 0: none).  A core streams 9-10 GB/s of text with the hardware prefetcher alone and 14 GB/s when it
 // also asks 2 KB ahead (16 threads of the B200 host: 76-89 -> 103-111 Gbases/s); the non-temporal hint measured slower
-// (profiles/r02_pack_h2d.md).
+// (profiles/r02_pack_h2d_auto.md, r02_pack_h2d_ab_ring.json).
 int pack_prefetch() {
     static const int v = [] {
         const char *e = getenv("HYPEREX_PACK_PF");
