@@ -712,15 +712,17 @@ def main():
             line["file_e2e"] = file_e2e
         if fast_ms_max > 0:
             fv = total_bases / (fast_ms_max * 1e-3) / 1e9
-            line["fast_path"] = {"what": "library default for -m 0..2: Shift-Or / Wu-Manber automata, two <= 16-symbol automata per "
-                                         "word + verification (DESIGN.md 3.5, 3.8), identical results (asserted), not counted as "
-                                         "Myers GCUPS; ms_per_step is the whole device step (tile build, classify, scan, combine)",
+            line["fast_path"] = {"what": "library default for -m 0..2: Shift-Or / Wu-Manber automata of primer suffixes, four <= 8-symbol "
+                                         "automata per word at -m 0 and two <= 16-symbol ones at -m 1..2, + verification (DESIGN.md "
+                                         "3.5, 3.8), identical results (asserted), not counted as Myers GCUPS; ms_per_step is the "
+                                         "whole device step (tile build, classify, scan, combine)",
                                  "value": fv, "unit": "Gbases/s",
                                  "ms_per_step": fast_ms_max, "speedup_vs_myers": dev_ms_max / args.steps / fast_ms_max,
                                  "groups": fast_groups[0], "automata_per_base": fast_groups[1] + fast_groups[2]}
-            # per text byte and thread, packed kernel of 8 words (SASS of the hot loop / ncu source page, profiles/r02_sass_*,
-            # r02_hot_*): ALU-pipe instructions, FMA-pipe instructions (IMAD.IADD shifts), LDS.128 of Peq rows
-            mix = {0: (17.25, 9.75, 2.0), 1: (40.0, 21.0, 2.0), 2: (64.0, 35.0, 2.0)}.get(args.k)
+            # per text byte and thread, packed kernel (4 words at -m 0, 8 at -m 1..2; SASS of the hot loop / ncu source
+            # page, profiles/r02_sass_*, r02_hot_*): ALU-pipe instructions, FMA-pipe instructions (IMAD.IADD shifts),
+            # LDS.128 of Peq rows
+            mix = {0: (11.4, 5.8, 1.0), 1: (40.0, 21.0, 2.0), 2: (64.0, 35.0, 2.0)}.get(args.k)
             if mix and args.workload == "c2":
                 sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
                 lds_peak = 148 * sm_hz * 128 / (mix[2] * 16)  # bases/s the 128 B/clk/SM shared-memory pipe allows
@@ -732,9 +734,11 @@ def main():
                     "lds": {"achieved": fv, "peak": lds_peak / 1e9, "unit": "Gbases/s at 128 B/clk/SM", "frac": fv * 1e9 / lds_peak},
                     "issue": {"achieved": fv, "peak": issue_peak / 1e9, "unit": "Gbases/s at 1 warp-instruction/clk/SMSP",
                               "frac": fv * 1e9 / issue_peak},
-                    "note": "no pipe is saturated: the scan is bound by latency at 5 resident CTAs (20 warps) per SM, see "
-                            "profiles/r02_ncu_shiftor_k0_packed.csv; the fractions include the tile-build / classify / combine "
-                            "kernels of the step in the time"}
+                    "note": "no pipe is saturated: with 15 primer sites in every read a third of all 4-byte trips is replayed "
+                            "symbol by symbol by the lane that saw a hit and the drain verifies the rest of the primer "
+                            "(hot loop = 67 % of the executed instructions, 46 % of the stall samples; "
+                            "profiles/r02_ncu_shiftor_k0_quarters.csv); the fractions include the tile-build / classify / "
+                            "combine kernels of the step in the time"}
         if not args.no_cpu_baseline:
             ns = min(args.cpu_sample, n)
             cb, cdt = cpu_port_run(arena, offsets, ns, pairs, args.k, 1)

@@ -190,7 +190,7 @@ struct hx_ctx {
     bool packable = true;  // every primer symbol is one of ACGTURYSWKMBDHVN (or lower case, which matches nothing)
     // options
     int64_t opt_tile_len = 0, opt_single_max = 0, opt_slab_bytes = 128ll << 20, opt_time = 0, opt_text_tma = 0, opt_fast_small_k = 1,
-            opt_long_filter = 1, opt_group_np_max = 0, opt_pack16 = 1, opt_pack_h2d = -1, opt_pack_threads = 0, opt_pack_piece_bytes = 4ll << 20;
+            opt_long_filter = 1, opt_group_np_max = 0, opt_pack16 = 1, opt_pack8 = 1, opt_pack_h2d = -1, opt_pack_threads = 0, opt_pack_piece_bytes = 4ll << 20;
     std::atomic<uint64_t> launches{0};
     std::mutex mu;  // guards err and timed: text lanes of one context run on several host threads
     DevPool find_pool;
@@ -504,7 +504,7 @@ int check_status(hx_ctx *ctx, const Slot &S) {
 
 // Host half of hx_set_primers (no CUDA): primer strings -> pattern groups, Peq tables, verification tables.
 struct PlanOpts {
-    int64_t fast_small_k, long_filter, group_np_max, pack16;
+    int64_t fast_small_k, long_filter, group_np_max, pack16, pack8;
 };
 struct PrimerPlan {
     std::vector<HxGroup> groups;
@@ -766,20 +766,38 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
             }
         }
     }
-    // packed tables of the groups of class 0: two 16-bit automata per word, pattern 2j in the low half
+    // packed tables of the groups of class 0: two 16-bit automata per word, pattern 2j in the low half — or, at -m 0,
+    // four 8-bit automata per word (pattern 4j + h in byte h) when the last 8 symbols of every pattern of the group are
+    // specific enough by themselves: >= 12 bits, i.e. a chance candidate every 4096 positions of random ACGT text at
+    // most (a pure 8-mer has 16; the built-in primers have 12.8..16).  Half the words again: 15 automata are 4 words and
+    // ONE 16-byte Peq row per text byte.  Candidates are verified against the rest of the primer in the drain.
+    auto suffix8_ok = [&](const std::string &pat) {
+        if (o.pack16 >= 3) return true;  // test-suite: force
+        double bits = 0;
+        for (size_t i = pat.size() > 8 ? pat.size() - 8 : 0; i < pat.size(); ++i) {
+            const char c = pat[i];
+            const int deg = strchr("RYSWKM", c) ? 2 : strchr("BDHV", c) ? 3 : c == 'N' ? 4 : 1;
+            bits += std::log2(4.0 / deg);
+        }
+        return pat.size() <= 8 || bits >= 12.0;
+    };
     P.blob_pk.clear();
     {
         for (size_t gi = 0; gi < groups.size(); ++gi) {
             HxGroup &g = groups[gi];
             if (!g.packed) continue;
             g.pk_longmask = 0;
-            const int nw = (g.np + 1) / 2, stride = hx_row_stride(nw, 4);
+            bool quarters = k == 0 && o.pack8;
+            for (int p = 0; p < g.np && quarters; ++p) quarters = suffix8_ok(gpats[gi][p].dna) && suffix8_ok(gpats[gi][p].rna);
+            const int parts = quarters ? 4 : 2, pb = 32 / parts;
+            g.pk_parts = parts;
+            const int nw = (g.np + parts - 1) / parts, stride = hx_row_stride(nw, 4);
             g.pk_table_off = (uint32_t)P.blob_pk.size();
             P.blob_pk.resize(P.blob_pk.size() + 2 * (size_t)hx_table_bytes(nw, 4), 0);
             for (int p = 0; p < g.np; ++p) {
                 const size_t full = gpats[gi][p].dna.size();
-                g.pk_m[p] = (uint8_t)std::min<size_t>(full, 16);
-                if (full > 16) {
+                g.pk_m[p] = (uint8_t)std::min<size_t>(full, (size_t)pb);
+                if (full > (size_t)pb) {
                     g.pk_longmask |= 1u << p;
                     if (g.longmask >> p & 1u) {
                         g.pk_vslot[p] = g.vslot[p];  // the 64-bit table of the whole primer exists already
@@ -795,23 +813,24 @@ int plan_primers(const PlanOpts &o, uint32_t n_pairs, const char *const *fwd, co
             }
             for (int alpha = 0; alpha < 2; ++alpha) {
                 uint8_t *tab = P.blob_pk.data() + g.pk_table_off + (size_t)alpha * hx_table_bytes(nw, 4);
+                const uint32_t part_all = parts == 4 ? 0xffu : 0xffffu;
                 for (int j = 0; j < nw; ++j) {
-                    uint64_t rows[2][256];
-                    uint32_t pmask[2] = {0xffffu, 0xffffu};  // a half without a pattern: all-ones in every row, never reports
-                    for (int h = 0; h < 2; ++h) {
-                        const int p = 2 * j + h;
+                    uint64_t rows[4][256];
+                    uint32_t pmask[4] = {part_all, part_all, part_all, part_all};  // a part without a pattern: all-ones in every row, never reports
+                    for (int h = 0; h < parts; ++h) {
+                        const int p = parts * j + h;
                         if (p >= g.np) {
                             for (int b = 0; b < 256; ++b) rows[h][b] = 0;
                             continue;
                         }
                         const std::string &full = alpha ? gpats[gi][p].rna : gpats[gi][p].dna;
-                        const std::string suf = full.size() > 16 ? full.substr(full.size() - 16) : full;
-                        peq_rows(suf, 16, rows[h]);  // top-aligned in 16 bits
-                        pmask[h] = (0xffffu << (16 - (int)suf.size())) & 0xffffu;
+                        const std::string suf = full.size() > (size_t)pb ? full.substr(full.size() - pb) : full;
+                        peq_rows(suf, pb, rows[h]);  // top-aligned in pb bits
+                        pmask[h] = (part_all << (pb - (int)suf.size())) & part_all;
                     }
                     for (int b = 0; b < 256; ++b) {  // complemented inside the pattern bits, 0 in the unused low bits
-                        const uint32_t lo = ~(uint32_t)rows[0][b] & pmask[0], hi = ~(uint32_t)rows[1][b] & pmask[1];
-                        const uint32_t w = lo | (hi << 16);
+                        uint32_t w = 0;
+                        for (int h = 0; h < parts; ++h) w |= (~(uint32_t)rows[h][b] & pmask[h]) << (pb * h);
                         memcpy(tab + (size_t)b * stride + (size_t)j * 4, &w, 4);
                     }
                 }
@@ -930,7 +949,8 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     else if (n == "fast_small_k") ctx->opt_fast_small_k = value ? 1 : 0;
     else if (n == "long_filter") ctx->opt_long_filter = value < 0 ? 0 : (value > 2 ? 2 : value);  // read by hx_set_primers
     else if (n == "group_np_max") ctx->opt_group_np_max = value;         // read by hx_set_primers; 0 = automatic
-    else if (n == "pack16") ctx->opt_pack16 = value < 0 ? 0 : (value > 2 ? 2 : value);  // hx_set_primers builds, every scan reads
+    else if (n == "pack16") ctx->opt_pack16 = value < 0 ? 0 : (value > 3 ? 3 : value);  // hx_set_primers builds, every scan reads
+    else if (n == "pack8") ctx->opt_pack8 = value ? 1 : 0;
     else if (n == "pack_h2d") {
         ctx->opt_pack_h2d = value < 0 ? -1 : (value ? 1 : 0);
         ctx->auto_pack = {};  // automatic: measure again
@@ -950,7 +970,7 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
     ctx->primers_set = false;
     PrimerPlan P;
     {
-        const PlanOpts o = {ctx->opt_fast_small_k, ctx->opt_long_filter, ctx->opt_group_np_max, ctx->opt_pack16};
+        const PlanOpts o = {ctx->opt_fast_small_k, ctx->opt_long_filter, ctx->opt_group_np_max, ctx->opt_pack16, ctx->opt_pack8};
         std::string err;
         const int rc = plan_primers(o, n_pairs, fwd, fwd_len, rev, rev_len, k, P, err);
         if (rc != HX_OK) return fail(ctx, rc, "%s", err.c_str());
@@ -1676,7 +1696,7 @@ int hx_plan_groups(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd
                    const uint32_t *rev_len, uint8_t k, int fast_small_k, int long_filter, int group_np_max,
                    uint32_t *n_groups, uint32_t *steps32_per_base, uint32_t *steps64_per_base, uint32_t *pair_group) {
     PrimerPlan P;
-    const PlanOpts o = {fast_small_k, long_filter, group_np_max, 1};
+    const PlanOpts o = {fast_small_k, long_filter, group_np_max, 1, 1};
     std::string err;
     const int rc = plan_primers(o, n_pairs, fwd, fwd_len, rev, rev_len, k, P, err);
     if (rc != HX_OK) return fail(nullptr, rc, "%s", err.c_str());
@@ -1698,7 +1718,7 @@ int hx_plan_peq_word(uint32_t n_pairs, const char *const *fwd, const uint32_t *f
                      int role, int alphabet, uint8_t byte, uint64_t *scan_word, uint64_t *wm_word, uint64_t *verify_word,
                      uint32_t *word_bits, uint32_t *m_scan, uint32_t *m_full) {
     PrimerPlan P;
-    const PlanOpts o = {fast_small_k, long_filter, group_np_max, 1};
+    const PlanOpts o = {fast_small_k, long_filter, group_np_max, 1, 1};
     std::string err;
     const int rc = plan_primers(o, n_pairs, fwd, fwd_len, rev, rev_len, k, P, err);
     if (rc != HX_OK) return fail(nullptr, rc, "%s", err.c_str());

@@ -53,9 +53,11 @@ struct HxGroup {
     // half of word j and pattern 2j + 1 in the high half.  A primer longer than 16 symbols is scanned as its last 16
     // symbols and every candidate end is verified against the rest of the primer in the drain.
     int32_t packed;                           // 1: the group has a packed table (hx_set_primers decided it pays)
+    int32_t pk_parts;                         // automata per word of that table: 2 (<= 16 symbols each), or at -m 0 4
+                                              // (<= 8 symbols each) when every 8-symbol suffix is specific enough
     uint32_t pk_table_off;                    // byte offset of the packed table in the packed blob
-    uint32_t pk_longmask;                     // bit p set: pattern p is the 16-symbol suffix of a longer primer
-    uint8_t pk_m[HX_MAX_NP32];                // scanned lengths (<= 16) in the packed table
+    uint32_t pk_longmask;                     // bit p set: pattern p is the 32 / pk_parts-symbol suffix of a longer primer
+    uint8_t pk_m[HX_MAX_NP32];                // scanned lengths (<= 32 / pk_parts) in the packed table
     uint32_t pk_vslot[HX_MAX_NP32];           // verification table of a packed pattern with pk_longmask set
 };
 

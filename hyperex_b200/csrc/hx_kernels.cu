@@ -559,13 +559,14 @@ __device__ __forceinline__ uint32_t hx_verify_long(const uint8_t *__restrict__ t
 // 16 symbols, so a candidate end `pos` means text[pos - 15 .. pos] matches that suffix exactly.  The primer occurs at
 // pos iff its first m - 16 symbols also match text[pos - m + 1 .. pos - 16]: vt (the top-aligned 64-bit Peq table of the
 // whole primer) has bit (64 - m + i) set in row b iff symbol i accepts the text byte b.
-template <bool NIB>
+template <bool NIB, int SFX>
 __device__ __forceinline__ bool hx_verify_exact(const uint8_t *__restrict__ text, uint64_t rec0, uint32_t pos,
                                                 const uint64_t *__restrict__ vt, uint32_t m, int rna) {
+    // SFX: symbols of the scanned suffix (16, or 8 with four automata per word)
     if (pos + 1u < m) return false;  // the primer does not fit before pos
     const uint64_t t0 = rec0 + (pos + 1u - m);
     uint64_t ok = 1;
-    for (uint32_t i = 0; i + 16u < m; ++i) ok &= __ldg(vt + hx_text_byte<NIB>(text, t0 + i, rna)) >> (64u - m + i);
+    for (uint32_t i = 0; i + (uint32_t)SFX < m; ++i) ok &= __ldg(vt + hx_text_byte<NIB>(text, t0 + i, rna)) >> (64u - m + i);
     return ok & 1ull;
 }
 
@@ -575,8 +576,8 @@ __device__ __forceinline__ bool hx_verify_exact(const uint8_t *__restrict__ text
 #ifndef HX_PK_MINB
 #define HX_PK_MINB 5    // resident CTAs per SM the packed kernels (8 words of state) are compiled for
 #endif
-template <typename W, int NP, bool TMA, int KWM, bool LF, bool PK = false, bool NIB = false>
-__global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <= 16) ? 8 : ((sizeof(W) * (PK ? NP / 2 : NP) <= 32) ? (PK ? HX_PK_MINB : 5) : 4)) * (128 / HX_THREADS))
+template <typename W, int NP, bool TMA, int KWM, bool LF, bool PK = false, bool NIB = false, int PPW = 2>
+__global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / PPW : NP) <= 16) ? 8 : ((sizeof(W) * (PK ? NP / PPW : NP) <= 32) ? (PK ? HX_PK_MINB : 5) : 4)) * (128 / HX_THREADS))
     hx_myers_pair_kernel(const HxScanArgs a) {
     // NIB: the arena holds 4-bit codes (hx_run_batch_packed); a 16-byte chunk is 32 symbols and the shared-memory
     // Peq table has 16 rows, gathered from the 256-row table of the record alphabet
@@ -601,8 +602,14 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     constexpr int NR = WM ? KWM + 1 : 1;    // error levels 0..k
     constexpr int WB = sizeof(W);
     // PK: NP is the (even) number of pattern halves; NW words hold them, two 16-bit automata each
-    static_assert(!PK || (KWM >= 0 && sizeof(W) == 4 && NP % 2 == 0 && !TMA), "packing: Shift-Or / Wu-Manber, 32-bit words, whole words");
-    constexpr int NW = PK ? NP / 2 : NP;    // automaton words a thread steps per text byte
+    // PPW: automata ("parts") per word when PK — 2 of <= 16 symbols, or at -m 0 4 of <= 8 symbols
+    static_assert(!PK || (KWM >= 0 && sizeof(W) == 4 && NP % PPW == 0 && !TMA), "packing: Shift-Or / Wu-Manber, 32-bit words, whole words");
+    static_assert(PPW == 2 || (PPW == 4 && PK && KWM == 0), "four automata per word: Shift-Or (-m 0) only");
+    constexpr int PB = 32 / PPW;                                      // bits per part
+    constexpr uint32_t PMASK = PPW == 4 ? 0xffu : 0xffffu;            // one part
+    constexpr uint32_t FENCE32 = PPW == 4 ? 0xfefefeffu : 0xfffeffffu;  // clears what a left shift moves across a part boundary
+    constexpr uint32_t TOPS = PPW == 4 ? 0x80808080u : 0x80008000u;   // the top bit of every part: 0 = hit
+    constexpr int NW = PK ? NP / PPW : NP;    // automaton words a thread steps per text byte
     constexpr int STRIDE = hx_row_stride(NW, WB);
     constexpr int TBYTES = 256 * STRIDE;   // one alphabet's table in global memory
     constexpr int SBYTES = NROWS * STRIDE; // ... and what of it is staged in shared memory
@@ -686,10 +693,14 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
         for (int j = 0; j < NW; ++j) {
 #pragma unroll
             for (int d = 0; d < NR; ++d) {
-                const int ml = g.pk_m[2 * j], mh = g.pk_m[2 * j + 1];
-                const uint32_t lo = 2 * j < g.np ? (d < ml ? (0xffffu << (16 - ml + d)) & 0xffffu : 0u) : 0xffffu;
-                const uint32_t hi = 2 * j + 1 < g.np ? (d < mh ? (0xffffu << (16 - mh + d)) & 0xffffu : 0u) : 0xffffu;
-                rv[d][j] = (W)(lo | (hi << 16));
+                uint32_t w = 0;
+#pragma unroll
+                for (int h = 0; h < PPW; ++h) {
+                    const int p = PPW * j + h, mp = g.pk_m[p];
+                    const uint32_t part = p < g.np ? (d < mp ? (PMASK << (PB - mp + d)) & PMASK : 0u) : PMASK;
+                    w |= part << (PB * h);
+                }
+                rv[d][j] = (W)w;
             }
             pv[j] = 0;
             mv[j] = 0;
@@ -873,7 +884,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                             row.load(tab + byte * STRIDE);
                             uint32_t t3[(NW + 2) / 3];
 #pragma unroll
-                            for (int j = 0; j < NW; ++j) rv[0][j] = ((rv[0][j] << 1) & (W)0xfffefffful) | row.eq(j);
+                            for (int j = 0; j < NW; ++j) rv[0][j] = ((rv[0][j] << 1) & (W)FENCE32) | row.eq(j);
 #pragma unroll
                             for (int j = 0; j < (NW + 2) / 3; ++j)
                                 t3[j] = hx_and3((uint32_t)rv[0][3 * j], 3 * j + 1 < NW ? (uint32_t)rv[0][3 * j + 1] : ~0u,
@@ -883,7 +894,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                         }
                         static_assert(NW <= 9 && UB <= 4, "AND tree of the fast trip");
                         const uint32_t hit = ~hx_and3(hx_and3(accb[0], accb[UB > 1 ? 1 : 0], accb[UB > 2 ? 2 : 0]), accb[UB > 3 ? 3 : 0], ~0u);
-                        if (!(hit & (W)0x80008000ul)) {
+                        if (!(hit & (W)TOPS)) {
                             w = wf;
                             continue;
                         }
@@ -903,7 +914,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                             // into the high half's bottom; the fence clears it (one LOP3 with the OR).
                             // The Wu-Manber levels (see below) use the same fenced shift for R(d-1) << 1; the other
                             // shifted terms are ANDed with it, which clears their stray bit as well.
-                            constexpr W FENCE = (W)0xfffefffful;
+                            constexpr W FENCE = (W)FENCE32;
                             W acc = ~(W)0;
 #pragma unroll
                             for (int j = 0; j < NW; ++j) {
@@ -923,7 +934,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                                 }
                                 acc &= prev_new;
                             }
-                            any = (~acc & (W)0x80008000ul) ? -1 : 0;
+                            any = (~acc & (W)TOPS) ? -1 : 0;
                         } else if constexpr (WM) {
                             // Wu-Manber, Shift-Or form: row.eq(p) is the COMPLEMENTED Peq word
                             //   R0' = (R0 << 1) | neq
@@ -968,9 +979,9 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                                     r[0] = pos;
 #pragma unroll
                                     for (int j = 0; j < NW; ++j) {
-                                        uint32_t lv = NR == 1 ? (uint32_t)rv[0][j] : (uint32_t)rv[0][j] & 0x80008000u;
+                                        uint32_t lv = NR == 1 ? (uint32_t)rv[0][j] : (uint32_t)rv[0][j] & TOPS;
 #pragma unroll
-                                        for (int d = 1; d < NR; ++d) lv |= ((uint32_t)rv[d][j] & 0x80008000u) >> d;
+                                        for (int d = 1; d < NR; ++d) lv |= ((uint32_t)rv[d][j] & TOPS) >> d;
                                         r[1 + j] = lv;
                                     }
                                     ++cnt;
@@ -1028,7 +1039,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                             for (int j = 0; j < SW; ++j) sw[j] = 0;
 #pragma unroll
                             for (int p = 0; p < NP; ++p) {
-                                const uint32_t lv = (r[1 + (p >> 1)] >> ((p & 1) ? 32 - NR : 16 - NR)) & ((1u << NR) - 1u);
+                                const uint32_t lv = (r[1 + p / PPW] >> (PB * (p % PPW + 1) - NR)) & ((1u << NR) - 1u);
                                 const int sc = __popc(lv) - bias;
                                 hm |= (sc < 0 ? 1u : 0u) << p;
                                 sw[p >> 2] |= ((uint32_t)sc & 0xffu) << (8 * (p & 3));
@@ -1047,8 +1058,8 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
                             while (lm) {
                                 const int p = __ffs((int)lm) - 1;
                                 lm &= lm - 1;
-                                if (!hx_verify_exact<NIB>(a.arena, rec0, pos, a.vtables + ((size_t)g.pk_vslot[p] * 2 + pass) * 256,
-                                                          g.mfull[p], pass))
+                                if (!hx_verify_exact<NIB, PB>(a.arena, rec0, pos, a.vtables + ((size_t)g.pk_vslot[p] * 2 + pass) * 256,
+                                                              g.mfull[p], pass))
                                     hm &= ~(1u << p);
                             }
                         } else if constexpr (LF) {
@@ -1177,9 +1188,9 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / 2 : NP) <
     }
 }
 
-template <typename W, int NP, bool TMA, int KWM, bool LF = false, bool PK = false, bool NIB = false>
+template <typename W, int NP, bool TMA, int KWM, bool LF = false, bool PK = false, bool NIB = false, int PPW = 2>
 static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
-    const int smem = hx_table_bytes(PK ? NP / 2 : NP, sizeof(W)) / (NIB ? 16 : 1) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
+    const int smem = hx_table_bytes(PK ? NP / PPW : NP, sizeof(W)) / (NIB ? 16 : 1) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
     // per (instantiation, device) once; contexts on different host threads may race here, so the flags are atomic
     // (setting the attribute twice is harmless, skipping it is not)
     // max_ctas: what the device holds at once (CTAs per SM x SMs) — the kernel's CTAs are persistent and walk the batches
@@ -1188,9 +1199,9 @@ static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream
     cudaGetDevice(&dev);
     int resident = dev < 64 ? max_ctas[dev].load(std::memory_order_acquire) : 0;
     if (resident <= 0) {
-        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB, PPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         int per_sm = 0, sms = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB>, HX_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB, PPW>, HX_THREADS, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         resident = per_sm > 0 && sms > 0 ? per_sm * sms : 1 << 30;
         if (dev < 64) max_ctas[dev].store(resident, std::memory_order_release);
@@ -1203,10 +1214,10 @@ static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream
     if (full_grid || static_rounds) {
         HxScanArgs b = a;
         b.sched = nullptr;
-        hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB><<<blocks, HX_THREADS, smem, st>>>(b);
+        hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB, PPW><<<blocks, HX_THREADS, smem, st>>>(b);
         return 1;
     }
-    hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB><<<blocks, HX_THREADS, smem, st>>>(a);
+    hx_myers_pair_kernel<W, NP, TMA, KWM, LF, PK, NIB, PPW><<<blocks, HX_THREADS, smem, st>>>(a);
     return 1;
 }
 
@@ -1246,23 +1257,24 @@ struct HxDispatch<W, 0> {
     static int run(int, bool, const HxScanArgs &, uint32_t, cudaStream_t) { return -1; }
 };
 
-// packed small-k scan: NW words = 2 * NW pattern halves
-template <int NW, int K>
+// packed small-k scan: NW words = PPW * NW automata of <= 32 / PPW symbols
+template <int NW, int K, int PPW = 2>
 static int hx_packed_dispatch(int nw, bool lf, const HxScanArgs &a, uint32_t cap, cudaStream_t st) {
     if (nw == NW) {
-        if (a.nib) return hx_scan_launch_one<uint32_t, 2 * NW, false, K, true, true, true>(a, cap, st);
-        return lf ? hx_scan_launch_one<uint32_t, 2 * NW, false, K, true, true>(a, cap, st)
-                  : hx_scan_launch_one<uint32_t, 2 * NW, false, K, false, true>(a, cap, st);
+        if (a.nib) return hx_scan_launch_one<uint32_t, PPW * NW, false, K, true, true, true, PPW>(a, cap, st);
+        return lf ? hx_scan_launch_one<uint32_t, PPW * NW, false, K, true, true, false, PPW>(a, cap, st)
+                  : hx_scan_launch_one<uint32_t, PPW * NW, false, K, false, true, false, PPW>(a, cap, st);
     }
-    if constexpr (NW > 1) return hx_packed_dispatch<NW - 1, K>(nw, lf, a, cap, st);
+    if constexpr (NW > 1) return hx_packed_dispatch<NW - 1, K, PPW>(nw, lf, a, cap, st);
     return -1;
 }
 
 int hx_launch_scan(const HxScanArgs &a, const HxGroup &hg, uint32_t tile_cap, cudaStream_t st) {
     if (tile_cap == 0) return 0;
     if (a.packed && hg.packed && !hg.word64) {
-        const int nw = (hg.np + 1) / 2;
         const bool lf = hg.pk_longmask != 0u;
+        if (hg.pk_parts == 4 && a.wm_k == 0) return hx_packed_dispatch<HX_MAX_NP32 / 4, 0, 4>((hg.np + 3) / 4, lf, a, tile_cap, st);
+        const int nw = (hg.np + 1) / 2;
         if (a.wm_k == 0) return hx_packed_dispatch<HX_MAX_NP32 / 2, 0>(nw, lf, a, tile_cap, st);
         if (a.wm_k == 1) return hx_packed_dispatch<HX_MAX_NP32 / 2, 1>(nw, lf, a, tile_cap, st);
         if (a.wm_k == 2) return hx_packed_dispatch<HX_MAX_NP32 / 2, 2>(nw, lf, a, tile_cap, st);

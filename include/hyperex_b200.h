@@ -80,7 +80,11 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
  * 32 symbols are so degenerate (mostly N) that too many positions would be candidates; 2: filter those too; 0: such
  * primers are stepped as 64-bit automata over the whole text), "group_np_max" (read by hx_set_primers; cap on the
  * automata one scan thread steps per text byte, 0 = automatic: 16 with 32-bit words, 8 with 64-bit words and on the
- * Wu-Manber path at -m 2), "pack_h2d" (hx_run_batch only: 1 = the host threads pack every slab of the caller's ASCII
+ * Wu-Manber path at -m 2), "pack16" / "pack8" (read by hx_set_primers; pattern packing of the -m 0..2 path: automata of
+ * the primers' last symbols share a 32-bit word and every candidate end is verified against the whole primer on the
+ * device, identical hits; pack16: 0 = off, 1, default = two <= 16-symbol automata per word when every suffix is specific
+ * enough, 2 / 3 = force two / four per word; pack8: 1, default = at -m 0 four <= 8-symbol automata per word when every
+ * 8-symbol suffix is specific enough (>= 12 bits), 0 = never), "pack_h2d" (hx_run_batch only: 1 = the host threads pack every slab of the caller's ASCII
  * arena to 4 bits per base while it is on its way to the device — see hx_pack_records for the code — so half the bytes
  * cross PCIe and the device runs its packed-text kernels; identical results; 0 = ASCII slabs; -1, default = automatic:
  * measured — the first four batches >= 64 MB of a context with >= 4 packer threads per device go ASCII, packed, ASCII,
@@ -237,7 +241,8 @@ void hx_fasta_close(hx_fasta *r);
 /* ---- the reference's seam itself ----------------------------------------------------- */
 /* utils.rs:231-414 get_hypervar_regions(file, primers, prefix, mismatch): reads FASTA
  * (plain / gzip / bzip2 / xz, utils.rs:148-154), runs the batch path on the GPU(s) of ctx,
- * writes <prefix>.fa and <prefix>.gff byte-identically to the reference.  log_fn (may be
+ * writes <prefix>.fa and <prefix>.gff with the bytes the CPU restatement of the reference (oracle/) writes — the
+ * reference binary itself cannot be built here (no Rust toolchain; oracle/ref_recipe makes its goldens elsewhere).  log_fn (may be
  * NULL) receives the reference's warn!/error! messages (level 1 = WARN, 2 = ERROR). */
 typedef void (*hx_log_fn)(int level, const char *msg, void *user);
 int hx_get_hypervar_regions(hx_ctx *ctx, const char *file, uint32_t n_pairs, const char *const *fwd,

@@ -31,7 +31,10 @@ def _run(ctx, arena, offsets, pairs, k, **opts):
     ctx.set_option("text_tma", opts.get("text_tma", 0))
     ctx.set_option("fast_small_k", opts.get("fast", 1))
     ctx.set_option("long_filter", opts.get("lf", 1))
+    # pattern packing of the small-k path: 0 off, 1 planner's choice, 2 two automata per word forced, 3 (-m 0) four forced;
+    # pack8 = 0 keeps the planner from choosing four 8-symbol automata per word at -m 0
     ctx.set_option("pack16", opts.get("pack", 1))
+    ctx.set_option("pack8", opts.get("pack8", 1))
     # 1: hx_run_batch packs every slab to 4 bits per base on its way to the device (ASCII in, nibble-text kernels)
     ctx.set_option("pack_h2d", opts.get("pack_h2d", -1))
     ctx.set_option("pack_threads", opts.get("pack_threads", 0))
@@ -121,12 +124,12 @@ def test_golden_batches(ctx, golden_dir, name, text_tma):
 
 
 # ---- seeded batches of the BASELINE.json shapes at oracle-friendly sizes -----------------------------
-@pytest.mark.parametrize("fast,pack", [(0, 1), (1, 0), (1, 1)])
-def test_c2_reads_all_regions_k0(ctx, fast, pack):
-    """fast 0: Myers; fast 1 + pack 0: Shift-Or, one automaton per word; fast 1 + pack 1 (library default): two
-    16-symbol suffix automata per word + verification of the rest of the primer"""
+@pytest.mark.parametrize("fast,pack,pack8", [(0, 1, 1), (1, 0, 1), (1, 1, 0), (1, 1, 1)])
+def test_c2_reads_all_regions_k0(ctx, fast, pack, pack8):
+    """fast 0: Myers; fast 1 + pack 0: Shift-Or, one automaton per word; fast 1 + pack 1: suffix automata + verification of
+    the rest of the primer — two 16-symbol automata per word (pack8 0) or four 8-symbol ones (library default)"""
     a, o = hx_synth.gen_reads(3000, seed=22)
-    res = _run(ctx, a, o, hx.default_primers(), 0, fast=fast, pack=pack)
+    res = _run(ctx, a, o, hx.default_primers(), 0, fast=fast, pack=pack, pack8=pack8)
     if fast and pack:
         assert hx.plan_groups(hx.default_primers(), 0)[:3] == (1, 15, 0)
     _cmp(res, O.run_batch(a, o, O.default_pairs(), 0, nthreads=8), a, o, O.default_pairs(), 0)
@@ -150,8 +153,8 @@ def test_all_regions_mutated_small_k_fast_path(ctx, k):
     pairs = hx.default_primers()
     ref = O.run_batch(a, o, pairs, k, nthreads=8)
     for tile in ((4096, 4096), (128, 128)):
-        for pack in (1, 0):  # two 16-symbol suffix automata per word + verification (library default) / one per word
-            _cmp(_run(ctx, a, o, pairs, k, tile_len=tile[0], single_max=tile[1], fast=1, pack=pack), ref, a, o, pairs, k)
+        for pack, pack8 in ((1, 1), (1, 0), (0, 1)):  # suffix automata + verification (library default: four per word at -m 0, else two) / one per word
+            _cmp(_run(ctx, a, o, pairs, k, tile_len=tile[0], single_max=tile[1], fast=1, pack=pack, pack8=pack8), ref, a, o, pairs, k)
 
 
 @pytest.mark.parametrize("text_tma", [0, 1])
@@ -266,8 +269,9 @@ def test_pattern_packing(ctx, k):
                 f, r = pairs[int(rng.integers(0, len(pairs)))]
                 site = f if rng.random() < 0.5 else O.to_reverse_complement(r, O.DNA).decode()
                 sb = bytearray(hx_synth._resolve(rng, site, 1)[0].tobytes())
-                if rng.random() < 0.4 and len(sb) > 16:       # damage the part in front of the 16-symbol suffix
-                    j = int(rng.integers(0, len(sb) - 16))
+                sfx = 16 if rng.random() < 0.5 else 8           # damage the part in front of the 16- / 8-symbol suffix
+                if rng.random() < 0.4 and len(sb) > sfx:
+                    j = int(rng.integers(0, len(sb) - sfx))
                     sb[j] = ord("ACGT"[("ACGT".index(chr(sb[j])) + 1) % 4]) if chr(sb[j]) in "ACGT" else ord("A")
                 elif rng.random() < 0.4:
                     sb = hx_synth._edit(rng, sb, int(rng.integers(1, k + 3)))
@@ -285,9 +289,11 @@ def test_pattern_packing(ctx, k):
         ref = O.run_batch(a, o, pairs, k, nthreads=8)
         assert (ref["flags"] & 3).any() and (n_pairs < len(base) or (ref["flags"] & 4).any())
         for tile in (0, 64, 4096):
-            for pack in (2, 1, 0):
+            for pack in (3, 2, 1, 0) if k == 0 else (2, 1, 0):  # 3: four 8-symbol automata per word forced (-m 0)
                 _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=1, pack=pack), ref, a, o, pairs, k)
             _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=1, pack=2, packed=1), ref, a, o, pairs, k)
+            if k == 0:
+                _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=1, pack=3, packed=1), ref, a, o, pairs, k)
 
 
 # ---- packed arena (north_star "2-bit/ASCII arena"): 4-bit text through hx_pack_records + hx_run_batch_packed --------
@@ -462,10 +468,10 @@ def test_random_primer_sets_fuzz(ctx, seed):
         _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, text_tma=tma, lf=lf), ref, a, o, pairs,
              k)
     if k <= 2:  # small-k pattern packing: off / forced for every group (degenerate 16-symbol suffixes included)
-        for pack in (0, 2):
+        for pack in (0, 2) if k else (0, 2, 3):
             _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=1, pack=pack), ref, a, o, pairs, k)
     # the packed arena (4-bit text): Myers, the fast paths, suffix filters; slabs cut at unaligned record starts
-    for fast, lf, pack in ((0, 1, 1), (1, 2, 2), (1, 1, 1), (0, 0, 0)):
+    for fast, lf, pack in ((0, 1, 1), (1, 2, 2), (1, 1, 1), (0, 0, 0)) + (((1, 1, 3),) if k == 0 else ()):
         _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, fast=fast, lf=lf, pack=pack, packed=1,
                   slab_bytes=int(rng.choice([1, 3000, 128 << 20]))), ref, a, o, pairs, k)
     _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, pack_h2d=1, pack_threads=int(rng.integers(1, 9)),

@@ -12,7 +12,7 @@ for mode in $MODES; do
   $CMD > gpurun_out/persist_bench_$mode.json 2> gpurun_out/persist_bench_$mode.err || { echo "$mode run failed"; tail -5 gpurun_out/persist_bench_$mode.err; exit 1; }
   [ $mode = static ] && continue
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-      -k "regex:hx_myers_pair_kernel<unsigned int, .int.15, .bool.0, .int.-1, .bool.0, .bool.0, .bool.0>" -s 2 -c 1 \
+      -k "regex:hx_myers_pair_kernel<unsigned int, .int.15, .bool.0, .int.-1, .bool.0, .bool.0, .bool.0, .int.2>" -s 2 -c 1 \
       -o gpurun_out/persist_$mode -f $PCMD > gpurun_out/persist_ncu_$mode.log 2>&1
   ncu -i gpurun_out/persist_$mode.ncu-rep --page raw --csv > gpurun_out/persist_$mode.raw.csv 2>/dev/null
   rm -f gpurun_out/persist_$mode.ncu-rep

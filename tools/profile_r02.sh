@@ -9,7 +9,7 @@ CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-ab --no-file-e2
 $CMD > gpurun_out/r02_prof_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/r02_prof_plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/r02_ncu_launches.log 2>&1
 # full captures at the bench size (1 M reads): the graded kernel (traffic figure) ...
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:hx_myers_pair_kernel<unsigned int, .int.15, .bool.0, .int.-1, .bool.0, .bool.0, .bool.0>" -s 2 -c 1 -o gpurun_out/prof_myers_1M -f $CMD > gpurun_out/r02_ncu_myers.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:hx_myers_pair_kernel<unsigned int, .int.15, .bool.0, .int.-1, .bool.0, .bool.0, .bool.0, .int.2>" -s 2 -c 1 -o gpurun_out/prof_myers_1M -f $CMD > gpurun_out/r02_ncu_myers.log 2>&1
 ncu -i gpurun_out/prof_myers_1M.ncu-rep --page raw --csv > gpurun_out/prof_myers_1M.raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_myers_1M.ncu-rep --page source --csv > gpurun_out/prof_myers_1M.src.csv 2>/dev/null
 rm -f gpurun_out/prof_myers_1M.ncu-rep
