@@ -1037,12 +1037,26 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / PPW : NP)
                             // distance of a half = the number of levels whose top bit is set (monotone over the levels)
 #pragma unroll
                             for (int j = 0; j < SW; ++j) sw[j] = 0;
+                            if constexpr (KWM == 0) {
+                                // -m 0: a hit is distance 0 (biased score -1), so only the hit mask is needed — the
+                                // complemented top bit of every part, gathered word by word
+#pragma unroll
+                                for (int j = 0; j < NW; ++j) {
+                                    const uint32_t hb = ~r[1 + j] & TOPS;
+                                    const uint32_t bits = PPW == 4 ? (((hb >> 7) & 1u) | ((hb >> 14) & 2u) | ((hb >> 21) & 4u) | ((hb >> 28) & 8u))
+                                                                   : (((hb >> 15) & 1u) | ((hb >> 30) & 2u));
+                                    hm |= bits << (PPW * j);
+                                }
+#pragma unroll
+                                for (int j = 0; j < SW; ++j) sw[j] = 0xffffffffu;  // every byte: biased score -1 (only read for hits)
+                            } else {
 #pragma unroll
                             for (int p = 0; p < NP; ++p) {
                                 const uint32_t lv = (r[1 + p / PPW] >> (PB * (p % PPW + 1) - NR)) & ((1u << NR) - 1u);
                                 const int sc = __popc(lv) - bias;
                                 hm |= (sc < 0 ? 1u : 0u) << p;
                                 sw[p >> 2] |= ((uint32_t)sc & 0xffu) << (8 * (p & 3));
+                            }
                             }
                         } else {
 #pragma unroll
