@@ -481,6 +481,9 @@ struct HxRow {
 //                serialised UBLKCPs; profiles/r01_text_path_ab.md)
 //   TMA = true   text staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier),
 //                two HX_CH-byte stages per thread; keeps the text out of the L1
+#ifndef HX_CPASYNC
+#define HX_CPASYNC 1  // packed -m 0 kernels: text through shared memory with cp.async (see CPA in the scan kernel)
+#endif
 #define HX_QCAP 16  // event records per thread queue (local memory; pushes are fire-and-forget stores)
 #ifndef HX_CH
 #define HX_CH 128   // bytes per text stage of one thread (two stages in flight)
@@ -593,6 +596,12 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / PPW : NP)
 #define HX_CHUNK32 0
 #endif
     constexpr int NH = (HX_CHUNK32 && KWM < 0 && !NIB) ? 2 : 1;  // 16-byte halves per chunk
+    // CPA: the packed -m 0 kernels stage their text through shared memory with cp.async (LDGSTS), one 16-byte slot per
+    // thread and stage.  Not for bandwidth: a register-destination prefetch holds one of the six scoreboards of a warp for
+    // a whole chunk, the hit / drain paths need scoreboards too, and ptxas made an instruction of the hot loop wait for
+    // the chunk in flight (ncu: one IMAD.MOV carried 10 % of all stall samples of the four-per-word kernel).  An
+    // asynchronous copy owns no scoreboard until cp.async.wait_group asks for it.
+    constexpr bool CPA = HX_CPASYNC && PK && KWM == 0 && !TMA;
     constexpr int CHB = 16 * NH;                     // bytes per chunk
     constexpr int CPS = HX_CH / CHB;                 // chunks per TMA stage
     constexpr int CSH = (NIB ? 5 : 4) + (NH - 1);    // log2(symbols per chunk)
@@ -801,8 +810,13 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / PPW : NP)
         uint4 nxt[NH];
 #pragma unroll
         for (int h = 0; h < NH; ++h) nxt[h] = make_uint4(0, 0, 0, 0);
+        const uint32_t cpa_slot = hx_smem_u32(txt + (size_t)threadIdx.x * 16);  // stage 1: + HX_THREADS * 16
         const auto fetch = [&](uint32_t c) {
-            if constexpr (NH == 2) hx_ldg32_stream(src + (uint64_t)CHB * c, pol, nxt[0], nxt[NH - 1]);
+            if constexpr (CPA) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" ::"r"(cpa_slot + (c & 1u) * (HX_THREADS * 16u)),
+                             "l"(src + (uint64_t)CHB * c)
+                             : "memory");
+            } else if constexpr (NH == 2) hx_ldg32_stream(src + (uint64_t)CHB * c, pol, nxt[0], nxt[NH - 1]);
             else nxt[0] = hx_ldg16_stream(src + (uint64_t)CHB * c, pol);
         };
         if constexpr (TMA) {
@@ -830,6 +844,15 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / PPW : NP)
                                      : "=r"(chunk[h].x), "=r"(chunk[h].y), "=r"(chunk[h].z), "=r"(chunk[h].w)
                                      : "r"(sa + 16u * h)
                                      : "memory");
+                }
+            } else if constexpr (CPA) {
+                if (c < nchunks) {  // chunk c was the only copy in flight
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(chunk[0].x), "=r"(chunk[0].y), "=r"(chunk[0].z), "=r"(chunk[0].w)
+                                 : "r"(cpa_slot + (c & 1u) * (HX_THREADS * 16u))
+                                 : "memory");
+                    if (c + 1 < nchunks) fetch(c + 1);
                 }
             } else {
 #pragma unroll
@@ -1204,7 +1227,8 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / PPW : NP)
 
 template <typename W, int NP, bool TMA, int KWM, bool LF = false, bool PK = false, bool NIB = false, int PPW = 2>
 static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
-    const int smem = hx_table_bytes(PK ? NP / PPW : NP, sizeof(W)) / (NIB ? 16 : 1) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0);
+    const int smem = hx_table_bytes(PK ? NP / PPW : NP, sizeof(W)) / (NIB ? 16 : 1) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0) +
+                     ((HX_CPASYNC && PK && KWM == 0 && !TMA) ? 2 * HX_THREADS * 16 : 0);  // + the cp.async text slots (CPA in the kernel)
     // per (instantiation, device) once; contexts on different host threads may race here, so the flags are atomic
     // (setting the attribute twice is harmless, skipping it is not)
     // max_ctas: what the device holds at once (CTAs per SM x SMs) — the kernel's CTAs are persistent and walk the batches
