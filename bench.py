@@ -658,7 +658,9 @@ def main():
         if roofline["traffic_detail"]:  # contract: `traffic` = dram bytes read + written per launch (ncu), a number
             roofline["traffic"] = roofline["traffic_detail"]["bytes"]
         if ab_ms is not None:
-            roofline["text_path_ab"] = {"ldg_ms_per_step": dev_ms_max / args.steps, "tma_ms_per_step": ab_ms}
+            roofline["text_path_ab"] = {"default_ms_per_step": dev_ms_max / args.steps, "tma_ms_per_step": ab_ms,
+                                        "what": "default: per-thread 16-byte cp.async copies into shared memory, one chunk ahead; "
+                                                "tma: per-thread cp.async.bulk + mbarrier (option text_tma)"}
         line = {"metric": "Gbases/s", "value": value, "unit": "Gbases/s", "gcups": value * cells,
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",

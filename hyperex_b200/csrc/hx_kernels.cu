@@ -482,7 +482,7 @@ struct HxRow {
 //   TMA = true   text staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier),
 //                two HX_CH-byte stages per thread; keeps the text out of the L1
 #ifndef HX_CPASYNC
-#define HX_CPASYNC 2  // text through shared memory with cp.async (see CPA in the scan kernel): 0 off, 1 packed -m 0 kernels, 2 all packed kernels
+#define HX_CPASYNC 3  // text through shared memory with cp.async (see CPA in the scan kernel): 0 off, 1 packed -m 0 kernels, 2 all packed kernels, 3 every kernel but the TMA variant
 #endif
 #define HX_QCAP 16  // event records per thread queue (local memory; pushes are fire-and-forget stores)
 #ifndef HX_CH
@@ -596,13 +596,16 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / PPW : NP)
 #define HX_CHUNK32 0
 #endif
     constexpr int NH = (HX_CHUNK32 && KWM < 0 && !NIB) ? 2 : 1;  // 16-byte halves per chunk
-    // CPA: the packed (-m 0..2) kernels stage their text through shared memory with cp.async (LDGSTS), one 16-byte slot per
+    // CPA: the kernels stage their text through shared memory with cp.async (LDGSTS), one 16-byte slot per
     // thread and stage.  Not for bandwidth: a register-destination prefetch holds one of the six scoreboards of a warp for
     // a whole chunk, the hit / drain paths need scoreboards too, and ptxas made an instruction of the hot loop wait for
     // the chunk in flight (ncu: one IMAD.MOV carried 10 % of all stall samples of the four-per-word kernel).  An
     // asynchronous copy owns no scoreboard until cp.async.wait_group asks for it.  Measured per 0.3 Gbases: -m 0 544 ->
-    // 518 us; device step on c2: -m 1 186 -> 215 Gbases/s, -m 2 126 -> 130.
-    constexpr bool CPA = HX_CPASYNC && PK && (KWM == 0 || HX_CPASYNC >= 2) && !TMA;
+    // 518 us; device step on c2: -m 1 186 -> 215 Gbases/s, -m 2 126 -> 130; the Myers kernels gain 0.5-1 % (13.56 -> 13.48 ms
+    // at -m 0, 14.81 -> 14.67 at -m 3) and take the same path: text reaches the automata through shared memory in every
+    // default kernel (north_star), by per-thread 16-byte asynchronous copies rather than per-thread TMA bulk copies
+    // (TMA = true: the tested option, 3 % slower, see above).
+    constexpr bool CPA = HX_CPASYNC && (PK || HX_CPASYNC >= 3) && (KWM == 0 || HX_CPASYNC >= 2) && !TMA && NH == 1;
     constexpr int CHB = 16 * NH;                     // bytes per chunk
     constexpr int CPS = HX_CH / CHB;                 // chunks per TMA stage
     constexpr int CSH = (NIB ? 5 : 4) + (NH - 1);    // log2(symbols per chunk)
@@ -1229,7 +1232,7 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / PPW : NP)
 template <typename W, int NP, bool TMA, int KWM, bool LF = false, bool PK = false, bool NIB = false, int PPW = 2>
 static int hx_scan_launch_one(const HxScanArgs &a, uint32_t tile_cap, cudaStream_t st) {
     const int smem = hx_table_bytes(PK ? NP / PPW : NP, sizeof(W)) / (NIB ? 16 : 1) + (TMA ? 2 * HX_THREADS * (HX_CH + 8) : 0) +
-                     ((HX_CPASYNC && PK && (KWM == 0 || HX_CPASYNC >= 2) && !TMA) ? 2 * HX_THREADS * 16 : 0);  // + the cp.async text slots (CPA in the kernel)
+                     ((HX_CPASYNC && (PK || HX_CPASYNC >= 3) && (KWM == 0 || HX_CPASYNC >= 2) && !TMA) ? 2 * HX_THREADS * 16 : 0);  // + the cp.async text slots (CPA in the kernel)
     // per (instantiation, device) once; contexts on different host threads may race here, so the flags are atomic
     // (setting the attribute twice is harmless, skipping it is not)
     // max_ctas: what the device holds at once (CTAs per SM x SMs) — the kernel's CTAs are persistent and walk the batches
