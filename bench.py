@@ -478,9 +478,9 @@ def main():
     def e2e_leg(pack_h2d):
         """args.steps timed hx_run_batch calls, host arena -> host result table; returns (seconds, hx_batch_stats, sha-able bytes)"""
         ctx.set_option("pack_h2d", pack_h2d)
-        # automatic: the library spends its first four large calls measuring both modes (all ranks at once, as in the
+        # automatic: the library spends its first six large calls measuring both modes (all ranks at once, as in the
         # timed region); they are warm-up here, plus one call in the mode it settled on
-        for _ in range(5 if pack_h2d < 0 else max(min(args.warmup, 3), 2)):
+        for _ in range(7 if pack_h2d < 0 else max(min(args.warmup, 3), 2)):
             ctx.run_batch(h_arena[:bases], offsets, out=h_out)
         barrier()
         t0_ = time.perf_counter()

@@ -196,7 +196,7 @@ struct hx_ctx {
     DevPool find_pool;
     PackRing pack_ring;
     uint64_t batch_stats[5] = {0, 0, 0, 0, 0};  // hx_batch_stats
-    // pack_h2d = automatic: the first four large batches alternate ASCII / packed-on-the-way slabs, the last two of them
+    // pack_h2d = automatic: the first six large batches alternate ASCII / packed-on-the-way slabs, the last four of them
     // are timed, and the faster mode serves every later call (run_batch_impl)
     struct {
         int calls = 0, decided = -1;
@@ -1332,8 +1332,9 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
     // on a 16-thread B200 host one process gets 76 Gbases/s packed against 53 ASCII, on a 24-thread host shared by two
     // processes (one GPU each) 26 against 51 per process (profiles/r02_pack_h2d_auto.md) — a process cannot see what its
     // siblings do to the memory system.  So automatic = measure: batches large enough for the pipeline to fill (>= 64 MB),
-    // with at least 4 packer threads per device, alternate ASCII, packed, ASCII, packed; the third and fourth call are
-    // timed (buffers exist, pages are mapped) and packing serves the later calls iff it was at least 5 % faster.
+    // with at least 4 packer threads per device, alternate ASCII and packed six times; calls three to six are timed
+    // (buffers exist, pages are mapped), the better of its two runs counts for each mode, and packing serves the later
+    // calls iff it was at least 5 % faster.
     const int pack_threads = ctx->opt_pack_threads > 0 ? (int)ctx->opt_pack_threads : (int)std::thread::hardware_concurrency();
     const bool pack_probe = !packed_in && ctx->packable && ctx->opt_pack_h2d < 0 && ctx->auto_pack.decided < 0 &&
                             offsets[n_records] - offsets[0] >= ((uint64_t)64 << 20) && pack_threads >= 4 * (int)ctx->devs.size();
@@ -1579,8 +1580,9 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
     if (pack_probe && rc == HX_OK) {
         auto &ap = ctx->auto_pack;
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call).count();
-        if (ap.calls >= 2) ap.rate[pack_otf ? 1 : 0] = (double)(offsets[n_records] - offsets[0]) / std::max(sec, 1e-9);
-        if (++ap.calls == 4) ap.decided = ap.rate[1] > 1.05 * ap.rate[0] ? 1 : 0;
+        if (ap.calls >= 2)  // (the first call of either mode allocates and maps its buffers: not timed)
+            ap.rate[pack_otf ? 1 : 0] = std::max(ap.rate[pack_otf ? 1 : 0], (double)(offsets[n_records] - offsets[0]) / std::max(sec, 1e-9));
+        if (++ap.calls == 6) ap.decided = ap.rate[1] > 1.05 * ap.rate[0] ? 1 : 0;
     }
     return rc;
 }

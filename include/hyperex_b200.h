@@ -87,8 +87,8 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
  * 8-symbol suffix is specific enough (>= 12 bits), 0 = never), "pack_h2d" (hx_run_batch only: 1 = the host threads pack every slab of the caller's ASCII
  * arena to 4 bits per base while it is on its way to the device — see hx_pack_records for the code — so half the bytes
  * cross PCIe and the device runs its packed-text kernels; identical results; 0 = ASCII slabs; -1, default = automatic:
- * measured — the first four batches >= 64 MB of a context with >= 4 packer threads per device go ASCII, packed, ASCII,
- * packed, and the faster of the last two modes (packed only when >= 5 % faster) serves every later call; setting the
+ * measured — the first six batches >= 64 MB of a context with >= 4 packer threads per device alternate ASCII and packed,
+ * the last four are timed, and the faster mode (packed only when >= 5 % faster) serves every later call; setting the
  * option again measures again; never for a primer set that packed text cannot represent), "pack_threads" (host threads of that path, 0 = all hardware threads; a process that shares the host
  * with other ranks passes its share), "pack_piece_bytes" (size of the pinned ring buffers the packed text goes through,
  * default 4 MiB: small enough to stay in the last-level cache between the packer's stores and the DMA reads). */

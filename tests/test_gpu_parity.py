@@ -336,18 +336,18 @@ def test_packed_arena_equals_oracle(ctx, k):
 
 
 def test_pack_h2d_automatic_measures_both_modes(ctx):
-    """pack_h2d = -1: the first four large batches go ASCII, packed, ASCII, packed (hx_batch_stats says which), the library
+    """pack_h2d = -1: the first six large batches alternate ASCII and packed slabs (hx_batch_stats says which), the library
     then keeps one mode; every call returns the same table.  Small batches and hosts without packer threads stay ASCII."""
     a, o = hx_synth.gen_reads(48_000, seed=77)  # ~72 MB: above the 64 MB bar
     assert int(o[-1]) >= 64 << 20
     pairs = hx.default_primers()
     first = _run(ctx, a, o, pairs, 0, pack_h2d=-1, pack_threads=4)
     seen = [ctx.batch_stats()["packed_text"]]
-    for _ in range(5):
+    for _ in range(7):
         res = ctx.run_batch(a, o)
         seen.append(ctx.batch_stats()["packed_text"])
         assert res.tobytes() == first.tobytes()
-    assert seen[:4] == [False, True, False, True] and seen[4] == seen[5]
+    assert seen[:6] == [False, True, False, True, False, True] and seen[6] == seen[7]
     _cmp(first[:300], O.run_batch(a[:int(o[300])], o[:301], pairs, 0, nthreads=8), a, o, pairs, 0)
     ctx.set_option("pack_h2d", -1)  # measures again
     ctx.run_batch(a, o)
