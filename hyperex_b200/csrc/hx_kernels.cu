@@ -484,7 +484,9 @@ struct HxRow {
 #ifndef HX_CPASYNC
 #define HX_CPASYNC 3  // text through shared memory with cp.async (see CPA in the scan kernel): 0 off, 1 packed -m 0 kernels, 2 all packed kernels, 3 every kernel but the TMA variant
 #endif
+#ifndef HX_QCAP
 #define HX_QCAP 16  // event records per thread queue (local memory; pushes are fire-and-forget stores)
+#endif
 #ifndef HX_CH
 #define HX_CH 128   // bytes per text stage of one thread (two stages in flight)
 #endif
