@@ -18,7 +18,7 @@ EXPORTS = [
     "hx_run_batch_device", "hx_find_all_end", "hx_alloc_pinned", "hx_free_pinned", "hx_launch_count",
     "hx_kernel_time", "hx_sequence_type", "hx_to_complement", "hx_to_reverse_complement", "hx_primers_to_region",
     "hx_region_to_primer", "hx_supported_regions", "hx_file_to_vec", "hx_free_primer_file",
-    "hx_get_hypervar_regions", "hx_fasta_open", "hx_fasta_next", "hx_fasta_close", "hx_int_peak", "hx_group_info", "hx_plan_groups", "hx_plan_peq_word", "hx_run_batch_fasta", "hx_run_batch_text",
+    "hx_get_hypervar_regions", "hx_fasta_open", "hx_fasta_next", "hx_fasta_close", "hx_int_peak", "hx_group_info", "hx_plan_groups", "hx_plan_peq_word", "hx_plan_packing", "hx_run_batch_fasta", "hx_run_batch_text",
     "hx_run_batch_text_stream", "hx_file_stats", "hx_batch_stats", "hx_fasta_descs", "hx_pack_records", "hx_run_batch_packed",
 ]
 
@@ -87,6 +87,8 @@ def load():
                                    C.c_int, C.c_uint8, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                    C.POINTER(C.c_uint32)]
+    L.hx_plan_packing.argtypes = [C.c_uint32, vp, vp, vp, vp, C.c_uint8, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_uint8,
+                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.hx_run_batch_fasta.argtypes = [vp, vp, vp, C.c_uint32, vp, cp, vp, cp, vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.hx_run_batch_text_stream.argtypes = [vp, vp, vp, C.c_uint32, vp, cp, vp, cp, vp, cp, vp, TEXT_SINK, vp,
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]

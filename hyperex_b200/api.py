@@ -361,6 +361,22 @@ def plan_groups(primers: Sequence[Sequence[str]], mismatch: int, fast_small_k: b
     return g.value, a.value, b.value, pg[:len(primers)].tolist()
 
 
+def plan_packing(primers: Sequence[Sequence[str]], mismatch: int, pair: int, role: int, alphabet: int = 0, byte: int = 65,
+                 pack16: int = 1, pack8: int = 1):
+    """hx_plan_packing (host only): dict(parts, index, m_scan, word) — how the small-k path packs this primer's automaton"""
+    L = _lib.load()
+    fw = [_b(p[0]) for p in primers]
+    rv = [_b(p[1]) for p in primers]
+    fl = (C.c_uint32 * max(1, len(fw)))(*[len(x) for x in fw])
+    rl = (C.c_uint32 * max(1, len(rv)))(*[len(x) for x in rv])
+    parts, idx, ms, w = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = L.hx_plan_packing(len(primers), _cstrs(fw), fl, _cstrs(rv), rl, mismatch, pack16, pack8, pair, role, alphabet, byte,
+                           C.byref(parts), C.byref(idx), C.byref(ms), C.byref(w))
+    if rc != 0:
+        raise HyperexError(rc, (L.hx_last_error(None) or b"").decode())
+    return {"parts": parts.value, "index": idx.value, "m_scan": ms.value, "word": w.value}
+
+
 def plan_peq_word(primers: Sequence[Sequence[str]], mismatch: int, pair: int, role: int, alphabet: int, byte: int,
                   fast_small_k: bool = True, long_filter: int = 1, group_np_max: int = 0):
     """hx_plan_peq_word (host only): dict(scan, wm, verify, bits, m_scan, m_full) for one table entry of the plan"""

@@ -1715,6 +1715,38 @@ int hx_plan_groups(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd
     return HX_OK;
 }
 
+int hx_plan_packing(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len, const char *const *rev,
+                    const uint32_t *rev_len, uint8_t k, int pack16, int pack8, uint32_t pair, int role, int alphabet, uint8_t byte,
+                    uint32_t *parts_per_word, uint32_t *part_index, uint32_t *m_scan, uint32_t *packed_word) {
+    PrimerPlan P;
+    const PlanOpts o = {1, 1, 0, pack16, pack8};
+    std::string err;
+    const int rc = plan_primers(o, n_pairs, fwd, fwd_len, rev, rev_len, k, P, err);
+    if (rc != HX_OK) return fail(nullptr, rc, "%s", err.c_str());
+    if (pair >= n_pairs || alphabet < 0 || alphabet > 1) return fail(nullptr, HX_ERR_ARG, "hx_plan_packing: bad arguments");
+    for (const HxGroup &g : P.groups)
+        for (int q = 0; q < g.npairs; ++q) {
+            if (g.pair_global[q] != pair) continue;
+            const int p = role ? g.pair_r[q] : g.pair_f[q];
+            if (!g.packed) {  // the pair's group scans one automaton per word
+                if (parts_per_word) *parts_per_word = 1;
+                if (part_index) *part_index = (uint32_t)p;
+                if (m_scan) *m_scan = g.m[p];
+                if (packed_word) *packed_word = 0;
+                return HX_OK;
+            }
+            const int parts = g.pk_parts, nw = (g.np + parts - 1) / parts, stride = hx_row_stride(nw, 4);
+            uint32_t w = 0;
+            memcpy(&w, P.blob_pk.data() + g.pk_table_off + (size_t)alphabet * hx_table_bytes(nw, 4) + (size_t)byte * stride + (size_t)(p / parts) * 4, 4);
+            if (parts_per_word) *parts_per_word = (uint32_t)parts;
+            if (part_index) *part_index = (uint32_t)p;
+            if (m_scan) *m_scan = g.pk_m[p];
+            if (packed_word) *packed_word = w;
+            return HX_OK;
+        }
+    return fail(nullptr, HX_ERR_STATE, "hx_plan_packing: pair not found in any group");
+}
+
 int hx_plan_peq_word(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len, const char *const *rev,
                      const uint32_t *rev_len, uint8_t k, int fast_small_k, int long_filter, int group_np_max, uint32_t pair,
                      int role, int alphabet, uint8_t byte, uint64_t *scan_word, uint64_t *wm_word, uint64_t *verify_word,

@@ -197,6 +197,15 @@ int hx_plan_peq_word(uint32_t n_pairs, const char *const *fwd, const uint32_t *f
                      int role, int alphabet, uint8_t byte, uint64_t *scan_word, uint64_t *wm_word, uint64_t *verify_word,
                      uint32_t *word_bits, uint32_t *m_scan, uint32_t *m_full);
 
+/* How that plan packs the small-k automata (host only; test-suite): for primer `role` of `pair` under options "pack16" /
+ * "pack8" — the automata per 32-bit word of its group's packed table (1: the group is not packed, 2, or 4 at -m 0), the
+ * primer's part index in the group (part p lives in bits [w * (p % parts), w * (p % parts + 1)) of word p / parts, w = 32 /
+ * parts), the symbols scanned (the primer's last w symbols when it is longer), and the packed table word of text byte
+ * `byte`: complemented Peq bits, top-aligned inside every part, 0 in a part's unused low bits. */
+int hx_plan_packing(uint32_t n_pairs, const char *const *fwd, const uint32_t *fwd_len, const char *const *rev,
+                    const uint32_t *rev_len, uint8_t k, int pack16, int pack8, uint32_t pair, int role, int alphabet, uint8_t byte,
+                    uint32_t *parts_per_word, uint32_t *part_index, uint32_t *m_scan, uint32_t *packed_word);
+
 /* number of kernels the context has launched so far (bench.py's gpu_launches) */
 uint64_t hx_launch_count(const hx_ctx *ctx);
 /* device time (ms) of the dominant kernel (hx_myers_pair_kernel) accumulated by CUDA events

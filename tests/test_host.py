@@ -217,6 +217,40 @@ def test_builtin_regions_are_one_group_of_15_automata():
     assert grp["v1v2"] == grp["v1v3"] == grp["v1v9"] == grp["v6v9"] == grp["v7v9"] and grp["v3v4"] == grp["v3v5"]
 
 
+def test_small_k_pattern_packing_plan_and_table_words():
+    """hx_plan_packing: which primers share a word on the small-k path, and the packed table words against a Python statement
+    of DESIGN.md §3.8 (complemented Peq bits of the scanned suffix, top-aligned inside the part, unused low bits 0)"""
+    pairs = hx.default_primers()
+    for k, want in ((0, 4), (1, 2), (2, 2), (3, 1)):      # -m 0: four 8-symbol automata per word; -m 1..2: two 16-symbol ones
+        assert {hx.plan_packing(pairs, k, q, role)["parts"] for q in range(len(pairs)) for role in (0, 1)} == {want}
+    assert hx.plan_packing(pairs, 0, 0, 0, pack8=0)["parts"] == 2 and hx.plan_packing(pairs, 0, 0, 0, pack16=0)["parts"] == 1
+    # a primer whose last 8 symbols are too degenerate (< 12 bits) keeps its whole group at two per word at -m 0 ...
+    vague8 = [["ACGTACGTACGTAC" + "NNNNACGT", "TTGACATTGACAGGT"]]
+    assert hx.plan_packing(vague8, 0, 0, 0)["parts"] == 2 and hx.plan_packing(vague8, 0, 0, 0, pack16=3)["parts"] == 4
+    # ... and one whose last 16 are too degenerate is not packed at all unless forced
+    vague16 = [["ACGTACGTAC" + "N" * 14, "TTGACATTGACAGGT"]]
+    assert hx.plan_packing(vague16, 0, 0, 0)["parts"] == 1 and hx.plan_packing(vague16, 0, 0, 0, pack16=2)["parts"] == 2
+    from oracle import oracle as O
+    rng = np.random.default_rng(8)
+    for k in (0, 1, 2):
+        for q in (0, 3, 9):
+            for role in (0, 1):
+                for alphabet in (0, 1):
+                    pat = pairs[q][0] if role == 0 else O.to_reverse_complement(pairs[q][1], O.RNA if alphabet else O.DNA).decode()
+                    for byte in [ord(c) for c in "ACGTUNRYacgtn-"] + [0, 200, int(rng.integers(1, 256))]:
+                        pl = hx.plan_packing(pairs, k, q, role, alphabet, byte)
+                        w = 32 // pl["parts"]
+                        suf = pat[-w:]
+                        assert pl["m_scan"] == len(suf)
+                        part = (pl["word"] >> (w * (pl["index"] % pl["parts"]))) & ((1 << w) - 1)
+                        up = bytes([byte]).upper()    # utils.rs:295 (ASCII upper-casing)
+                        model = 0
+                        for i, c in enumerate(suf):   # bit (w - m + i) = 0 iff symbol i accepts the (upper-cased) text byte
+                            if not (byte != 0 and O.find_all_end(c, up, 0)):   # rust-bio's ambig table, via the oracle
+                                model |= 1 << (w - len(suf) + i)
+                        assert part == model, (k, q, role, alphabet, byte, hex(part), hex(model))
+
+
 def test_grouping_invariants_on_random_primer_sets():
     import hx_synth
     rng = np.random.default_rng(5)
