@@ -576,7 +576,7 @@ __device__ __forceinline__ bool hx_verify_exact(const uint8_t *__restrict__ text
 }
 
 #ifndef HX_WI_UNROLL
-#define HX_WI_UNROLL ((PK && NR == 1) ? 4 : 1)  // see the loop over the four text words of a chunk
+#define HX_WI_UNROLL ((PK && NR == 1) ? 2 : 1)  // see the loop over the four text words of a chunk
 #endif
 #ifndef HX_PK_MINB
 #define HX_PK_MINB 5    // resident CTAs per SM the packed kernels (8 words of state) are compiled for
@@ -888,9 +888,11 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / PPW : NP)
 #pragma unroll 1
             for (int h = 0; h < NH; ++h) {
             const uint4 cur = (NH == 2 && h) ? chunk[NH - 1] : chunk[0];
-            // The four words of a chunk: a rolled loop rotates them through cur.x, and ptxas then makes the rotation wait
-            // for the chunk that is being prefetched (measured: 7 % of all stall samples of the packed -m 0 kernel, the
-            // prefetch hid nothing).  HX_WI_UNROLL words are therefore taken straight from their registers.
+            // The four words of a chunk.  With the register-destination prefetch of round 1 a rolled loop rotated them
+            // through cur.x and ptxas made the rotation wait for the chunk in flight, so the packed -m 0 kernel unrolled all
+            // four.  Since the chunk comes out of shared memory (CPA) that reason is gone and the copies only cost
+            // instruction-cache space (the trip AND its replay path are replicated): c2 device step at -m 0, words
+            // unrolled 4 / 1 / 2: 535 / 567 / 578 Gbases/s.  HX_WI_UNROLL = 2.
 #pragma unroll(WI_UNROLL)
             for (int wi = 0; wi < 4; ++wi) {
                 uint32_t w = hx_w32(cur, wi);
