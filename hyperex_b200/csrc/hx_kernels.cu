@@ -762,10 +762,13 @@ __global__ void __launch_bounds__(HX_THREADS, ((sizeof(W) * (PK ? NP / PPW : NP)
 // 8 automata at -m 2 (5.93 -> 5.54 ms per 0.75 Gbases): the level shifts of a byte are reused by the next one
 #define HX_WM_UB24 4
 #endif
+#ifndef HX_PK0_UB
+#define HX_PK0_UB 4  // text symbols per trip of the packed -m 0 loop (one hit test per trip; a trip with a hit is replayed)
+#endif
 #ifndef HX_WM_UBWIDE
 #define HX_WM_UBWIDE 2  // ... and beyond 24 (15 automata at -m 1): 2 is 7 % faster than 1 (2.62 -> 2.44 ms per 0.45 Gbases)
 #endif
-    constexpr int UB = WM ? ((KWM == 0 || NW * (KWM + 1) <= 16) ? 4 : (NW * (KWM + 1) <= 24 ? HX_WM_UB24 : HX_WM_UBWIDE))
+    constexpr int UB = WM ? ((PK && KWM == 0) ? HX_PK0_UB : (KWM == 0 || NW * (KWM + 1) <= 16) ? 4 : (NW * (KWM + 1) <= 24 ? HX_WM_UB24 : HX_WM_UBWIDE))
                           : (NP * WB <= 24) ? 4 : (NP * WB <= 40 ? 2 : 1);
     static_assert(SPW % UB == 0, "text symbols per trip must divide the word");
     constexpr int WI_UNROLL = HX_WI_UNROLL;
