@@ -265,9 +265,63 @@ def file_e2e_leg(hx, devices, arena, offsets, pairs, k, steps, work_override="")
                                                               "close_s", "parsers", "lanes", "writers", "batches")},
                "phases_note": "stage seconds are summed over the threads of the stage (pipeline: they overlap)",
                "host_cores": os.cpu_count()}
+        try:
+            out["file_to_table"] = file_to_table_leg(hx, devices, path, pairs, k, n, bases, min(steps, 2))
+        except Exception as e:  # pragma: no cover - reported, never hidden
+            out["file_to_table"] = {"error": repr(e)}
         return out
     finally:
         shutil.rmtree(work, ignore_errors=True)
+
+
+def file_to_table_leg(hx, devices, path, pairs, k, n, bases, steps):
+    """FASTA file -> result table on the host through the library's own reader and batch calls (what a caller that wants
+    coordinates, not text, runs): hx_fasta_next + hx_run_batch on the calling thread (round 1's only way), the same with
+    the chunks parsed ahead by background threads (hx_fasta_configure), and hx_fasta_next_packed + hx_run_batch_packed
+    with the chunks parsed AND packed ahead (the producer emits the packed arena).  One table per variant, hashed."""
+    import hashlib
+    from hyperex_b200.api import RESULT_DTYPE
+    raw = hx.pinned_empty(n * len(pairs) * RESULT_DTYPE.itemsize)
+    table = raw.view(RESULT_DTYPE).reshape(n, len(pairs))
+    chunk = 32 << 20
+    variants = (("one_thread_ascii", 1, False), ("read_ahead_ascii", 0, False), ("read_ahead_packed", 0, True))
+    out = {"what": "FASTA file -> host result table: library reader + hx_run_batch[_packed], 32 MiB chunks, reader and "
+                   "pinned buffers created inside the timed region", "unit": "Gbases/s", "host_cores": os.cpu_count()}
+    try:
+        with hx.Context(tuple(devices)) as tctx:
+            tctx.set_primers(pairs, k)
+            for name, threads, packed in variants:
+                times, moved = [], None
+                for it in range(steps + 1):
+                    raw[:] = 0
+                    t0 = time.perf_counter()
+                    r0 = 0
+                    if packed:
+                        for pk, fl, off, _ids, _ar in hx.read_fasta_packed(path, chunk, threads=threads, pack_ahead=True,
+                                                                           copy=False, want_ids=False):
+                            nb = len(off) - 1
+                            tctx.run_batch_packed(pk, fl, off, table[r0:r0 + nb])
+                            r0 += nb
+                    else:
+                        for ar, off, _ids in hx.read_fasta(path, chunk, threads=threads, copy=False, want_ids=False):
+                            nb = len(off) - 1
+                            tctx.run_batch(ar, off, table[r0:r0 + nb])
+                            r0 += nb
+                    dt = time.perf_counter() - t0
+                    if it:
+                        times.append(dt)
+                    moved = tctx.batch_stats()
+                if r0 != n:
+                    raise RuntimeError(f"{name}: {r0} records read, {n} written")
+                mean = sum(times) / len(times)
+                out[name] = {"value": bases / mean / 1e9, "best": bases / min(times) / 1e9, "seconds": times,
+                             "reader_threads": threads if threads else max(1, (os.cpu_count() or 2) - 1),
+                             "text_crossed_packed": moved["packed_text"],
+                             "table_sha256": hashlib.sha256(table.tobytes()).hexdigest()}
+            out["tables_equal"] = len({out[v[0]]["table_sha256"] for v in variants}) == 1
+    finally:
+        hx.pinned_free(raw)
+    return out
 
 
 def run_reference(args, rank, world):

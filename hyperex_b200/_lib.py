@@ -20,6 +20,7 @@ EXPORTS = [
     "hx_region_to_primer", "hx_supported_regions", "hx_file_to_vec", "hx_free_primer_file",
     "hx_get_hypervar_regions", "hx_fasta_open", "hx_fasta_next", "hx_fasta_close", "hx_int_peak", "hx_group_info", "hx_plan_groups", "hx_plan_peq_word", "hx_plan_packing", "hx_run_batch_fasta", "hx_run_batch_text",
     "hx_run_batch_text_stream", "hx_file_stats", "hx_batch_stats", "hx_fasta_descs", "hx_pack_records", "hx_run_batch_packed",
+    "hx_fasta_configure", "hx_fasta_next_packed",
 ]
 
 LOG_FN = C.CFUNCTYPE(None, C.c_int, C.c_char_p, C.c_void_p)
@@ -75,6 +76,10 @@ def load():
     L.hx_fasta_open.argtypes = [cp, C.POINTER(vp)]
     L.hx_fasta_next.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.POINTER(cp))]
     L.hx_fasta_next.restype = C.c_int64
+    L.hx_fasta_configure.argtypes = [vp, C.c_int, C.c_int]
+    L.hx_fasta_next_packed.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                       C.POINTER(C.POINTER(cp)), C.POINTER(vp)]
+    L.hx_fasta_next_packed.restype = C.c_int64
     L.hx_fasta_descs.argtypes = [vp]
     L.hx_fasta_descs.restype = C.POINTER(cp)
     L.hx_fasta_close.argtypes = [vp]

@@ -123,14 +123,32 @@ def pack_records(arena: np.ndarray, offsets: np.ndarray, n_threads: int = 0, pac
     return packed, rec_flags[:n]
 
 
-def read_fasta(path: str, max_bytes: int = 0):
-    """fasta::Reader::new(read_file(path)).records() (utils.rs:237-238) -> iterator of
-    (arena u8[], offsets u64[n+1], ids [str]) batches; arrays are copies"""
+def _fasta_open(path: str, threads: int, pack_ahead: bool):
     L = _lib.load()
     h = C.c_void_p()
     rc = L.hx_fasta_open(_b(path), C.byref(h))
     if rc != 0:
         raise HyperexError(rc, f"cannot open {path}")
+    if threads != 1 or pack_ahead:
+        rc = L.hx_fasta_configure(h, threads, 1 if pack_ahead else 0)
+        if rc != 0:
+            L.hx_fasta_close(h)
+            raise HyperexError(rc, "hx_fasta_configure")
+    return L, h
+
+
+def _view(ptr, n, dtype, copy):
+    ct = {np.uint8: C.c_uint8, np.uint64: C.c_uint64}[dtype]
+    v = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(max(n, 1),))[:n]
+    return v.copy() if copy else v
+
+
+def read_fasta(path: str, max_bytes: int = 0, threads: int = 1, copy: bool = True, want_ids: bool = True):
+    """fasta::Reader::new(read_file(path)).records() (utils.rs:237-238) -> iterator of
+    (arena u8[], offsets u64[n+1], ids [str]) batches.  threads > 1 (0: all but one): chunks are parsed ahead of the
+    caller by background threads (hx_fasta_configure), same batches.  copy=False yields views into the reader's pinned
+    arenas, valid until the next batch is asked for."""
+    L, h = _fasta_open(path, threads, False)
     try:
         while True:
             a, o, ids = C.c_void_p(), C.c_void_p(), C.POINTER(C.c_char_p)()
@@ -139,10 +157,31 @@ def read_fasta(path: str, max_bytes: int = 0):
                 raise HyperexError(int(n), "read error")
             if n == 0:
                 return
-            offsets = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+            offsets = _view(o, n + 1, np.uint64, copy)
+            arena = _view(a, int(offsets[-1]), np.uint8, copy)
+            yield arena, offsets, ([ids[i].decode("utf-8", "replace") for i in range(n)] if want_ids else None)
+    finally:
+        L.hx_fasta_close(h)
+
+
+def read_fasta_packed(path: str, max_bytes: int = 0, threads: int = 1, pack_ahead: bool = True, copy: bool = True,
+                      want_ids: bool = True):
+    """hx_fasta_next_packed: iterator of (packed u8[], rec_flags u8[n], offsets u64[n+1], ids, arena u8[]) — the batch as
+    the packed arena hx_run_batch_packed takes, plus its ASCII arena.  ids is None when want_ids is false."""
+    L, h = _fasta_open(path, threads, pack_ahead)
+    try:
+        while True:
+            pk, fl, o, a, ids = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.POINTER(C.c_char_p)()
+            n = L.hx_fasta_next_packed(h, max_bytes, C.byref(pk), C.byref(fl), C.byref(o), C.byref(ids), C.byref(a))
+            if n < 0:
+                raise HyperexError(int(n), "read error")
+            if n == 0:
+                return
+            offsets = _view(o, n + 1, np.uint64, copy)
             total = int(offsets[-1])
-            arena = np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_uint8)), shape=(max(total, 1),)).copy()[:total]
-            yield arena, offsets, [ids[i].decode("utf-8", "replace") for i in range(n)]
+            yield (_view(pk, total // 2 + 1, np.uint8, copy), _view(fl, n, np.uint8, copy), offsets,
+                   [ids[i].decode("utf-8", "replace") for i in range(n)] if want_ids else None,
+                   _view(a, total, np.uint8, copy))
     finally:
         L.hx_fasta_close(h)
 

@@ -1099,32 +1099,204 @@ bool HxhChunker::next(size_t target, std::vector<uint8_t> &buf, const uint8_t *&
     return true;
 }
 
-int64_t HxhFastaReader::next_batch(HxhRecordBatch &b, size_t max_bytes, bool keep_desc) {
-    b.clear();
-    while (!finished_) {
+// ------------------------------------------------------------------------------------
+// The reader behind hx_fasta_open / hx_fasta_next / hx_fasta_next_packed.  With one thread (the default) a call cuts the
+// next chunk, parses it and returns.  With more (hx_fasta_configure) the chunks are parsed — and, when asked, packed to
+// 4 bits per base — ahead of the caller by background threads: a thread takes a free slot and cuts the next chunk in
+// one step (one cutter at a time), so slots go to chunks in input order and the chunk the caller waits for always owns
+// one; batches are handed out in input order.  The iteration ends with the first chunk whose parse set `stop`
+// (rust-bio's Records stops at the first malformed / empty record): what was parsed ahead of it is dropped.
+// ------------------------------------------------------------------------------------
+struct hx_fasta {
+    struct Slot {
+        HxhRecordBatch batch;
+        std::vector<uint8_t> buf;  // decoded text of a compressed input
+        uint8_t *packed = nullptr;
+        size_t packed_cap = 0;
+        bool packed_pinned = false, is_packed = false;
+        std::vector<uint8_t> rec_flags;
+        std::vector<char> id_cstr;  // ids with terminators, for the C strings handed out
+        std::vector<const char *> id_ptrs, desc_ptrs;
+        int rc = HX_OK;
+        ~Slot() {
+            if (packed) {
+                if (packed_pinned) hx_free_pinned(packed);
+                else free(packed);
+            }
+        }
+    };
+    HxhChunker chunker;
+    int threads = 1;
+    bool pack_ahead = false, started = false;
+    std::vector<std::unique_ptr<Slot>> slots;
+    std::vector<Slot *> free_slots;
+    std::map<uint64_t, Slot *> ready;
+    Slot *held = nullptr;  // the batch in the caller's hands (valid until the next call)
+    Slot *held_view = nullptr;  // ... as the accessors see it (NULL after the end / an error)
+    std::mutex mu, cut_mu;
+    std::condition_variable cv;
+    std::vector<std::thread> workers;
+    uint64_t n_cut = 0, next_out = 0, last_index = UINT64_MAX;
+    size_t chunk_bytes = (size_t)256 << 20;
+    bool cut_done = false, quit = false;
+
+    static void finish(Slot &s) {  // C strings of the batch
+        const HxhRecordBatch &b = s.batch;
+        const size_t n = b.n_records();
+        s.id_cstr.clear();
+        s.id_cstr.reserve(b.ids.size() + n);
+        s.id_ptrs.resize(n);
+        s.desc_ptrs.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            s.id_cstr.insert(s.id_cstr.end(), b.ids.begin() + (ptrdiff_t)b.id_off[i], b.ids.begin() + (ptrdiff_t)b.id_off[i + 1]);
+            s.id_cstr.push_back('\0');
+        }
+        size_t at = 0;
+        for (size_t i = 0; i < n; ++i) {
+            s.id_ptrs[i] = s.id_cstr.data() + at;
+            at += (size_t)(b.id_off[i + 1] - b.id_off[i]) + 1;
+            s.desc_ptrs[i] = b.has_desc[i] ? b.descs[i].c_str() : nullptr;
+        }
+    }
+
+    static int pack(Slot &s, int n_threads) {
+        const HxhRecordBatch &b = s.batch;
+        const size_t n = b.n_records();
+        const size_t want = (size_t)(b.offsets[n] / 2 + 1);
+        if (want > s.packed_cap) {
+            if (s.packed) {
+                if (s.packed_pinned) hx_free_pinned(s.packed);
+                else free(s.packed);
+                s.packed = nullptr;
+                s.packed_cap = 0;
+            }
+            const size_t cap = std::max(want + want / 16, (size_t)1 << 19);
+            uint8_t *p = (uint8_t *)hx_alloc_pinned(cap);
+            s.packed_pinned = p != nullptr;
+            if (!p) p = (uint8_t *)malloc(cap);
+            if (!p) return HX_ERR_NOMEM;
+            s.packed = p;
+            s.packed_cap = cap;
+        }
+        s.rec_flags.assign(std::max<size_t>(n, 1), 0);
+        s.packed[want - 1] = 0;  // the last byte may be half used
+        const int rc = hxh_pack_slab(b.arena, b.offsets.data(), (uint32_t)n, s.packed, 0, s.rec_flags.data(), n_threads);
+        s.is_packed = rc == HX_OK;
+        return rc;
+    }
+
+    // cuts the next chunk into `s` and parses it; false at the end of the input
+    bool cut_and_parse(Slot &s, size_t target, bool do_pack, int pack_threads, uint64_t *index, std::unique_lock<std::mutex> *cut_lock) {
         const uint8_t *p = nullptr;
         size_t n = 0;
         bool err = false;
-        if (!chunker_.next(max_bytes, buf_, p, n, err)) {
-            finished_ = true;
-            break;
+        const bool got = chunker.next(target, s.buf, p, n, err);
+        if (got && index) {
+            std::lock_guard<std::mutex> lk(mu);
+            *index = n_cut++;
         }
-        const int rc = hxh_parse_fasta_text(p, n, err, keep_desc, b);
-        if (rc != HX_OK) {
-            finished_ = true;
-            return rc;
-        }
-        if (b.stop) finished_ = true;
-        if (b.n_records()) return (int64_t)b.n_records();
+        if (cut_lock) cut_lock->unlock();  // the next cutter may go on while this chunk is parsed
+        if (!got) return false;
+        s.is_packed = false;
+        s.rc = hxh_parse_fasta_text(p, n, err, true, s.batch);
+        if (s.rc == HX_OK && s.batch.n_records() > UINT32_MAX) s.rc = HX_ERR_ARG;
+        if (s.rc == HX_OK && do_pack) s.rc = pack(s, pack_threads);
+        if (s.rc == HX_OK) finish(s);
+        return true;
     }
-    return 0;
-}
 
-struct hx_fasta {
-    HxhFastaReader reader;
-    HxhRecordBatch batch;
-    std::vector<char> id_cstr;  // ids with terminators, for the C strings handed out
-    std::vector<const char *> id_ptrs, desc_ptrs;
+    void worker() {
+        for (;;) {
+            Slot *s = nullptr;
+            size_t target = 0;
+            uint64_t index = 0;
+            std::unique_lock<std::mutex> cut(cut_mu);
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || cut_done || n_cut > last_index || !free_slots.empty(); });
+                if (quit || cut_done || n_cut > last_index) return;
+                s = free_slots.back();
+                free_slots.pop_back();
+                target = chunk_bytes;
+            }
+            if (!cut_and_parse(*s, target, pack_ahead, 1, &index, &cut)) {
+                std::lock_guard<std::mutex> lk(mu);
+                cut_done = true;
+                free_slots.push_back(s);
+                cv.notify_all();
+                return;
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if ((s->rc != HX_OK || s->batch.stop) && index < last_index) last_index = index;
+            ready[index] = s;
+            cv.notify_all();
+        }
+    }
+
+    void start() {
+        started = true;
+        const int n_slots = threads > 1 ? threads + 2 : 1;
+        for (int i = 0; i < n_slots; ++i) {
+            slots.emplace_back(new Slot());
+            free_slots.push_back(slots.back().get());
+        }
+        if (threads > 1)
+            for (int i = 0; i < threads; ++i) workers.emplace_back([this] { worker(); });
+    }
+
+    // the next batch in input order: > 0 records and *out, 0 at the end of the iteration, < 0 hx_status
+    int64_t next(size_t max_bytes, Slot **out) {
+        *out = nullptr;
+        if (!started) {
+            chunk_bytes = max_bytes;
+            start();
+        }
+        if (threads <= 1) {
+            Slot &s = *slots[0];
+            if (cut_done) return 0;
+            if (!cut_and_parse(s, max_bytes, false, 1, nullptr, nullptr)) {
+                cut_done = true;
+                return 0;
+            }
+            if (s.rc != HX_OK || s.batch.stop) cut_done = true;
+            if (s.rc != HX_OK) return s.rc;
+            *out = &s;
+            return (int64_t)s.batch.n_records();
+        }
+        std::unique_lock<std::mutex> lk(mu);
+        chunk_bytes = max_bytes;
+        if (held) {
+            free_slots.push_back(held);
+            held = nullptr;
+            cv.notify_all();
+        }
+        Slot *s = nullptr;
+        for (;;) {
+            if (next_out > last_index) return 0;
+            auto it = ready.find(next_out);
+            if (it != ready.end()) {
+                s = it->second;
+                ready.erase(it);
+                break;
+            }
+            if (cut_done && next_out >= n_cut) return 0;
+            cv.wait(lk);
+        }
+        ++next_out;
+        held = s;
+        if (s->rc != HX_OK) return s->rc;
+        *out = s;
+        return (int64_t)s->batch.n_records();
+    }
+
+    ~hx_fasta() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+            cv.notify_all();
+        }
+        for (std::thread &t : workers) t.join();
+    }
 };
 
 extern "C" int hx_fasta_open(const char *path, hx_fasta **out) {
@@ -1133,7 +1305,7 @@ extern "C" int hx_fasta_open(const char *path, hx_fasta **out) {
     hx_fasta *r = new (std::nothrow) hx_fasta();
     if (!r) return HX_ERR_NOMEM;
     std::string err;
-    int rc = r->reader.open(path, err);
+    int rc = r->chunker.open(path, err);
     if (rc != HX_OK) {
         delete r;
         return rc;
@@ -1142,30 +1314,49 @@ extern "C" int hx_fasta_open(const char *path, hx_fasta **out) {
     return HX_OK;
 }
 
+extern "C" int hx_fasta_configure(hx_fasta *r, int n_threads, int pack_ahead) {
+    if (!r) return HX_ERR_ARG;
+    if (r->started) return HX_ERR_STATE;
+    if (n_threads <= 0) n_threads = std::max(1, (int)std::thread::hardware_concurrency() - 1);
+    r->threads = std::min(n_threads, 256);
+    r->pack_ahead = pack_ahead != 0;
+    return HX_OK;
+}
+
 extern "C" int64_t hx_fasta_next(hx_fasta *r, size_t max_bytes, const uint8_t **arena, const uint64_t **offsets,
                                  const char *const **ids) {
     if (!r) return HX_ERR_ARG;
-    const int64_t n = r->reader.next_batch(r->batch, max_bytes ? max_bytes : ((size_t)256 << 20), true);
-    if (n < 0) return n;
-    const HxhRecordBatch &b = r->batch;
-    r->id_cstr.clear();
-    r->id_ptrs.clear();
-    std::vector<size_t> starts;
-    for (int64_t i = 0; i < n; ++i) {
-        starts.push_back(r->id_cstr.size());
-        r->id_cstr.insert(r->id_cstr.end(), b.ids.begin() + (ptrdiff_t)b.id_off[i], b.ids.begin() + (ptrdiff_t)b.id_off[i + 1]);
-        r->id_cstr.push_back('\0');
+    hx_fasta::Slot *s = nullptr;
+    const int64_t n = r->next(max_bytes ? max_bytes : ((size_t)256 << 20), &s);
+    if (n <= 0 || !s) {
+        r->held_view = nullptr;
+        return n;
     }
-    for (size_t s : starts) r->id_ptrs.push_back(r->id_cstr.data() + s);
-    r->desc_ptrs.clear();
-    for (int64_t i = 0; i < n; ++i) r->desc_ptrs.push_back(b.has_desc[i] ? b.descs[i].c_str() : nullptr);
-    if (arena) *arena = b.arena;
-    if (offsets) *offsets = b.offsets.data();
-    if (ids) *ids = r->id_ptrs.data();
+    r->held_view = s;
+    if (arena) *arena = s->batch.arena;
+    if (offsets) *offsets = s->batch.offsets.data();
+    if (ids) *ids = s->id_ptrs.data();
     return n;
 }
 
-extern "C" const char *const *hx_fasta_descs(hx_fasta *r) { return r ? r->desc_ptrs.data() : nullptr; }
+extern "C" int64_t hx_fasta_next_packed(hx_fasta *r, size_t max_bytes, const uint8_t **packed, const uint8_t **rec_flags,
+                                        const uint64_t **offsets, const char *const **ids, const uint8_t **arena) {
+    if (!r) return HX_ERR_ARG;
+    const uint8_t *a = nullptr;
+    const int64_t n = hx_fasta_next(r, max_bytes, &a, offsets, ids);
+    if (n <= 0) return n;
+    hx_fasta::Slot *s = r->held_view;
+    if (!s->is_packed) {  // not packed ahead: all the reader's threads pack it now
+        const int rc = hx_fasta::pack(*s, r->threads);
+        if (rc != HX_OK) return rc;
+    }
+    if (packed) *packed = s->packed;
+    if (rec_flags) *rec_flags = s->rec_flags.data();
+    if (arena) *arena = a;
+    return n;
+}
+
+extern "C" const char *const *hx_fasta_descs(hx_fasta *r) { return r && r->held_view ? r->held_view->desc_ptrs.data() : nullptr; }
 
 extern "C" void hx_fasta_close(hx_fasta *r) { delete r; }
 

@@ -113,17 +113,3 @@ class HxhChunker {
     std::vector<uint8_t> carry_;  // bytes after the last record boundary of the previous chunk
     bool eof_ = false, error_ = false;
 };
-
-// Sequential reader behind the C ABI's hx_fasta_open / hx_fasta_next: chunker + parser on the calling thread.
-class HxhFastaReader {
-  public:
-    int open(const char *path, std::string &err) { return chunker_.open(path, err); }
-    // parses the next chunk of about max_bytes of FASTA text; returns the number of records, 0 at the end of the
-    // input, or a negative hx_status
-    int64_t next_batch(HxhRecordBatch &batch, size_t max_bytes, bool keep_desc);
-
-  private:
-    HxhChunker chunker_;
-    std::vector<uint8_t> buf_;
-    bool finished_ = false;
-};

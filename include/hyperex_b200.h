@@ -240,8 +240,21 @@ void hx_free_primer_file(char **fwd, char **rev, int n);
  * input, negative hx_status on error, e.g. HX_ERR_NOMEM). */
 typedef struct hx_fasta hx_fasta;
 int hx_fasta_open(const char *path, hx_fasta **out);
+/* Before the first hx_fasta_next*: parse (and, with pack_ahead != 0, pack to 4 bits per base) the chunks ahead of the
+ * caller on n_threads background threads (<= 0: all hardware threads but one; 1, the default: everything happens on the
+ * calling thread inside hx_fasta_next).  Batches still arrive in input order and are byte for byte the ones the single
+ * thread returns for the same max_bytes; the reader then owns n_threads + 2 arenas of about max_bytes each.
+ * HX_ERR_STATE once reading has begun. */
+int hx_fasta_configure(hx_fasta *r, int n_threads, int pack_ahead);
 int64_t hx_fasta_next(hx_fasta *r, size_t max_bytes, const uint8_t **arena, const uint64_t **offsets,
                       const char *const **ids);
+/* hx_fasta_next that hands the batch over as the packed arena of hx_run_batch_packed (north_star: the producer emits
+ * the packed arena): *packed = 4-bit codes (offsets[n] / 2 + 1 bytes, pinned), *rec_flags = the HX_REC_* evidence of
+ * every record — exactly what hx_pack_records makes of the batch's ASCII arena, which stays available through *arena
+ * (may be NULL) for a caller that extracts region text.  Packed by the background threads when configured with
+ * pack_ahead, otherwise inside the call. */
+int64_t hx_fasta_next_packed(hx_fasta *r, size_t max_bytes, const uint8_t **packed, const uint8_t **rec_flags,
+                             const uint64_t **offsets, const char *const **ids, const uint8_t **arena);
 /* descriptions of the records of the last hx_fasta_next batch: the header text after the first whitespace, NULL for
  * a header without one (rust-bio Record::desc; fasta::Writer::write_record prints ">id desc", utils.rs:447-449) */
 const char *const *hx_fasta_descs(hx_fasta *r);

@@ -122,9 +122,9 @@ def test_file_to_vec(golden_dir, tmp_path):
 
 
 # ---- FASTA ingest (rust-bio reader rules + niffler sniffing) ------------------------------------
-def _read_all(path, max_bytes=0):
+def _read_all(path, max_bytes=0, threads=1):
     arenas, ids, lens = [], [], []
-    for a, o, i in hx.read_fasta(path, max_bytes):
+    for a, o, i in hx.read_fasta(path, max_bytes, threads=threads):
         arenas.append(a)
         ids += i
         lens += list(np.diff(o.astype(np.int64)))
@@ -147,8 +147,8 @@ def test_read_fasta_matches_oracle_reader(tmp_path, codec):
     path = tmp_path / f"in.fa.{codec}"
     path.write_bytes({"plain": lambda b: b, "gz": gzip.compress, "bz2": bz2.compress, "xz": lzma.compress}[codec](buf))
     oa, oo, oi = O.parse_fasta(buf)
-    for mb in (0, 1000):  # whole file / many small batches
-        arena, rid, lens = _read_all(str(path), mb)
+    for mb, threads in ((0, 1), (1000, 1), (1000, 4), (0, 3)):  # whole file / many small batches; read-ahead threads
+        arena, rid, lens = _read_all(str(path), mb, threads)
         assert rid == oi and lens == list(np.diff(oo.astype(np.int64))) and arena.tobytes() == oa.tobytes()
 
 
@@ -175,8 +175,8 @@ def test_read_fasta_fuzz_against_oracle_reader(tmp_path):
         path = tmp_path / f"fuzz{case}.fa"
         path.write_bytes(buf)
         oa, oo, oi = O.parse_fasta(buf)
-        for mb in (0, 64):
-            arena, rid, lens = _read_all(str(path), mb)
+        for mb, threads in ((0, 1), (64, 1), (64, 3)):
+            arena, rid, lens = _read_all(str(path), mb, threads)
             assert rid == oi, (case, buf[:200])
             assert lens == list(np.diff(oo.astype(np.int64))), (case, buf[:200])
             assert arena.tobytes() == oa.tobytes(), (case, buf[:200])
@@ -193,6 +193,60 @@ def test_read_fasta_errors(tmp_path):
     notfa = tmp_path / "not.fa"
     notfa.write_bytes(b"ACGTACGT\n>x\nAC\n")
     assert list(hx.read_fasta(str(notfa))) == []
+
+
+def _batches(it):
+    return [tuple(x.tobytes() if isinstance(x, np.ndarray) else x for x in b) for b in it]
+
+
+@pytest.mark.parametrize("codec", ["plain", "gz"])
+def test_read_ahead_reader_returns_the_single_thread_batches(tmp_path, codec):
+    """hx_fasta_configure: the batches parsed ahead on background threads are, one by one and in order, the batches the
+    calling thread alone cuts and parses for the same max_bytes — also when the iteration ends inside a later chunk
+    (chunks parsed ahead of a malformed record are dropped) and when the caller stops early"""
+    a, o = hx_synth.gen_reads_mutated(600, seed=5, lower_frac=0.2, lmin=1, lmax=900)
+    ids = [f"r{i}" if i % 4 else f"r{i} desc {i}" for i in range(600)]
+    good = hx_synth.to_fasta(a, o, ids, width=70)
+    for name, buf in (("good", good), ("stops", good[: len(good) // 2] + b">\n>after\nACGT\n" + good[len(good) // 2:])):
+        path = tmp_path / f"{name}.fa.{codec}"
+        path.write_bytes(gzip.compress(buf) if codec == "gz" else buf)
+        for mb in (5000, 40000, 0):
+            one = _batches(hx.read_fasta(str(path), mb, threads=1))
+            for threads in (2, 5, 0):
+                assert _batches(hx.read_fasta(str(path), mb, threads=threads)) == one, (name, mb, threads)
+        oa, oo, oi = O.parse_fasta(buf)
+        assert b"".join(b[0] for b in one) == oa.tobytes() and sum((b[2] for b in one), []) == oi
+    it = hx.read_fasta(str(path), 5000, threads=4)  # abandoned mid-way: close joins the threads
+    next(it)
+    it.close()
+
+
+def test_packed_reader_equals_pack_records(tmp_path):
+    """hx_fasta_next_packed = hx_pack_records of the batch hx_fasta_next returns: packed on the calling thread, by all
+    the reader's threads, or ahead by the background threads — records with U, with T and U, with non-IUPAC bytes, empty
+    records, odd and even batch lengths"""
+    rng = np.random.default_rng(77)
+    recs = []
+    for i in range(500):
+        n = int(rng.integers(0, 400))
+        alpha = [b"ACGT", b"ACGU", b"ACGTU", b"ACGTRYSWKMBDHVNacgtn", b"ACGTXZ*-."][int(rng.integers(5))]
+        recs.append(bytes(rng.choice(np.frombuffer(alpha, np.uint8), n)))
+    buf = b"".join(b">s%d\n%s\n" % (i, r) for i, r in enumerate(recs) if i == 0 or r or i % 2)
+    path = tmp_path / "p.fa"
+    path.write_bytes(buf)
+    for mb in (3000, 0):
+        plain = list(hx.read_fasta(str(path), mb))
+        for threads, ahead in ((1, False), (1, True), (4, False), (4, True)):
+            got = list(hx.read_fasta_packed(str(path), mb, threads=threads, pack_ahead=ahead))
+            assert len(got) == len(plain)
+            for (pk, fl, off, ids, arena), (pa, po, pi) in zip(got, plain):
+                assert arena.tobytes() == pa.tobytes() and off.tobytes() == po.tobytes() and ids == pi
+                want_pk, want_fl = hx.pack_records(pa, po, 1)
+                total = int(po[-1])
+                assert fl.tobytes() == want_fl.tobytes(), (mb, threads, ahead)
+                assert pk[: total // 2].tobytes() == want_pk[: total // 2].tobytes()
+                if total & 1:
+                    assert pk[total // 2] & 15 == want_pk[total // 2] & 15
 
 
 # ---- pattern grouping (host half of hx_set_primers; hx_plan_groups needs no GPU) -------------------------
