@@ -335,6 +335,29 @@ def test_packed_arena_equals_oracle(ctx, k):
     _cmp(_run(ctx, a2, o2, pairs, k, pack_h2d=1, pack_piece=4096), ref, a2, o2, pairs, k)
 
 
+@pytest.mark.parametrize("k", [0, 2])
+def test_packed_reader_feeds_run_batch_packed(ctx, tmp_path, k):
+    """FASTA file -> hx_fasta_next_packed (chunks parsed and packed ahead by background threads) -> hx_run_batch_packed:
+    the producer emits the packed arena; the table equals the oracle's over the oracle's own parse of the file"""
+    a, o = hx_synth.gen_reads_mutated(2500, seed=610 + k, max_edits=2, revcomp_frac=0.3, lower_frac=0.3, rna_frac=0.2)
+    ids = [f"r{i}" for i in range(2500)]
+    buf = hx_synth.to_fasta(a, o, ids, width=80)
+    path = tmp_path / "in.fa"
+    path.write_bytes(buf)
+    oa, oo, _oi = O.parse_fasta(buf)
+    pairs = hx.default_primers()
+    ref = O.run_batch(oa, oo, pairs, k, nthreads=8)
+    assert (ref["flags"] & 4).any()
+    _run(ctx, a[:int(o[1])], o[:2], pairs, k)  # options and primers of the suite's defaults
+    for threads, ahead, mb in ((4, True, 200_000), (1, False, 0), (3, False, 1 << 20)):
+        parts = []
+        for pk, fl, off, _ids, ar in hx.read_fasta_packed(str(path), mb, threads=threads, pack_ahead=ahead, want_ids=False):
+            got = ctx.run_batch_packed(pk, fl, off)
+            assert got.tobytes() == ctx.run_batch(ar, off).tobytes()
+            parts.append(got)
+        _cmp(np.concatenate(parts), ref, oa, oo, pairs, k)
+
+
 def test_pack_h2d_automatic_measures_both_modes(ctx):
     """pack_h2d = -1: the first six large batches alternate ASCII and packed slabs (hx_batch_stats says which), the library
     then keeps one mode; every call returns the same table.  Small batches and hosts without packer threads stay ASCII."""
