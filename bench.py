@@ -285,8 +285,9 @@ def file_to_table_leg(hx, devices, path, pairs, k, n, bases, steps):
     table = raw.view(RESULT_DTYPE).reshape(n, len(pairs))
     chunk = 32 << 20
     variants = (("one_thread_ascii", 1, False), ("read_ahead_ascii", 0, False), ("read_ahead_packed", 0, True))
-    out = {"what": "FASTA file -> host result table: library reader + hx_run_batch[_packed], 32 MiB chunks, reader and "
-                   "pinned buffers created inside the timed region", "unit": "Gbases/s", "host_cores": os.cpu_count()}
+    out = {"what": "FASTA file -> host result table: library reader + hx_run_batch[_packed], 32 MiB chunks; the reader is opened and "
+                   "closed inside the timed region, its pinned slots come from the process-wide cache the untimed first "
+                   "pass filled (pinning costs 1.5 ms per MB on these hosts)", "unit": "Gbases/s", "host_cores": os.cpu_count()}
     try:
         with hx.Context(tuple(devices)) as tctx:
             tctx.set_primers(pairs, k)

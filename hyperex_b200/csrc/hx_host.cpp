@@ -1233,12 +1233,40 @@ struct hx_fasta {
         }
     }
 
+    // Slots (pinned arenas, packed buffers, id tables) of closed readers wait here for the next reader of the process:
+    // pinning memory costs about 1.5 ms per MB on the B200 hosts — more than parsing the text that goes into it — so a
+    // caller that reads file after file pays for its slots once.  At most HYPEREX_READER_CACHE_MB (default 1024) are kept.
+    struct SlotPool {
+        std::mutex mu;
+        std::vector<std::unique_ptr<Slot>> idle;
+        size_t bytes = 0;
+    };
+    static SlotPool &pool() {
+        static SlotPool *p = new SlotPool();  // never destroyed: cudaFreeHost after the runtime has shut down is an error
+        return *p;
+    }
+    static size_t pool_cap() {
+        const char *e = getenv("HYPEREX_READER_CACHE_MB");
+        return (size_t)(e ? std::max(0L, atol(e)) : 1024L) << 20;
+    }
+
     void start() {
         started = true;
         const int n_slots = threads > 1 ? threads + 2 : 1;
-        for (int i = 0; i < n_slots; ++i) {
-            slots.emplace_back(new Slot());
-            free_slots.push_back(slots.back().get());
+        {
+            SlotPool &P = pool();
+            std::lock_guard<std::mutex> lk(P.mu);
+            while ((int)slots.size() < n_slots && !P.idle.empty()) {
+                P.bytes -= P.idle.back()->batch.arena_cap + P.idle.back()->packed_cap;
+                slots.push_back(std::move(P.idle.back()));
+                P.idle.pop_back();
+            }
+        }
+        while ((int)slots.size() < n_slots) slots.emplace_back(new Slot());
+        for (auto &s : slots) {
+            s->rc = HX_OK;
+            s->is_packed = false;
+            free_slots.push_back(s.get());
         }
         if (threads > 1)
             for (int i = 0; i < threads; ++i) workers.emplace_back([this] { worker(); });
@@ -1296,6 +1324,16 @@ struct hx_fasta {
             cv.notify_all();
         }
         for (std::thread &t : workers) t.join();
+        SlotPool &P = pool();
+        const size_t cap = pool_cap();
+        std::lock_guard<std::mutex> lk(P.mu);
+        for (auto &s : slots) {
+            const size_t b = s->batch.arena_cap + s->packed_cap;
+            if (b == 0 || P.bytes + b > cap) continue;  // freed with the reader
+            std::vector<uint8_t>().swap(s->buf);
+            P.bytes += b;
+            P.idle.push_back(std::move(s));
+        }
     }
 };
 
@@ -1317,7 +1355,8 @@ extern "C" int hx_fasta_open(const char *path, hx_fasta **out) {
 extern "C" int hx_fasta_configure(hx_fasta *r, int n_threads, int pack_ahead) {
     if (!r) return HX_ERR_ARG;
     if (r->started) return HX_ERR_STATE;
-    if (n_threads <= 0) n_threads = std::max(1, (int)std::thread::hardware_concurrency() - 1);
+    // automatic: a parser thread moves 3-6 GB/s of text, eight of them more than one PCIe link takes
+    if (n_threads <= 0) n_threads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() - 1));
     r->threads = std::min(n_threads, 256);
     r->pack_ahead = pack_ahead != 0;
     return HX_OK;

@@ -241,9 +241,11 @@ void hx_free_primer_file(char **fwd, char **rev, int n);
 typedef struct hx_fasta hx_fasta;
 int hx_fasta_open(const char *path, hx_fasta **out);
 /* Before the first hx_fasta_next*: parse (and, with pack_ahead != 0, pack to 4 bits per base) the chunks ahead of the
- * caller on n_threads background threads (<= 0: all hardware threads but one; 1, the default: everything happens on the
+ * caller on n_threads background threads (<= 0: hardware threads - 1, at most 8; 1, the default: everything happens on the
  * calling thread inside hx_fasta_next).  Batches still arrive in input order and are byte for byte the ones the single
- * thread returns for the same max_bytes; the reader then owns n_threads + 2 arenas of about max_bytes each.
+ * thread returns for the same max_bytes; the reader then owns n_threads + 2 arenas of about max_bytes each (kept for
+ * the next reader of the process after hx_fasta_close, up to HYPEREX_READER_CACHE_MB = 1024 MiB: pinning costs more
+ * than parsing).
  * HX_ERR_STATE once reading has begun. */
 int hx_fasta_configure(hx_fasta *r, int n_threads, int pack_ahead);
 int64_t hx_fasta_next(hx_fasta *r, size_t max_bytes, const uint8_t **arena, const uint64_t **offsets,
