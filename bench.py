@@ -274,7 +274,7 @@ def file_e2e_leg(hx, devices, arena, offsets, pairs, k, steps, work_override="")
         shutil.rmtree(work, ignore_errors=True)
 
 
-def file_to_table_leg(hx, devices, path, pairs, k, n, bases, steps):
+def file_to_table_leg(hx, devices, path, pairs, k, n, bases, steps, chunk=32 << 20, variants=None):
     """FASTA file -> result table on the host through the library's own reader and batch calls (what a caller that wants
     coordinates, not text, runs): hx_fasta_next + hx_run_batch on the calling thread (round 1's only way), the same with
     the chunks parsed ahead by background threads (hx_fasta_configure), and hx_fasta_next_packed + hx_run_batch_packed
@@ -283,9 +283,8 @@ def file_to_table_leg(hx, devices, path, pairs, k, n, bases, steps):
     from hyperex_b200.api import RESULT_DTYPE
     raw = hx.pinned_empty(n * len(pairs) * RESULT_DTYPE.itemsize)
     table = raw.view(RESULT_DTYPE).reshape(n, len(pairs))
-    chunk = 32 << 20
-    variants = (("one_thread_ascii", 1, False), ("read_ahead_ascii", 0, False), ("read_ahead_packed", 0, True))
-    out = {"what": "FASTA file -> host result table: library reader + hx_run_batch[_packed], 32 MiB chunks; the reader is opened and "
+    variants = variants or (("one_thread_ascii", 1, False), ("read_ahead_ascii", 0, False), ("read_ahead_packed", 0, True))
+    out = {"what": f"FASTA file -> host result table: library reader + hx_run_batch[_packed], {chunk >> 20} MiB chunks; the reader is opened and "
                    "closed inside the timed region, its pinned slots come from the process-wide cache the untimed first "
                    "pass filled (pinning costs 1.5 ms per MB on these hosts)", "unit": "Gbases/s", "host_cores": os.cpu_count()}
     try:
@@ -316,7 +315,7 @@ def file_to_table_leg(hx, devices, path, pairs, k, n, bases, steps):
                     raise RuntimeError(f"{name}: {r0} records read, {n} written")
                 mean = sum(times) / len(times)
                 out[name] = {"value": bases / mean / 1e9, "best": bases / min(times) / 1e9, "seconds": times,
-                             "reader_threads": threads if threads else max(1, (os.cpu_count() or 2) - 1),
+                             "reader_threads": threads if threads else max(1, min(8, (os.cpu_count() or 2) - 1)),
                              "text_crossed_packed": moved["packed_text"],
                              "table_sha256": hashlib.sha256(table.tobytes()).hexdigest()}
             out["tables_equal"] = len({out[v[0]]["table_sha256"] for v in variants}) == 1
