@@ -246,9 +246,10 @@ class Context:
 
     def batch_stats(self) -> dict:
         """hx_batch_stats: what the last run_batch / run_batch_packed call moved"""
-        v = (C.c_uint64 * 5)()
-        self._check(self._L.hx_batch_stats(self._h, v, 5))
-        return {"h2d_bytes": int(v[0]), "d2h_bytes": int(v[1]), "packed_text": bool(v[2]), "slabs": int(v[3]), "pack_threads": int(v[4])}
+        v = (C.c_uint64 * 7)()
+        self._check(self._L.hx_batch_stats(self._h, v, 7))
+        return {"h2d_bytes": int(v[0]), "d2h_bytes": int(v[1]), "packed_text": bool(v[2]), "slabs": int(v[3]), "pack_threads": int(v[4]),
+                "slabs_packed": int(v[5]), "mode": ("ascii", "packed_on_the_way", "mixed", "packed_arena")[int(v[6]) & 3]}
 
     def run_batch_packed(self, packed: np.ndarray, rec_flags: np.ndarray, offsets: np.ndarray,
                          out: np.ndarray | None = None) -> np.ndarray:

@@ -29,7 +29,7 @@ static_assert(sizeof(hx_result) == 12, "hx_result must be 12 bytes");
 
 namespace {
 
-constexpr int HX_NSLOT = 3;  // pipeline depth per device (H2D / scan / D2H overlap)
+constexpr int HX_NSLOT = 4;  // pipeline depth per device (H2D / scan / D2H overlap; the mixed path of hx_run_batch fills two at once)
 constexpr int HX_NLANE = 2;  // text lanes per device (see TextLane)
 
 std::string g_create_error;
@@ -159,6 +159,7 @@ struct Device {
     int dev = 0;
     Slot slots[HX_NSLOT];
     std::vector<cudaEvent_t> ring_ev;  // per ring buffer of the context: end of this device's copy out of it
+    std::vector<cudaEvent_t> link_ev;  // mixed path: ends of the ASCII chunk copies in flight
     TextLane lanes[HX_NLANE];
     uint8_t *d_tables = nullptr;
     uint8_t *d_tables_wm = nullptr;
@@ -195,7 +196,7 @@ struct hx_ctx {
     std::mutex mu;  // guards err and timed: text lanes of one context run on several host threads
     DevPool find_pool;
     PackRing pack_ring;
-    uint64_t batch_stats[5] = {0, 0, 0, 0, 0};  // hx_batch_stats
+    uint64_t batch_stats[7] = {0, 0, 0, 0, 0, 0, 0};  // hx_batch_stats
     // pack_h2d = automatic: the first six large batches alternate ASCII / packed-on-the-way slabs, the last four of them
     // are timed, and the faster mode serves every later call (run_batch_impl)
     struct {
@@ -928,6 +929,8 @@ void hx_destroy(hx_ctx *ctx) {
         for (TextLane &L : D.lanes) L.release();
         for (cudaEvent_t e : D.ring_ev)
             if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : D.link_ev)
+            if (e) cudaEventDestroy(e);
         if (D.d_tables) cudaFree(D.d_tables);
         if (D.d_tables_wm) cudaFree(D.d_tables_wm);
         if (D.d_tables_pk) cudaFree(D.d_tables_pk);
@@ -952,7 +955,7 @@ int hx_set_option(hx_ctx *ctx, const char *name, int64_t value) {
     else if (n == "pack16") ctx->opt_pack16 = value < 0 ? 0 : (value > 3 ? 3 : value);  // hx_set_primers builds, every scan reads
     else if (n == "pack8") ctx->opt_pack8 = value ? 1 : 0;
     else if (n == "pack_h2d") {
-        ctx->opt_pack_h2d = value < 0 ? -1 : (value ? 1 : 0);
+        ctx->opt_pack_h2d = value < 0 ? -1 : (value >= 2 ? 2 : value ? 1 : 0);
         ctx->auto_pack = {};  // automatic: measure again
     } else if (n == "pack_threads") {
         ctx->opt_pack_threads = std::max<int64_t>(value, 0);
@@ -1316,6 +1319,400 @@ struct PackRange {
 };
 }  // namespace
 
+// ---- hx_run_batch, pack_h2d = 2: BOTH the link and the packer threads work all the time ----------------------------------
+// ASCII slabs keep the link busy and cost no host work; packed slabs cost host work and half the link time.  With a link
+// that moves L bases per second as ASCII and packers that make P, sending the fraction f = 2P / (2L + P) of the batch packed
+// finishes both at the same moment: L + P / 2 bases per second, against max(L, P) for either pure mode.  f is not computed:
+// the issuing thread takes ASCII slabs from the FRONT of the batch whenever no packed piece is waiting, the packer threads
+// claim slabs from the BACK, and the two meet wherever the host they run on makes them meet (all packed on a host with many
+// idle cores, nearly all ASCII on a host whose cores are busy).  Slabs get (device, slot) pairs as those become free.
+namespace {
+// The issuing thread is the link's scheduler: an ASCII slab crosses in chunks, and at most HYB_LINKQ copies (chunks and
+// packed pieces together) are queued at any time, so a packed piece that becomes ready waits for a fraction of a
+// millisecond, not for a whole slab — the packers' ring holds less than a millisecond of their work.
+constexpr int HYB_LINKQ = 3;
+constexpr uint64_t HYB_CHUNK = 8ull << 20;
+struct HybSlab {
+    uint32_t r0, r1;
+    uint64_t base_a, copy_a;  // ASCII: 16-byte phase of the arena kept
+    uint64_t base_p, copy_p;  // packed on the way: base rounded down to 128 symbols
+    int64_t first_piece = 0;
+    int di = -1, si = -1;     // where it runs (known once issued / first piece issued)
+};
+}  // namespace
+
+static int run_batch_hybrid(hx_ctx *ctx, const uint8_t *arena, const uint64_t *offsets, uint32_t n_records, hx_result *out) {
+    const size_t np = ctx->n_pairs;
+    const int ndev = (int)ctx->devs.size();
+    const int pack_threads = ctx->opt_pack_threads > 0 ? (int)ctx->opt_pack_threads : (int)std::thread::hardware_concurrency();
+    const uint64_t total = offsets[n_records] - offsets[0];
+    // slabs a quarter of the usual size: the two sides meet inside one slab's worth of time, and that time is the tail
+    uint64_t slab_bytes = std::max<uint64_t>((uint64_t)ctx->opt_slab_bytes / 4, 1);
+    slab_bytes = std::min(slab_bytes, std::max<uint64_t>(total / (8ull * ndev) + 1, (uint64_t)8 << 20));
+    std::vector<HybSlab> slabs;
+    for (uint32_t r0 = 0; r0 < n_records;) {
+        const uint64_t limit = offsets[r0] + slab_bytes;
+        uint32_t r1 = (uint32_t)(std::upper_bound(offsets + r0 + 1, offsets + n_records + 1, limit) - offsets) - 1;
+        if (r1 <= r0) r1 = r0 + 1;
+        for (uint32_t i = r0; i < r1; ++i)
+            if (offsets[i + 1] < offsets[i]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
+        HybSlab c;
+        c.r0 = r0;
+        c.r1 = r1;
+        c.base_a = offsets[r0] & ~15ull;
+        c.copy_a = offsets[r1] - c.base_a;
+        c.base_p = offsets[r0] & ~127ull;
+        c.copy_p = (offsets[r1] + 1) / 2 - c.base_p / 2;
+        slabs.push_back(c);
+        r0 = r1;
+    }
+    const int64_t n_slabs = (int64_t)slabs.size();
+
+    // pieces and ranges of every slab in the packers' order: last slab first (most of them are never packed)
+    std::vector<PackPiece> pieces;
+    std::vector<PackRange> ranges;
+    const uint64_t piece_bases = 2ull * (uint64_t)ctx->opt_pack_piece_bytes;  // a multiple of 128
+    const uint64_t range_bases = 128u << 10;
+    const int n_buf = HX_NRING * ndev;
+    for (int64_t j = n_slabs - 1; j >= 0; --j) {
+        HybSlab &c = slabs[j];
+        const uint64_t begin = offsets[c.r0], end = offsets[c.r1];
+        c.first_piece = (int64_t)pieces.size();
+        for (uint64_t al = c.base_p;; al += piece_bases) {
+            PackPiece P;
+            P.slab = j;
+            P.al = al;
+            P.p = std::max(al, begin);
+            P.q = std::max(P.p, std::min(end, al + piece_bases));
+            P.dst_off = (al - c.base_p) / 2;
+            P.bytes = P.q > P.al ? (P.q + 1) / 2 - P.al / 2 : 0;
+            P.slot = (int)(pieces.size() % (size_t)n_buf);
+            P.first_range = (int64_t)ranges.size();
+            for (uint64_t x = P.p; x < P.q;) {
+                const uint64_t y = std::min(P.q, (x + range_bases) & ~(uint64_t)127);
+                ranges.push_back({x, y, (int64_t)pieces.size(), x == begin});
+                x = y;
+            }
+            P.n_ranges = (int64_t)ranges.size() - P.first_range;
+            P.last_of_slab = al + piece_bases >= end;
+            pieces.push_back(P);
+            if (P.last_of_slab) break;
+        }
+    }
+    const int64_t n_pieces = (int64_t)pieces.size();
+    std::vector<HxhPackPart> parts(ranges.size());
+    std::unique_ptr<std::atomic<int>[]> piece_done(new std::atomic<int>[pieces.size()]);
+    for (size_t g = 0; g < pieces.size(); ++g) piece_done[g].store(0, std::memory_order_relaxed);
+
+    // ring, flags, events (as on the all-packed path; nothing is enqueued yet, so an error can simply return)
+    PackRing &R = ctx->pack_ring;
+    {
+        const size_t buf_bytes = (size_t)ctx->opt_pack_piece_bytes + 64;
+        if (R.n_buf != n_buf || R.buf_bytes != buf_bytes) {
+            if (R.p) cudaFreeHost(R.p);
+            R.p = nullptr;
+            R.n_buf = 0;
+            if (cudaHostAlloc((void **)&R.p, buf_bytes * (size_t)n_buf, cudaHostAllocPortable) != cudaSuccess)
+                return fail(ctx, HX_ERR_NOMEM, "hx_run_batch: cannot allocate %zu bytes of pinned staging", buf_bytes * (size_t)n_buf);
+            R.n_buf = n_buf;
+            R.buf_bytes = buf_bytes;
+        }
+        if (R.flags_cap < (size_t)n_records + 64) {
+            if (R.flags) cudaFreeHost(R.flags);
+            R.flags = nullptr;
+            R.flags_cap = 0;
+            const size_t want = (size_t)n_records + (size_t)n_records / 4 + 64;
+            if (cudaHostAlloc((void **)&R.flags, want, cudaHostAllocPortable) != cudaSuccess)
+                return fail(ctx, HX_ERR_NOMEM, "hx_run_batch: cannot allocate %zu bytes of pinned staging", want);
+            R.flags_cap = want;
+        }
+        for (Device &D : ctx->devs) {
+            if (cudaSetDevice(D.dev) != cudaSuccess) return fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaSetDevice failed");
+            while ((int)D.ring_ev.size() < n_buf) {
+                cudaEvent_t e = nullptr;
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaEventCreate failed");
+                D.ring_ev.push_back(e);
+            }
+            while ((int)D.link_ev.size() < HYB_LINKQ) {
+                cudaEvent_t e = nullptr;
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaEventCreate failed");
+                D.link_ev.push_back(e);
+            }
+            for (int si = 0; si < HX_NSLOT; ++si)
+                if (!D.slots[si].done_ev && cudaEventCreateWithFlags(&D.slots[si].done_ev, cudaEventDisableTiming) != cudaSuccess)
+                    return fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaEventCreate failed");
+        }
+    }
+
+    // who owns which slabs: [0, front) were taken as ASCII by the issuing thread, [back, n_slabs) by the packers
+    std::mutex claim_mu;
+    int64_t front = 0;
+    std::atomic<int64_t> back{n_slabs};
+    std::atomic<int64_t> next_range{0}, allowed_piece{n_buf};
+    std::atomic<bool> pack_abort{false};
+    bool pack_stop = false;                            // under claim_mu: a claim was refused, the packers are leaving
+    std::atomic<int64_t> ascii_ns{0}, pack_ns{0};      // issue-to-issue time of the last ASCII / packed slab
+    const int workers = std::max(1, pack_threads - 1);  // the issuing thread polls, so it is not idle
+    std::thread packer([&, workers] {
+        hxh_parallel_run(workers, workers, [&](int) {
+            for (;;) {
+                const int64_t i = next_range.fetch_add(1, std::memory_order_relaxed);
+                if (i >= (int64_t)ranges.size() || pack_abort.load(std::memory_order_relaxed)) return;
+                const PackRange &rg = ranges[i];
+                const PackPiece &P = pieces[rg.piece];
+                if (P.slab < back.load(std::memory_order_acquire)) {  // ranges come in order: this is slab back - 1 or the claim fails
+                    std::lock_guard<std::mutex> lk(claim_mu);
+                    if (P.slab < back.load(std::memory_order_relaxed)) {
+                        // The slab is taken only if the packers can be through with it before the ASCII side has eaten its way
+                        // up to it (a claim cannot be given back, and whatever the packers still hold when the sides meet is
+                        // the tail of the call): (slabs still between the sides) x (time per ASCII slab) >= time per packed slab,
+                        // both measured in this call; one slab of margin until they are.  A refusal is final.
+                        const int64_t between = P.slab - front;  // unclaimed slabs below this one
+                        const int64_t ta = ascii_ns.load(std::memory_order_relaxed), tp = pack_ns.load(std::memory_order_relaxed);
+                        const bool ok = !pack_stop && front <= P.slab && (ta > 0 && tp > 0 ? between * ta >= tp : between >= 1 || n_slabs == 1);
+                        if (!ok) {
+                            pack_stop = true;
+                            return;  // every later range belongs to the ASCII side too
+                        }
+                        back.store(P.slab, std::memory_order_release);
+                    }
+                }
+                while (rg.piece >= allowed_piece.load(std::memory_order_acquire)) {  // the ring buffer is still being read
+                    if (pack_abort.load(std::memory_order_relaxed)) return;
+                    hx_cpu_relax();
+                }
+                uint8_t *buf = R.p + (size_t)P.slot * R.buf_bytes;
+                hxh_pack_range(arena, offsets, n_records, rg.p, rg.q, (uint8_t *)((uintptr_t)buf - (uintptr_t)(P.al / 2)), R.flags, false,
+                               rg.slab_first, &parts[i]);
+                piece_done[rg.piece].fetch_add(1, std::memory_order_release);
+            }
+        });
+    });
+
+    // slots: 0 free, 1 in flight (done_ev recorded), 2 being filled by a packed slab
+    std::vector<int> state(ndev * HX_NSLOT, 0), used(ndev * HX_NSLOT, 0);
+    int rc = HX_OK;
+    int rr = 0;  // round-robin start of the device search
+    auto retire = [&] {  // slabs whose result copy has completed give their slots back
+        for (int di = 0; di < ndev && rc == HX_OK; ++di)
+            for (int si = 0; si < HX_NSLOT && rc == HX_OK; ++si) {
+                int &st = state[di * HX_NSLOT + si];
+                if (st != 1) continue;
+                const cudaError_t q = cudaEventQuery(ctx->devs[di].slots[si].done_ev);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess) rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: %s", cudaGetErrorString(q));
+                else rc = check_status(ctx, ctx->devs[di].slots[si]);
+                st = 0;
+            }
+    };
+    auto find_slot = [&](int &di_out, int &si_out) -> bool {  // a free (device, slot), devices in turn
+        for (int t = 0; t < ndev; ++t) {
+            const int di = (rr + t) % ndev;
+            for (int si = 0; si < HX_NSLOT; ++si)
+                if (state[di * HX_NSLOT + si] == 0) {
+                    di_out = di;
+                    si_out = si;
+                    rr = (di + 1) % ndev;
+                    return true;
+                }
+        }
+        return false;
+    };
+    int64_t oldest = 0, issued = 0;  // ring: first piece whose copy is not known to be complete / pieces whose copies are enqueued
+    auto piece_ev = [&](int64_t g) -> cudaEvent_t { return ctx->devs[slabs[pieces[g].slab].di].ring_ev[pieces[g].slot]; };
+    auto poll_ring = [&] {
+        while (oldest < issued && cudaEventQuery(piece_ev(oldest)) == cudaSuccess) ++oldest;
+        allowed_piece.store(oldest + n_buf, std::memory_order_release);
+    };
+    uint64_t h2d = 0, n_packed_slabs = 0;
+    int64_t g = 0;  // next piece to issue, in the packers' order
+    int64_t af_j = -1;  // the ASCII slab that is crossing chunk by chunk, and how far it is
+    uint64_t af_off = 0;
+    int64_t a_issued = 0, a_done = 0;  // ASCII chunk copies enqueued / known to be complete
+    int a_dev[HYB_LINKQ] = {0};
+    const bool dbg = getenv("HYPEREX_HYB_DEBUG") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    uint64_t n_iter = 0, n_no_slot = 0, n_queue_full = 0, n_chunks = 0, n_idle = 0, n_pk_no_slot = 0;
+    double t_first_piece = -1, t_met = -1, t_last_ascii = -1;
+    int64_t t_pack_prev = 0, t_ascii_prev = 0;
+    uint64_t n_ascii_slabs = 0;
+    while (rc == HX_OK) {
+        ++n_iter;
+        poll_ring();
+        retire();
+        if (rc != HX_OK) break;
+        bool did = false;
+        // (a) a packed piece that is ready goes first: it is what the packer threads are waiting to get rid of
+        if (g < n_pieces && pieces[g].slab >= back.load(std::memory_order_acquire) &&
+            piece_done[g].load(std::memory_order_acquire) >= (int)pieces[g].n_ranges) {
+            const PackPiece &P = pieces[g];
+            HybSlab &c = slabs[P.slab];
+            const uint32_t n = c.r1 - c.r0;
+            if (t_first_piece < 0) t_first_piece = since();
+            if (c.di < 0) {  // first piece of its slab: the slab needs a slot
+                int di, si;
+                if (!find_slot(di, si)) ++n_pk_no_slot;
+                else {
+                    Device &D = ctx->devs[di];
+                    HX_CUDA_BREAK(ctx, rc, cudaSetDevice(D.dev));
+                    const SlabPlan pl = plan_slab(ctx, n, offsets[c.r1] - offsets[c.r0]);
+                    rc = prepare_slab(ctx, D.slots[si], pl, n, c.copy_p + 64, true);
+                    if (rc != HX_OK) break;
+                    c.di = di;
+                    c.si = si;
+                    state[di * HX_NSLOT + si] = 2;
+                    used[di * HX_NSLOT + si] = 1;
+                }
+            }
+            if (rc != HX_OK) break;
+            if (c.di >= 0) {
+                Device &D = ctx->devs[c.di];
+                Slot &S = D.slots[c.si];
+                HX_CUDA_BREAK(ctx, rc, cudaSetDevice(D.dev));
+                if (P.bytes) HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.arena.p + P.dst_off, R.p + (size_t)P.slot * R.buf_bytes, P.bytes, cudaMemcpyHostToDevice, S.stream));
+                HX_CUDA_BREAK(ctx, rc, cudaEventRecord(piece_ev(g), S.stream));
+                issued = g + 1;
+                ++g;
+                did = true;
+                if (P.last_of_slab) {  // evidence merge, rec_flags, offsets, kernels, result copy
+                    const PackPiece &P0 = pieces[c.first_piece];
+                    uint32_t open_rec = UINT32_MAX, open_acc = 0;
+                    hxh_pack_merge(R.flags, parts.data() + P0.first_range, (size_t)(P.first_range + P.n_ranges - P0.first_range), open_rec, open_acc);
+                    // empty records at the head of the slab end before its first base: no range of THIS slab finalises them (the
+                    // last range of the slab before it does, with the same 0, if that slab is packed at all)
+                    for (uint32_t r = c.r0; r < c.r1 && offsets[r + 1] == offsets[c.r0]; ++r) R.flags[r] = 0;
+                    const SlabPlan pl = plan_slab(ctx, n, offsets[c.r1] - offsets[c.r0]);
+                    HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.flags.p, R.flags + c.r0, n, cudaMemcpyHostToDevice, S.stream));
+                    HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.offsets.p, offsets + c.r0, ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, S.stream));
+                    rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, c.base_p, n, S.out.p, S.stream, S.flags.p);
+                    if (rc != HX_OK) break;
+                    HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(out + (size_t)c.r0 * np, S.out.p, (size_t)n * np * sizeof(hx_result), cudaMemcpyDeviceToHost, S.stream));
+                    HX_CUDA_BREAK(ctx, rc, cudaEventRecord(S.done_ev, S.stream));
+                    state[c.di * HX_NSLOT + c.si] = 1;
+                    h2d += c.copy_p + ((uint64_t)n + 1) * sizeof(uint64_t) + n;
+                    ++n_packed_slabs;
+                    {
+                        const int64_t now = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
+                        if (n_packed_slabs > 1) pack_ns.store(std::max<int64_t>(now - t_pack_prev, 1), std::memory_order_relaxed);
+                        t_pack_prev = now;
+                    }
+                }
+            }
+        }
+        // (b) otherwise the link gets the next chunk of an ASCII slab from the front.  One free slot per device is left to the
+        //     packed side while it has work, so that a finished piece never waits for its slab's slot.
+        if (!did && rc == HX_OK) {
+            while (a_done < a_issued && cudaEventQuery(ctx->devs[a_dev[a_done % HYB_LINKQ]].link_ev[a_done % HYB_LINKQ]) == cudaSuccess) ++a_done;
+            if (af_j < 0) {
+                int di = -1, si = -1, n_free = 0;
+                for (int x : state) n_free += x == 0;
+                bool packed_pending;
+                {
+                    std::lock_guard<std::mutex> lk(claim_mu);
+                    const int64_t b = back.load(std::memory_order_relaxed);
+                    packed_pending = g < n_pieces && (pieces[g].slab >= b || front < b);
+                }
+                int64_t j = -1;
+                if (n_free >= (packed_pending ? 2 : 1) && find_slot(di, si)) {
+                    std::lock_guard<std::mutex> lk(claim_mu);
+                    if (front < back.load(std::memory_order_relaxed)) j = front++;
+                    else if (t_met < 0) t_met = since();
+                } else {
+                    ++n_no_slot;
+                }
+                if (j >= 0) {
+                    HybSlab &c = slabs[j];
+                    HX_CUDA_BREAK(ctx, rc, cudaSetDevice(ctx->devs[di].dev));
+                    const SlabPlan pl = plan_slab(ctx, c.r1 - c.r0, offsets[c.r1] - offsets[c.r0]);
+                    rc = prepare_slab(ctx, ctx->devs[di].slots[si], pl, c.r1 - c.r0, c.copy_a + 64, false);
+                    if (rc != HX_OK) break;
+                    c.di = di;
+                    c.si = si;
+                    used[di * HX_NSLOT + si] = 1;
+                    state[di * HX_NSLOT + si] = 2;
+                    af_j = j;
+                    af_off = 0;
+                    did = true;
+                }
+            }
+            if (af_j >= 0 && (a_issued - a_done) + (issued - oldest) >= HYB_LINKQ) ++n_queue_full;
+            if (af_j >= 0 && (a_issued - a_done) + (issued - oldest) < HYB_LINKQ) {
+                HybSlab &c = slabs[af_j];
+                const uint32_t n = c.r1 - c.r0;
+                Device &D = ctx->devs[c.di];
+                Slot &S = D.slots[c.si];
+                HX_CUDA_BREAK(ctx, rc, cudaSetDevice(D.dev));
+                if (af_off < c.copy_a) {
+                    const uint64_t chunk = std::min<uint64_t>(HYB_CHUNK, c.copy_a - af_off);
+                    HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.arena.p + af_off, arena + c.base_a + af_off, chunk, cudaMemcpyHostToDevice, S.stream));
+                    HX_CUDA_BREAK(ctx, rc, cudaEventRecord(D.link_ev[a_issued % HYB_LINKQ], S.stream));
+                    a_dev[a_issued % HYB_LINKQ] = c.di;
+                    ++a_issued;
+                    ++n_chunks;
+                    t_last_ascii = since();
+                    af_off += chunk;
+                }
+                if (af_off >= c.copy_a) {  // the whole slab is on its way: offsets, kernels, result copy
+                    const SlabPlan pl = plan_slab(ctx, n, offsets[c.r1] - offsets[c.r0]);
+                    HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(S.offsets.p, offsets + c.r0, ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, S.stream));
+                    rc = enqueue_slab(ctx, D, S, pl, S.arena.p, S.offsets.p, c.base_a, n, S.out.p, S.stream, nullptr);
+                    if (rc != HX_OK) break;
+                    HX_CUDA_BREAK(ctx, rc, cudaMemcpyAsync(out + (size_t)c.r0 * np, S.out.p, (size_t)n * np * sizeof(hx_result), cudaMemcpyDeviceToHost, S.stream));
+                    HX_CUDA_BREAK(ctx, rc, cudaEventRecord(S.done_ev, S.stream));
+                    state[c.di * HX_NSLOT + c.si] = 1;
+                    h2d += c.copy_a + ((uint64_t)n + 1) * sizeof(uint64_t);
+                    af_j = -1;
+                    {
+                        const int64_t now = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
+                        if (++n_ascii_slabs > 1) ascii_ns.store(std::max<int64_t>(now - t_ascii_prev, 1), std::memory_order_relaxed);
+                        t_ascii_prev = now;
+                    }
+                }
+                did = true;
+            }
+        }
+        if (rc != HX_OK) break;
+        // (c) done when the two sides have met and every piece of the packed side is on its way
+        if (!did) {
+            bool finished;
+            {
+                std::lock_guard<std::mutex> lk(claim_mu);
+                const int64_t b = back.load(std::memory_order_relaxed);
+                finished = af_j < 0 && front >= b && (g >= n_pieces || pieces[g].slab < b);
+            }
+            if (finished) break;
+            ++n_idle;
+            hx_cpu_relax();
+        }
+    }
+    const double t_loop = since();
+    if (rc != HX_OK) pack_abort.store(true);
+    packer.join();
+    for (int di = 0; di < ndev; ++di) {  // epilogue on every path, as in run_batch_impl
+        cudaSetDevice(ctx->devs[di].dev);
+        for (int si = 0; si < HX_NSLOT; ++si) {
+            if (!used[di * HX_NSLOT + si]) continue;
+            cudaError_t e = cudaStreamSynchronize(ctx->devs[di].slots[si].stream);
+            if (e != cudaSuccess && rc == HX_OK) rc = fail(ctx, HX_ERR_CUDA, "hx_run_batch: %s", cudaGetErrorString(e));
+            if (rc == HX_OK && e == cudaSuccess && state[di * HX_NSLOT + si] != 2) rc = check_status(ctx, ctx->devs[di].slots[si]);
+        }
+    }
+    sync_timed(ctx);
+    if (dbg)
+        fprintf(stderr, "[hyb] slabs %lld packed %llu pieces %lld | iter %llu idle %llu ascii: chunks %llu no_slot %llu queue_full %llu | packed first-slot misses %llu | ms: first piece %.2f last ascii chunk %.2f met %.2f loop %.2f total %.2f\n",
+                (long long)n_slabs, (unsigned long long)n_packed_slabs, (long long)g, (unsigned long long)n_iter, (unsigned long long)n_idle, (unsigned long long)n_chunks,
+                (unsigned long long)n_no_slot, (unsigned long long)n_queue_full, (unsigned long long)n_pk_no_slot, t_first_piece, t_last_ascii, t_met, t_loop, since());
+    ctx->batch_stats[0] = h2d;
+    ctx->batch_stats[1] = (uint64_t)n_records * np * sizeof(hx_result);
+    ctx->batch_stats[2] = n_packed_slabs ? 1 : 0;
+    ctx->batch_stats[3] = (uint64_t)n_slabs;
+    ctx->batch_stats[4] = (uint64_t)pack_threads;
+    ctx->batch_stats[5] = n_packed_slabs;
+    ctx->batch_stats[6] = 2;
+    return rc;
+}
+
 static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_flags, const uint64_t *offsets, uint32_t n_records,
                           hx_result *out) {
     DeviceGuard device_guard;
@@ -1336,12 +1733,28 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
     // (buffers exist, pages are mapped), the better of its two runs counts for each mode, and packing serves the later
     // calls iff it was at least 5 % faster.
     const int pack_threads = ctx->opt_pack_threads > 0 ? (int)ctx->opt_pack_threads : (int)std::thread::hardware_concurrency();
-    const bool pack_probe = !packed_in && ctx->packable && ctx->opt_pack_h2d < 0 && ctx->auto_pack.decided < 0 &&
-                            offsets[n_records] - offsets[0] >= ((uint64_t)64 << 20) && pack_threads >= 4 * (int)ctx->devs.size();
-    const bool pack_otf = !packed_in && ctx->packable &&
-                          (ctx->opt_pack_h2d == 1 ||
-                           (ctx->opt_pack_h2d < 0 && (pack_probe ? (ctx->auto_pack.calls & 1) != 0 : ctx->auto_pack.decided == 1)));
+    const bool can_pack = !packed_in && ctx->packable && arena && offsets[n_records] > offsets[0];
+    const bool pack_probe = can_pack && ctx->opt_pack_h2d < 0 && ctx->auto_pack.decided < 0 &&
+                            offsets[n_records] - offsets[0] >= ((uint64_t)64 << 20) && pack_threads >= 2 * (int)ctx->devs.size();
+    // what automatic measures against ASCII slabs is the mixed path (pack_h2d = 2): it is at least as fast as packing every
+    // slab at every thread count measured (profiles/r02_mixed_slabs.md), so pack_h2d = 1 only runs when asked for
+    const bool mixed = can_pack && (ctx->opt_pack_h2d == 2 ||
+                                    (ctx->opt_pack_h2d < 0 && (pack_probe ? (ctx->auto_pack.calls & 1) != 0 : ctx->auto_pack.decided == 1)));
+    const bool pack_otf = can_pack && ctx->opt_pack_h2d == 1;
     const auto t_call = std::chrono::steady_clock::now();
+    auto probe_done = [&](int rc_) {
+        if (!pack_probe || rc_ != HX_OK) return;
+        auto &ap = ctx->auto_pack;
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call).count();
+        if (ap.calls >= 2)  // (the first call of either mode allocates and maps its buffers: not timed)
+            ap.rate[mixed ? 1 : 0] = std::max(ap.rate[mixed ? 1 : 0], (double)(offsets[n_records] - offsets[0]) / std::max(sec, 1e-9));
+        if (++ap.calls == 6) ap.decided = ap.rate[1] > 1.05 * ap.rate[0] ? 1 : 0;
+    };
+    if (mixed) {
+        const int rc_ = run_batch_hybrid(ctx, arena, offsets, n_records, out);
+        probe_done(rc_);
+        return rc_;
+    }
     const bool nib = packed_in || pack_otf;
     const size_t np = ctx->n_pairs;
     const int ndev = (int)ctx->devs.size();
@@ -1383,6 +1796,8 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
         ctx->batch_stats[2] = nib ? 1 : 0;
         ctx->batch_stats[3] = (uint64_t)n_slabs;
         ctx->batch_stats[4] = pack_otf ? (uint64_t)pack_threads : 0;
+        ctx->batch_stats[5] = nib ? (uint64_t)n_slabs : 0;
+        ctx->batch_stats[6] = packed_in ? 3 : pack_otf ? 1 : 0;
     }
     // per (device, slot): the slab it last ran, so its status word can be checked before reuse
     std::vector<int> used(ndev * HX_NSLOT, 0);
@@ -1577,13 +1992,7 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
         }
     }
     sync_timed(ctx);
-    if (pack_probe && rc == HX_OK) {
-        auto &ap = ctx->auto_pack;
-        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call).count();
-        if (ap.calls >= 2)  // (the first call of either mode allocates and maps its buffers: not timed)
-            ap.rate[pack_otf ? 1 : 0] = std::max(ap.rate[pack_otf ? 1 : 0], (double)(offsets[n_records] - offsets[0]) / std::max(sec, 1e-9));
-        if (++ap.calls == 6) ap.decided = ap.rate[1] > 1.05 * ap.rate[0] ? 1 : 0;
-    }
+    probe_done(rc);
     return rc;
 }
 
@@ -1678,7 +2087,7 @@ void hx_free_pinned(void *p) {
 
 int hx_batch_stats(const hx_ctx *ctx, uint64_t *out, int n) {
     if (!ctx || !out || n < 0) return HX_ERR_ARG;
-    for (int i = 0; i < n && i < 5; ++i) out[i] = ctx->batch_stats[i];
+    for (int i = 0; i < n && i < 7; ++i) out[i] = ctx->batch_stats[i];
     return HX_OK;
 }
 

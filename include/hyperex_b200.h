@@ -86,10 +86,12 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
  * enough, 2 / 3 = force two / four per word; pack8: 1, default = at -m 0 four <= 8-symbol automata per word when every
  * 8-symbol suffix is specific enough (>= 12 bits), 0 = never), "pack_h2d" (hx_run_batch only: 1 = the host threads pack every slab of the caller's ASCII
  * arena to 4 bits per base while it is on its way to the device — see hx_pack_records for the code — so half the bytes
- * cross PCIe and the device runs its packed-text kernels; identical results; 0 = ASCII slabs; -1, default = automatic:
- * measured — the first six batches >= 64 MB of a context with >= 4 packer threads per device alternate ASCII and packed,
- * the last four are timed, and the faster mode (packed only when >= 5 % faster) serves every later call; setting the
- * option again measures again; never for a primer set that packed text cannot represent), "pack_threads" (host threads of that path, 0 = all hardware threads; a process that shares the host
+ * cross PCIe and the device runs its packed-text kernels; 2 = mixed: ASCII slabs from the front of the batch keep the link
+ * busy while the host threads pack slabs from its back, the two sides meet where this host makes them meet (link rate +
+ * half the packers' rate instead of the larger of the two); identical results in every mode; 0 = ASCII slabs; -1,
+ * default = automatic: measured — the first six batches >= 64 MB of a context with >= 2 packer threads per device
+ * alternate ASCII and mixed, the last four are timed, and the faster mode (mixed only when >= 5 % faster) serves every
+ * later call; setting the option again measures again; never for a primer set that packed text cannot represent), "pack_threads" (host threads of that path, 0 = all hardware threads; a process that shares the host
  * with other ranks passes its share), "pack_piece_bytes" (size of the pinned ring buffers the packed text goes through,
  * default 4 MiB: small enough to stay in the last-level cache between the packer's stores and the DMA reads). */
 int hx_set_option(hx_ctx *ctx, const char *name, int64_t value);
@@ -301,7 +303,9 @@ int hx_file_stats(hx_ctx *ctx, double *out, int n);
 /* What the last hx_run_batch / hx_run_batch_packed call of this context moved: out[0] bytes copied host -> device
  * (text, offsets, rec_flags), out[1] bytes copied device -> host (the result table), out[2] 1 when the text crossed
  * PCIe as 4-bit codes (a packed arena, or an ASCII arena packed on the way: option pack_h2d), out[3] slabs,
- * out[4] host threads that packed (0: none).  n = entries of out (fewer are fine). */
+ * out[4] host threads that packed (0: none), out[5] slabs that crossed packed (pack_h2d = 2 mixes both kinds in one
+ * call), out[6] how the call ran: 0 ASCII slabs, 1 every slab packed on the way, 2 mixed, 3 packed arena.  n = entries
+ * of out (fewer are fine). */
 int hx_batch_stats(const hx_ctx *ctx, uint64_t *out, int n);
 
 #ifdef __cplusplus

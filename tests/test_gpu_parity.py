@@ -327,12 +327,22 @@ def test_packed_arena_equals_oracle(ctx, k):
     for slab, th, piece in ((128 << 20, 0, 4 << 20), (50_000, 3, 4096), (1, 2, 4096), (333_333, 8, 8192), (128 << 20, 5, 4096),
                             (128 << 20, 0, 65536)):
         _cmp(_run(ctx, a, o, pairs, k, pack_h2d=1, slab_bytes=slab, pack_threads=th, pack_piece=piece), ref, a, o, pairs, k)
+    # pack_h2d = 2: ASCII slabs from the front and packed slabs from the back of the batch in ONE call; which slab goes which
+    # way depends on timing, the table must not
+    for slab, th, piece in ((128 << 20, 0, 4 << 20), (50_000, 3, 4096), (1, 2, 4096), (333_333, 8, 8192), (20_000, 1, 4096),
+                            (100_000, 16, 65536)):
+        for _ in range(3):
+            _cmp(_run(ctx, a, o, pairs, k, pack_h2d=2, slab_bytes=slab, pack_threads=th, pack_piece=piece), ref, a, o, pairs, k)
+    st = ctx.batch_stats()
+    assert st["slabs"] >= 1 and 0 <= st["slabs_packed"] <= st["slabs"]
     # an arena whose first record starts at an odd offset
     a2 = np.concatenate([np.frombuffer(b"GTGCCAG", np.uint8), a])
     o2 = o + np.uint64(7)
     _cmp(_run(ctx, a2, o2, pairs, k, packed=1, slab_bytes=30_000), ref, a2, o2, pairs, k)
     _cmp(_run(ctx, a2, o2, pairs, k, pack_h2d=1, slab_bytes=30_000), ref, a2, o2, pairs, k)
     _cmp(_run(ctx, a2, o2, pairs, k, pack_h2d=1, pack_piece=4096), ref, a2, o2, pairs, k)
+    _cmp(_run(ctx, a2, o2, pairs, k, pack_h2d=2, slab_bytes=30_000), ref, a2, o2, pairs, k)
+    _cmp(_run(ctx, a2, o2, pairs, k, pack_h2d=2, slab_bytes=64, pack_piece=4096, pack_threads=4), ref, a2, o2, pairs, k)
 
 
 @pytest.mark.parametrize("k", [0, 2])
@@ -359,32 +369,38 @@ def test_packed_reader_feeds_run_batch_packed(ctx, tmp_path, k):
 
 
 def test_pack_h2d_automatic_measures_both_modes(ctx):
-    """pack_h2d = -1: the first six large batches alternate ASCII and packed slabs (hx_batch_stats says which), the library
-    then keeps one mode; every call returns the same table.  Small batches and hosts without packer threads stay ASCII."""
+    """pack_h2d = -1: the first six large batches alternate ASCII slabs and the mixed path (hx_batch_stats says which), the
+    library then keeps one mode; every call returns the same table.  Small batches and hosts without packer threads stay ASCII."""
     a, o = hx_synth.gen_reads(48_000, seed=77)  # ~72 MB: above the 64 MB bar
     assert int(o[-1]) >= 64 << 20
     pairs = hx.default_primers()
     first = _run(ctx, a, o, pairs, 0, pack_h2d=-1, pack_threads=4)
-    seen = [ctx.batch_stats()["packed_text"]]
+    seen = [ctx.batch_stats()["mode"]]
     for _ in range(7):
         res = ctx.run_batch(a, o)
-        seen.append(ctx.batch_stats()["packed_text"])
+        seen.append(ctx.batch_stats()["mode"])
         assert res.tobytes() == first.tobytes()
-    assert seen[:6] == [False, True, False, True, False, True] and seen[6] == seen[7]
+    assert seen[:6] == ["ascii", "mixed"] * 3 and seen[6] == seen[7]
     _cmp(first[:300], O.run_batch(a[:int(o[300])], o[:301], pairs, 0, nthreads=8), a, o, pairs, 0)
     ctx.set_option("pack_h2d", -1)  # measures again
     ctx.run_batch(a, o)
     ctx.run_batch(a, o)
-    assert ctx.batch_stats()["packed_text"]
-    ctx.set_option("pack_threads", 3)  # fewer than 4 packer threads per device: never packed
+    st = ctx.batch_stats()
+    assert st["mode"] == "mixed" and 0 <= st["slabs_packed"] <= st["slabs"]
+    ctx.set_option("pack_threads", 1)  # fewer than 2 packer threads per device: ASCII
     for _ in range(2):
         ctx.run_batch(a, o)
-        assert not ctx.batch_stats()["packed_text"]
+        assert ctx.batch_stats()["mode"] == "ascii"
     ctx.set_option("pack_threads", 8)
     n = 2000  # a small batch never is
     for _ in range(2):
         ctx.run_batch(a[:int(o[n])], o[:n + 1])
-        assert not ctx.batch_stats()["packed_text"]
+        assert ctx.batch_stats()["mode"] == "ascii"
+    ctx.set_option("pack_h2d", 1)
+    ctx.run_batch(a, o)
+    assert ctx.batch_stats()["mode"] == "packed_on_the_way" and ctx.batch_stats()["packed_text"]
+    pk, fl = hx.pack_records(a, o)
+    assert ctx.run_batch_packed(pk, fl, o).tobytes() == first.tobytes() and ctx.batch_stats()["mode"] == "packed_arena"
 
 
 def test_packed_arena_contigs_long_primers_and_refusal(ctx):
@@ -395,6 +411,7 @@ def test_packed_arena_contigs_long_primers_and_refusal(ctx):
     _cmp(_run(ctx, a, o, pairs, 3, packed=1, tile_len=1024, single_max=1500), ref, a, o, pairs, 3)
     _cmp(_run(ctx, a, o, pairs, 3, pack_h2d=1, slab_bytes=200_000), ref, a, o, pairs, 3)
     _cmp(_run(ctx, a, o, pairs, 3, pack_h2d=1, pack_piece=16384), ref, a, o, pairs, 3)
+    _cmp(_run(ctx, a, o, pairs, 3, pack_h2d=2, slab_bytes=400_000, pack_piece=16384), ref, a, o, pairs, 3)
     # primers of 33..64 nt: suffix filter + verification read the text as nibbles too; 64-bit groups
     a, o = hx_synth.gen_reads(300, seed=46)
     pairs = hx_synth.gen_primer_pairs(12, seed=5, builtins=hx.default_primers())
@@ -500,6 +517,9 @@ def test_random_primer_sets_fuzz(ctx, seed):
     _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, pack_h2d=1, pack_threads=int(rng.integers(1, 9)),
               slab_bytes=int(rng.choice([1, 3000, 128 << 20])), pack_piece=int(rng.choice([4096, 8192, 4 << 20]))), ref, a, o,
          pairs, k)
+    _cmp(_run(ctx, a, o, pairs, k, tile_len=tile, single_max=tile, pack_h2d=2, pack_threads=int(rng.integers(1, 9)),
+              slab_bytes=int(rng.choice([1, 3000, 128 << 20])), pack_piece=int(rng.choice([4096, 8192, 4 << 20]))), ref, a, o,
+         pairs, k)
 
 
 def test_rna_records_use_rna_reverse_complement(ctx):
@@ -526,6 +546,7 @@ def test_slab_pipeline_and_unaligned_offsets(ctx):
     for slab in (1, 4096, 50_000, 1 << 20):
         _cmp(_run(ctx, a, o, pairs, 2, slab_bytes=slab), ref, a, o, pairs, 2)
         _cmp(_run(ctx, a, o, pairs, 2, slab_bytes=slab, pack_h2d=1), ref, a, o, pairs, 2)
+        _cmp(_run(ctx, a, o, pairs, 2, slab_bytes=slab, pack_h2d=2), ref, a, o, pairs, 2)
     # an arena whose first record does not start at offset 0
     pad = 7
     a2 = np.concatenate([np.frombuffer(b"GTGCCAG", np.uint8), a])
