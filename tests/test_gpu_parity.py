@@ -699,6 +699,13 @@ def test_multi_device_context_equals_single_device(ctx, tmp_path, host_format, m
         mctx.set_option("slab_bytes", 1 << 20)  # many slabs so every device gets work
         mctx.set_primers(pairs, 2)
         assert mctx.run_batch(a, o).tobytes() == ref.tobytes()
+        for mode, slab, threads in ((1, 1 << 20, 4), (2, 1 << 20, 4), (2, 200_000, 2), (2, 64 << 20, 8)):
+            # packed on the way / mixed slabs, spread over the devices of the context
+            mctx.set_option("pack_h2d", mode)
+            mctx.set_option("slab_bytes", slab)
+            mctx.set_option("pack_threads", threads)
+            assert mctx.run_batch(a, o).tobytes() == ref.tobytes(), (mode, slab, threads)
+        mctx.set_option("pack_h2d", -1)
         logs = []
         mctx.get_hypervar_regions(str(path), pairs, str(tmp_path / "m"), 2, log=lambda lvl, msg: logs.append(msg))
         assert (tmp_path / "m.fa").read_bytes() == fa and (tmp_path / "m.gff").read_bytes() == gff
