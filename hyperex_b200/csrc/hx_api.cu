@@ -1330,8 +1330,21 @@ namespace {
 // The issuing thread is the link's scheduler: an ASCII slab crosses in chunks, and at most HYB_LINKQ copies (chunks and
 // packed pieces together) are queued at any time, so a packed piece that becomes ready waits for a fraction of a
 // millisecond, not for a whole slab — the packers' ring holds less than a millisecond of their work.
-constexpr int HYB_LINKQ = 3;
-constexpr uint64_t HYB_CHUNK = 8ull << 20;
+constexpr int HYB_LINKQ_MAX = 8;
+int hyb_linkq() {  // HYPEREX_MIXED_LINKQ / HYPEREX_MIXED_CHUNK_MB: A/B knobs (tools/mixed_ab.py)
+    static const int v = [] {
+        const char *e = getenv("HYPEREX_MIXED_LINKQ");
+        return e ? std::max(1, std::min(HYB_LINKQ_MAX, atoi(e))) : 3;
+    }();
+    return v;
+}
+uint64_t hyb_chunk() {
+    static const uint64_t v = [] {
+        const char *e = getenv("HYPEREX_MIXED_CHUNK_MB");
+        return (uint64_t)(e ? std::max(1, atoi(e)) : 8) << 20;
+    }();
+    return v;
+}
 struct HybSlab {
     uint32_t r0, r1;
     uint64_t base_a, copy_a;  // ASCII: 16-byte phase of the arena kept
@@ -1433,7 +1446,7 @@ static int run_batch_hybrid(hx_ctx *ctx, const uint8_t *arena, const uint64_t *o
                 if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaEventCreate failed");
                 D.ring_ev.push_back(e);
             }
-            while ((int)D.link_ev.size() < HYB_LINKQ) {
+            while ((int)D.link_ev.size() < HYB_LINKQ_MAX) {
                 cudaEvent_t e = nullptr;
                 if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(ctx, HX_ERR_CUDA, "hx_run_batch: cudaEventCreate failed");
                 D.link_ev.push_back(e);
@@ -1529,7 +1542,9 @@ static int run_batch_hybrid(hx_ctx *ctx, const uint8_t *arena, const uint64_t *o
     int64_t af_j = -1;  // the ASCII slab that is crossing chunk by chunk, and how far it is
     uint64_t af_off = 0;
     int64_t a_issued = 0, a_done = 0;  // ASCII chunk copies enqueued / known to be complete
-    int a_dev[HYB_LINKQ] = {0};
+    int a_dev[HYB_LINKQ_MAX] = {0};
+    const int HYB_LINKQ = hyb_linkq();
+    const uint64_t HYB_CHUNK = hyb_chunk();
     const bool dbg = getenv("HYPEREX_HYB_DEBUG") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };

@@ -22,7 +22,10 @@ with hx.Context((0,)) as ctx:
     ctx.set_primers(pairs, 0)
     h_out = hx.pinned_empty(n * len(pairs) * 12).view(hx.RESULT_DTYPE).reshape(n, len(pairs))
     ref = None
-    for mode, threads in [(0, 0), (1, 0), (2, 0), (2, 12), (2, 8), (1, 8), (2, 4), (1, 4), (2, 0)]:
+    cases = [(0, 0), (1, 0), (2, 0), (2, 12), (2, 8), (1, 8), (2, 4), (1, 4), (2, 0)]
+    if os.environ.get("HX_AB_CASES"):  # "mode:threads,mode:threads"
+        cases = [tuple(int(x) for x in c.split(":")) for c in os.environ["HX_AB_CASES"].split(",")]
+    for mode, threads in cases:
         ctx.set_option("pack_h2d", mode)
         ctx.set_option("pack_threads", threads)
         for _ in range(3):
@@ -39,4 +42,5 @@ with hx.Context((0,)) as ctx:
         ts.sort()
         print(json.dumps({"pack_h2d": mode, "pack_threads": threads, "ms_median": ts[len(ts) // 2] * 1e3, "ms_min": ts[0] * 1e3,
                           "gbases_per_s_median": bases / ts[len(ts) // 2] / 1e9, "slabs": st["slabs"], "slabs_packed": st["slabs_packed"],
-                          "h2d_bytes": st["h2d_bytes"]}), flush=True)
+                          "h2d_bytes": st["h2d_bytes"], "linkq": os.environ.get("HYPEREX_MIXED_LINKQ", "3"),
+                          "chunk_mb": os.environ.get("HYPEREX_MIXED_CHUNK_MB", "8")}), flush=True)
