@@ -197,11 +197,11 @@ struct hx_ctx {
     DevPool find_pool;
     PackRing pack_ring;
     uint64_t batch_stats[7] = {0, 0, 0, 0, 0, 0, 0};  // hx_batch_stats
-    // pack_h2d = automatic: the first six large batches alternate ASCII / packed-on-the-way slabs, the last four of them
+    // pack_h2d = automatic: the first six large batches alternate ASCII slabs / the mixed path, the last four of them
     // are timed, and the faster mode serves every later call (run_batch_impl)
     struct {
         int calls = 0, decided = -1;
-        double rate[2] = {0, 0};  // bases per second of the timed ASCII / packed call
+        double rate[2] = {0, 0};  // bases per second of the timed ASCII / mixed call
     } auto_pack;
     // host-side state the file-level driver (hx_host.cpp) keeps across calls: pinned record batches etc.
     void *host_cache = nullptr;
@@ -1740,13 +1740,13 @@ static int run_batch_impl(hx_ctx *ctx, const uint8_t *arena, const uint8_t *rec_
     if (!offsets || !out) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL offsets/out");
     if (offsets[n_records] < offsets[0]) return fail(ctx, HX_ERR_ARG, "hx_run_batch: offsets must be non-decreasing");
     if (offsets[n_records] > offsets[0] && !arena) return fail(ctx, HX_ERR_ARG, "hx_run_batch: NULL arena");
-    // pack on the way: always / never / automatic.  Whether packing pays is a property of the host, not of the library:
-    // on a 16-thread B200 host one process gets 76 Gbases/s packed against 53 ASCII, on a 24-thread host shared by two
-    // processes (one GPU each) 26 against 51 per process (profiles/r02_pack_h2d_auto.md) — a process cannot see what its
-    // siblings do to the memory system.  So automatic = measure: batches large enough for the pipeline to fill (>= 64 MB),
-    // with at least 4 packer threads per device, alternate ASCII and packed six times; calls three to six are timed
-    // (buffers exist, pages are mapped), the better of its two runs counts for each mode, and packing serves the later
-    // calls iff it was at least 5 % faster.
+    // pack on the way: every slab (1) / never (0) / mixed (2) / automatic (-1).  Whether packing pays is a property of the host,
+    // not of the library: on a 16-thread B200 host one process gets 66-79 Gbases/s mixed against 50-53 ASCII, on a 24-thread
+    // host shared by two processes (one GPU each) mixed equals ASCII and packing every slab halves it
+    // (profiles/r02_mixed_slabs.md, r02_pack_h2d_auto.md) — a process cannot see what its siblings do to the memory system.
+    // So automatic = measure: batches large enough for the pipeline to fill (>= 64 MB), with at least 2 packer threads per
+    // device, alternate ASCII and mixed six times; calls three to six are timed (buffers exist, pages are mapped), the
+    // better of its two runs counts for each mode, and mixed serves the later calls iff it was at least 5 % faster.
     const int pack_threads = ctx->opt_pack_threads > 0 ? (int)ctx->opt_pack_threads : (int)std::thread::hardware_concurrency();
     const bool can_pack = !packed_in && ctx->packable && arena && offsets[n_records] > offsets[0];
     const bool pack_probe = can_pack && ctx->opt_pack_h2d < 0 && ctx->auto_pack.decided < 0 &&
