@@ -10,9 +10,12 @@ max over ranks.
 
   value        Gbases/s with the arena resident in HBM (CUDA events on the launching stream)
   e2e          Gbases/s through hx_run_batch with HOST buffers: pinned arena -> H2D -> kernels -> D2H
-               result table, every step (library defaults: the small-k fast path is on, as shipped)
+               result table, every step (library defaults: the small-k fast path is on, as shipped; how the text
+               crosses the link — ASCII slabs, or ASCII and packed slabs at once — is what the library measured,
+               e2e.mode; ascii_slabs / packed_slabs / mixed_slabs are the forced modes next to it)
   file_e2e     Gbases/s of the drop-in seam itself, hx_get_hypervar_regions: FASTA file in, <prefix>.fa and
-               <prefix>.gff out (utils.rs:231-414 / main.rs:38), with the parse / device / write phases
+               <prefix>.gff out (utils.rs:231-414 / main.rs:38), with the parse / device / write phases;
+               file_e2e.file_to_table: the same file -> host result table through hx_fasta_next* + hx_run_batch*
   roofline     the Myers kernel against the measured integer-ALU peak (hx_int_peak) and HBM peak
   cpu_baseline the CPU oracle (C port of the reference path) on a bounded sample, one thread like the
                single-threaded reference
@@ -758,7 +761,7 @@ def main():
                 "gpu_launches": int(total_launches), "roofline": roofline, "clocks": clocks,
                 "result_table_sha256_rank0": table_sha}
         line["e2e"]["path"] = ("library defaults (fast_small_k = 1, pack_h2d automatic; --pack-h2d %d given): result table asserted "
-                               "equal to the Myers kernel's and equal between the ASCII and packed paths" % args.pack_h2d)
+                               "equal to the Myers kernel's and equal between the ASCII, packed and mixed paths" % args.pack_h2d)
         line["e2e_packed"] = {
             "what": "hx_run_batch_packed: pinned PACKED arena (4-bit codes, hx_pack_records) -> H2D -> kernels on nibble text -> D2H "
                     "result table, every step; result table asserted equal to the ASCII leg's",
