@@ -1026,6 +1026,9 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
     ctx->pair_refs.swap(refs);
     ctx->tables.swap(blob);
     ctx->primers_set = true;
+    // what pack_h2d = automatic measured belongs to the primer set it was measured with: a set that makes the call
+    // link-bound wants the mixed path, one that makes it kernel-bound does not (profiles/r02_mixed_slabs.md)
+    ctx->auto_pack = {};
     return HX_OK;
 }
 

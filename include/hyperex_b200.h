@@ -91,7 +91,7 @@ int hx_set_primers(hx_ctx *ctx, uint32_t n_pairs, const char *const *fwd, const 
  * half the packers' rate instead of the larger of the two); identical results in every mode; 0 = ASCII slabs; -1,
  * default = automatic: measured — the first six batches >= 64 MB of a context with >= 2 packer threads per device
  * alternate ASCII and mixed, the last four are timed, and the faster mode (mixed only when >= 5 % faster) serves every
- * later call; setting the option again measures again; never for a primer set that packed text cannot represent), "pack_threads" (host threads of that path, 0 = all hardware threads; a process that shares the host
+ * later call; setting the option again, or another primer set, measures again; never for a primer set that packed text cannot represent), "pack_threads" (host threads of that path, 0 = all hardware threads; a process that shares the host
  * with other ranks passes its share), "pack_piece_bytes" (size of the pinned ring buffers the packed text goes through,
  * default 4 MiB: small enough to stay in the last-level cache between the packer's stores and the DMA reads). */
 int hx_set_option(hx_ctx *ctx, const char *name, int64_t value);
